@@ -1,0 +1,47 @@
+"""Synthetic action sources for the benchmark configurations.
+
+The reference ships no CPG controller (its only action source is the kinematic
+replay clip, ``src/flygym_demo/spotlight_data/preprocessing.py``); BASELINE.json's
+config 2 asks for "sinusoidal CPG tripod-gait actions", defined here
+deterministically: for actuated DoF i of leg l,
+
+    target_i(t) = neutral_i + A_i * sin(2 pi f t + phi_l + delta_i + psi_k)
+
+f = 12 Hz; tripod phases phi = 0 for {lf, rm, lh}, pi for {rf, lm, rh}; amplitudes
+coxa-pitch 0.35, trochanterfemur-pitch 0.30, tibia-pitch 0.40, tarsus1-pitch 0.15 rad
+(the last three with delta = pi/2), roll / yaw 0; per-fly phase psi_k = 2 pi k / n.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TRIPOD_PHASE = {"lf": 0.0, "rm": 0.0, "lh": 0.0, "rf": np.pi, "lm": np.pi, "rh": np.pi}
+AMPLITUDE = {"coxa-pitch": (0.35, 0.0), "trochanterfemur-pitch": (0.30, np.pi / 2),
+             "tibia-pitch": (0.40, np.pi / 2), "tarsus1-pitch": (0.15, np.pi / 2)}
+
+
+def cpg_parameters(model):
+    """Per-actuator (neutral, amplitude, phase) for the model's position actuators."""
+    names = model.names["actuated_position"]
+    neutral = model.arrays["key_ctrl"][: len(names)].astype(np.float64)
+    amp = np.zeros(len(names))
+    phase = np.zeros(len(names))
+    for i, nm in enumerate(names):
+        _, child, axis = nm.split("-")
+        leg, link = child.split("_")
+        a, d = AMPLITUDE.get(f"{link}-{axis}", (0.0, 0.0))
+        amp[i] = a
+        phase[i] = TRIPOD_PHASE[leg] + d
+    return neutral, amp, phase
+
+
+def cpg_table(model, n_flies: int, n_steps: int, *, freq_hz: float = 12.0, fly_offset: int = 0,
+              n_flies_total: int | None = None, dtype=np.float32) -> np.ndarray:
+    """Action table ``(n_flies, n_steps, n_position_actuators)``; fly k of the *global* batch gets
+    phase offset 2 pi k / n_flies_total, so results do not depend on how flies are sharded over ranks."""
+    neutral, amp, phase = cpg_parameters(model)
+    total = n_flies if n_flies_total is None else n_flies_total
+    t = np.arange(n_steps) * model.timestep
+    psi = 2 * np.pi * (np.arange(n_flies) + fly_offset) / total
+    arg = 2 * np.pi * freq_hz * t[None, :, None] + phase[None, None, :] + psi[:, None, None]
+    return (neutral[None, None, :] + amp[None, None, :] * np.sin(arg)).astype(dtype)

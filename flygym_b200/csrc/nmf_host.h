@@ -1,0 +1,170 @@
+// nmf_host.h — host-side model ingestion for the sm_100a step path (plain C++).
+//
+// Parses the baked-model blob (flygym_b200/model.py::NMFModel.to_blob), checks that
+// the model has the topology the kernels are written for and flattens it into the
+// per-thread "role table" (nmf_layout.h) plus the scalar step parameters.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nmf_layout.h"
+
+namespace nmf {
+
+struct BlobView {
+  const char* p = nullptr; size_t n = 0;
+  bool ok() const { return p && n >= 16 && memcmp(p, "NMFB200", 8) == 0; }
+  template <typename T> const T* get(const char* name, int* count = nullptr) const {
+    int32_t nsec; memcpy(&nsec, p + 12, 4);
+    for (int i = 0; i < nsec; i++) {
+      const char* e = p + 16 + 40 * i; char nm[25] = {0}; memcpy(nm, e, 24);
+      int32_t cnt; int64_t off; memcpy(&cnt, e + 28, 4); memcpy(&off, e + 32, 8);
+      if (!strcmp(nm, name)) { if (count) *count = cnt; return reinterpret_cast<const T*>(p + off); }
+    }
+    return nullptr;
+  }
+};
+
+inline void qmul_d(const double* a, const double* b, double* r) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+inline void q2mat_d(const double* q, double* m) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = 1 - 2 * (x * x + y * y);
+}
+inline float i2f(int v) { float f; memcpy(&f, &v, 4); return f; }
+
+struct HostModel {
+  std::vector<float> role;     // RF_COUNT * CTA
+  std::vector<float> hull;     // 3 * nhullvert
+  std::vector<float> seg_tab;  // nseg * 8
+  std::vector<float> key_state;  // S_STRIDE, the neutral keyframe as a state record
+  StepParams par{};            // pointer members left null
+  int nu = 0, nseg = 0;
+  std::string err;
+
+  bool build(const void* blob, size_t nbytes) {
+    BlobView b{(const char*)blob, nbytes};
+    if (!b.ok()) { err = "bad model blob"; return false; }
+    const int32_t* dims = b.get<int32_t>("dims");
+    if (!dims) { err = "blob has no dims"; return false; }
+    const int nbody = dims[0], nq = dims[1], nv = dims[2], nu_pos = dims[3], nu_adh = dims[4], ngeom = dims[5];
+    nseg = dims[7]; const int nleg = dims[8], nhv = dims[9];
+    nu = nu_pos + nu_adh;
+    if (nbody != 1 + NLEG * NLINK || nv != NV || nq != NQ || nleg != NLEG) { err = "unsupported topology: need hub + 6 legs x 8 links, nv=72"; return false; }
+    if (nu > MAXU) { err = "too many actuators"; return false; }
+    auto D = [&](const char* n) { return b.get<double>(n); };
+    auto I = [&](const char* n) { return b.get<int32_t>(n); };
+    const double *body_pos = D("body_pos"), *body_quat = D("body_quat"), *body_mass = D("body_mass"), *body_ipos = D("body_ipos"),
+                 *body_iquat = D("body_iquat"), *body_inertia = D("body_inertia"), *invw = D("body_invweight0"), *dof_axis = D("dof_axis"),
+                 *stiff = D("dof_stiffness"), *damp = D("dof_damping"), *arm = D("dof_armature"), *sref = D("dof_springref"),
+                 *kp = D("act_kp"), *kv = D("act_kv"), *frc = D("act_frcrange"), *again = D("adh_gain"), *actrl = D("adh_ctrlrange"),
+                 *gpos = D("geom_pos"), *gquat = D("geom_quat"), *gsize = D("geom_size"), *hv = D("hull_vert"), *segpos = D("seg_pos"),
+                 *segquat = D("seg_quat"), *key_qpos = D("key_qpos"), *key_ctrl = D("key_ctrl"), *opt = D("opt"), *contact = D("contact");
+    const int32_t *body_parent = I("body_parent"), *dofadr = I("body_dofadr"), *dofnum = I("body_dofnum"), *body_leg = I("body_leg"),
+                  *act_dof = I("act_dof"), *adh_body = I("adh_body"), *geom_body = I("geom_body"), *geom_type = I("geom_type"),
+                  *gvadr = I("geom_vertadr"), *gvnum = I("geom_vertnum"), *seg_body = I("seg_body"), *leg_root = I("leg_rootbody");
+    if (!body_pos || !body_parent || !opt || !contact || !key_qpos) { err = "blob is missing sections"; return false; }
+    static const int want_dofs[NLINK] = {3, 2, 1, 1, 1, 1, 1, 1};
+    for (int l = 0; l < NLEG; l++) for (int k = 0; k < NLINK; k++) {
+      int bb = 1 + l * NLINK + k;
+      if (dofnum[bb] != want_dofs[k] || body_parent[bb] != (k == 0 ? 0 : bb - 1) || body_leg[bb] != l) { err = "unsupported leg chain layout"; return false; }
+    }
+    role.assign((size_t)RF_COUNT * CTA, 0.f);
+    auto set = [&](int field, int tid, float v) { role[(size_t)field * CTA + tid] = v; };
+    auto lane_of_body = [&](int bb) { return bb == 0 ? NLEG * NLINK : bb - 1; };
+    double mtot = 0;
+    for (int bb = 0; bb < nbody; bb++) mtot += body_mass[bb];
+    // body-level fields (hub replicated on all 16 hub lanes)
+    for (int tid = 0; tid < CTA; tid++) {
+      int bb = tid < NLEG * NLINK ? tid + 1 : 0;
+      for (int i = 0; i < 3; i++) set(RF_BPOS + i, tid, (float)body_pos[3 * bb + i]);
+      for (int i = 0; i < 4; i++) set(RF_BQUAT + i, tid, (float)body_quat[4 * bb + i]);
+      for (int i = 0; i < 3; i++) set(RF_IPOS + i, tid, (float)body_ipos[3 * bb + i]);
+      double Rm[9]; q2mat_d(body_iquat + 4 * bb, Rm);
+      double Ib[9];
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += Rm[3 * i + k] * body_inertia[3 * bb + k] * Rm[3 * j + k]; Ib[3 * i + j] = s; }
+      set(RF_IB + 0, tid, (float)Ib[0]); set(RF_IB + 1, tid, (float)Ib[4]); set(RF_IB + 2, tid, (float)Ib[8]);
+      set(RF_IB + 3, tid, (float)Ib[1]); set(RF_IB + 4, tid, (float)Ib[2]); set(RF_IB + 5, tid, (float)Ib[5]);
+      set(RF_MASS, tid, (float)body_mass[bb]); set(RF_INVW, tid, (float)invw[2 * bb]);
+      set(RF_GTYPE, tid, i2f(-1)); set(RF_ADH_CIDX, tid, i2f(-1));
+      for (int j = 0; j < 3; j++) set(RF_CIDX + j, tid, i2f(-1));
+      if (bb > 0) {
+        set(RF_NDOF, tid, i2f(dofnum[bb])); set(RF_DOF0, tid, i2f(dofadr[bb]));
+        for (int j = 0; j < dofnum[bb]; j++) {
+          int d = dofadr[bb] + j;
+          for (int i = 0; i < 3; i++) set(RF_AXIS + 3 * j + i, tid, (float)dof_axis[3 * d + i]);
+          set(RF_STIFF + j, tid, (float)stiff[d]); set(RF_DAMP + j, tid, (float)damp[d]); set(RF_ARM + j, tid, (float)arm[d]);
+          set(RF_SREF + j, tid, (float)sref[d]);
+        }
+        bool sens = false;   // the leg sensor covers the subtree rooted at the most proximal contact segment
+        int l = body_leg[bb]; if (l >= 0 && leg_root[l] >= 0 && bb >= leg_root[l]) sens = true;
+        set(RF_LEGSENSOR, tid, i2f(sens ? 1 : 0));
+      } else { set(RF_NDOF, tid, i2f(0)); set(RF_DOF0, tid, i2f(0)); }
+    }
+    for (int a = 0; a < nu_pos; a++) {
+      int d = act_dof[a], bb = -1, j = 0;
+      for (int c = 1; c < nbody; c++) if (d >= dofadr[c] && d < dofadr[c] + dofnum[c]) { bb = c; j = d - dofadr[c]; }
+      if (bb < 0) { err = "actuator on a free-joint dof is not supported"; return false; }
+      int tid = lane_of_body(bb);
+      set(RF_KP + j, tid, (float)kp[a]); set(RF_KV + j, tid, (float)kv[a]); set(RF_FLO + j, tid, (float)frc[2 * a]);
+      set(RF_FHI + j, tid, (float)frc[2 * a + 1]); set(RF_CIDX + j, tid, i2f(a));
+    }
+    for (int a = 0; a < nu_adh; a++) {
+      int bb = adh_body[a]; if (bb <= 0) { err = "adhesion on the hub is not supported"; return false; }
+      int tid = lane_of_body(bb);
+      set(RF_ADH_GAIN, tid, (float)again[a]); set(RF_ADH_LO, tid, (float)actrl[2 * a]); set(RF_ADH_HI, tid, (float)actrl[2 * a + 1]);
+      set(RF_ADH_CIDX, tid, i2f(nu_pos + a));
+    }
+    int nhub = 0;
+    std::vector<char> used(CTA, 0);
+    for (int g = 0; g < ngeom; g++) {
+      int bb = geom_body[g], tid;
+      if (bb == 0) { if (nhub >= NHUBLANE) { err = "more than 16 contact geoms on the hub"; return false; } tid = NLEG * NLINK + nhub++; }
+      else { tid = lane_of_body(bb); if (used[tid]) { err = "more than one contact geom on a leg body"; return false; } }
+      used[tid] = 1;
+      set(RF_GTYPE, tid, i2f(geom_type[g]));
+      double Rm[9]; q2mat_d(gquat + 4 * g, Rm);
+      for (int i = 0; i < 3; i++) { set(RF_GPOS + i, tid, (float)gpos[3 * g + i]); set(RF_GAXIS + i, tid, (float)Rm[3 * i + 2]); }
+      set(RF_GRAD, tid, (float)gsize[2 * g]); set(RF_GHALF, tid, (float)gsize[2 * g + 1]);
+      set(RF_GVADR, tid, i2f(gvadr[g])); set(RF_GVNUM, tid, i2f(gvnum[g]));
+    }
+    hull.assign((size_t)3 * (nhv > 0 ? nhv : 1), 0.f);
+    for (int i = 0; i < 3 * nhv; i++) hull[i] = (float)hv[i];
+    seg_tab.assign((size_t)nseg * 8, 0.f);
+    for (int s = 0; s < nseg; s++) {
+      seg_tab[8 * s] = i2f(lane_of_body(seg_body[s]));
+      for (int i = 0; i < 3; i++) seg_tab[8 * s + 1 + i] = (float)segpos[3 * s + i];
+      for (int i = 0; i < 4; i++) seg_tab[8 * s + 4 + i] = (float)segquat[4 * s + i];
+    }
+    key_state.assign(S_STRIDE, 0.f);
+    for (int i = 0; i < nq; i++) key_state[S_QPOS + i] = (float)key_qpos[i];
+    for (int i = 0; i < nu; i++) key_state[S_CTRL + i] = (float)key_ctrl[i];
+    par = StepParams{};
+    par.nu_pos = nu_pos; par.nu_adh = nu_adh; par.nseg = nseg; par.nhubgeom = nhub;
+    par.dt = (float)opt[0]; par.gx = (float)opt[1]; par.gy = (float)opt[2]; par.gz = (float)opt[3];
+    par.inv_total_mass = (float)(1.0 / mtot);
+    par.impratio = (float)opt[10];
+    par.mu = (float)contact[0];
+    double tc = std::fmax(contact[1], 2 * opt[0]), dr = contact[2];
+    auto clampimp = [](double v) { return std::fmin(0.9999, std::fmax(0.0001, v)); };
+    double dmax = clampimp(contact[4]);
+    par.cK = (float)(1.0 / (dmax * dmax * tc * tc * dr * dr)); par.cB = (float)(2.0 / (dmax * tc));
+    par.solimp[0] = (float)clampimp(contact[3]); par.solimp[1] = (float)dmax; par.solimp[2] = (float)std::fmax(0.0, contact[5]);
+    par.solimp[3] = (float)clampimp(contact[6]); par.solimp[4] = (float)std::fmax(1.0, contact[7]);
+    par.margin = (float)(contact[8] - contact[9]);
+    par.max_newton = 8; par.max_ls = 8; par.nsteps = 1;
+    (void)body_parent;
+    return true;
+  }
+};
+
+}  // namespace nmf

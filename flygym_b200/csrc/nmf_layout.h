@@ -1,0 +1,97 @@
+// nmf_layout.h — shared constants of the sm_100a step path (host + device).
+//
+// Topology handled by the kernels: the reference benchmark model
+// (/root/reference/src/flygym_demo/benchmark/time_gpu_simulation.py:21-64):
+// one free "hub" body (thorax + all jointless segments fused,
+// mujoco_globals.yaml:5 fusestatic) carrying six identical 8-link leg chains with
+// (3,2,1,1,1,1,1,1) hinge DoFs -> nv = 6 + 6*11 = 72.
+#pragma once
+
+namespace nmf {
+
+constexpr int NLEG = 6;
+constexpr int NLINK = 8;        // bodies per leg  (coxa .. tarsus5)
+constexpr int NLEGDOF = 11;     // hinge DoFs per leg
+constexpr int NV = 6 + NLEG * NLEGDOF;   // 72
+constexpr int NQ = NV + 1;               // 73
+constexpr int CTA = 64;         // threads per fly: 48 leg-body lanes + 16 hub lanes
+constexpr int NHUBLANE = 16;
+constexpr int MAXU = 80;        // max controls kept in the state record
+
+// per-fly state record (floats), every section 16-byte aligned so one TMA bulk
+// copy (cp.async.bulk) moves the whole record between HBM and shared memory
+constexpr int S_QPOS = 0;       // 73 (+3 pad)
+constexpr int S_QVEL = 76;      // 72
+constexpr int S_WARM = 148;     // 72  qacc_warmstart
+constexpr int S_CTRL = 220;     // nu <= MAXU
+constexpr int S_TIME = 300;     // time, status, 2 pad
+constexpr int S_STRIDE = 304;
+
+// thread-role constant table: role[field * CTA + tid]
+enum RoleField {
+  RF_BPOS = 0,            // 3  body_pos (parent frame)
+  RF_BQUAT = 3,           // 4
+  RF_IPOS = 7,            // 3  inertial-frame origin in the body frame
+  RF_IB = 10,             // 6  body-frame inertia tensor about the COM: xx yy zz xy xz yz
+  RF_MASS = 16,
+  RF_INVW = 17,           // body_invweight0[.,0]
+  RF_NDOF = 18,           // int
+  RF_AXIS = 19,           // 9  local hinge axes (3 x xyz)
+  RF_STIFF = 28,          // 3
+  RF_DAMP = 31,           // 3
+  RF_ARM = 34,            // 3
+  RF_SREF = 37,           // 3
+  RF_KP = 40,             // 3
+  RF_KV = 43,             // 3
+  RF_FLO = 46,            // 3
+  RF_FHI = 49,            // 3
+  RF_CIDX = 52,           // 3 int: ctrl index of the position actuator on this dof, -1 = none
+  RF_GTYPE = 55,          // int: -1 none, 0 capsule, 1 convex hull
+  RF_GPOS = 56,           // 3  capsule centre (body frame)
+  RF_GAXIS = 59,          // 3  capsule axis (body frame)
+  RF_GRAD = 62,
+  RF_GHALF = 63,
+  RF_GVADR = 64,          // int
+  RF_GVNUM = 65,          // int
+  RF_ADH_GAIN = 66,
+  RF_ADH_LO = 67,
+  RF_ADH_HI = 68,
+  RF_ADH_CIDX = 69,       // int, -1 = no adhesion actuator on this body
+  RF_DOF0 = 70,           // int: global dof index of the lane's first dof
+  RF_LEGSENSOR = 71,      // int: 1 if this body's contacts count for the leg contact sensor
+  RF_COUNT = 72
+};
+
+// debug dump (floats per fly), only written when a dump buffer is passed
+constexpr int DBG_NITER = 0, DBG_NCON = 1, DBG_NLS = 2, DBG_NCHG = 3;
+constexpr int DBG_FS = 4;                    // qfrc_smooth[72]
+constexpr int DBG_QACC = DBG_FS + NV;        // qacc[72]
+constexpr int DBG_FC = DBG_QACC + NV;        // qfrc_constraint[72]
+constexpr int DBG_QACCE = DBG_FC + NV;       // Euler (implicit-damping) acceleration[72]
+constexpr int DBG_CON = DBG_QACCE + NV;      // per thread, 2 slots x (active, dist, x, y, z, fn) = 12
+constexpr int DBG_XPOS = DBG_CON + CTA * 12; // per thread xpos (3)
+constexpr int DBG_CDOF = DBG_XPOS + CTA * 3; // cdof[72][6]
+constexpr int DBG_HROWS = DBG_CDOF + NV * 6; // Euler matrix rows: 6 legs x 177, then 21 base
+constexpr int DBG_STRIDE = DBG_HROWS + NLEG * 177 + 21 + 3;
+
+struct StepParams {
+  float* state;              // [n_flies][S_STRIDE]
+  const float* role;         // [RF_COUNT][CTA]
+  const float* hull;         // hull vertices (xyz) in body frames
+  const float* act_table;    // optional [n_flies][table_T][nu_pos]; nullptr = use ctrl in state
+  const float* seg_tab;      // [nseg][8]: body lane (as float), pos xyz, quat wxyz  (static segments on the hub)
+  float* out_xpos;           // optional [n_flies][nseg][3]
+  float* out_xquat;          // optional [n_flies][nseg][4]
+  float* out_actf;           // optional [n_flies][nu]
+  float* out_sensor;         // optional [n_flies][NLEG*16]
+  float* dbg;                // optional [n_flies][DBG_STRIDE]
+  const int* seg_lane;       // [nseg] thread id whose body carries the segment
+  int n_flies, nsteps, table_T, table_t0;
+  int nu_pos, nu_adh, nseg, nhubgeom;
+  float dt, gx, gy, gz, inv_total_mass;
+  float mu, cK, cB, margin, impratio;
+  float solimp[5];           // sanitised: d0, dmax, width, midpoint, power
+  int max_newton, max_ls;
+};
+
+}  // namespace nmf

@@ -1,0 +1,1102 @@
+// nmf_step.cuh — one NeuroMechFly physics step per thread block (sm_100a).
+//
+// Replaces, for the reference benchmark model, the whole of
+//   GPUSimulation.step -> mujoco_warp.step   (reference src/flygym/warp/simulation.py:260-263)
+//   Simulation.step    -> mujoco.mj_step     (reference src/flygym/simulation.py:74-76)
+// with ONE fused kernel: forward kinematics, composite inertias, bias forces,
+// position + adhesion actuators, geom-plane collision, soft-contact Newton solve
+// and semi-implicit Euler, state staying in shared memory / registers for
+// `nsteps` consecutive steps.
+//
+// Mapping (B200-first, not a port): a block of 64 threads owns one fly.
+//   tid  0..47 : leg-body lanes, (leg = tid/8, link = tid%8); 8-lane shuffle
+//                segments = one kinematic chain, so every chain recursion of the
+//                classical algorithms becomes a 3-step warp-shuffle scan:
+//                  FK           = inclusive scan of rigid transforms
+//                  velocities   = prefix sums of spatial vectors (common c-frame)
+//                  CRBA / RNE   = suffix sums of spatial inertias / wrenches
+//   tid 48..63 : hub lanes (free body, its 6 DoFs, its contact geoms)
+// Newton Hessian: M + J'DJ is assembled as a CRBA over *contact-augmented*
+// spatial inertias (each contact adds X'WX to its body), so it keeps M's
+// arrowhead sparsity (hub 6x6 + six 11x11 chains); each chain block is factorised
+// L'DL in registers, one matrix column per lane, the hub block by Schur complement.
+//
+// The same source is compiled by g++ against tests/simt_emu/simt_emu.h
+// (NMF_SIMT_EMU) so it can be exercised without a GPU; that is test
+// infrastructure, not a fallback: the shipped library only contains the nvcc build.
+#pragma once
+#include "nmf_layout.h"
+
+namespace nmf {
+
+#define NMF_FULL 0xffffffffu
+#define NMF_MINVAL 1e-15f
+
+// ------------------------------------------------------------------ small math
+__device__ __forceinline__ void qmul(const float* a, const float* b, float* r) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+__device__ __forceinline__ void qrot(const float* q, const float* v, float* r) {
+  // r = v + 2 w (u x v) + 2 u x (u x v)
+  float tx = 2.f * (q[2] * v[2] - q[3] * v[1]), ty = 2.f * (q[3] * v[0] - q[1] * v[2]), tz = 2.f * (q[1] * v[1] - q[2] * v[0]);
+  float rx = v[0] + q[0] * tx + (q[2] * tz - q[3] * ty);
+  float ry = v[1] + q[0] * ty + (q[3] * tx - q[1] * tz);
+  float rz = v[2] + q[0] * tz + (q[1] * ty - q[2] * tx);
+  r[0] = rx; r[1] = ry; r[2] = rz;
+}
+__device__ __forceinline__ void q2mat(const float* q, float* m) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = 1.f - 2.f * (y * y + z * z); m[1] = 2.f * (x * y - w * z); m[2] = 2.f * (x * z + w * y);
+  m[3] = 2.f * (x * y + w * z); m[4] = 1.f - 2.f * (x * x + z * z); m[5] = 2.f * (y * z - w * x);
+  m[6] = 2.f * (x * z - w * y); m[7] = 2.f * (y * z + w * x); m[8] = 1.f - 2.f * (x * x + y * y);
+}
+__device__ __forceinline__ void qnormalize(float* q) {
+  float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 < 1e-30f) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }
+  float s = rsqrtf(n2);
+  q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s;
+}
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* r) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ float dot6(const float* a, const float* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+// spatial inertia (Ixx Iyy Izz Ixy Ixz Iyz | hx hy hz | m) times motion vector (ang, lin)
+__device__ __forceinline__ void mul_inert(const float* i, const float* v, float* r) {
+  float r0 = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  float r1 = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  float r2 = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  float r3 = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  float r4 = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  float r5 = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5;
+}
+__device__ __forceinline__ void cross_motion(const float* vel, const float* v, float* r) {
+  float a[3], b[3], c[3];
+  cross3(vel, v, a); cross3(vel, v + 3, b); cross3(vel + 3, v, c);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+__device__ __forceinline__ void cross_force(const float* vel, const float* f, float* r) {
+  float a[3], b[3], c[3];
+  cross3(vel, f, a); cross3(vel + 3, f + 3, b); cross3(vel, f + 3, c);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+// packed upper-triangular index of a symmetric 6x6, a <= b
+__device__ __forceinline__ constexpr int s6(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }
+// expand a 10-float spatial inertia into packed symmetric 6x6 (order: wx wy wz vx vy vz)
+__device__ __forceinline__ void expand_inert(const float* i, float* P) {
+  P[s6(0, 0)] = i[0]; P[s6(0, 1)] = i[3]; P[s6(0, 2)] = i[4]; P[s6(0, 3)] = 0.f;   P[s6(0, 4)] = -i[8]; P[s6(0, 5)] = i[7];
+  P[s6(1, 1)] = i[1]; P[s6(1, 2)] = i[5]; P[s6(1, 3)] = i[8];  P[s6(1, 4)] = 0.f;  P[s6(1, 5)] = -i[6];
+  P[s6(2, 2)] = i[2]; P[s6(2, 3)] = -i[7]; P[s6(2, 4)] = i[6]; P[s6(2, 5)] = 0.f;
+  P[s6(3, 3)] = i[9]; P[s6(3, 4)] = 0.f; P[s6(3, 5)] = 0.f; P[s6(4, 4)] = i[9]; P[s6(4, 5)] = 0.f; P[s6(5, 5)] = i[9];
+}
+__device__ __forceinline__ void sym6_mul(const float* P, const float* v, float* r) {
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    float s = 0.f;
+#pragma unroll
+    for (int b = 0; b < 6; b++) s += P[a <= b ? s6(a, b) : s6(b, a)] * v[b];
+    r[a] = s;
+  }
+}
+
+// ------------------------------------------------------------------ 8-lane chain scans
+template <int N>
+__device__ __forceinline__ void chain_prefix(float* v, unsigned mask, int k) {  // inclusive, root -> tip
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
+    for (int n = 0; n < N; n++) { float t = __shfl_up_sync(mask, v[n], off, 8); if (k >= off) v[n] += t; }
+  }
+}
+template <int N>
+__device__ __forceinline__ void chain_suffix(float* v, unsigned mask, int k) {  // inclusive, tip -> root
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
+    for (int n = 0; n < N; n++) { float t = __shfl_down_sync(mask, v[n], off, 8); if (k + off < 8) v[n] += t; }
+  }
+}
+
+// block-wide sum of N values; call from converged code only (all 64 threads)
+template <int N>
+__device__ __forceinline__ void cta_reduce(float* v, float* s_red, int& parity, int tid) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int n = 0; n < N; n++) v[n] += __shfl_xor_sync(NMF_FULL, v[n], off);
+  }
+  float* buf = s_red + parity * 16;
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int n = 0; n < N; n++) buf[(tid >> 5) * 8 + n] = v[n];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < N; n++) v[n] = buf[n] + buf[8 + n];
+  parity ^= 1;
+}
+
+// ------------------------------------------------------------------ contact slot (kept in registers)
+struct Contact {
+  float active;      // 1 if dist < margin
+  float r[3];        // contact position relative to the subtree COM
+  float cx, cy;      // first tangent (cx, cy, 0); second = (-cy, cx, 0); normal = +z
+  float D;           // 1/R of the four pyramid rows
+  float c0;          // K * imp * (dist - margin)
+  float w[3];        // (n, mu t1, mu t2) . (a_p + B v_p)  for the current qacc
+  float s[3];        // (n, mu t1, mu t2) . a_p(search)
+  float dist;
+};
+
+__device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
+  const float d0 = p.solimp[0], d1 = p.solimp[1], width = p.solimp[2], mid = p.solimp[3], power = p.solimp[4];
+  if (d0 == d1 || width <= NMF_MINVAL) return 0.5f * (d0 + d1);
+  float x = x_abs / width;
+  if (x >= 1.f) return d1;
+  if (x <= 0.f) return d0;
+  float y;
+  if (power == 1.f) y = x;
+  else if (power == 2.f) y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  else y = (x <= mid) ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  return d0 + y * (d1 - d0);
+}
+
+// geom-vs-ground-plane narrow phase for the geom carried by this lane's body
+// (plane z = 0, normal +z: reference world.py:251-260).  Fills two slots.
+__device__ __forceinline__ void collide(const StepParams& p, const float* role, int tid, const float* xpos, const float* R,
+                                        const float* com, const float* cvel, float invw, Contact* con) {
+  con[0].active = 0.f; con[1].active = 0.f;
+  const int gtype = __float_as_int(role[RF_GTYPE * CTA + tid]);
+  if (gtype < 0) return;
+  float pos[2][3], dist[2], hint[2] = {0.f, 1.f};
+  int ncand = 0;
+  if (gtype == 0) {  // capsule: two sphere-plane tests, frame aligned with the capsule axis
+    float gp[3] = {role[(RF_GPOS + 0) * CTA + tid], role[(RF_GPOS + 1) * CTA + tid], role[(RF_GPOS + 2) * CTA + tid]};
+    float ga[3] = {role[(RF_GAXIS + 0) * CTA + tid], role[(RF_GAXIS + 1) * CTA + tid], role[(RF_GAXIS + 2) * CTA + tid]};
+    float rad = role[RF_GRAD * CTA + tid], half = role[RF_GHALF * CTA + tid];
+    float c[3], a[3];
+    for (int i = 0; i < 3; i++) {
+      c[i] = xpos[i] + R[3 * i] * gp[0] + R[3 * i + 1] * gp[1] + R[3 * i + 2] * gp[2];
+      a[i] = R[3 * i] * ga[0] + R[3 * i + 1] * ga[1] + R[3 * i + 2] * ga[2];
+    }
+    float hn = sqrtf(a[0] * a[0] + a[1] * a[1]);
+    if (hn < 1e-12f) { hint[0] = 1.f; hint[1] = 0.f; } else { hint[0] = a[0] / hn; hint[1] = a[1] / hn; }
+    for (int s = 0; s < 2; s++) {
+      float sg = s == 0 ? 1.f : -1.f;
+      float ez = c[2] + sg * half * a[2];
+      dist[s] = ez - rad;
+      pos[s][0] = c[0] + sg * half * a[0]; pos[s][1] = c[1] + sg * half * a[1]; pos[s][2] = 0.5f * dist[s];
+      con[s].active = (ez <= p.margin + rad) ? 1.f : 0.f;
+    }
+    ncand = 2;
+  } else {  // convex hull: deepest vertex
+    const int adr = __float_as_int(role[RF_GVADR * CTA + tid]), num = __float_as_int(role[RF_GVNUM * CTA + tid]);
+    float best = 3.0e38f; int bi = 0;
+    for (int v = 0; v < num; v++) {
+      const float* hv = p.hull + 3 * (adr + v);
+      float z = R[6] * __ldg(hv) + R[7] * __ldg(hv + 1) + R[8] * __ldg(hv + 2);
+      if (z < best) { best = z; bi = v; }
+    }
+    const float* hv = p.hull + 3 * (adr + bi);
+    float h0 = __ldg(hv), h1 = __ldg(hv + 1), h2 = __ldg(hv + 2);
+    dist[0] = best + xpos[2];
+    pos[0][0] = xpos[0] + R[0] * h0 + R[1] * h1 + R[2] * h2;
+    pos[0][1] = xpos[1] + R[3] * h0 + R[4] * h1 + R[5] * h2;
+    pos[0][2] = 0.5f * dist[0];
+    con[0].active = (num > 0 && dist[0] <= p.margin) ? 1.f : 0.f;
+    ncand = 1;
+  }
+  for (int s = 0; s < ncand; s++) {
+    Contact& c = con[s];
+    c.dist = dist[s];
+    c.r[0] = pos[s][0] - com[0]; c.r[1] = pos[s][1] - com[1]; c.r[2] = pos[s][2] - com[2];
+    c.cx = hint[0]; c.cy = hint[1];
+    float imp = impedance(p, fabsf(dist[s] - p.margin));
+    float diag0 = invw * (1.f + p.mu * p.mu);
+    float R0 = fmaxf(NMF_MINVAL, (1.f - imp) * diag0 / imp);
+    float mucon2 = p.mu * p.mu / p.impratio;
+    c.D = 1.f / (2.f * mucon2 * R0);
+    c.c0 = p.cK * imp * (dist[s] - p.margin);
+    // B * velocity of the contact point, projected on (n, mu t1, mu t2)
+    float vp[3] = {cvel[3] + cvel[1] * c.r[2] - cvel[2] * c.r[1], cvel[4] + cvel[2] * c.r[0] - cvel[0] * c.r[2],
+                   cvel[5] + cvel[0] * c.r[1] - cvel[1] * c.r[0]};
+    c.w[0] = p.cB * vp[2];
+    c.w[1] = p.cB * p.mu * (c.cx * vp[0] + c.cy * vp[1]);
+    c.w[2] = p.cB * p.mu * (-c.cy * vp[0] + c.cx * vp[1]);
+    c.s[0] = c.s[1] = c.s[2] = 0.f;
+  }
+}
+
+// point "acceleration" of a contact for a body spatial vector S (ang, lin), projected on (n, mu t1, mu t2)
+__device__ __forceinline__ void project_point(const Contact& c, const float* S, float mu, float* out) {
+  float ax = S[3] + S[1] * c.r[2] - S[2] * c.r[1];
+  float ay = S[4] + S[2] * c.r[0] - S[0] * c.r[2];
+  float az = S[5] + S[0] * c.r[1] - S[1] * c.r[0];
+  out[0] = az; out[1] = mu * (c.cx * ax + c.cy * ay); out[2] = mu * (-c.cy * ax + c.cx * ay);
+}
+
+// pyramid rows of one contact: jar_r = base +- w1 / w2
+__device__ __forceinline__ void rows4(const float* w, float c0, float* jar) {
+  float b = w[0] + c0;
+  jar[0] = b + w[1]; jar[1] = b - w[1]; jar[2] = b + w[2]; jar[3] = b - w[2];
+}
+
+// contact forces for the current jar: accumulates the world wrench about the COM (ang, lin) into Wc,
+// optionally the contact-augmentation A = X' W X (21 packed) into A, returns the active-row bitmask
+__device__ __forceinline__ int contact_forces(const Contact& c, float mu, float* Wc, float* A, float* fn_out) {
+  float jar[4]; rows4(c.w, c.c0, jar);
+  float a[4], f[4]; int bits = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) { a[r] = jar[r] < 0.f ? 1.f : 0.f; f[r] = -c.D * fminf(jar[r], 0.f); bits |= (jar[r] < 0.f) << r; }
+  float fn = f[0] + f[1] + f[2] + f[3], f1 = mu * (f[0] - f[1]), f2 = mu * (f[2] - f[3]);
+  float F[3] = {f1 * c.cx - f2 * c.cy, f1 * c.cy + f2 * c.cx, fn};
+  float T[3]; cross3(c.r, F, T);
+  Wc[0] += T[0]; Wc[1] += T[1]; Wc[2] += T[2]; Wc[3] += F[0]; Wc[4] += F[1]; Wc[5] += F[2];
+  if (fn_out) *fn_out = fn;
+  if (A && bits) {
+    float s1 = a[0] + a[1], s2 = a[2] + a[3], d1 = a[0] - a[1], d2 = a[2] - a[3], m2 = mu * mu;
+    float W[9];
+    W[0] = c.D * m2 * (s1 * c.cx * c.cx + s2 * c.cy * c.cy);
+    W[4] = c.D * m2 * (s1 * c.cy * c.cy + s2 * c.cx * c.cx);
+    W[1] = W[3] = c.D * m2 * (s1 - s2) * c.cx * c.cy;
+    W[8] = c.D * (s1 + s2);
+    W[2] = W[6] = c.D * mu * (d1 * c.cx - d2 * c.cy);
+    W[5] = W[7] = c.D * mu * (d1 * c.cy + d2 * c.cx);
+    // T = [r]x W  (columns: r x W[:,j]);  A_ww = T (-[r]x) -> row i: r x T[i,:]
+    float Tm[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float col[3] = {W[j], W[3 + j], W[6 + j]}, t[3]; cross3(c.r, col, t);
+      Tm[j] = t[0]; Tm[3 + j] = t[1]; Tm[6 + j] = t[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float row[3] = {Tm[3 * i], Tm[3 * i + 1], Tm[3 * i + 2]}, t[3]; cross3(c.r, row, t);
+#pragma unroll
+      for (int j = i; j < 3; j++) A[s6(i, j)] += t[j];
+#pragma unroll
+      for (int j = 0; j < 3; j++) A[s6(i, 3 + j)] += Tm[3 * i + j];
+    }
+    A[s6(3, 3)] += W[0]; A[s6(3, 4)] += W[1]; A[s6(3, 5)] += W[2]; A[s6(4, 4)] += W[4]; A[s6(4, 5)] += W[5]; A[s6(5, 5)] += W[8];
+  }
+  return bits;
+}
+
+// line-search partial sums of one contact at step alpha: d0 += D x jv, d1 += D jv^2 over rows with x < 0
+__device__ __forceinline__ void ls_eval(const Contact& c, float alpha, float& d0, float& d1) {
+  float jar[4], jv[4]; rows4(c.w, c.c0, jar); rows4(c.s, 0.f, jv);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    float x = jar[r] + alpha * jv[r];
+    if (x < 0.f) { d0 += c.D * x * jv[r]; d1 += c.D * jv[r] * jv[r]; }
+  }
+}
+
+// ------------------------------------------------------------------ shared-memory plan (floats)
+constexpr int SM_STATE = 0;                         // S_STRIDE
+constexpr int SM_CDOF = SM_STATE + S_STRIDE;        // NV * 8
+constexpr int SM_FS = SM_CDOF + NV * 8;             // qfrc_smooth
+constexpr int SM_GRAD = SM_FS + NV;                 // gradient / rhs
+constexpr int SM_X = SM_GRAD + NV;                  // search direction / solve result
+constexpr int SM_FC = SM_X + NV;                    // qfrc_constraint
+constexpr int SM_HS = SM_FC + NV;                   // row staging: NLEG * 184
+constexpr int HS_STRIDE = 184;
+constexpr int SM_ROOT = SM_HS + NLEG * HS_STRIDE;   // per-leg root publications: NLEG * 40
+constexpr int ROOT_STRIDE = 40;                     // [0..5] wrench, [6..15] crb, [16..36] A-hat
+constexpr int SM_BASE = SM_ROOT + NLEG * ROOT_STRIDE;  // NLEG*21 Schur contributions, then NLEG*6 rhs contributions
+constexpr int SM_HBB = SM_BASE + NLEG * 21 + NLEG * 6; // 21 hub block + 6 xb + 6 S_h + misc
+constexpr int SM_HUB = SM_HBB + 48;                 // hub uniforms: xpos(3) R(9) com(3) cvel(6) cacc(6) cinert(10) crbtot(10) q(4)
+constexpr int SM_HUBC = SM_HUB + 64;                // hub contact accumulation: 16 lanes * 28
+constexpr int SM_POSE = SM_HUBC + NHUBLANE * 28;    // body poses for the output epilogue: CTA * 8
+constexpr int SM_RED = SM_POSE + CTA * 8;           // 32
+constexpr int SM_TOTAL = SM_RED + 32;
+
+// hub uniform offsets inside SM_HUB
+constexpr int HU_XPOS = 0, HU_R = 3, HU_COM = 12, HU_CVEL = 15, HU_CACC = 21, HU_CINERT = 27, HU_CRB = 37, HU_Q = 47, HU_FB = 51;
+// inside SM_HBB
+constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27, HB_ATOT = 0;
+
+// ------------------------------------------------------------------ the step
+__device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
+  const int tid = threadIdx.x;
+  const int fly = blockIdx.x;
+  const bool is_leg = tid < NLEG * NLINK;
+  const int leg = tid >> 3, k = tid & 7, t = k;
+  const int hl = tid - NLEG * NLINK;
+  const unsigned gmask = tid < 32 ? NMF_FULL : (is_leg ? 0x0000ffffu : 0xffff0000u);
+  const float* role = p.role;
+  float* st = sm + SM_STATE;
+  float* s_cdof = sm + SM_CDOF;
+  float* s_hub = sm + SM_HUB;
+  float* s_red = sm + SM_RED;
+  int parity = 0;
+
+  // ---- load the state record (coalesced; 304 floats)
+  {
+    float* g = p.state + (size_t)fly * S_STRIDE;
+    for (int i = tid; i < S_STRIDE; i += CTA) st[i] = g[i];
+    for (int i = tid; i < NLEG * HS_STRIDE; i += CTA) sm[SM_HS + i] = 0.f;
+  }
+  __syncthreads();
+
+  // per-lane constants that stay in registers for the whole launch
+  const int ndof = is_leg ? __float_as_int(role[RF_NDOF * CTA + tid]) : 0;
+  const int dof0 = is_leg ? __float_as_int(role[RF_DOF0 * CTA + tid]) : (hl < 6 ? hl : 0);
+  const int ldof0 = is_leg ? dof0 - 6 - NLEGDOF * leg : 0;   // first dof index inside the leg
+  const float mass = role[RF_MASS * CTA + tid];
+  const float invw = role[RF_INVW * CTA + tid];
+
+  for (int step = 0; step < p.nsteps; step++) {
+    // ---- controls for this step
+    if (p.act_table) {
+      const float* row = p.act_table + ((size_t)fly * p.table_T + (size_t)((p.table_t0 + step) % p.table_T)) * p.nu_pos;
+      for (int i = tid; i < p.nu_pos; i += CTA) st[S_CTRL + i] = row[i];
+      __syncthreads();
+    }
+
+    // =====================================================================
+    // A. kinematics: scan of rigid transforms along each chain
+    // =====================================================================
+    float qh[4] = {st[S_QPOS + 3], st[S_QPOS + 4], st[S_QPOS + 5], st[S_QPOS + 6]};
+    qnormalize(qh);
+    const float xh[3] = {st[S_QPOS], st[S_QPOS + 1], st[S_QPOS + 2]};
+    float xpos[3], xq[4], R[9], laxis[9];   // laxis: hinge axes in the parent frame, later world
+    if (is_leg) {
+      float q[4] = {role[(RF_BQUAT + 0) * CTA + tid], role[(RF_BQUAT + 1) * CTA + tid], role[(RF_BQUAT + 2) * CTA + tid], role[(RF_BQUAT + 3) * CTA + tid]};
+      float pp[3] = {role[(RF_BPOS + 0) * CTA + tid], role[(RF_BPOS + 1) * CTA + tid], role[(RF_BPOS + 2) * CTA + tid]};
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float ax[3] = {role[(RF_AXIS + 3 * j) * CTA + tid], role[(RF_AXIS + 3 * j + 1) * CTA + tid], role[(RF_AXIS + 3 * j + 2) * CTA + tid]};
+        qrot(q, ax, laxis + 3 * j);
+        if (j < ndof) {
+          float ang = st[S_QPOS + 1 + dof0 + j], sn, cs; sincosf(0.5f * ang, &sn, &cs);
+          float ql[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, nq[4];
+          qmul(q, ql, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+        }
+      }
+      if (k == 0) {  // seed the chain with the hub pose
+        float t3[3]; qrot(qh, pp, t3); pp[0] = xh[0] + t3[0]; pp[1] = xh[1] + t3[1]; pp[2] = xh[2] + t3[2];
+        float nq[4]; qmul(qh, q, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+      }
+      float qpar[4] = {qh[0], qh[1], qh[2], qh[3]};
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        float uq[4], up[3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) uq[i] = __shfl_up_sync(gmask, q[i], off, 8);
+#pragma unroll
+        for (int i = 0; i < 3; i++) up[i] = __shfl_up_sync(gmask, pp[i], off, 8);
+        if (k >= off) {
+          float t3[3]; qrot(uq, pp, t3); pp[0] = up[0] + t3[0]; pp[1] = up[1] + t3[1]; pp[2] = up[2] + t3[2];
+          float nq[4]; qmul(uq, q, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+        }
+      }
+      qnormalize(q);
+      {  // parent world orientation -> world hinge axes
+        float pq[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) pq[i] = __shfl_up_sync(gmask, q[i], 1, 8);
+        if (k > 0) { qpar[0] = pq[0]; qpar[1] = pq[1]; qpar[2] = pq[2]; qpar[3] = pq[3]; }
+#pragma unroll
+        for (int j = 0; j < 3; j++) { float w[3]; qrot(qpar, laxis + 3 * j, w); laxis[3 * j] = w[0]; laxis[3 * j + 1] = w[1]; laxis[3 * j + 2] = w[2]; }
+      }
+      xpos[0] = pp[0]; xpos[1] = pp[1]; xpos[2] = pp[2]; xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
+    } else {
+      xpos[0] = xh[0]; xpos[1] = xh[1]; xpos[2] = xh[2]; xq[0] = qh[0]; xq[1] = qh[1]; xq[2] = qh[2]; xq[3] = qh[3];
+    }
+    q2mat(xq, R);
+
+    // ---- subtree COM (block reduction), inertial quantities about it
+    float xipos[3];
+    {
+      float ip[3] = {role[(RF_IPOS + 0) * CTA + tid], role[(RF_IPOS + 1) * CTA + tid], role[(RF_IPOS + 2) * CTA + tid]};
+      for (int i = 0; i < 3; i++) xipos[i] = xpos[i] + R[3 * i] * ip[0] + R[3 * i + 1] * ip[1] + R[3 * i + 2] * ip[2];
+    }
+    float com[3];
+    {
+      float contributes = (is_leg || hl == 0) ? mass : 0.f;
+      float v[3] = {contributes * xipos[0], contributes * xipos[1], contributes * xipos[2]};
+      cta_reduce<3>(v, s_red, parity, tid);
+      com[0] = v[0] * p.inv_total_mass; com[1] = v[1] * p.inv_total_mass; com[2] = v[2] * p.inv_total_mass;
+    }
+    float cinert[10];
+    {
+      float ib[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) ib[i] = role[(RF_IB + i) * CTA + tid];
+      float Ib[9] = {ib[0], ib[3], ib[4], ib[3], ib[1], ib[5], ib[4], ib[5], ib[2]}, T[9], G[9];
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Ib[j] + R[3 * i + 1] * Ib[3 + j] + R[3 * i + 2] * Ib[6 + j];
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) G[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+      float off[3] = {xipos[0] - com[0], xipos[1] - com[1], xipos[2] - com[2]};
+      float o2 = dot3(off, off);
+      cinert[0] = G[0] + mass * (o2 - off[0] * off[0]); cinert[1] = G[4] + mass * (o2 - off[1] * off[1]); cinert[2] = G[8] + mass * (o2 - off[2] * off[2]);
+      cinert[3] = G[1] - mass * off[0] * off[1]; cinert[4] = G[2] - mass * off[0] * off[2]; cinert[5] = G[5] - mass * off[1] * off[2];
+      cinert[6] = mass * off[0]; cinert[7] = mass * off[1]; cinert[8] = mass * off[2]; cinert[9] = mass;
+    }
+    // cdof of own dofs -> shared; hub lanes 0..5 own the free-joint dofs
+    if (is_leg) {
+      float off[3] = {com[0] - xpos[0], com[1] - xpos[1], com[2] - xpos[2]};
+      for (int j = 0; j < ndof; j++) {
+        float* cd = s_cdof + 8 * (dof0 + j); float l[3]; cross3(laxis + 3 * j, off, l);
+        cd[0] = laxis[3 * j]; cd[1] = laxis[3 * j + 1]; cd[2] = laxis[3 * j + 2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
+      }
+    } else {
+      float off[3] = {com[0] - xpos[0], com[1] - xpos[1], com[2] - xpos[2]};
+      if (hl < 3) {
+        float* cd = s_cdof + 8 * hl; cd[0] = cd[1] = cd[2] = 0.f; cd[3] = hl == 0; cd[4] = hl == 1; cd[5] = hl == 2;
+      } else if (hl < 6) {
+        int a = hl - 3; float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
+        float* cd = s_cdof + 8 * hl; cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
+      }
+      if (hl == 0) {
+        // hub velocity / bias acceleration (free joint: translations first, rotations against the updated velocity)
+        float wl[3] = {st[S_QVEL + 3], st[S_QVEL + 4], st[S_QVEL + 5]};
+        float vlin[3] = {st[S_QVEL], st[S_QVEL + 1], st[S_QVEL + 2]};
+        float cv0[6] = {0.f, 0.f, 0.f, vlin[0], vlin[1], vlin[2]};
+        float cacc[6] = {0.f, 0.f, 0.f, -p.gx, -p.gy, -p.gz};
+        float cvel[6] = {cv0[0], cv0[1], cv0[2], cv0[3], cv0[4], cv0[5]};
+        for (int a = 0; a < 3; a++) {
+          float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
+          float cd[6] = {ax[0], ax[1], ax[2], l[0], l[1], l[2]}, cdd[6];
+          cross_motion(cv0, cd, cdd);
+          for (int i = 0; i < 6; i++) { cacc[i] += cdd[i] * wl[a]; cvel[i] += cd[i] * wl[a]; }
+        }
+        for (int i = 0; i < 6; i++) { s_hub[HU_CVEL + i] = cvel[i]; s_hub[HU_CACC + i] = cacc[i]; }
+        for (int i = 0; i < 10; i++) s_hub[HU_CINERT + i] = cinert[i];
+        // hub part of the spatial acceleration generated by the warm-start qacc
+        float Sh[6] = {0, 0, 0, st[S_WARM], st[S_WARM + 1], st[S_WARM + 2]};
+        for (int a = 0; a < 3; a++) {
+          float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
+          float qa = st[S_WARM + 3 + a];
+          Sh[0] += ax[0] * qa; Sh[1] += ax[1] * qa; Sh[2] += ax[2] * qa; Sh[3] += l[0] * qa; Sh[4] += l[1] * qa; Sh[5] += l[2] * qa;
+        }
+        for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
+      }
+    }
+    __syncthreads();   // cdof, hub cvel/cacc/cinert, S_h visible
+
+    // =====================================================================
+    // B. velocities, composite inertia, collision, bias + actuator forces
+    // =====================================================================
+    float crb[10], cvel[6], Sa[6];
+    Contact con[2];
+    float fs_own[3] = {0.f, 0.f, 0.f};
+    float actf[3] = {0.f, 0.f, 0.f}, adhf = 0.f;
+    if (is_leg) {
+      float loc[6] = {0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); float qv = st[S_QVEL + dof0 + j]; for (int i = 0; i < 6; i++) loc[i] += cd[i] * qv; }
+      float pre[6] = {loc[0], loc[1], loc[2], loc[3], loc[4], loc[5]};
+      chain_prefix<6>(pre, gmask, k);
+      float cv[6], ad[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < 6; i++) cv[i] = pre[i] - loc[i] + s_hub[HU_CVEL + i];
+      for (int j = 0; j < ndof; j++) {
+        const float* cd = s_cdof + 8 * (dof0 + j); float qv = st[S_QVEL + dof0 + j], cdd[6];
+        cross_motion(cv, cd, cdd);
+        for (int i = 0; i < 6; i++) { ad[i] += cdd[i] * qv; cv[i] += cd[i] * qv; }
+      }
+      for (int i = 0; i < 6; i++) cvel[i] = cv[i];
+      chain_prefix<6>(ad, gmask, k);
+      float cacc[6];
+      for (int i = 0; i < 6; i++) cacc[i] = ad[i] + s_hub[HU_CACC + i];
+      // body wrench  W = -(I a + v x* I v)  (+ adhesion below)
+      float t1[6], t2[6], t3[6], W[6];
+      mul_inert(cinert, cacc, t1); mul_inert(cinert, cvel, t2); cross_force(cvel, t2, t3);
+      for (int i = 0; i < 6; i++) W[i] = -(t1[i] + t3[i]);
+      // composite inertia
+      for (int i = 0; i < 10; i++) crb[i] = cinert[i];
+      chain_suffix<10>(crb, gmask, k);
+      // collision for this body's geom
+      collide(p, role, tid, xpos, R, com, cvel, invw, con);
+      // adhesion (body transmission): force pulls the body onto the plane along each contact normal
+      const int acidx = __float_as_int(role[RF_ADH_CIDX * CTA + tid]);
+      if (acidx >= 0) {
+        float c = fminf(role[RF_ADH_HI * CTA + tid], fmaxf(role[RF_ADH_LO * CTA + tid], st[S_CTRL + acidx]));
+        adhf = role[RF_ADH_GAIN * CTA + tid] * c;
+        float n = con[0].active + con[1].active;
+        if (n > 0.f) {
+          float fz = -adhf / n;
+          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) {
+            W[0] += con[s].r[1] * fz; W[1] += -con[s].r[0] * fz; W[5] += fz;
+          }
+        }
+      }
+      chain_suffix<6>(W, gmask, k);
+      // joint-space smooth force of own dofs: passive + actuator + C'W
+      for (int j = 0; j < 3; j++) if (j < ndof) {
+        int d = dof0 + j; const float* cd = s_cdof + 8 * d;
+        float q = st[S_QPOS + 1 + d], qv = st[S_QVEL + d];
+        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - role[(RF_DAMP + j) * CTA + tid] * qv;
+        int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]);
+        if (ci >= 0) {
+          float kp = role[(RF_KP + j) * CTA + tid], kv = role[(RF_KV + j) * CTA + tid];
+          float af = kp * st[S_CTRL + ci] - kp * q - kv * qv;
+          af = fminf(role[(RF_FHI + j) * CTA + tid], fmaxf(role[(RF_FLO + j) * CTA + tid], af));
+          actf[j] = af; f += af;
+        }
+        f += dot6(cd, W);
+        fs_own[j] = f; sm[SM_FS + d] = f;
+      }
+      if (k == 0) {
+        float* rt = sm + SM_ROOT + leg * ROOT_STRIDE;
+        for (int i = 0; i < 6; i++) rt[i] = W[i];
+        for (int i = 0; i < 10; i++) rt[6 + i] = crb[i];
+      }
+      // spatial acceleration of this body generated by the warm-start qacc
+      float sl[6] = {0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); float qa = st[S_WARM + dof0 + j]; for (int i = 0; i < 6; i++) sl[i] += cd[i] * qa; }
+      chain_prefix<6>(sl, gmask, k);
+      for (int i = 0; i < 6; i++) Sa[i] = sl[i] + sm[SM_HBB + HB_SH + i];
+    } else {
+      for (int i = 0; i < 6; i++) { cvel[i] = s_hub[HU_CVEL + i]; Sa[i] = sm[SM_HBB + HB_SH + i]; }
+      for (int i = 0; i < 10; i++) crb[i] = 0.f;
+      if (hl < p.nhubgeom) collide(p, role, tid, xpos, R, com, cvel, invw, con);
+      else { con[0].active = con[1].active = 0.f; }
+    }
+    // contact rows at the warm-start acceleration
+    for (int s = 0; s < 2; s++) if (con[s].active > 0.f) {
+      float ap[3]; project_point(con[s], Sa, p.mu, ap);
+      con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
+    }
+    __syncthreads();   // leg roots (wrench, crb) visible to the hub
+    float crbh[10];    // hub lanes: total composite inertia of the whole fly
+    if (!is_leg) {
+      for (int i = 0; i < 10; i++) { float s = s_hub[HU_CINERT + i]; for (int l = 0; l < NLEG; l++) s += sm[SM_ROOT + l * ROOT_STRIDE + 6 + i]; crbh[i] = s; }
+      if (hl < 6) {
+        float t1[6], t2[6], t3[6], W[6], ci[10], cv[6], ca[6];
+        for (int i = 0; i < 10; i++) ci[i] = s_hub[HU_CINERT + i];
+        for (int i = 0; i < 6; i++) { cv[i] = s_hub[HU_CVEL + i]; ca[i] = s_hub[HU_CACC + i]; }
+        mul_inert(ci, ca, t1); mul_inert(ci, cv, t2); cross_force(cv, t2, t3);
+        for (int i = 0; i < 6; i++) { W[i] = -(t1[i] + t3[i]); for (int l = 0; l < NLEG; l++) W[i] += sm[SM_ROOT + l * ROOT_STRIDE + i]; }
+        fs_own[0] = dot6(s_cdof + 8 * hl, W); sm[SM_FS + hl] = fs_own[0];
+      }
+    }
+
+    // =====================================================================
+    // C. soft-contact solve: primal Newton on  1/2 (a-a0)'M(a-a0) + s(Ja - aref)
+    //    started from qacc_warmstart (unique minimiser => same result as the
+    //    reference's mj_solNewton; solver=Newton in mujoco_globals.yaml:12)
+    // =====================================================================
+    float* qacc = st + S_WARM;      // qacc lives in the warm-start slot of the record
+    int niter = 0, nls_total = 0, nchanged_last = 0;
+    int prev_bits = 0;
+    float hk0[NLEGDOF], hk1[NLEGDOF];   // column-distributed L'DL factor (leg lanes)
+    float i0own = 0.f, i1own = 0.f, i10 = 0.f;
+    // hub small factor lives in shared (SM_HBB)
+    for (int iter = 0;; iter++) {
+      // ---- forces, active set, contact augmentation
+      float Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
+#pragma unroll
+      for (int i = 0; i < 21; i++) A[i] = 0.f;
+      int bits = 0;
+      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) bits |= contact_forces(con[s], p.mu, Wc, A, nullptr) << (4 * s);
+      int changed = (iter > 0 && bits != prev_bits) ? 1 : 0;
+      prev_bits = bits;
+      bool last = false;
+      if (iter > 0) {
+        float v[1] = {(float)changed};
+        cta_reduce<1>(v, s_red, parity, tid);
+        nchanged_last = (int)v[0];
+        last = (nchanged_last == 0) || iter >= p.max_newton;
+      }
+      // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
+      float y[12];
+      {
+        float t6[6]; mul_inert(cinert, Sa, t6);
+        if (!is_leg && hl != 0) for (int i = 0; i < 6; i++) t6[i] = 0.f;   // hub inertia counted once
+        for (int i = 0; i < 6; i++) { y[i] = t6[i] - Wc[i]; y[6 + i] = Wc[i]; }
+      }
+      float gown[3] = {0.f, 0.f, 0.f};
+      if (is_leg) {
+        chain_suffix<12>(y, gmask, k);
+        if (!last) chain_suffix<21>(A, gmask, k);
+        for (int j = 0; j < 3; j++) if (j < ndof) {
+          int d = dof0 + j; const float* cd = s_cdof + 8 * d;
+          float g = dot6(cd, y) + role[(RF_ARM + j) * CTA + tid] * qacc[d] - fs_own[j];
+          gown[j] = g; sm[SM_GRAD + d] = g; sm[SM_FC + d] = dot6(cd, y + 6);
+        }
+        if (k == 0) {
+          float* rt = sm + SM_ROOT + leg * ROOT_STRIDE;
+          for (int i = 0; i < 6; i++) rt[i] = y[i];
+          for (int i = 0; i < 21; i++) rt[16 + i] = A[i];
+          for (int i = 0; i < 6; i++) rt[6 + i] = y[6 + i];          // crb slot reused for the fc wrench (crb already consumed)
+        }
+      } else {
+        float* hc = sm + SM_HUBC + hl * 28;
+        for (int i = 0; i < 6; i++) hc[i] = y[i];
+        for (int i = 0; i < 21; i++) hc[6 + i] = A[i];
+        hc[27] = 0.f;
+        // second wrench (fc) packed separately below
+      }
+      __syncthreads();
+      float Ah[21];
+      if (!is_leg) {
+        // hub totals: own contacts (16 lanes) + leg roots
+        float yh[6], fch[6];
+        for (int i = 0; i < 6; i++) {
+          float s = 0.f; for (int l2 = 0; l2 < NHUBLANE; l2++) s += sm[SM_HUBC + l2 * 28 + i];
+          float s2 = s; for (int l = 0; l < NLEG; l++) s2 += sm[SM_ROOT + l * ROOT_STRIDE + i];
+          yh[i] = s2;
+          // fc wrench of the hub's own contacts = I S - y_own  => recover from y: Wc_own = I S - y_own
+          fch[i] = 0.f;
+        }
+        {
+          float ci[10], t6[6], Sh6[6];
+          for (int i = 0; i < 10; i++) ci[i] = s_hub[HU_CINERT + i];
+          for (int i = 0; i < 6; i++) Sh6[i] = Sa[i];
+          mul_inert(ci, Sh6, t6);
+          for (int i = 0; i < 6; i++) {
+            float s = 0.f; for (int l2 = 0; l2 < NHUBLANE; l2++) s += sm[SM_HUBC + l2 * 28 + i];
+            float wc_own = t6[i] - s;
+            float f = wc_own; for (int l = 0; l < NLEG; l++) f += sm[SM_ROOT + l * ROOT_STRIDE + 6 + i];
+            fch[i] = f;
+          }
+        }
+        for (int i = 0; i < 21; i++) {
+          float s = 0.f; for (int l2 = 0; l2 < NHUBLANE; l2++) s += sm[SM_HUBC + l2 * 28 + 6 + i];
+          for (int l = 0; l < NLEG; l++) s += sm[SM_ROOT + l * ROOT_STRIDE + 16 + i];
+          Ah[i] = s;
+        }
+        if (hl < 6) {
+          const float* cd = s_cdof + 8 * hl;
+          float g = dot6(cd, yh) - fs_own[0];
+          gown[0] = g; sm[SM_GRAD + hl] = g; sm[SM_FC + hl] = dot6(cd, fch);
+        }
+      }
+      if (last) { niter = iter; break; }
+
+      // ---- Hessian rows  H = C'(crb + A-hat)C + armature, staged in shared, then column-distributed
+      float d10 = 0.f;
+      if (is_leg) {
+        float P[21]; expand_inert(crb, P);
+#pragma unroll
+        for (int i = 0; i < 21; i++) P[i] += A[i];
+        float* hs = sm + SM_HS + leg * HS_STRIDE;
+        for (int j = 0; j < 3; j++) if (j < ndof) {
+          int li = ldof0 + j; float u[6]; sym6_mul(P, s_cdof + 8 * (dof0 + j), u);
+          for (int c = 0; c < 6; c++) hs[li * 16 + c] = dot6(s_cdof + 8 * c, u);
+          for (int jj = 0; jj <= li; jj++) {
+            float v = dot6(s_cdof + 8 * (6 + NLEGDOF * leg + jj), u);
+            if (jj == li) v += role[(RF_ARM + j) * CTA + tid];
+            if (li == 10 && jj == 10) hs[176] = v; else hs[li * 16 + 6 + jj] = v;
+          }
+        }
+        __syncwarp(gmask);
+#pragma unroll
+        for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
+        d10 = hs[176];
+      } else if (hl < 6) {
+        float P[21]; expand_inert(crbh, P);
+#pragma unroll
+        for (int i = 0; i < 21; i++) P[i] += Ah[i];
+        float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
+        for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
+      }
+
+      // ---- L'DL of each chain block in registers (one column per lane), Schur contributions for the hub
+      if (is_leg) {
+        float contrib[3] = {0.f, 0.f, 0.f};
+        int pb[3], pc[3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) {  // pair (b >= c) number t + 8 s of the 21 lower-triangular hub entries
+          int idx = t + 8 * s, b = 0; while ((b + 1) * (b + 2) / 2 <= idx) b++;
+          pb[s] = b; pc[s] = idx - b * (b + 1) / 2; if (idx >= 21) { pb[s] = 0; pc[s] = 0; }
+        }
+#pragma unroll
+        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
+          float dk;
+          if (kk == 10) dk = d10; else { const int c = 6 + kk; dk = __shfl_sync(gmask, c < 8 ? hk0[kk] : hk1[kk], c & 7, 8); }
+          float ik = 1.0f / dk;
+          if (kk == 10) i10 = ik;
+          if (6 + kk == t) i0own = ik;
+          if (kk == t + 2) i1own = ik;
+          float l0 = hk0[kk] * ik, l1 = hk1[kk] * ik;
+#pragma unroll
+          for (int s = 0; s < 3; s++) {
+            float lb = __shfl_sync(gmask, l0, pb[s], 8), hc = __shfl_sync(gmask, hk0[kk], pc[s], 8);
+            contrib[s] += lb * hc;
+          }
+#pragma unroll
+          for (int j = 0; j < kk; j++) {
+            const int cj = 6 + j;
+            float l = __shfl_sync(gmask, cj < 8 ? l0 : l1, cj & 7, 8);
+            hk0[j] -= (t <= cj ? l : 0.f) * hk0[kk];
+            hk1[j] -= (t + 2 <= j ? l : 0.f) * hk1[kk];
+          }
+          hk0[kk] = l0; hk1[kk] = l1;
+        }
+        float* bs = sm + SM_BASE + leg * 21;
+#pragma unroll
+        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) bs[t + 8 * s] = contrib[s];
+      }
+      // ---- solve H x = -g : chain pass 1 (x <- L^-T x), hub rhs contributions
+      float x0 = 0.f, x1 = 0.f, x10 = 0.f;
+      if (is_leg) {
+        const int ld = NLEGDOF * leg + 6;
+        if (t >= 6) x0 = -sm[SM_GRAD + ld + t - 6];
+        x1 = -sm[SM_GRAD + ld + t + 2];
+        x10 = -sm[SM_GRAD + ld + 10];
+#pragma unroll
+        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
+          float xk;
+          if (kk == 10) xk = x10; else { const int c = 6 + kk; xk = __shfl_sync(gmask, c < 8 ? x0 : x1, c & 7, 8); }
+          x0 -= (t < 6 + kk ? hk0[kk] : 0.f) * xk;
+          x1 -= (t + 2 < kk ? hk1[kk] : 0.f) * xk;
+        }
+        if (t < 6) sm[SM_BASE + NLEG * 21 + leg * 6 + t] = x0;
+      }
+      __syncthreads();
+      if (!is_leg && hl == 0) {
+        // hub block: S = Hbb - sum contributions ; rhs = -g_b + sum chain parts ; dense 6x6 L'DL solve (serial, tiny)
+        float S[21], xb[6];
+        for (int i = 0; i < 21; i++) { float s = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) s -= sm[SM_BASE + l * 21 + i]; S[i] = s; }
+        for (int b = 0; b < 6; b++) { float s = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) s += sm[SM_BASE + NLEG * 21 + l * 6 + b]; xb[b] = s; }
+        float dinv[6];
+#pragma unroll
+        for (int kk = 5; kk >= 0; kk--) {
+          dinv[kk] = 1.0f / S[kk * (kk + 1) / 2 + kk];
+#pragma unroll
+          for (int j = 0; j < kk; j++) {
+            float l = S[kk * (kk + 1) / 2 + j] * dinv[kk];
+#pragma unroll
+            for (int c = 0; c <= j; c++) S[j * (j + 1) / 2 + c] -= l * S[kk * (kk + 1) / 2 + c];
+          }
+#pragma unroll
+          for (int j = 0; j < kk; j++) S[kk * (kk + 1) / 2 + j] *= dinv[kk];
+        }
+#pragma unroll
+        for (int kk = 5; kk >= 0; kk--)
+#pragma unroll
+          for (int j = 0; j < kk; j++) xb[j] -= S[kk * (kk + 1) / 2 + j] * xb[kk];
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) xb[kk] *= dinv[kk];
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++)
+#pragma unroll
+          for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
+        float Sh[6] = {0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < 6; b++) { sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b]; const float* cd = s_cdof + 8 * b; for (int i = 0; i < 6; i++) Sh[i] += cd[i] * xb[b]; }
+        for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
+      }
+      __syncthreads();
+      // ---- chain passes 2, 3 (x <- D^-1 x ; x <- L^-1 x)
+      float sown[3] = {0.f, 0.f, 0.f};
+      if (is_leg) {
+        float xb = t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f;
+        if (t >= 6) x0 *= i0own;
+        x1 *= i1own; x10 *= i10;
+#pragma unroll
+        for (int kk = 0; kk < NLEGDOF; kk++) {
+          float part = (t < 6 ? hk0[kk] * xb : (t - 6 < kk ? hk0[kk] * x0 : 0.f)) + (t + 2 < kk ? hk1[kk] * x1 : 0.f);
+          part += __shfl_xor_sync(gmask, part, 1, 8); part += __shfl_xor_sync(gmask, part, 2, 8); part += __shfl_xor_sync(gmask, part, 4, 8);
+          if (6 + kk == t) x0 -= part;
+          if (kk == t + 2) x1 -= part;
+          if (kk == 10) x10 -= part;
+        }
+        float* sx = sm + SM_X + 6 + NLEGDOF * leg;
+        if (t >= 6) sx[t - 6] = x0;
+        sx[t + 2] = x1;
+        if (t == 0) sx[10] = x10;
+        __syncwarp(gmask);
+        for (int j = 0; j < 3; j++) if (j < ndof) sown[j] = sm[SM_X + dof0 + j];
+      } else if (hl < 6) sown[0] = sm[SM_X + hl];
+
+      // ---- spatial acceleration of the search direction, row directions, quadratic terms
+      float Ss[6];
+      if (is_leg) {
+        float sl[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); for (int i = 0; i < 6; i++) sl[i] += cd[i] * sown[j]; }
+        chain_prefix<6>(sl, gmask, k);
+        for (int i = 0; i < 6; i++) Ss[i] = sl[i] + sm[SM_HBB + HB_SH + i];
+      } else for (int i = 0; i < 6; i++) Ss[i] = sm[SM_HBB + HB_SH + i];
+      float red[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // s.g , s'Ms , d0 rows(0), d1 rows(0), |s|^2
+      {
+        float t6[6]; mul_inert(cinert, Ss, t6);
+        if (is_leg || hl == 0) red[1] += dot6(Ss, t6);
+        for (int j = 0; j < 3; j++) {
+          bool own = is_leg ? (j < ndof) : (j == 0 && hl < 6);
+          if (own) {
+            float arm = is_leg ? role[(RF_ARM + j) * CTA + tid] : 0.f;
+            red[0] += sown[j] * gown[j]; red[1] += arm * sown[j] * sown[j]; red[4] += sown[j] * sown[j];
+          }
+        }
+        for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { project_point(con[s], Ss, p.mu, con[s].s); ls_eval(con[s], 0.f, red[2], red[3]); }
+      }
+      cta_reduce<5>(red, s_red, parity, tid);
+      // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
+      float alpha = 0.f;
+      {
+        const float q1 = red[0] - red[2], q2 = red[1];
+        float d0 = red[0], d1 = q2 + red[3], lo = 0.f, hi = 3.0e38f;
+        const int nls = (red[4] > 1e-30f && d1 > 0.f) ? p.max_ls : 0;   // zero direction: nothing to search
+        for (int it = 0; it < nls; it++) {
+          if (fabsf(d0) <= 2e-6f * d1 * fmaxf(fabsf(alpha), 1e-3f) && it > 0) break;
+          if (d0 < 0.f) lo = alpha; else hi = alpha;
+          float nx = alpha - d0 / d1;
+          if (nx <= lo || nx >= hi) nx = (hi > 1.0e38f) ? 2.f * fmaxf(alpha, 1.f) : 0.5f * (lo + hi);
+          alpha = nx;
+          float e[2] = {0.f, 0.f};
+          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) ls_eval(con[s], alpha, e[0], e[1]);
+          cta_reduce<2>(e, s_red, parity, tid);
+          d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
+          nls_total++;
+        }
+      }
+      // ---- move
+      for (int j = 0; j < 3; j++) {
+        bool own = is_leg ? (j < ndof) : (j == 0 && hl < 6);
+        if (own) qacc[dof0 + j] += alpha * sown[j];
+      }
+      for (int i = 0; i < 6; i++) Sa[i] += alpha * Ss[i];
+      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { con[s].w[0] += alpha * con[s].s[0]; con[s].w[1] += alpha * con[s].s[1]; con[s].w[2] += alpha * con[s].s[2]; }
+    }
+
+    // =====================================================================
+    // D. semi-implicit Euler with implicit joint damping:
+    //    (M + dt diag(damping)) a' = qfrc_smooth + qfrc_constraint ; v += dt a' ; q integrates with the new v
+    // =====================================================================
+    __syncthreads();
+    {
+      float d10 = 0.f;
+      if (is_leg) {
+        float P[21]; expand_inert(crb, P);
+        float* hs = sm + SM_HS + leg * HS_STRIDE;
+        for (int j = 0; j < 3; j++) if (j < ndof) {
+          int li = ldof0 + j; float u[6]; sym6_mul(P, s_cdof + 8 * (dof0 + j), u);
+          for (int c = 0; c < 6; c++) hs[li * 16 + c] = dot6(s_cdof + 8 * c, u);
+          for (int jj = 0; jj <= li; jj++) {
+            float v = dot6(s_cdof + 8 * (6 + NLEGDOF * leg + jj), u);
+            if (jj == li) v += role[(RF_ARM + j) * CTA + tid] + p.dt * role[(RF_DAMP + j) * CTA + tid];
+            if (li == 10 && jj == 10) hs[176] = v; else hs[li * 16 + 6 + jj] = v;
+          }
+          sm[SM_GRAD + dof0 + j] = -(fs_own[j] + sm[SM_FC + dof0 + j]);   // rhs = -(grad slot)
+        }
+        __syncwarp(gmask);
+#pragma unroll
+        for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
+        d10 = hs[176];
+        if (p.dbg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + leg * 177; for (int i = t; i < 177; i += 8) dg[i] = hs[i]; }
+      } else if (hl < 6) {
+        float P[21]; expand_inert(crbh, P);
+        float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
+        for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
+        sm[SM_GRAD + hl] = -(fs_own[0] + sm[SM_FC + hl]);
+      }
+      if (is_leg) {
+        float contrib[3] = {0.f, 0.f, 0.f};
+        int pb[3], pc[3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          int idx = t + 8 * s, b = 0; while ((b + 1) * (b + 2) / 2 <= idx) b++;
+          pb[s] = b; pc[s] = idx - b * (b + 1) / 2; if (idx >= 21) { pb[s] = 0; pc[s] = 0; }
+        }
+#pragma unroll
+        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
+          float dk;
+          if (kk == 10) dk = d10; else { const int c = 6 + kk; dk = __shfl_sync(gmask, c < 8 ? hk0[kk] : hk1[kk], c & 7, 8); }
+          float ik = 1.0f / dk;
+          if (kk == 10) i10 = ik;
+          if (6 + kk == t) i0own = ik;
+          if (kk == t + 2) i1own = ik;
+          float l0 = hk0[kk] * ik, l1 = hk1[kk] * ik;
+#pragma unroll
+          for (int s = 0; s < 3; s++) {
+            float lb = __shfl_sync(gmask, l0, pb[s], 8), hc = __shfl_sync(gmask, hk0[kk], pc[s], 8);
+            contrib[s] += lb * hc;
+          }
+#pragma unroll
+          for (int j = 0; j < kk; j++) {
+            const int cj = 6 + j;
+            float l = __shfl_sync(gmask, cj < 8 ? l0 : l1, cj & 7, 8);
+            hk0[j] -= (t <= cj ? l : 0.f) * hk0[kk];
+            hk1[j] -= (t + 2 <= j ? l : 0.f) * hk1[kk];
+          }
+          hk0[kk] = l0; hk1[kk] = l1;
+        }
+        float* bs = sm + SM_BASE + leg * 21;
+#pragma unroll
+        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) bs[t + 8 * s] = contrib[s];
+      }
+      float x0 = 0.f, x1 = 0.f, x10 = 0.f;
+      if (is_leg) {
+        const int ld = NLEGDOF * leg + 6;
+        if (t >= 6) x0 = -sm[SM_GRAD + ld + t - 6];
+        x1 = -sm[SM_GRAD + ld + t + 2];
+        x10 = -sm[SM_GRAD + ld + 10];
+#pragma unroll
+        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
+          float xk;
+          if (kk == 10) xk = x10; else { const int c = 6 + kk; xk = __shfl_sync(gmask, c < 8 ? x0 : x1, c & 7, 8); }
+          x0 -= (t < 6 + kk ? hk0[kk] : 0.f) * xk;
+          x1 -= (t + 2 < kk ? hk1[kk] : 0.f) * xk;
+        }
+        if (t < 6) sm[SM_BASE + NLEG * 21 + leg * 6 + t] = x0;
+      }
+      __syncthreads();
+      if (!is_leg && hl == 0) {
+        float S[21], xb[6];
+        if (p.dbg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + NLEG * 177; for (int i = 0; i < 21; i++) dg[i] = sm[SM_HBB + HB_S + i]; }
+        for (int i = 0; i < 21; i++) { float s = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) s -= sm[SM_BASE + l * 21 + i]; S[i] = s; }
+        for (int b = 0; b < 6; b++) { float s = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) s += sm[SM_BASE + NLEG * 21 + l * 6 + b]; xb[b] = s; }
+        float dinv[6];
+#pragma unroll
+        for (int kk = 5; kk >= 0; kk--) {
+          dinv[kk] = 1.0f / S[kk * (kk + 1) / 2 + kk];
+#pragma unroll
+          for (int j = 0; j < kk; j++) {
+            float l = S[kk * (kk + 1) / 2 + j] * dinv[kk];
+#pragma unroll
+            for (int c = 0; c <= j; c++) S[j * (j + 1) / 2 + c] -= l * S[kk * (kk + 1) / 2 + c];
+          }
+#pragma unroll
+          for (int j = 0; j < kk; j++) S[kk * (kk + 1) / 2 + j] *= dinv[kk];
+        }
+#pragma unroll
+        for (int kk = 5; kk >= 0; kk--)
+#pragma unroll
+          for (int j = 0; j < kk; j++) xb[j] -= S[kk * (kk + 1) / 2 + j] * xb[kk];
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) xb[kk] *= dinv[kk];
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++)
+#pragma unroll
+          for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
+        for (int b = 0; b < 6; b++) { sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b]; }
+      }
+      __syncthreads();
+      if (is_leg) {
+        float xb = t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f;
+        if (t >= 6) x0 *= i0own;
+        x1 *= i1own; x10 *= i10;
+#pragma unroll
+        for (int kk = 0; kk < NLEGDOF; kk++) {
+          float part = (t < 6 ? hk0[kk] * xb : (t - 6 < kk ? hk0[kk] * x0 : 0.f)) + (t + 2 < kk ? hk1[kk] * x1 : 0.f);
+          part += __shfl_xor_sync(gmask, part, 1, 8); part += __shfl_xor_sync(gmask, part, 2, 8); part += __shfl_xor_sync(gmask, part, 4, 8);
+          if (6 + kk == t) x0 -= part;
+          if (kk == t + 2) x1 -= part;
+          if (kk == 10) x10 -= part;
+        }
+        float* sx = sm + SM_X + 6 + NLEGDOF * leg;
+        if (t >= 6) sx[t - 6] = x0;
+        sx[t + 2] = x1;
+        if (t == 0) sx[10] = x10;
+      }
+    }
+    __syncthreads();
+
+    // ---- optional outputs of this step (derived quantities belong to the pre-integration state, as in mj_step)
+    const bool last_step = step == p.nsteps - 1;
+    if (last_step) {
+      if (p.dbg) {
+        float* dg = p.dbg + (size_t)fly * DBG_STRIDE;
+        if (tid == 0) { dg[DBG_NITER] = (float)niter; dg[DBG_NLS] = (float)nls_total; dg[DBG_NCHG] = (float)nchanged_last; }
+        for (int i = tid; i < NV; i += CTA) { dg[DBG_FS + i] = sm[SM_FS + i]; dg[DBG_QACC + i] = qacc[i]; dg[DBG_FC + i] = sm[SM_FC + i]; dg[DBG_QACCE + i] = sm[SM_X + i]; }
+        for (int s = 0; s < 2; s++) {
+          float* c = dg + DBG_CON + (tid * 2 + s) * 6; float fn = 0.f, Wt[6] = {0, 0, 0, 0, 0, 0};
+          if (con[s].active > 0.f) contact_forces(con[s], p.mu, Wt, nullptr, &fn);
+          c[0] = con[s].active; c[1] = con[s].active > 0.f ? con[s].dist : 0.f;
+          c[2] = con[s].active > 0.f ? con[s].r[0] + com[0] : 0.f; c[3] = con[s].active > 0.f ? con[s].r[1] + com[1] : 0.f;
+          c[4] = con[s].active > 0.f ? con[s].r[2] + com[2] : 0.f; c[5] = fn;
+        }
+        for (int i = 0; i < 3; i++) dg[DBG_XPOS + tid * 3 + i] = xpos[i];
+        for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[8 * (i / 6) + i % 6];
+        float nc[1] = {con[0].active + con[1].active};
+        cta_reduce<1>(nc, s_red, parity, tid);
+        if (tid == 0) dg[DBG_NCON] = nc[0];
+      }
+      if (p.out_actf) {
+        float* o = p.out_actf + (size_t)fly * (p.nu_pos + p.nu_adh);
+        if (is_leg) {
+          for (int j = 0; j < 3; j++) if (j < ndof) { int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]); if (ci >= 0) o[ci] = actf[j]; }
+          int ai = __float_as_int(role[RF_ADH_CIDX * CTA + tid]); if (ai >= 0) o[ai] = adhf;
+        }
+      }
+      if (p.out_sensor) {
+        // per-leg contact sensor (world.py:311-331), reduce="netforce": found, force, torque, pos, normal, tangent
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // F(3), fn-weighted pos(3), fn sum, count
+        float Fc[2][3], fnv[2] = {0.f, 0.f};
+        for (int s = 0; s < 2; s++) {
+          Fc[s][0] = Fc[s][1] = Fc[s][2] = 0.f;
+          if (is_leg && con[s].active > 0.f && __float_as_int(role[RF_LEGSENSOR * CTA + tid])) {
+            float Wt[6] = {0, 0, 0, 0, 0, 0}; contact_forces(con[s], p.mu, Wt, nullptr, &fnv[s]);
+            Fc[s][0] = Wt[3]; Fc[s][1] = Wt[4]; Fc[s][2] = Wt[5];
+            for (int i = 0; i < 3; i++) { acc[i] += Fc[s][i]; acc[3 + i] += fnv[s] * (con[s].r[i] + com[i]); }
+            acc[6] += fnv[s]; acc[7] += 1.f;
+          }
+        }
+        float plain[3] = {0, 0, 0};
+        for (int s = 0; s < 2; s++) if (is_leg && con[s].active > 0.f && __float_as_int(role[RF_LEGSENSOR * CTA + tid])) for (int i = 0; i < 3; i++) plain[i] += con[s].r[i] + com[i];
+        if (is_leg) {
+#pragma unroll
+          for (int off = 1; off < 8; off <<= 1) {
+            for (int i = 0; i < 8; i++) acc[i] += __shfl_xor_sync(gmask, acc[i], off, 8);
+            for (int i = 0; i < 3; i++) plain[i] += __shfl_xor_sync(gmask, plain[i], off, 8);
+          }
+          float P3[3] = {0, 0, 0};
+          if (acc[7] > 0.f) for (int i = 0; i < 3; i++) P3[i] = acc[6] > NMF_MINVAL ? acc[3 + i] / acc[6] : plain[i] / acc[7];
+          float T[3] = {0, 0, 0};
+          for (int s = 0; s < 2; s++) if (fnv[s] != 0.f || Fc[s][0] != 0.f || Fc[s][1] != 0.f) {
+            float rr[3] = {con[s].r[0] + com[0] - P3[0], con[s].r[1] + com[1] - P3[1], con[s].r[2] + com[2] - P3[2]}, tt[3];
+            cross3(rr, Fc[s], tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
+          }
+#pragma unroll
+          for (int off = 1; off < 8; off <<= 1) for (int i = 0; i < 3; i++) T[i] += __shfl_xor_sync(gmask, T[i], off, 8);
+          if (k == 0) {
+            float* o = p.out_sensor + ((size_t)fly * NLEG + leg) * 16;
+            o[0] = acc[7];
+            for (int i = 0; i < 3; i++) { o[1 + i] = acc[7] > 0.f ? -acc[i] : 0.f; o[4 + i] = acc[7] > 0.f ? -T[i] : 0.f; o[7 + i] = P3[i]; }
+            o[10] = acc[7] > 0.f ? 1.f : 0.f; o[11] = 0.f; o[12] = 0.f; o[13] = 0.f; o[14] = acc[7] > 0.f ? 1.f : 0.f; o[15] = 0.f;
+          }
+        }
+      }
+      if (p.out_xpos || p.out_xquat) {
+        float* ps = sm + SM_POSE + tid * 8;
+        ps[0] = xpos[0]; ps[1] = xpos[1]; ps[2] = xpos[2]; ps[3] = xq[0]; ps[4] = xq[1]; ps[5] = xq[2]; ps[6] = xq[3];
+        __syncthreads();
+        for (int sgi = tid; sgi < p.nseg; sgi += CTA) {
+          const float* tb = p.seg_tab + sgi * 8; const float* bp = sm + SM_POSE + __float_as_int(tb[0]) * 8;
+          float lp[3] = {tb[1], tb[2], tb[3]}, lq[4] = {tb[4], tb[5], tb[6], tb[7]}, w[3], wq[4];
+          qrot(bp + 3, lp, w); qmul(bp + 3, lq, wq);
+          if (p.out_xpos) { float* o = p.out_xpos + ((size_t)fly * p.nseg + sgi) * 3; o[0] = bp[0] + w[0]; o[1] = bp[1] + w[1]; o[2] = bp[2] + w[2]; }
+          if (p.out_xquat) { float* o = p.out_xquat + ((size_t)fly * p.nseg + sgi) * 4; o[0] = wq[0]; o[1] = wq[1]; o[2] = wq[2]; o[3] = wq[3]; }
+        }
+      }
+    }
+
+    // ---- advance: qvel += dt a' ; positions integrate with the NEW velocity ; qacc stays as next warm start
+    __syncthreads();
+    for (int i = tid; i < NV; i += CTA) st[S_QVEL + i] += p.dt * sm[SM_X + i];
+    __syncthreads();
+    for (int i = tid + 6; i < NV; i += CTA) st[S_QPOS + 1 + i] += p.dt * st[S_QVEL + i];
+    if (tid == 0) {
+      for (int i = 0; i < 3; i++) st[S_QPOS + i] += p.dt * st[S_QVEL + i];
+      float w[3] = {st[S_QVEL + 3], st[S_QVEL + 4], st[S_QVEL + 5]};
+      float n = sqrtf(dot3(w, w));
+      float q[4] = {st[S_QPOS + 3], st[S_QPOS + 4], st[S_QPOS + 5], st[S_QPOS + 6]};
+      if (n > NMF_MINVAL) {
+        float sn, cs; sincosf(0.5f * p.dt * n, &sn, &cs);
+        float dq[4] = {cs, w[0] / n * sn, w[1] / n * sn, w[2] / n * sn}, nq[4];
+        qmul(q, dq, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+      }
+      qnormalize(q);
+      st[S_QPOS + 3] = q[0]; st[S_QPOS + 4] = q[1]; st[S_QPOS + 5] = q[2]; st[S_QPOS + 6] = q[3];
+      st[S_TIME] += p.dt;
+    }
+    __syncthreads();
+  }
+
+  // ---- write the record back
+  {
+    float* g = p.state + (size_t)fly * S_STRIDE;
+    for (int i = tid; i < S_STRIDE; i += CTA) g[i] = st[i];
+  }
+}
+
+}  // namespace nmf

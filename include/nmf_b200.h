@@ -1,0 +1,87 @@
+/*
+ * nmf_b200.h — C ABI of the B200-native NeuroMechFly step path (libnmf_b200.so).
+ *
+ * The reference (flygym 2.0.1) has no FFI of its own for this path: the backend is
+ * swapped by subclassing `flygym.Simulation` the way `flygym.warp.GPUSimulation`
+ * does (reference src/flygym/warp/simulation.py:28-71,213-263).  The entry points
+ * below are what such a subclass binds through ctypes; each one names the reference
+ * method(s) it stands behind.  Plain pointers and sizes only; all `float*` buffers
+ * marked DEVICE are borrowed device pointers (e.g. torch.Tensor.data_ptr()), HOST
+ * buffers are ordinary (preferably pinned) host memory.  Every call returns 0 on
+ * success or a negative nmf_status; nmf_last_error() gives the message.
+ */
+#ifndef NMF_B200_H
+#define NMF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nmf_handle nmf_handle;
+
+enum nmf_status {
+  NMF_OK = 0,
+  NMF_EINVAL = -1,     /* bad argument / unsupported model topology */
+  NMF_ECUDA = -2,      /* CUDA runtime error */
+  NMF_ENOTBOUND = -3   /* nmf_bind() has not been called */
+};
+
+/* Offsets (in floats) of the sections of one fly's state record, and model sizes. */
+typedef struct nmf_info {
+  int32_t n_flies, nq, nv, nu_pos, nu_adh, nseg, nleg;
+  int32_t state_stride, off_qpos, off_qvel, off_qacc_warmstart, off_ctrl, off_time;
+  int32_t dbg_stride;
+  float timestep;
+} nmf_info;
+
+/* Device buffers owned by the caller (PyTorch tensors in the Python host). `state`
+ * is required; the observation buffers are optional (NULL = not produced). */
+typedef struct nmf_buffers {
+  float* state;        /* DEVICE [n_flies][state_stride]  qpos|qvel|qacc_warmstart|ctrl|time */
+  float* seg_xpos;     /* DEVICE [n_flies][nseg][3]   -> Simulation.get_body_positions / get_site_positions */
+  float* seg_xquat;    /* DEVICE [n_flies][nseg][4]   -> Simulation.get_body_rotations (w,x,y,z) */
+  float* act_force;    /* DEVICE [n_flies][nu]        -> Simulation.get_actuator_forces */
+  float* sensordata;   /* DEVICE [n_flies][nleg*16]   -> Simulation.get_ground_contact_info */
+  float* debug;        /* DEVICE [n_flies][dbg_stride] solver internals for the parity tests (optional) */
+} nmf_buffers;
+
+/* Simulation.__init__ / GPUSimulation.__init__ (simulation.py:32-57, warp/simulation.py:49-62):
+ * ingest the compiled model (blob from flygym_b200.model.NMFModel.to_blob()). */
+int nmf_create(const void* model_blob, size_t nbytes, int n_flies, int device, nmf_handle** out);
+int nmf_destroy(nmf_handle* h);
+int nmf_model_info(const nmf_handle* h, nmf_info* info);
+const char* nmf_last_error(const nmf_handle* h);
+
+int nmf_bind(nmf_handle* h, const nmf_buffers* buffers);
+
+/* Simulation.reset / GPUSimulation.reset (simulation.py:59-72, warp/simulation.py:64-71): every fly (or the
+ * flies whose byte in the DEVICE mask is non-zero) <- keyframe "neutral". */
+int nmf_reset(nmf_handle* h, const uint8_t* mask_or_null, void* cuda_stream);
+
+/* GPUSimulation.step (warp/simulation.py:260-263), `nsteps` times inside one launch.  With an action table
+ * (DEVICE [n_flies][table_T][nu_pos], as the reference benchmark keeps it: time_gpu_simulation.py:89-98,133-146)
+ * step s uses row (table_t0 + s) % table_T as the position-actuator inputs; NULL = use ctrl in the state. */
+int nmf_step(nmf_handle* h, int nsteps, const float* action_table_or_null, int table_T, int table_t0, void* cuda_stream);
+
+/* set_actuator_inputs / set_leg_adhesion_states (warp/simulation.py:213-258; kernel warp/utils.py:84-104):
+ * state.ctrl[:, cols[k]] = src[:, k]   (src DEVICE [n_flies][ncols], cols DEVICE int32[ncols]) */
+int nmf_scatter_ctrl(nmf_handle* h, const float* src, const int32_t* cols, int ncols, void* cuda_stream);
+/* get_joint_angles / get_joint_velocities (warp/simulation.py:73-115; kernel warp/utils.py:107-127):
+ * dst[:, k] = state[:, section_offset + cols[k]] */
+int nmf_gather_state(nmf_handle* h, int section_offset, const int32_t* cols, int ncols, float* dst, void* cuda_stream);
+
+/* Host-buffer convenience used for end-to-end timing: copies `actions` (HOST [n_flies][nu_pos]) to the device,
+ * steps `nsteps`, copies qpos (HOST [n_flies][nq]) back.  Synchronises the stream. */
+int nmf_step_host(nmf_handle* h, const float* actions_host, int nsteps, float* qpos_host, void* cuda_stream);
+
+int nmf_set_solver(nmf_handle* h, int max_newton_iterations, int max_linesearch_iterations);
+
+/* Number of kernels this library has launched on behalf of the handle (bench.py's gpu_launches). */
+int64_t nmf_launch_count(const nmf_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

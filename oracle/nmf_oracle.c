@@ -659,6 +659,12 @@ void nmfo_step(nmfo* o) {
   free(L); free(a);
 }
 
+void nmfo_step_n(nmfo* o, int n) { for (int i = 0; i < n; i++) nmfo_step(o); }
+/* n steps with a per-step action table [n][nu_pos] written into ctrl[0:nu_pos] */
+void nmfo_step_table(nmfo* o, const double* table, int n) {
+  for (int i = 0; i < n; i++) { memcpy(o->ctrl, table + (size_t)i * o->nu_pos, sizeof(double) * o->nu_pos); nmfo_step(o); }
+}
+
 /* ------------------------------------------------------------------ accessors for the test harness */
 int nmfo_dim(const nmfo* o, const char* name) {
   if (!strcmp(name, "nq")) return o->nq; if (!strcmp(name, "nv")) return o->nv; if (!strcmp(name, "nu")) return o->nu;

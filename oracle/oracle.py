@@ -35,6 +35,8 @@ def _lib():
         lib.nmfo_reset.argtypes = [ctypes.c_void_p]
         lib.nmfo_forward.argtypes = [ctypes.c_void_p]
         lib.nmfo_step.argtypes = [ctypes.c_void_p]
+        lib.nmfo_step_n.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.nmfo_step_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.nmfo_dim.restype = ctypes.c_int
         lib.nmfo_dim.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         lib.nmfo_array.restype = ctypes.POINTER(ctypes.c_double)
@@ -94,8 +96,12 @@ class Oracle:
     def forward(self): self._lib.nmfo_forward(self._h)
 
     def step(self, n: int = 1):
-        for _ in range(n):
-            self._lib.nmfo_step(self._h)
+        self._lib.nmfo_step_n(self._h, int(n))
+
+    def step_table(self, table):
+        """One step per row of ``table`` (float64 ``[n][nu_pos]``) used as position-actuator inputs."""
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        self._lib.nmfo_step_table(self._h, table.ctypes.data_as(ctypes.c_void_p), int(table.shape[0]))
 
     def error(self) -> str:
         return self._lib.nmfo_last_error(self._h).decode()

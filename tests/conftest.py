@@ -1,0 +1,25 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def model_capsule():
+    from flygym_b200.model import NMFModel
+    return NMFModel.bench(simplify_geom=True)
+
+
+@pytest.fixture(scope="session")
+def model_mesh():
+    from flygym_b200.model import NMFModel
+    return NMFModel.bench(simplify_geom=False)

@@ -1,0 +1,30 @@
+// emu_driver.cpp — runs the *real* kernel source (flygym_b200/csrc/nmf_step.cuh) on the CPU
+// through the SIMT emulator.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
+#include "simt_emu.h"
+#include "../../flygym_b200/csrc/nmf_host.h"
+#include "../../flygym_b200/csrc/nmf_step.cuh"
+
+static float g_sm[nmf::SM_TOTAL];
+
+extern "C" int emu_key_state(const void* blob, size_t nbytes, float* out) {
+  nmf::HostModel hm;
+  if (!hm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", hm.err.c_str()); return -1; }
+  memcpy(out, hm.key_state.data(), sizeof(float) * nmf::S_STRIDE);
+  return 0;
+}
+
+extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_flies, int nsteps, float* dbg, float* out_xpos,
+                        float* out_xquat, float* out_actf, float* out_sensor, const float* act_table, int table_T, int table_t0,
+                        int max_newton, int max_ls) {
+  nmf::HostModel hm;
+  if (!hm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", hm.err.c_str()); return -1; }
+  nmf::StepParams p = hm.par;
+  p.state = state; p.role = hm.role.data(); p.hull = hm.hull.data(); p.seg_tab = hm.seg_tab.data();
+  p.act_table = act_table; p.table_T = table_T; p.table_t0 = table_t0;
+  p.out_xpos = out_xpos; p.out_xquat = out_xquat; p.out_actf = out_actf; p.out_sensor = out_sensor; p.dbg = dbg;
+  p.n_flies = n_flies; p.nsteps = nsteps;
+  if (max_newton > 0) p.max_newton = max_newton;
+  if (max_ls > 0) p.max_ls = max_ls;
+  for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() { nmf::step_block(p, g_sm); });
+  return 0;
+}
