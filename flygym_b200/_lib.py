@@ -41,7 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if nvcc is None:
         raise RuntimeError("flygym_b200: nvcc not found and libnmf_b200.so is missing/out of date")
     srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(SO_PATH), *srcs]
+    extra = os.environ.get("NMF_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(SO_PATH), *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

@@ -13,7 +13,10 @@
 using namespace nmf;
 
 // ------------------------------------------------------------------ kernels
-extern "C" __global__ void __launch_bounds__(CTA) nmf_step_kernel(const StepParams p) {
+#ifndef NMF_MINBLOCKS
+#define NMF_MINBLOCKS 1
+#endif
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) {
   __shared__ __align__(16) float sm[SM_TOTAL];
   step_block(p, sm);
 }

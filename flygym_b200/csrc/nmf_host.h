@@ -161,7 +161,9 @@ struct HostModel {
     par.solimp[0] = (float)clampimp(contact[3]); par.solimp[1] = (float)dmax; par.solimp[2] = (float)std::fmax(0.0, contact[5]);
     par.solimp[3] = (float)clampimp(contact[6]); par.solimp[4] = (float)std::fmax(1.0, contact[7]);
     par.margin = (float)(contact[8] - contact[9]);
-    par.max_newton = 8; par.max_ls = 8; par.nsteps = 1;
+    par.max_newton = (int)opt[4]; par.max_ls = (int)opt[6]; par.nsteps = 1;   // reference: iterations=100 (mujoco_globals.yaml:14), ls_iterations=50 (MuJoCo default)
+    if (par.max_newton < 1) par.max_newton = 100;
+    if (par.max_ls < 1) par.max_ls = 50;
     (void)body_parent;
     return true;
   }
