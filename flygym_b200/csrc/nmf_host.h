@@ -86,8 +86,9 @@ struct HostModel {
     // body-level fields (hub replicated on all 16 hub lanes)
     for (int tid = 0; tid < CTA; tid++) {
       int bb = tid < NLEG * NLINK ? tid + 1 : 0;
-      for (int i = 0; i < 3; i++) set(RF_BPOS + i, tid, (float)body_pos[3 * bb + i]);
-      for (int i = 0; i < 4; i++) set(RF_BQUAT + i, tid, (float)body_quat[4 * bb + i]);
+      const bool hublane = tid >= NLEG * NLINK;   // hub chains: identity offset from the hub frame (seeded with the hub pose)
+      for (int i = 0; i < 3; i++) set(RF_BPOS + i, tid, hublane ? 0.f : (float)body_pos[3 * bb + i]);
+      for (int i = 0; i < 4; i++) set(RF_BQUAT + i, tid, hublane ? (i == 0 ? 1.f : 0.f) : (float)body_quat[4 * bb + i]);
       for (int i = 0; i < 3; i++) set(RF_IPOS + i, tid, (float)body_ipos[3 * bb + i]);
       double Rm[9]; q2mat_d(body_iquat + 4 * bb, Rm);
       double Ib[9];
@@ -95,6 +96,10 @@ struct HostModel {
       set(RF_IB + 0, tid, (float)Ib[0]); set(RF_IB + 1, tid, (float)Ib[4]); set(RF_IB + 2, tid, (float)Ib[8]);
       set(RF_IB + 3, tid, (float)Ib[1]); set(RF_IB + 4, tid, (float)Ib[2]); set(RF_IB + 5, tid, (float)Ib[5]);
       set(RF_MASS, tid, (float)body_mass[bb]); set(RF_INVW, tid, (float)invw[2 * bb]);
+      if (hublane && tid != NLEG * NLINK) {       // only lane 48 carries the hub's mass / inertia
+        set(RF_MASS, tid, 0.f);
+        for (int i = 0; i < 6; i++) set(RF_IB + i, tid, 0.f);
+      }
       set(RF_GTYPE, tid, i2f(-1)); set(RF_ADH_CIDX, tid, i2f(-1));
       for (int j = 0; j < 3; j++) set(RF_CIDX + j, tid, i2f(-1));
       if (bb > 0) {

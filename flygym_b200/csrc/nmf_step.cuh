@@ -32,6 +32,10 @@ namespace nmf {
 #define NMF_FULL 0xffffffffu
 #define NMF_MINVAL 1e-15f
 
+// Block barrier that first reconverges each warp: __syncthreads() is the *aligned* barrier and is undefined when a warp
+// reaches it diverged (ptxas may leave lanes diverged after predicated stores; compute-sanitizer synccheck flags it).
+__device__ __forceinline__ void block_sync() { __syncwarp(NMF_FULL); __syncthreads(); }
+
 // ------------------------------------------------------------------ small math
 __device__ __forceinline__ void qmul(const float* a, const float* b, float* r) {
   float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -138,7 +142,7 @@ __device__ __forceinline__ void cta_reduce(float* v, float* s_red, int& parity, 
 #pragma unroll
     for (int n = 0; n < N; n++) buf[(tid >> 5) * 8 + n] = v[n];
   }
-  __syncthreads();
+  block_sync();
 #pragma unroll
   for (int n = 0; n < N; n++) v[n] = buf[n] + buf[8 + n];
   parity ^= 1;
@@ -291,75 +295,190 @@ __device__ __forceinline__ int contact_forces(const Contact& c, float mu, float*
 }
 
 // line-search partial sums of one contact at step alpha: d0 += D x jv, d1 += D jv^2 over rows with x < 0
-__device__ __forceinline__ void ls_eval(const Contact& c, float alpha, float& d0, float& d1) {
+__device__ __forceinline__ void ls_eval(const Contact& c, float alpha, float& d0, float& d1, float& nchanged) {
   float jar[4], jv[4]; rows4(c.w, c.c0, jar); rows4(c.s, 0.f, jv);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     float x = jar[r] + alpha * jv[r];
     if (x < 0.f) { d0 += c.D * x * jv[r]; d1 += c.D * jv[r] * jv[r]; }
+    nchanged += ((x < 0.f) != (jar[r] < 0.f)) ? 1.f : 0.f;   // rows whose state differs from the one the Hessian was built for
   }
 }
 
 // ------------------------------------------------------------------ shared-memory plan (floats)
+// The 64 lanes form 8 shuffle groups of 8: groups 0..5 are the leg chains, groups 6..7 are
+// "hub chains": massless, joint-less bodies welded to the hub that carry the hub's contact
+// geoms (lane 48 additionally carries the hub's inertia).  Every chain scan therefore runs
+// convergently on all lanes with the full warp mask; hub-specific work (the six free-joint
+// DoFs and the 6x6 Schur block) is smem-only code executed by the hub lanes afterwards.
+constexpr int NGROUP = 8;
 constexpr int SM_STATE = 0;                         // S_STRIDE
 constexpr int SM_CDOF = SM_STATE + S_STRIDE;        // NV * 8
 constexpr int SM_FS = SM_CDOF + NV * 8;             // qfrc_smooth
 constexpr int SM_GRAD = SM_FS + NV;                 // gradient / rhs
 constexpr int SM_X = SM_GRAD + NV;                  // search direction / solve result
 constexpr int SM_FC = SM_X + NV;                    // qfrc_constraint
-constexpr int SM_HS = SM_FC + NV;                   // row staging: NLEG * 184
+constexpr int SM_HS = SM_FC + NV;                   // row staging NGROUP * 184 (reused as pose buffer in the epilogue)
 constexpr int HS_STRIDE = 184;
-constexpr int SM_ROOT = SM_HS + NLEG * HS_STRIDE;   // per-leg root publications: NLEG * 40
-constexpr int ROOT_STRIDE = 40;                     // [0..5] wrench, [6..15] crb, [16..36] A-hat
-constexpr int SM_BASE = SM_ROOT + NLEG * ROOT_STRIDE;  // NLEG*21 Schur contributions, then NLEG*6 rhs contributions
-constexpr int SM_HBB = SM_BASE + NLEG * 21 + NLEG * 6; // 21 hub block + 6 xb + 6 S_h + misc
-constexpr int SM_HUB = SM_HBB + 48;                 // hub uniforms: xpos(3) R(9) com(3) cvel(6) cacc(6) cinert(10) crbtot(10) q(4)
-constexpr int SM_HUBC = SM_HUB + 64;                // hub contact accumulation: 16 lanes * 28
-constexpr int SM_POSE = SM_HUBC + NHUBLANE * 28;    // body poses for the output epilogue: CTA * 8
-constexpr int SM_RED = SM_POSE + CTA * 8;           // 32
+constexpr int SM_ROOT = SM_HS + NGROUP * HS_STRIDE; // per-group root publications
+constexpr int ROOT_STRIDE = 40;                     // [0..5] wrench, [6..15] crb / fc wrench, [16..36] A-hat
+constexpr int SM_BASE = SM_ROOT + NGROUP * ROOT_STRIDE;  // NLEG*21 Schur contributions, then NLEG*6 rhs contributions
+constexpr int SM_HBB = SM_BASE + 168;               // 21 hub block + 6 xb + 6 S_h
+constexpr int SM_HUB = SM_HBB + 48;                 // hub uniforms
+constexpr int SM_RED = SM_HUB + 64;                 // 32
 constexpr int SM_TOTAL = SM_RED + 32;
+constexpr int HU_CVEL = 0, HU_CACC = 6;
+constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27;
 
-// hub uniform offsets inside SM_HUB
-constexpr int HU_XPOS = 0, HU_R = 3, HU_COM = 12, HU_CVEL = 15, HU_CACC = 21, HU_CINERT = 27, HU_CRB = 37, HU_Q = 47, HU_FB = 51;
-// inside SM_HBB
-constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27, HB_ATOT = 0;
+// rows of the (contact-augmented) joint-space inertia for this lane's DoFs -> staging
+__device__ __forceinline__ void build_rows(const float* P, const float* s_cdof, float* hs, int grp, int dof0, int ldof0, int ndof,
+                                           const float* diag_add) {
+  for (int j = 0; j < 3; j++) if (j < ndof) {
+    int li = ldof0 + j; float u[6]; sym6_mul(P, s_cdof + 8 * (dof0 + j), u);
+    for (int c = 0; c < 6; c++) hs[li * 16 + c] = dot6(s_cdof + 8 * c, u);
+    for (int jj = 0; jj <= li; jj++) {
+      float v = dot6(s_cdof + 8 * (6 + NLEGDOF * grp + jj), u);
+      if (jj == li) v += diag_add[j];
+      if (li == 10 && jj == 10) hs[176] = v; else hs[li * 16 + 6 + jj] = v;
+    }
+  }
+}
+
+// L'DL of the 11x11 chain block + its 11x6 border, one matrix column per lane (columns t and 8+t of 16; the last
+// diagonal entry d10 is held by every lane).  Leaves L (unit lower, scaled rows) in hk0/hk1, the inverse pivots of
+// the lane's own DoFs in i0own/i1own/i10 and this chain's Schur contribution to the hub block in contrib[3].
+__device__ __forceinline__ void chain_factor(float* hk0, float* hk1, float d10, int t, float& i0own, float& i1own, float& i10,
+                                             float* contrib) {
+  int pb[3], pc[3];
+#pragma unroll
+  for (int s = 0; s < 3; s++) {  // pair (b >= c) number t + 8 s of the 21 lower-triangular hub entries
+    int idx = t + 8 * s, b = 0; while ((b + 1) * (b + 2) / 2 <= idx) b++;
+    pb[s] = b; pc[s] = idx - b * (b + 1) / 2; if (idx >= 21) { pb[s] = 0; pc[s] = 0; }
+    contrib[s] = 0.f;
+  }
+#pragma unroll
+  for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
+    float dk;
+    if (kk == 10) dk = d10; else { const int c = 6 + kk; dk = __shfl_sync(NMF_FULL, c < 8 ? hk0[kk] : hk1[kk], c & 7, 8); }
+    float ik = 1.0f / dk;
+    if (kk == 10) i10 = ik;
+    if (6 + kk == t) i0own = ik;
+    if (kk == t + 2) i1own = ik;
+    float l0 = hk0[kk] * ik, l1 = hk1[kk] * ik;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      float lb = __shfl_sync(NMF_FULL, l0, pb[s], 8), hc = __shfl_sync(NMF_FULL, hk0[kk], pc[s], 8);
+      contrib[s] += lb * hc;
+    }
+#pragma unroll
+    for (int j = 0; j < kk; j++) {
+      const int cj = 6 + j;
+      float l = __shfl_sync(NMF_FULL, cj < 8 ? l0 : l1, cj & 7, 8);
+      hk0[j] -= (t <= cj ? l : 0.f) * hk0[kk];
+      hk1[j] -= (t + 2 <= j ? l : 0.f) * hk1[kk];
+    }
+    hk0[kk] = l0; hk1[kk] = l1;
+  }
+}
+// x <- L^-T x on the chain; lanes t < 6 return (in x0) minus the chain's contribution to the hub right-hand side
+__device__ __forceinline__ void chain_solve_up(const float* hk0, const float* hk1, int t, float& x0, float& x1, float x10) {
+#pragma unroll
+  for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
+    float xk;
+    if (kk == 10) xk = x10; else { const int c = 6 + kk; xk = __shfl_sync(NMF_FULL, c < 8 ? x0 : x1, c & 7, 8); }
+    x0 -= (t < 6 + kk ? hk0[kk] : 0.f) * xk;
+    x1 -= (t + 2 < kk ? hk1[kk] : 0.f) * xk;
+  }
+}
+// x <- L^-1 D^-1 x given the hub solution xb (lanes t < 6)
+__device__ __forceinline__ void chain_solve_down(const float* hk0, const float* hk1, int t, float xb, float i0own, float i1own,
+                                                 float i10, float& x0, float& x1, float& x10) {
+  if (t >= 6) x0 *= i0own;
+  x1 *= i1own; x10 *= i10;
+#pragma unroll
+  for (int kk = 0; kk < NLEGDOF; kk++) {
+    float part = (t < 6 ? hk0[kk] * xb : (t - 6 < kk ? hk0[kk] * x0 : 0.f)) + (t + 2 < kk ? hk1[kk] * x1 : 0.f);
+    part += __shfl_xor_sync(NMF_FULL, part, 1, 8); part += __shfl_xor_sync(NMF_FULL, part, 2, 8); part += __shfl_xor_sync(NMF_FULL, part, 4, 8);
+    if (6 + kk == t) x0 -= part;
+    if (kk == t + 2) x1 -= part;
+    if (kk == 10) x10 -= part;
+  }
+}
+// hub 6x6 block: S = Hbb - sum(chain contributions); solve S xb = rhs (dense L'DL, serial, one lane)
+__device__ __forceinline__ void hub_solve(float* sm, float* xb) {
+  float S[21];
+  for (int i = 0; i < 21; i++) { float s = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) s -= sm[SM_BASE + l * 21 + i]; S[i] = s; }
+  for (int b = 0; b < 6; b++) { float s = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) s += sm[SM_BASE + NLEG * 21 + l * 6 + b]; xb[b] = s; }
+  float dinv[6];
+#pragma unroll
+  for (int kk = 5; kk >= 0; kk--) {
+    dinv[kk] = 1.0f / S[kk * (kk + 1) / 2 + kk];
+#pragma unroll
+    for (int j = 0; j < kk; j++) {
+      float l = S[kk * (kk + 1) / 2 + j] * dinv[kk];
+#pragma unroll
+      for (int c = 0; c <= j; c++) S[j * (j + 1) / 2 + c] -= l * S[kk * (kk + 1) / 2 + c];
+    }
+#pragma unroll
+    for (int j = 0; j < kk; j++) S[kk * (kk + 1) / 2 + j] *= dinv[kk];
+  }
+#pragma unroll
+  for (int kk = 5; kk >= 0; kk--)
+#pragma unroll
+    for (int j = 0; j < kk; j++) xb[j] -= S[kk * (kk + 1) / 2 + j] * xb[kk];
+#pragma unroll
+  for (int kk = 0; kk < 6; kk++) xb[kk] *= dinv[kk];
+#pragma unroll
+  for (int kk = 0; kk < 6; kk++)
+#pragma unroll
+    for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
+}
 
 // ------------------------------------------------------------------ the step
 __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   const int tid = threadIdx.x;
   const int fly = blockIdx.x;
-  const bool is_leg = tid < NLEG * NLINK;
-  const int leg = tid >> 3, k = tid & 7, t = k;
-  const int hl = tid - NLEG * NLINK;
-  const unsigned gmask = tid < 32 ? NMF_FULL : (is_leg ? 0x0000ffffu : 0xffff0000u);
+  const int grp = tid >> 3, k = tid & 7, t = k;
+  const bool is_leg = grp < NLEG;
+  const int hl = tid - NLEG * NLINK;          // hub lane index (valid when !is_leg)
+  const bool hubdof = !is_leg && hl < 6;      // hub lanes 0..5 own the six free-joint DoFs
   const float* role = p.role;
   float* st = sm + SM_STATE;
   float* s_cdof = sm + SM_CDOF;
   float* s_hub = sm + SM_HUB;
   float* s_red = sm + SM_RED;
+  float* hs = sm + SM_HS + grp * HS_STRIDE;
+  float* rt = sm + SM_ROOT + grp * ROOT_STRIDE;
   int parity = 0;
 
-  // ---- load the state record (coalesced; 304 floats)
+  // ---- load the state record (coalesced; 304 floats), clear the row staging
   {
-    float* g = p.state + (size_t)fly * S_STRIDE;
+    const float* g = p.state + (size_t)fly * S_STRIDE;
     for (int i = tid; i < S_STRIDE; i += CTA) st[i] = g[i];
-    for (int i = tid; i < NLEG * HS_STRIDE; i += CTA) sm[SM_HS + i] = 0.f;
+    for (int i = tid; i < NGROUP * HS_STRIDE; i += CTA) sm[SM_HS + i] = 0.f;
   }
-  __syncthreads();
+  block_sync();
+  if (!is_leg) {  // hub chains carry no DoFs: unit pivots keep their (unused) factorisation finite
+    if (t == 0) { for (int i = 0; i < 10; i++) hs[i * 16 + 6 + i] = 1.f; hs[176] = 1.f; }
+  }
 
   // per-lane constants that stay in registers for the whole launch
-  const int ndof = is_leg ? __float_as_int(role[RF_NDOF * CTA + tid]) : 0;
+  const int ndof = __float_as_int(role[RF_NDOF * CTA + tid]);                 // 0 on hub lanes
   const int dof0 = is_leg ? __float_as_int(role[RF_DOF0 * CTA + tid]) : (hl < 6 ? hl : 0);
-  const int ldof0 = is_leg ? dof0 - 6 - NLEGDOF * leg : 0;   // first dof index inside the leg
+  const int ldof0 = is_leg ? dof0 - 6 - NLEGDOF * grp : 0;                    // first dof index inside the leg
+  const int lbase = is_leg ? 6 + NLEGDOF * grp : 6;                           // first global dof of this chain
   const float mass = role[RF_MASS * CTA + tid];
   const float invw = role[RF_INVW * CTA + tid];
+  float armv[3], dampv[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) { armv[j] = role[(RF_ARM + j) * CTA + tid]; dampv[j] = role[(RF_DAMP + j) * CTA + tid]; }
 
   for (int step = 0; step < p.nsteps; step++) {
     // ---- controls for this step
     if (p.act_table) {
       const float* row = p.act_table + ((size_t)fly * p.table_T + (size_t)((p.table_t0 + step) % p.table_T)) * p.nu_pos;
       for (int i = tid; i < p.nu_pos; i += CTA) st[S_CTRL + i] = row[i];
-      __syncthreads();
+      block_sync();
     }
 
     // =====================================================================
@@ -369,7 +488,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     qnormalize(qh);
     const float xh[3] = {st[S_QPOS], st[S_QPOS + 1], st[S_QPOS + 2]};
     float xpos[3], xq[4], R[9], laxis[9];   // laxis: hinge axes in the parent frame, later world
-    if (is_leg) {
+    {
       float q[4] = {role[(RF_BQUAT + 0) * CTA + tid], role[(RF_BQUAT + 1) * CTA + tid], role[(RF_BQUAT + 2) * CTA + tid], role[(RF_BQUAT + 3) * CTA + tid]};
       float pp[3] = {role[(RF_BPOS + 0) * CTA + tid], role[(RF_BPOS + 1) * CTA + tid], role[(RF_BPOS + 2) * CTA + tid]};
 #pragma unroll
@@ -386,14 +505,13 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         float t3[3]; qrot(qh, pp, t3); pp[0] = xh[0] + t3[0]; pp[1] = xh[1] + t3[1]; pp[2] = xh[2] + t3[2];
         float nq[4]; qmul(qh, q, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
       }
-      float qpar[4] = {qh[0], qh[1], qh[2], qh[3]};
 #pragma unroll
       for (int off = 1; off < 8; off <<= 1) {
         float uq[4], up[3];
 #pragma unroll
-        for (int i = 0; i < 4; i++) uq[i] = __shfl_up_sync(gmask, q[i], off, 8);
+        for (int i = 0; i < 4; i++) uq[i] = __shfl_up_sync(NMF_FULL, q[i], off, 8);
 #pragma unroll
-        for (int i = 0; i < 3; i++) up[i] = __shfl_up_sync(gmask, pp[i], off, 8);
+        for (int i = 0; i < 3; i++) up[i] = __shfl_up_sync(NMF_FULL, pp[i], off, 8);
         if (k >= off) {
           float t3[3]; qrot(uq, pp, t3); pp[0] = up[0] + t3[0]; pp[1] = up[1] + t3[1]; pp[2] = up[2] + t3[2];
           float nq[4]; qmul(uq, q, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
@@ -401,16 +519,14 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       }
       qnormalize(q);
       {  // parent world orientation -> world hinge axes
-        float pq[4];
+        float pq[4], qpar[4] = {qh[0], qh[1], qh[2], qh[3]};
 #pragma unroll
-        for (int i = 0; i < 4; i++) pq[i] = __shfl_up_sync(gmask, q[i], 1, 8);
+        for (int i = 0; i < 4; i++) pq[i] = __shfl_up_sync(NMF_FULL, q[i], 1, 8);
         if (k > 0) { qpar[0] = pq[0]; qpar[1] = pq[1]; qpar[2] = pq[2]; qpar[3] = pq[3]; }
 #pragma unroll
         for (int j = 0; j < 3; j++) { float w[3]; qrot(qpar, laxis + 3 * j, w); laxis[3 * j] = w[0]; laxis[3 * j + 1] = w[1]; laxis[3 * j + 2] = w[2]; }
       }
       xpos[0] = pp[0]; xpos[1] = pp[1]; xpos[2] = pp[2]; xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
-    } else {
-      xpos[0] = xh[0]; xpos[1] = xh[1]; xpos[2] = xh[2]; xq[0] = qh[0]; xq[1] = qh[1]; xq[2] = qh[2]; xq[3] = qh[3];
     }
     q2mat(xq, R);
 
@@ -422,8 +538,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     }
     float com[3];
     {
-      float contributes = (is_leg || hl == 0) ? mass : 0.f;
-      float v[3] = {contributes * xipos[0], contributes * xipos[1], contributes * xipos[2]};
+      float v[3] = {mass * xipos[0], mass * xipos[1], mass * xipos[2]};
       cta_reduce<3>(v, s_red, parity, tid);
       com[0] = v[0] * p.inv_total_mass; com[1] = v[1] * p.inv_total_mass; com[2] = v[2] * p.inv_total_mass;
     }
@@ -442,59 +557,48 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       cinert[6] = mass * off[0]; cinert[7] = mass * off[1]; cinert[8] = mass * off[2]; cinert[9] = mass;
     }
     // cdof of own dofs -> shared; hub lanes 0..5 own the free-joint dofs
-    if (is_leg) {
+    {
       float off[3] = {com[0] - xpos[0], com[1] - xpos[1], com[2] - xpos[2]};
       for (int j = 0; j < ndof; j++) {
         float* cd = s_cdof + 8 * (dof0 + j); float l[3]; cross3(laxis + 3 * j, off, l);
         cd[0] = laxis[3 * j]; cd[1] = laxis[3 * j + 1]; cd[2] = laxis[3 * j + 2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
       }
-    } else {
-      float off[3] = {com[0] - xpos[0], com[1] - xpos[1], com[2] - xpos[2]};
-      if (hl < 3) {
-        float* cd = s_cdof + 8 * hl; cd[0] = cd[1] = cd[2] = 0.f; cd[3] = hl == 0; cd[4] = hl == 1; cd[5] = hl == 2;
-      } else if (hl < 6) {
-        int a = hl - 3; float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
-        float* cd = s_cdof + 8 * hl; cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
+      if (hubdof) {
+        float* cd = s_cdof + 8 * hl;
+        if (hl < 3) { cd[0] = cd[1] = cd[2] = 0.f; cd[3] = hl == 0; cd[4] = hl == 1; cd[5] = hl == 2; }
+        else { int a = hl - 3; float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l); cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2]; }
       }
-      if (hl == 0) {
+      if (!is_leg && hl == 0) {
         // hub velocity / bias acceleration (free joint: translations first, rotations against the updated velocity)
         float wl[3] = {st[S_QVEL + 3], st[S_QVEL + 4], st[S_QVEL + 5]};
-        float vlin[3] = {st[S_QVEL], st[S_QVEL + 1], st[S_QVEL + 2]};
-        float cv0[6] = {0.f, 0.f, 0.f, vlin[0], vlin[1], vlin[2]};
+        float cv0[6] = {0.f, 0.f, 0.f, st[S_QVEL], st[S_QVEL + 1], st[S_QVEL + 2]};
         float cacc[6] = {0.f, 0.f, 0.f, -p.gx, -p.gy, -p.gz};
         float cvel[6] = {cv0[0], cv0[1], cv0[2], cv0[3], cv0[4], cv0[5]};
+        float Sh[6] = {0, 0, 0, st[S_WARM], st[S_WARM + 1], st[S_WARM + 2]};
         for (int a = 0; a < 3; a++) {
           float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
           float cd[6] = {ax[0], ax[1], ax[2], l[0], l[1], l[2]}, cdd[6];
           cross_motion(cv0, cd, cdd);
-          for (int i = 0; i < 6; i++) { cacc[i] += cdd[i] * wl[a]; cvel[i] += cd[i] * wl[a]; }
-        }
-        for (int i = 0; i < 6; i++) { s_hub[HU_CVEL + i] = cvel[i]; s_hub[HU_CACC + i] = cacc[i]; }
-        for (int i = 0; i < 10; i++) s_hub[HU_CINERT + i] = cinert[i];
-        // hub part of the spatial acceleration generated by the warm-start qacc
-        float Sh[6] = {0, 0, 0, st[S_WARM], st[S_WARM + 1], st[S_WARM + 2]};
-        for (int a = 0; a < 3; a++) {
-          float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
           float qa = st[S_WARM + 3 + a];
-          Sh[0] += ax[0] * qa; Sh[1] += ax[1] * qa; Sh[2] += ax[2] * qa; Sh[3] += l[0] * qa; Sh[4] += l[1] * qa; Sh[5] += l[2] * qa;
+          for (int i = 0; i < 6; i++) { cacc[i] += cdd[i] * wl[a]; cvel[i] += cd[i] * wl[a]; Sh[i] += cd[i] * qa; }
         }
-        for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
+        for (int i = 0; i < 6; i++) { s_hub[HU_CVEL + i] = cvel[i]; s_hub[HU_CACC + i] = cacc[i]; sm[SM_HBB + HB_SH + i] = Sh[i]; }
       }
     }
-    __syncthreads();   // cdof, hub cvel/cacc/cinert, S_h visible
+    block_sync();   // cdof, hub cvel/cacc, S_h visible
 
     // =====================================================================
-    // B. velocities, composite inertia, collision, bias + actuator forces
+    // B. velocities, composite inertia, collision, bias + actuator forces (all lanes, convergent)
     // =====================================================================
     float crb[10], cvel[6], Sa[6];
     Contact con[2];
     float fs_own[3] = {0.f, 0.f, 0.f};
     float actf[3] = {0.f, 0.f, 0.f}, adhf = 0.f;
-    if (is_leg) {
+    {
       float loc[6] = {0, 0, 0, 0, 0, 0};
       for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); float qv = st[S_QVEL + dof0 + j]; for (int i = 0; i < 6; i++) loc[i] += cd[i] * qv; }
       float pre[6] = {loc[0], loc[1], loc[2], loc[3], loc[4], loc[5]};
-      chain_prefix<6>(pre, gmask, k);
+      chain_prefix<6>(pre, NMF_FULL, k);
       float cv[6], ad[6] = {0, 0, 0, 0, 0, 0};
       for (int i = 0; i < 6; i++) cv[i] = pre[i] - loc[i] + s_hub[HU_CVEL + i];
       for (int j = 0; j < ndof; j++) {
@@ -503,7 +607,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         for (int i = 0; i < 6; i++) { ad[i] += cdd[i] * qv; cv[i] += cd[i] * qv; }
       }
       for (int i = 0; i < 6; i++) cvel[i] = cv[i];
-      chain_prefix<6>(ad, gmask, k);
+      chain_prefix<6>(ad, NMF_FULL, k);
       float cacc[6];
       for (int i = 0; i < 6; i++) cacc[i] = ad[i] + s_hub[HU_CACC + i];
       // body wrench  W = -(I a + v x* I v)  (+ adhesion below)
@@ -512,7 +616,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int i = 0; i < 6; i++) W[i] = -(t1[i] + t3[i]);
       // composite inertia
       for (int i = 0; i < 10; i++) crb[i] = cinert[i];
-      chain_suffix<10>(crb, gmask, k);
+      chain_suffix<10>(crb, NMF_FULL, k);
       // collision for this body's geom
       collide(p, role, tid, xpos, R, com, cvel, invw, con);
       // adhesion (body transmission): force pulls the body onto the plane along each contact normal
@@ -523,17 +627,15 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         float n = con[0].active + con[1].active;
         if (n > 0.f) {
           float fz = -adhf / n;
-          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) {
-            W[0] += con[s].r[1] * fz; W[1] += -con[s].r[0] * fz; W[5] += fz;
-          }
+          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { W[0] += con[s].r[1] * fz; W[1] += -con[s].r[0] * fz; W[5] += fz; }
         }
       }
-      chain_suffix<6>(W, gmask, k);
+      chain_suffix<6>(W, NMF_FULL, k);
       // joint-space smooth force of own dofs: passive + actuator + C'W
       for (int j = 0; j < 3; j++) if (j < ndof) {
         int d = dof0 + j; const float* cd = s_cdof + 8 * d;
         float q = st[S_QPOS + 1 + d], qv = st[S_QVEL + d];
-        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - role[(RF_DAMP + j) * CTA + tid] * qv;
+        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - dampv[j] * qv;
         int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]);
         if (ci >= 0) {
           float kp = role[(RF_KP + j) * CTA + tid], kv = role[(RF_KV + j) * CTA + tid];
@@ -545,39 +647,29 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         fs_own[j] = f; sm[SM_FS + d] = f;
       }
       if (k == 0) {
-        float* rt = sm + SM_ROOT + leg * ROOT_STRIDE;
         for (int i = 0; i < 6; i++) rt[i] = W[i];
         for (int i = 0; i < 10; i++) rt[6 + i] = crb[i];
       }
       // spatial acceleration of this body generated by the warm-start qacc
       float sl[6] = {0, 0, 0, 0, 0, 0};
       for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); float qa = st[S_WARM + dof0 + j]; for (int i = 0; i < 6; i++) sl[i] += cd[i] * qa; }
-      chain_prefix<6>(sl, gmask, k);
+      chain_prefix<6>(sl, NMF_FULL, k);
       for (int i = 0; i < 6; i++) Sa[i] = sl[i] + sm[SM_HBB + HB_SH + i];
-    } else {
-      for (int i = 0; i < 6; i++) { cvel[i] = s_hub[HU_CVEL + i]; Sa[i] = sm[SM_HBB + HB_SH + i]; }
-      for (int i = 0; i < 10; i++) crb[i] = 0.f;
-      if (hl < p.nhubgeom) collide(p, role, tid, xpos, R, com, cvel, invw, con);
-      else { con[0].active = con[1].active = 0.f; }
-    }
-    // contact rows at the warm-start acceleration
-    for (int s = 0; s < 2; s++) if (con[s].active > 0.f) {
-      float ap[3]; project_point(con[s], Sa, p.mu, ap);
-      con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
-    }
-    __syncthreads();   // leg roots (wrench, crb) visible to the hub
-    float crbh[10];    // hub lanes: total composite inertia of the whole fly
-    if (!is_leg) {
-      for (int i = 0; i < 10; i++) { float s = s_hub[HU_CINERT + i]; for (int l = 0; l < NLEG; l++) s += sm[SM_ROOT + l * ROOT_STRIDE + 6 + i]; crbh[i] = s; }
-      if (hl < 6) {
-        float t1[6], t2[6], t3[6], W[6], ci[10], cv[6], ca[6];
-        for (int i = 0; i < 10; i++) ci[i] = s_hub[HU_CINERT + i];
-        for (int i = 0; i < 6; i++) { cv[i] = s_hub[HU_CVEL + i]; ca[i] = s_hub[HU_CACC + i]; }
-        mul_inert(ci, ca, t1); mul_inert(ci, cv, t2); cross_force(cv, t2, t3);
-        for (int i = 0; i < 6; i++) { W[i] = -(t1[i] + t3[i]); for (int l = 0; l < NLEG; l++) W[i] += sm[SM_ROOT + l * ROOT_STRIDE + i]; }
-        fs_own[0] = dot6(s_cdof + 8 * hl, W); sm[SM_FS + hl] = fs_own[0];
+      // contact rows at the warm-start acceleration
+      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) {
+        float ap[3]; project_point(con[s], Sa, p.mu, ap);
+        con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
       }
     }
+    block_sync();   // chain roots (wrench, crb) visible to the hub lanes
+    float crbh[10];    // hub-dof lanes: composite inertia of the whole fly
+    if (hubdof) {
+      float W[6];
+      for (int i = 0; i < 10; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + 6 + i]; crbh[i] = s; }
+      for (int i = 0; i < 6; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; W[i] = s; }
+      fs_own[0] = dot6(s_cdof + 8 * hl, W); sm[SM_FS + hl] = fs_own[0];
+    }
+    block_sync();   // roots consumed before the solver overwrites them
 
     // =====================================================================
     // C. soft-contact solve: primal Newton on  1/2 (a-a0)'M(a-a0) + s(Ja - aref)
@@ -586,272 +678,138 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     // =====================================================================
     float* qacc = st + S_WARM;      // qacc lives in the warm-start slot of the record
     int niter = 0, nls_total = 0, nchanged_last = 0;
-    int prev_bits = 0;
-    float hk0[NLEGDOF], hk1[NLEGDOF];   // column-distributed L'DL factor (leg lanes)
+    float hk0[NLEGDOF], hk1[NLEGDOF];   // column-distributed L'DL factor of this chain
     float i0own = 0.f, i1own = 0.f, i10 = 0.f;
-    // hub small factor lives in shared (SM_HBB)
     for (int iter = 0;; iter++) {
+      const bool last = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
       // ---- forces, active set, contact augmentation
       float Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
 #pragma unroll
       for (int i = 0; i < 21; i++) A[i] = 0.f;
-      int bits = 0;
-      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) bits |= contact_forces(con[s], p.mu, Wc, A, nullptr) << (4 * s);
-      int changed = (iter > 0 && bits != prev_bits) ? 1 : 0;
-      prev_bits = bits;
-      bool last = false;
-      if (iter > 0) {
-        float v[1] = {(float)changed};
-        cta_reduce<1>(v, s_red, parity, tid);
-        nchanged_last = (int)v[0];
-        last = (nchanged_last == 0) || iter >= p.max_newton;
-      }
+      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) contact_forces(con[s], p.mu, Wc, last ? nullptr : A, nullptr);
       // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
       float y[12];
       {
         float t6[6]; mul_inert(cinert, Sa, t6);
-        if (!is_leg && hl != 0) for (int i = 0; i < 6; i++) t6[i] = 0.f;   // hub inertia counted once
         for (int i = 0; i < 6; i++) { y[i] = t6[i] - Wc[i]; y[6 + i] = Wc[i]; }
       }
       float gown[3] = {0.f, 0.f, 0.f};
-      if (is_leg) {
-        chain_suffix<12>(y, gmask, k);
-        if (!last) chain_suffix<21>(A, gmask, k);
-        for (int j = 0; j < 3; j++) if (j < ndof) {
-          int d = dof0 + j; const float* cd = s_cdof + 8 * d;
-          float g = dot6(cd, y) + role[(RF_ARM + j) * CTA + tid] * qacc[d] - fs_own[j];
-          gown[j] = g; sm[SM_GRAD + d] = g; sm[SM_FC + d] = dot6(cd, y + 6);
-        }
-        if (k == 0) {
-          float* rt = sm + SM_ROOT + leg * ROOT_STRIDE;
-          for (int i = 0; i < 6; i++) rt[i] = y[i];
-          for (int i = 0; i < 21; i++) rt[16 + i] = A[i];
-          for (int i = 0; i < 6; i++) rt[6 + i] = y[6 + i];          // crb slot reused for the fc wrench (crb already consumed)
-        }
-      } else {
-        float* hc = sm + SM_HUBC + hl * 28;
-        for (int i = 0; i < 6; i++) hc[i] = y[i];
-        for (int i = 0; i < 21; i++) hc[6 + i] = A[i];
-        hc[27] = 0.f;
-        // second wrench (fc) packed separately below
+      chain_suffix<12>(y, NMF_FULL, k);
+      if (!last) chain_suffix<21>(A, NMF_FULL, k);
+      for (int j = 0; j < 3; j++) if (j < ndof) {
+        int d = dof0 + j; const float* cd = s_cdof + 8 * d;
+        float g = dot6(cd, y) + armv[j] * qacc[d] - fs_own[j];
+        gown[j] = g; sm[SM_GRAD + d] = g; sm[SM_FC + d] = dot6(cd, y + 6);
       }
-      __syncthreads();
+      if (k == 0) {
+        for (int i = 0; i < 12; i++) rt[i] = y[i];
+        if (!last) for (int i = 0; i < 21; i++) rt[16 + i] = A[i];
+      }
+      block_sync();
       float Ah[21];
-      if (!is_leg) {
-        // hub totals: own contacts (16 lanes) + leg roots
-        float yh[6], fch[6];
-        for (int i = 0; i < 6; i++) {
-          float s = 0.f; for (int l2 = 0; l2 < NHUBLANE; l2++) s += sm[SM_HUBC + l2 * 28 + i];
-          float s2 = s; for (int l = 0; l < NLEG; l++) s2 += sm[SM_ROOT + l * ROOT_STRIDE + i];
-          yh[i] = s2;
-          // fc wrench of the hub's own contacts = I S - y_own  => recover from y: Wc_own = I S - y_own
-          fch[i] = 0.f;
-        }
-        {
-          float ci[10], t6[6], Sh6[6];
-          for (int i = 0; i < 10; i++) ci[i] = s_hub[HU_CINERT + i];
-          for (int i = 0; i < 6; i++) Sh6[i] = Sa[i];
-          mul_inert(ci, Sh6, t6);
-          for (int i = 0; i < 6; i++) {
-            float s = 0.f; for (int l2 = 0; l2 < NHUBLANE; l2++) s += sm[SM_HUBC + l2 * 28 + i];
-            float wc_own = t6[i] - s;
-            float f = wc_own; for (int l = 0; l < NLEG; l++) f += sm[SM_ROOT + l * ROOT_STRIDE + 6 + i];
-            fch[i] = f;
-          }
-        }
-        for (int i = 0; i < 21; i++) {
-          float s = 0.f; for (int l2 = 0; l2 < NHUBLANE; l2++) s += sm[SM_HUBC + l2 * 28 + 6 + i];
-          for (int l = 0; l < NLEG; l++) s += sm[SM_ROOT + l * ROOT_STRIDE + 16 + i];
-          Ah[i] = s;
-        }
-        if (hl < 6) {
-          const float* cd = s_cdof + 8 * hl;
-          float g = dot6(cd, yh) - fs_own[0];
-          gown[0] = g; sm[SM_GRAD + hl] = g; sm[SM_FC + hl] = dot6(cd, fch);
-        }
+      if (hubdof) {
+        float yh[12];
+        for (int i = 0; i < 12; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; yh[i] = s; }
+        const float* cd = s_cdof + 8 * hl;
+        float g = dot6(cd, yh) - fs_own[0];
+        gown[0] = g; sm[SM_GRAD + hl] = g; sm[SM_FC + hl] = dot6(cd, yh + 6);
+        if (!last) for (int i = 0; i < 21; i++) { float s = 0.f; for (int gg = 0; gg < NGROUP; gg++) s += sm[SM_ROOT + gg * ROOT_STRIDE + 16 + i]; Ah[i] = s; }
       }
       if (last) { niter = iter; break; }
 
       // ---- Hessian rows  H = C'(crb + A-hat)C + armature, staged in shared, then column-distributed
-      float d10 = 0.f;
-      if (is_leg) {
-        float P[21]; expand_inert(crb, P);
+      {
+        float P[21];
+        if (hubdof) {
+          expand_inert(crbh, P);
 #pragma unroll
-        for (int i = 0; i < 21; i++) P[i] += A[i];
-        float* hs = sm + SM_HS + leg * HS_STRIDE;
-        for (int j = 0; j < 3; j++) if (j < ndof) {
-          int li = ldof0 + j; float u[6]; sym6_mul(P, s_cdof + 8 * (dof0 + j), u);
-          for (int c = 0; c < 6; c++) hs[li * 16 + c] = dot6(s_cdof + 8 * c, u);
-          for (int jj = 0; jj <= li; jj++) {
-            float v = dot6(s_cdof + 8 * (6 + NLEGDOF * leg + jj), u);
-            if (jj == li) v += role[(RF_ARM + j) * CTA + tid];
-            if (li == 10 && jj == 10) hs[176] = v; else hs[li * 16 + 6 + jj] = v;
-          }
+          for (int i = 0; i < 21; i++) P[i] += Ah[i];
+          float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
+          for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
+        } else {
+          expand_inert(crb, P);
+#pragma unroll
+          for (int i = 0; i < 21; i++) P[i] += A[i];
+          build_rows(P, s_cdof, hs, grp, dof0, ldof0, ndof, armv);
         }
-        __syncwarp(gmask);
-#pragma unroll
-        for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
-        d10 = hs[176];
-      } else if (hl < 6) {
-        float P[21]; expand_inert(crbh, P);
-#pragma unroll
-        for (int i = 0; i < 21; i++) P[i] += Ah[i];
-        float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
-        for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
       }
-
-      // ---- L'DL of each chain block in registers (one column per lane), Schur contributions for the hub
+      __syncwarp(NMF_FULL);
+#pragma unroll
+      for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
+      float contrib[3];
+      chain_factor(hk0, hk1, hs[176], t, i0own, i1own, i10, contrib);
       if (is_leg) {
-        float contrib[3] = {0.f, 0.f, 0.f};
-        int pb[3], pc[3];
 #pragma unroll
-        for (int s = 0; s < 3; s++) {  // pair (b >= c) number t + 8 s of the 21 lower-triangular hub entries
-          int idx = t + 8 * s, b = 0; while ((b + 1) * (b + 2) / 2 <= idx) b++;
-          pb[s] = b; pc[s] = idx - b * (b + 1) / 2; if (idx >= 21) { pb[s] = 0; pc[s] = 0; }
-        }
-#pragma unroll
-        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
-          float dk;
-          if (kk == 10) dk = d10; else { const int c = 6 + kk; dk = __shfl_sync(gmask, c < 8 ? hk0[kk] : hk1[kk], c & 7, 8); }
-          float ik = 1.0f / dk;
-          if (kk == 10) i10 = ik;
-          if (6 + kk == t) i0own = ik;
-          if (kk == t + 2) i1own = ik;
-          float l0 = hk0[kk] * ik, l1 = hk1[kk] * ik;
-#pragma unroll
-          for (int s = 0; s < 3; s++) {
-            float lb = __shfl_sync(gmask, l0, pb[s], 8), hc = __shfl_sync(gmask, hk0[kk], pc[s], 8);
-            contrib[s] += lb * hc;
-          }
-#pragma unroll
-          for (int j = 0; j < kk; j++) {
-            const int cj = 6 + j;
-            float l = __shfl_sync(gmask, cj < 8 ? l0 : l1, cj & 7, 8);
-            hk0[j] -= (t <= cj ? l : 0.f) * hk0[kk];
-            hk1[j] -= (t + 2 <= j ? l : 0.f) * hk1[kk];
-          }
-          hk0[kk] = l0; hk1[kk] = l1;
-        }
-        float* bs = sm + SM_BASE + leg * 21;
-#pragma unroll
-        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) bs[t + 8 * s] = contrib[s];
+        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) sm[SM_BASE + grp * 21 + t + 8 * s] = contrib[s];
       }
-      // ---- solve H x = -g : chain pass 1 (x <- L^-T x), hub rhs contributions
-      float x0 = 0.f, x1 = 0.f, x10 = 0.f;
-      if (is_leg) {
-        const int ld = NLEGDOF * leg + 6;
-        if (t >= 6) x0 = -sm[SM_GRAD + ld + t - 6];
-        x1 = -sm[SM_GRAD + ld + t + 2];
-        x10 = -sm[SM_GRAD + ld + 10];
-#pragma unroll
-        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
-          float xk;
-          if (kk == 10) xk = x10; else { const int c = 6 + kk; xk = __shfl_sync(gmask, c < 8 ? x0 : x1, c & 7, 8); }
-          x0 -= (t < 6 + kk ? hk0[kk] : 0.f) * xk;
-          x1 -= (t + 2 < kk ? hk1[kk] : 0.f) * xk;
-        }
-        if (t < 6) sm[SM_BASE + NLEG * 21 + leg * 6 + t] = x0;
-      }
-      __syncthreads();
+      // ---- solve H x = -g
+      float x0 = (is_leg && t >= 6) ? -sm[SM_GRAD + lbase + t - 6] : 0.f, x1 = is_leg ? -sm[SM_GRAD + lbase + t + 2] : 0.f, x10 = is_leg ? -sm[SM_GRAD + lbase + 10] : 0.f;
+      chain_solve_up(hk0, hk1, t, x0, x1, x10);
+      if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
+      block_sync();
       if (!is_leg && hl == 0) {
-        // hub block: S = Hbb - sum contributions ; rhs = -g_b + sum chain parts ; dense 6x6 L'DL solve (serial, tiny)
-        float S[21], xb[6];
-        for (int i = 0; i < 21; i++) { float s = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) s -= sm[SM_BASE + l * 21 + i]; S[i] = s; }
-        for (int b = 0; b < 6; b++) { float s = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) s += sm[SM_BASE + NLEG * 21 + l * 6 + b]; xb[b] = s; }
-        float dinv[6];
-#pragma unroll
-        for (int kk = 5; kk >= 0; kk--) {
-          dinv[kk] = 1.0f / S[kk * (kk + 1) / 2 + kk];
-#pragma unroll
-          for (int j = 0; j < kk; j++) {
-            float l = S[kk * (kk + 1) / 2 + j] * dinv[kk];
-#pragma unroll
-            for (int c = 0; c <= j; c++) S[j * (j + 1) / 2 + c] -= l * S[kk * (kk + 1) / 2 + c];
-          }
-#pragma unroll
-          for (int j = 0; j < kk; j++) S[kk * (kk + 1) / 2 + j] *= dinv[kk];
-        }
-#pragma unroll
-        for (int kk = 5; kk >= 0; kk--)
-#pragma unroll
-          for (int j = 0; j < kk; j++) xb[j] -= S[kk * (kk + 1) / 2 + j] * xb[kk];
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) xb[kk] *= dinv[kk];
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++)
-#pragma unroll
-          for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
+        float xb[6]; hub_solve(sm, xb);
         float Sh[6] = {0, 0, 0, 0, 0, 0};
         for (int b = 0; b < 6; b++) { sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b]; const float* cd = s_cdof + 8 * b; for (int i = 0; i < 6; i++) Sh[i] += cd[i] * xb[b]; }
         for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
       }
-      __syncthreads();
-      // ---- chain passes 2, 3 (x <- D^-1 x ; x <- L^-1 x)
-      float sown[3] = {0.f, 0.f, 0.f};
+      block_sync();
+      chain_solve_down(hk0, hk1, t, t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f, i0own, i1own, i10, x0, x1, x10);
       if (is_leg) {
-        float xb = t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f;
-        if (t >= 6) x0 *= i0own;
-        x1 *= i1own; x10 *= i10;
-#pragma unroll
-        for (int kk = 0; kk < NLEGDOF; kk++) {
-          float part = (t < 6 ? hk0[kk] * xb : (t - 6 < kk ? hk0[kk] * x0 : 0.f)) + (t + 2 < kk ? hk1[kk] * x1 : 0.f);
-          part += __shfl_xor_sync(gmask, part, 1, 8); part += __shfl_xor_sync(gmask, part, 2, 8); part += __shfl_xor_sync(gmask, part, 4, 8);
-          if (6 + kk == t) x0 -= part;
-          if (kk == t + 2) x1 -= part;
-          if (kk == 10) x10 -= part;
-        }
-        float* sx = sm + SM_X + 6 + NLEGDOF * leg;
+        float* sx = sm + SM_X + lbase;
         if (t >= 6) sx[t - 6] = x0;
         sx[t + 2] = x1;
         if (t == 0) sx[10] = x10;
-        __syncwarp(gmask);
-        for (int j = 0; j < 3; j++) if (j < ndof) sown[j] = sm[SM_X + dof0 + j];
-      } else if (hl < 6) sown[0] = sm[SM_X + hl];
+      }
+      __syncwarp(NMF_FULL);
+      float sown[3] = {0.f, 0.f, 0.f};
+      for (int j = 0; j < 3; j++) if (j < ndof) sown[j] = sm[SM_X + dof0 + j];
+      if (hubdof) sown[0] = sm[SM_X + hl];
 
       // ---- spatial acceleration of the search direction, row directions, quadratic terms
       float Ss[6];
-      if (is_leg) {
+      {
         float sl[6] = {0, 0, 0, 0, 0, 0};
         for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); for (int i = 0; i < 6; i++) sl[i] += cd[i] * sown[j]; }
-        chain_prefix<6>(sl, gmask, k);
+        chain_prefix<6>(sl, NMF_FULL, k);
         for (int i = 0; i < 6; i++) Ss[i] = sl[i] + sm[SM_HBB + HB_SH + i];
-      } else for (int i = 0; i < 6; i++) Ss[i] = sm[SM_HBB + HB_SH + i];
+      }
       float red[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // s.g , s'Ms , d0 rows(0), d1 rows(0), |s|^2
       {
         float t6[6]; mul_inert(cinert, Ss, t6);
-        if (is_leg || hl == 0) red[1] += dot6(Ss, t6);
+        red[1] += dot6(Ss, t6);
         for (int j = 0; j < 3; j++) {
-          bool own = is_leg ? (j < ndof) : (j == 0 && hl < 6);
-          if (own) {
-            float arm = is_leg ? role[(RF_ARM + j) * CTA + tid] : 0.f;
-            red[0] += sown[j] * gown[j]; red[1] += arm * sown[j] * sown[j]; red[4] += sown[j] * sown[j];
-          }
+          bool own = (j < ndof) || (j == 0 && hubdof);
+          if (own) { red[0] += sown[j] * gown[j]; red[1] += (hubdof ? 0.f : armv[j]) * sown[j] * sown[j]; red[4] += sown[j] * sown[j]; }
         }
-        for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { project_point(con[s], Ss, p.mu, con[s].s); ls_eval(con[s], 0.f, red[2], red[3]); }
+        float dummy = 0.f;
+        for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { project_point(con[s], Ss, p.mu, con[s].s); ls_eval(con[s], 0.f, red[2], red[3], dummy); }
       }
       cta_reduce<5>(red, s_red, parity, tid);
       // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
       float alpha = 0.f;
+      nchanged_last = 0;
       {
         const float q1 = red[0] - red[2], q2 = red[1];
         float d0 = red[0], d1 = q2 + red[3], lo = 0.f, hi = 3.0e38f;
         const int nls = (red[4] > 1e-30f && d1 > 0.f) ? p.max_ls : 0;   // zero direction: nothing to search
         for (int it = 0; it < nls; it++) {
-          if (fabsf(d0) <= 2e-6f * d1 * fmaxf(fabsf(alpha), 1e-3f) && it > 0) break;
+          if (it > 0 && (fabsf(d0) <= 2e-6f * d1 * fmaxf(fabsf(alpha), 1e-3f) || (hi < 1.0e38f && hi - lo <= 1e-6f * hi))) break;
           if (d0 < 0.f) lo = alpha; else hi = alpha;
           float nx = alpha - d0 / d1;
           if (nx <= lo || nx >= hi) nx = (hi > 1.0e38f) ? 2.f * fmaxf(alpha, 1.f) : 0.5f * (lo + hi);
           alpha = nx;
-          float e[2] = {0.f, 0.f};
-          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) ls_eval(con[s], alpha, e[0], e[1]);
-          cta_reduce<2>(e, s_red, parity, tid);
+          float e[3] = {0.f, 0.f, 0.f};
+          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) ls_eval(con[s], alpha, e[0], e[1], e[2]);
+          cta_reduce<3>(e, s_red, parity, tid);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
+          nchanged_last = (int)e[2];
           nls_total++;
         }
       }
       // ---- move
       for (int j = 0; j < 3; j++) {
-        bool own = is_leg ? (j < ndof) : (j == 0 && hl < 6);
+        bool own = (j < ndof) || (j == 0 && hubdof);
         if (own) qacc[dof0 + j] += alpha * sown[j];
       }
       for (int i = 0; i < 6; i++) Sa[i] += alpha * Ss[i];
@@ -862,134 +820,49 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     // D. semi-implicit Euler with implicit joint damping:
     //    (M + dt diag(damping)) a' = qfrc_smooth + qfrc_constraint ; v += dt a' ; q integrates with the new v
     // =====================================================================
-    __syncthreads();
+    block_sync();
     {
-      float d10 = 0.f;
-      if (is_leg) {
-        float P[21]; expand_inert(crb, P);
-        float* hs = sm + SM_HS + leg * HS_STRIDE;
-        for (int j = 0; j < 3; j++) if (j < ndof) {
-          int li = ldof0 + j; float u[6]; sym6_mul(P, s_cdof + 8 * (dof0 + j), u);
-          for (int c = 0; c < 6; c++) hs[li * 16 + c] = dot6(s_cdof + 8 * c, u);
-          for (int jj = 0; jj <= li; jj++) {
-            float v = dot6(s_cdof + 8 * (6 + NLEGDOF * leg + jj), u);
-            if (jj == li) v += role[(RF_ARM + j) * CTA + tid] + p.dt * role[(RF_DAMP + j) * CTA + tid];
-            if (li == 10 && jj == 10) hs[176] = v; else hs[li * 16 + 6 + jj] = v;
-          }
-          sm[SM_GRAD + dof0 + j] = -(fs_own[j] + sm[SM_FC + dof0 + j]);   // rhs = -(grad slot)
-        }
-        __syncwarp(gmask);
-#pragma unroll
-        for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
-        d10 = hs[176];
-        if (p.dbg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + leg * 177; for (int i = t; i < 177; i += 8) dg[i] = hs[i]; }
-      } else if (hl < 6) {
-        float P[21]; expand_inert(crbh, P);
+      float P[21];
+      if (hubdof) {
+        expand_inert(crbh, P);
         float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
         for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
         sm[SM_GRAD + hl] = -(fs_own[0] + sm[SM_FC + hl]);
+      } else {
+        expand_inert(crb, P);
+        float dadd[3] = {armv[0] + p.dt * dampv[0], armv[1] + p.dt * dampv[1], armv[2] + p.dt * dampv[2]};
+        build_rows(P, s_cdof, hs, grp, dof0, ldof0, ndof, dadd);
+        for (int j = 0; j < 3; j++) if (j < ndof) sm[SM_GRAD + dof0 + j] = -(fs_own[j] + sm[SM_FC + dof0 + j]);   // rhs = -(grad slot)
       }
+      __syncwarp(NMF_FULL);
+#pragma unroll
+      for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
+      if (p.dbg && is_leg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + grp * 177; for (int i = t; i < 177; i += 8) dg[i] = hs[i]; }
+      float contrib[3];
+      chain_factor(hk0, hk1, hs[176], t, i0own, i1own, i10, contrib);
       if (is_leg) {
-        float contrib[3] = {0.f, 0.f, 0.f};
-        int pb[3], pc[3];
 #pragma unroll
-        for (int s = 0; s < 3; s++) {
-          int idx = t + 8 * s, b = 0; while ((b + 1) * (b + 2) / 2 <= idx) b++;
-          pb[s] = b; pc[s] = idx - b * (b + 1) / 2; if (idx >= 21) { pb[s] = 0; pc[s] = 0; }
-        }
-#pragma unroll
-        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
-          float dk;
-          if (kk == 10) dk = d10; else { const int c = 6 + kk; dk = __shfl_sync(gmask, c < 8 ? hk0[kk] : hk1[kk], c & 7, 8); }
-          float ik = 1.0f / dk;
-          if (kk == 10) i10 = ik;
-          if (6 + kk == t) i0own = ik;
-          if (kk == t + 2) i1own = ik;
-          float l0 = hk0[kk] * ik, l1 = hk1[kk] * ik;
-#pragma unroll
-          for (int s = 0; s < 3; s++) {
-            float lb = __shfl_sync(gmask, l0, pb[s], 8), hc = __shfl_sync(gmask, hk0[kk], pc[s], 8);
-            contrib[s] += lb * hc;
-          }
-#pragma unroll
-          for (int j = 0; j < kk; j++) {
-            const int cj = 6 + j;
-            float l = __shfl_sync(gmask, cj < 8 ? l0 : l1, cj & 7, 8);
-            hk0[j] -= (t <= cj ? l : 0.f) * hk0[kk];
-            hk1[j] -= (t + 2 <= j ? l : 0.f) * hk1[kk];
-          }
-          hk0[kk] = l0; hk1[kk] = l1;
-        }
-        float* bs = sm + SM_BASE + leg * 21;
-#pragma unroll
-        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) bs[t + 8 * s] = contrib[s];
+        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) sm[SM_BASE + grp * 21 + t + 8 * s] = contrib[s];
       }
-      float x0 = 0.f, x1 = 0.f, x10 = 0.f;
-      if (is_leg) {
-        const int ld = NLEGDOF * leg + 6;
-        if (t >= 6) x0 = -sm[SM_GRAD + ld + t - 6];
-        x1 = -sm[SM_GRAD + ld + t + 2];
-        x10 = -sm[SM_GRAD + ld + 10];
-#pragma unroll
-        for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
-          float xk;
-          if (kk == 10) xk = x10; else { const int c = 6 + kk; xk = __shfl_sync(gmask, c < 8 ? x0 : x1, c & 7, 8); }
-          x0 -= (t < 6 + kk ? hk0[kk] : 0.f) * xk;
-          x1 -= (t + 2 < kk ? hk1[kk] : 0.f) * xk;
-        }
-        if (t < 6) sm[SM_BASE + NLEG * 21 + leg * 6 + t] = x0;
-      }
-      __syncthreads();
+      float x0 = (is_leg && t >= 6) ? -sm[SM_GRAD + lbase + t - 6] : 0.f, x1 = is_leg ? -sm[SM_GRAD + lbase + t + 2] : 0.f, x10 = is_leg ? -sm[SM_GRAD + lbase + 10] : 0.f;
+      chain_solve_up(hk0, hk1, t, x0, x1, x10);
+      if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
+      block_sync();
       if (!is_leg && hl == 0) {
-        float S[21], xb[6];
         if (p.dbg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + NLEG * 177; for (int i = 0; i < 21; i++) dg[i] = sm[SM_HBB + HB_S + i]; }
-        for (int i = 0; i < 21; i++) { float s = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) s -= sm[SM_BASE + l * 21 + i]; S[i] = s; }
-        for (int b = 0; b < 6; b++) { float s = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) s += sm[SM_BASE + NLEG * 21 + l * 6 + b]; xb[b] = s; }
-        float dinv[6];
-#pragma unroll
-        for (int kk = 5; kk >= 0; kk--) {
-          dinv[kk] = 1.0f / S[kk * (kk + 1) / 2 + kk];
-#pragma unroll
-          for (int j = 0; j < kk; j++) {
-            float l = S[kk * (kk + 1) / 2 + j] * dinv[kk];
-#pragma unroll
-            for (int c = 0; c <= j; c++) S[j * (j + 1) / 2 + c] -= l * S[kk * (kk + 1) / 2 + c];
-          }
-#pragma unroll
-          for (int j = 0; j < kk; j++) S[kk * (kk + 1) / 2 + j] *= dinv[kk];
-        }
-#pragma unroll
-        for (int kk = 5; kk >= 0; kk--)
-#pragma unroll
-          for (int j = 0; j < kk; j++) xb[j] -= S[kk * (kk + 1) / 2 + j] * xb[kk];
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) xb[kk] *= dinv[kk];
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++)
-#pragma unroll
-          for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
+        float xb[6]; hub_solve(sm, xb);
         for (int b = 0; b < 6; b++) { sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b]; }
       }
-      __syncthreads();
+      block_sync();
+      chain_solve_down(hk0, hk1, t, t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f, i0own, i1own, i10, x0, x1, x10);
       if (is_leg) {
-        float xb = t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f;
-        if (t >= 6) x0 *= i0own;
-        x1 *= i1own; x10 *= i10;
-#pragma unroll
-        for (int kk = 0; kk < NLEGDOF; kk++) {
-          float part = (t < 6 ? hk0[kk] * xb : (t - 6 < kk ? hk0[kk] * x0 : 0.f)) + (t + 2 < kk ? hk1[kk] * x1 : 0.f);
-          part += __shfl_xor_sync(gmask, part, 1, 8); part += __shfl_xor_sync(gmask, part, 2, 8); part += __shfl_xor_sync(gmask, part, 4, 8);
-          if (6 + kk == t) x0 -= part;
-          if (kk == t + 2) x1 -= part;
-          if (kk == 10) x10 -= part;
-        }
-        float* sx = sm + SM_X + 6 + NLEGDOF * leg;
+        float* sx = sm + SM_X + lbase;
         if (t >= 6) sx[t - 6] = x0;
         sx[t + 2] = x1;
         if (t == 0) sx[10] = x10;
       }
     }
-    __syncthreads();
+    block_sync();
 
     // ---- optional outputs of this step (derived quantities belong to the pre-integration state, as in mj_step)
     const bool last_step = step == p.nsteps - 1;
@@ -1013,67 +886,67 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       }
       if (p.out_actf) {
         float* o = p.out_actf + (size_t)fly * (p.nu_pos + p.nu_adh);
-        if (is_leg) {
-          for (int j = 0; j < 3; j++) if (j < ndof) { int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]); if (ci >= 0) o[ci] = actf[j]; }
-          int ai = __float_as_int(role[RF_ADH_CIDX * CTA + tid]); if (ai >= 0) o[ai] = adhf;
-        }
+        for (int j = 0; j < 3; j++) if (j < ndof) { int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]); if (ci >= 0) o[ci] = actf[j]; }
+        int ai = __float_as_int(role[RF_ADH_CIDX * CTA + tid]); if (ai >= 0) o[ai] = adhf;
       }
       if (p.out_sensor) {
         // per-leg contact sensor (world.py:311-331), reduce="netforce": found, force, torque, pos, normal, tangent
+        const bool sens = is_leg && __float_as_int(role[RF_LEGSENSOR * CTA + tid]) != 0;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // F(3), fn-weighted pos(3), fn sum, count
-        float Fc[2][3], fnv[2] = {0.f, 0.f};
+        float Fc[2][3], fnv[2] = {0.f, 0.f}, plain[3] = {0, 0, 0};
         for (int s = 0; s < 2; s++) {
           Fc[s][0] = Fc[s][1] = Fc[s][2] = 0.f;
-          if (is_leg && con[s].active > 0.f && __float_as_int(role[RF_LEGSENSOR * CTA + tid])) {
+          if (sens && con[s].active > 0.f) {
             float Wt[6] = {0, 0, 0, 0, 0, 0}; contact_forces(con[s], p.mu, Wt, nullptr, &fnv[s]);
             Fc[s][0] = Wt[3]; Fc[s][1] = Wt[4]; Fc[s][2] = Wt[5];
-            for (int i = 0; i < 3; i++) { acc[i] += Fc[s][i]; acc[3 + i] += fnv[s] * (con[s].r[i] + com[i]); }
+            for (int i = 0; i < 3; i++) { acc[i] += Fc[s][i]; acc[3 + i] += fnv[s] * (con[s].r[i] + com[i]); plain[i] += con[s].r[i] + com[i]; }
             acc[6] += fnv[s]; acc[7] += 1.f;
           }
         }
-        float plain[3] = {0, 0, 0};
-        for (int s = 0; s < 2; s++) if (is_leg && con[s].active > 0.f && __float_as_int(role[RF_LEGSENSOR * CTA + tid])) for (int i = 0; i < 3; i++) plain[i] += con[s].r[i] + com[i];
-        if (is_leg) {
 #pragma unroll
-          for (int off = 1; off < 8; off <<= 1) {
-            for (int i = 0; i < 8; i++) acc[i] += __shfl_xor_sync(gmask, acc[i], off, 8);
-            for (int i = 0; i < 3; i++) plain[i] += __shfl_xor_sync(gmask, plain[i], off, 8);
-          }
-          float P3[3] = {0, 0, 0};
-          if (acc[7] > 0.f) for (int i = 0; i < 3; i++) P3[i] = acc[6] > NMF_MINVAL ? acc[3 + i] / acc[6] : plain[i] / acc[7];
-          float T[3] = {0, 0, 0};
-          for (int s = 0; s < 2; s++) if (fnv[s] != 0.f || Fc[s][0] != 0.f || Fc[s][1] != 0.f) {
-            float rr[3] = {con[s].r[0] + com[0] - P3[0], con[s].r[1] + com[1] - P3[1], con[s].r[2] + com[2] - P3[2]}, tt[3];
-            cross3(rr, Fc[s], tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
-          }
+        for (int off = 1; off < 8; off <<= 1) {
+          for (int i = 0; i < 8; i++) acc[i] += __shfl_xor_sync(NMF_FULL, acc[i], off, 8);
+          for (int i = 0; i < 3; i++) plain[i] += __shfl_xor_sync(NMF_FULL, plain[i], off, 8);
+        }
+        float P3[3] = {0, 0, 0};
+        if (acc[7] > 0.f) for (int i = 0; i < 3; i++) P3[i] = acc[6] > NMF_MINVAL ? acc[3 + i] / acc[6] : plain[i] / acc[7];
+        float T[3] = {0, 0, 0};
+        for (int s = 0; s < 2; s++) if (sens && con[s].active > 0.f) {
+          float rr[3] = {con[s].r[0] + com[0] - P3[0], con[s].r[1] + com[1] - P3[1], con[s].r[2] + com[2] - P3[2]}, tt[3];
+          cross3(rr, Fc[s], tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
+        }
 #pragma unroll
-          for (int off = 1; off < 8; off <<= 1) for (int i = 0; i < 3; i++) T[i] += __shfl_xor_sync(gmask, T[i], off, 8);
-          if (k == 0) {
-            float* o = p.out_sensor + ((size_t)fly * NLEG + leg) * 16;
-            o[0] = acc[7];
-            for (int i = 0; i < 3; i++) { o[1 + i] = acc[7] > 0.f ? -acc[i] : 0.f; o[4 + i] = acc[7] > 0.f ? -T[i] : 0.f; o[7 + i] = P3[i]; }
-            o[10] = acc[7] > 0.f ? 1.f : 0.f; o[11] = 0.f; o[12] = 0.f; o[13] = 0.f; o[14] = acc[7] > 0.f ? 1.f : 0.f; o[15] = 0.f;
-          }
+        for (int off = 1; off < 8; off <<= 1) for (int i = 0; i < 3; i++) T[i] += __shfl_xor_sync(NMF_FULL, T[i], off, 8);
+        if (is_leg && k == 0) {
+          float* o = p.out_sensor + ((size_t)fly * NLEG + grp) * 16;
+          o[0] = acc[7];
+          for (int i = 0; i < 3; i++) { o[1 + i] = acc[7] > 0.f ? -acc[i] : 0.f; o[4 + i] = acc[7] > 0.f ? -T[i] : 0.f; o[7 + i] = P3[i]; }
+          o[10] = acc[7] > 0.f ? 1.f : 0.f; o[11] = 0.f; o[12] = 0.f; o[13] = 0.f; o[14] = acc[7] > 0.f ? 1.f : 0.f; o[15] = 0.f;
         }
       }
       if (p.out_xpos || p.out_xquat) {
-        float* ps = sm + SM_POSE + tid * 8;
+        block_sync();   // the row staging is free again: reuse it as the pose exchange buffer
+        float* ps = sm + SM_HS + tid * 8;
         ps[0] = xpos[0]; ps[1] = xpos[1]; ps[2] = xpos[2]; ps[3] = xq[0]; ps[4] = xq[1]; ps[5] = xq[2]; ps[6] = xq[3];
-        __syncthreads();
+        block_sync();
         for (int sgi = tid; sgi < p.nseg; sgi += CTA) {
-          const float* tb = p.seg_tab + sgi * 8; const float* bp = sm + SM_POSE + __float_as_int(tb[0]) * 8;
+          const float* tb = p.seg_tab + sgi * 8; const float* bp = sm + SM_HS + __float_as_int(tb[0]) * 8;
           float lp[3] = {tb[1], tb[2], tb[3]}, lq[4] = {tb[4], tb[5], tb[6], tb[7]}, w[3], wq[4];
           qrot(bp + 3, lp, w); qmul(bp + 3, lq, wq);
           if (p.out_xpos) { float* o = p.out_xpos + ((size_t)fly * p.nseg + sgi) * 3; o[0] = bp[0] + w[0]; o[1] = bp[1] + w[1]; o[2] = bp[2] + w[2]; }
           if (p.out_xquat) { float* o = p.out_xquat + ((size_t)fly * p.nseg + sgi) * 4; o[0] = wq[0]; o[1] = wq[1]; o[2] = wq[2]; o[3] = wq[3]; }
         }
+        block_sync();
+        for (int i = tid; i < NGROUP * HS_STRIDE; i += CTA) sm[SM_HS + i] = 0.f;   // restore the staging invariants
+        block_sync();
+        if (!is_leg && t == 0) { for (int i = 0; i < 10; i++) hs[i * 16 + 6 + i] = 1.f; hs[176] = 1.f; }
       }
     }
 
     // ---- advance: qvel += dt a' ; positions integrate with the NEW velocity ; qacc stays as next warm start
-    __syncthreads();
+    block_sync();
     for (int i = tid; i < NV; i += CTA) st[S_QVEL + i] += p.dt * sm[SM_X + i];
-    __syncthreads();
+    block_sync();
     for (int i = tid + 6; i < NV; i += CTA) st[S_QPOS + 1 + i] += p.dt * st[S_QVEL + i];
     if (tid == 0) {
       for (int i = 0; i < 3; i++) st[S_QPOS + i] += p.dt * st[S_QVEL + i];
@@ -1089,7 +962,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       st[S_QPOS + 3] = q[0]; st[S_QPOS + 4] = q[1]; st[S_QPOS + 5] = q[2]; st[S_QPOS + 6] = q[3];
       st[S_TIME] += p.dt;
     }
-    __syncthreads();
+    block_sync();
   }
 
   // ---- write the record back
