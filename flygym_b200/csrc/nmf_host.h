@@ -115,6 +115,13 @@ struct HostModel {
         set(RF_LEGSENSOR, tid, i2f(sens ? 1 : 0));
       } else { set(RF_NDOF, tid, i2f(0)); set(RF_DOF0, tid, i2f(0)); }
     }
+    // armature / damping of the matrix columns each lane holds in the chain factorisation
+    for (int tid = 0; tid < CTA; tid++) {
+      const int g = tid / NLINK, t = tid % NLINK;
+      if (g >= NLEG) { for (int s = 0; s < 3; s++) { set(RF_CARM + s, tid, 1.f); set(RF_CDMP + s, tid, 0.f); } continue; }
+      const int lb = 6 + NLEGDOF * g; const int cols[3] = {t >= 6 ? lb + t - 6 : -1, lb + t + 2, lb + 10};
+      for (int s = 0; s < 3; s++) { set(RF_CARM + s, tid, cols[s] >= 0 ? (float)arm[cols[s]] : 0.f); set(RF_CDMP + s, tid, cols[s] >= 0 ? (float)damp[cols[s]] : 0.f); }
+    }
     for (int a = 0; a < nu_pos; a++) {
       int d = act_dof[a], bb = -1, j = 0;
       for (int c = 1; c < nbody; c++) if (d >= dofadr[c] && d < dofadr[c] + dofnum[c]) { bb = c; j = d - dofadr[c]; }

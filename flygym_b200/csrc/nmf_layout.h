@@ -59,7 +59,9 @@ enum RoleField {
   RF_ADH_CIDX = 69,       // int, -1 = no adhesion actuator on this body
   RF_DOF0 = 70,           // int: global dof index of the lane's first dof
   RF_LEGSENSOR = 71,      // int: 1 if this body's contacts count for the leg contact sensor
-  RF_COUNT = 72
+  RF_CARM = 72,           // 3: armature of the lane's matrix-column DoFs (leg dof t-6 | t+2 | 10); 1 on hub chains
+  RF_CDMP = 75,           // 3: damping of the same DoFs
+  RF_COUNT = 78
 };
 
 // debug dump (floats per fly), only written when a dump buffer is passed

@@ -149,6 +149,7 @@ __device__ __forceinline__ void cta_reduce(float* v, float* s_red, int& parity, 
 }
 
 // ------------------------------------------------------------------ contact slot (kept in registers)
+// Branch-free convention: an inactive slot has D = c0 = w = s = 0, so it contributes nothing anywhere.
 struct Contact {
   float active;      // 1 if dist < margin
   float r[3];        // contact position relative to the subtree COM
@@ -162,10 +163,8 @@ struct Contact {
 
 __device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
   const float d0 = p.solimp[0], d1 = p.solimp[1], width = p.solimp[2], mid = p.solimp[3], power = p.solimp[4];
-  if (d0 == d1 || width <= NMF_MINVAL) return 0.5f * (d0 + d1);
-  float x = x_abs / width;
-  if (x >= 1.f) return d1;
-  if (x <= 0.f) return d0;
+  if (d0 == d1 || width <= NMF_MINVAL) return 0.5f * (d0 + d1);   // (uniform branch)
+  float x = fminf(x_abs / width, 1.f);
   float y;
   if (power == 1.f) y = x;
   else if (power == 2.f) y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
@@ -173,35 +172,53 @@ __device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
   return d0 + y * (d1 - d0);
 }
 
+// finishes a candidate contact: solver parameters and the B*velocity part of the rows
+__device__ __forceinline__ void finish_contact(const StepParams& p, Contact& c, float active, float dist, const float* pos, float hx, float hy,
+                                               const float* com, const float* cvel, float invw) {
+  c.active = active; c.dist = dist;
+  c.r[0] = pos[0] - com[0]; c.r[1] = pos[1] - com[1]; c.r[2] = pos[2] - com[2];
+  c.cx = hx; c.cy = hy;
+  float imp = impedance(p, fabsf(dist - p.margin));
+  float R0 = fmaxf(NMF_MINVAL, (1.f - imp) * invw * (1.f + p.mu * p.mu) / imp);
+  c.D = active / (2.f * (p.mu * p.mu / p.impratio) * R0);
+  c.c0 = active * p.cK * imp * (dist - p.margin);
+  float vp[3] = {cvel[3] + cvel[1] * c.r[2] - cvel[2] * c.r[1], cvel[4] + cvel[2] * c.r[0] - cvel[0] * c.r[2],
+                 cvel[5] + cvel[0] * c.r[1] - cvel[1] * c.r[0]};
+  c.w[0] = active * p.cB * vp[2];
+  c.w[1] = active * p.cB * p.mu * (c.cx * vp[0] + c.cy * vp[1]);
+  c.w[2] = active * p.cB * p.mu * (-c.cy * vp[0] + c.cx * vp[1]);
+  c.s[0] = c.s[1] = c.s[2] = 0.f;
+}
+
 // geom-vs-ground-plane narrow phase for the geom carried by this lane's body
 // (plane z = 0, normal +z: reference world.py:251-260).  Fills two slots.
 __device__ __forceinline__ void collide(const StepParams& p, const float* role, int tid, const float* xpos, const float* R,
                                         const float* com, const float* cvel, float invw, Contact* con) {
-  con[0].active = 0.f; con[1].active = 0.f;
   const int gtype = __float_as_int(role[RF_GTYPE * CTA + tid]);
-  if (gtype < 0) return;
-  float pos[2][3], dist[2], hint[2] = {0.f, 1.f};
-  int ncand = 0;
-  if (gtype == 0) {  // capsule: two sphere-plane tests, frame aligned with the capsule axis
+  float pos0[3] = {0.f, 0.f, 0.f}, pos1[3] = {0.f, 0.f, 0.f}, d0 = 1.f, d1 = 1.f, a0 = 0.f, a1 = 0.f, hx = 0.f, hy = 1.f;
+  {  // capsule: two sphere-plane tests, frame aligned with the capsule axis (evaluated on every lane, masked by type)
     float gp[3] = {role[(RF_GPOS + 0) * CTA + tid], role[(RF_GPOS + 1) * CTA + tid], role[(RF_GPOS + 2) * CTA + tid]};
     float ga[3] = {role[(RF_GAXIS + 0) * CTA + tid], role[(RF_GAXIS + 1) * CTA + tid], role[(RF_GAXIS + 2) * CTA + tid]};
     float rad = role[RF_GRAD * CTA + tid], half = role[RF_GHALF * CTA + tid];
     float c[3], a[3];
+#pragma unroll
     for (int i = 0; i < 3; i++) {
       c[i] = xpos[i] + R[3 * i] * gp[0] + R[3 * i + 1] * gp[1] + R[3 * i + 2] * gp[2];
       a[i] = R[3 * i] * ga[0] + R[3 * i + 1] * ga[1] + R[3 * i + 2] * ga[2];
     }
-    float hn = sqrtf(a[0] * a[0] + a[1] * a[1]);
-    if (hn < 1e-12f) { hint[0] = 1.f; hint[1] = 0.f; } else { hint[0] = a[0] / hn; hint[1] = a[1] / hn; }
-    for (int s = 0; s < 2; s++) {
-      float sg = s == 0 ? 1.f : -1.f;
-      float ez = c[2] + sg * half * a[2];
-      dist[s] = ez - rad;
-      pos[s][0] = c[0] + sg * half * a[0]; pos[s][1] = c[1] + sg * half * a[1]; pos[s][2] = 0.5f * dist[s];
-      con[s].active = (ez <= p.margin + rad) ? 1.f : 0.f;
+    float hn2 = a[0] * a[0] + a[1] * a[1];
+    float inv = rsqrtf(fmaxf(hn2, 1e-24f));
+    const bool cap = gtype == 0;
+    if (cap) { hx = hn2 < 1e-24f ? 1.f : a[0] * inv; hy = hn2 < 1e-24f ? 0.f : a[1] * inv; }
+    float e0 = c[2] + half * a[2], e1 = c[2] - half * a[2];
+    if (cap) {
+      d0 = e0 - rad; d1 = e1 - rad;
+      pos0[0] = c[0] + half * a[0]; pos0[1] = c[1] + half * a[1]; pos0[2] = 0.5f * d0;
+      pos1[0] = c[0] - half * a[0]; pos1[1] = c[1] - half * a[1]; pos1[2] = 0.5f * d1;
+      a0 = (e0 <= p.margin + rad) ? 1.f : 0.f; a1 = (e1 <= p.margin + rad) ? 1.f : 0.f;
     }
-    ncand = 2;
-  } else {  // convex hull: deepest vertex
+  }
+  if (gtype == 1) {  // convex hull: deepest vertex (lane-dependent trip count: the caller reconverges afterwards)
     const int adr = __float_as_int(role[RF_GVADR * CTA + tid]), num = __float_as_int(role[RF_GVNUM * CTA + tid]);
     float best = 3.0e38f; int bi = 0;
     for (int v = 0; v < num; v++) {
@@ -211,32 +228,15 @@ __device__ __forceinline__ void collide(const StepParams& p, const float* role, 
     }
     const float* hv = p.hull + 3 * (adr + bi);
     float h0 = __ldg(hv), h1 = __ldg(hv + 1), h2 = __ldg(hv + 2);
-    dist[0] = best + xpos[2];
-    pos[0][0] = xpos[0] + R[0] * h0 + R[1] * h1 + R[2] * h2;
-    pos[0][1] = xpos[1] + R[3] * h0 + R[4] * h1 + R[5] * h2;
-    pos[0][2] = 0.5f * dist[0];
-    con[0].active = (num > 0 && dist[0] <= p.margin) ? 1.f : 0.f;
-    ncand = 1;
+    d0 = best + xpos[2];
+    pos0[0] = xpos[0] + R[0] * h0 + R[1] * h1 + R[2] * h2;
+    pos0[1] = xpos[1] + R[3] * h0 + R[4] * h1 + R[5] * h2;
+    pos0[2] = 0.5f * d0;
+    a0 = (num > 0 && d0 <= p.margin) ? 1.f : 0.f;
   }
-  for (int s = 0; s < ncand; s++) {
-    Contact& c = con[s];
-    c.dist = dist[s];
-    c.r[0] = pos[s][0] - com[0]; c.r[1] = pos[s][1] - com[1]; c.r[2] = pos[s][2] - com[2];
-    c.cx = hint[0]; c.cy = hint[1];
-    float imp = impedance(p, fabsf(dist[s] - p.margin));
-    float diag0 = invw * (1.f + p.mu * p.mu);
-    float R0 = fmaxf(NMF_MINVAL, (1.f - imp) * diag0 / imp);
-    float mucon2 = p.mu * p.mu / p.impratio;
-    c.D = 1.f / (2.f * mucon2 * R0);
-    c.c0 = p.cK * imp * (dist[s] - p.margin);
-    // B * velocity of the contact point, projected on (n, mu t1, mu t2)
-    float vp[3] = {cvel[3] + cvel[1] * c.r[2] - cvel[2] * c.r[1], cvel[4] + cvel[2] * c.r[0] - cvel[0] * c.r[2],
-                   cvel[5] + cvel[0] * c.r[1] - cvel[1] * c.r[0]};
-    c.w[0] = p.cB * vp[2];
-    c.w[1] = p.cB * p.mu * (c.cx * vp[0] + c.cy * vp[1]);
-    c.w[2] = p.cB * p.mu * (-c.cy * vp[0] + c.cx * vp[1]);
-    c.s[0] = c.s[1] = c.s[2] = 0.f;
-  }
+  __syncwarp(NMF_FULL);
+  finish_contact(p, con[0], a0, d0, pos0, hx, hy, com, cvel, invw);
+  finish_contact(p, con[1], a1, d1, pos1, hx, hy, com, cvel, invw);
 }
 
 // point "acceleration" of a contact for a body spatial vector S (ang, lin), projected on (n, mu t1, mu t2)
@@ -244,7 +244,7 @@ __device__ __forceinline__ void project_point(const Contact& c, const float* S, 
   float ax = S[3] + S[1] * c.r[2] - S[2] * c.r[1];
   float ay = S[4] + S[2] * c.r[0] - S[0] * c.r[2];
   float az = S[5] + S[0] * c.r[1] - S[1] * c.r[0];
-  out[0] = az; out[1] = mu * (c.cx * ax + c.cy * ay); out[2] = mu * (-c.cy * ax + c.cx * ay);
+  out[0] = c.active * az; out[1] = c.active * mu * (c.cx * ax + c.cy * ay); out[2] = c.active * mu * (-c.cy * ax + c.cx * ay);
 }
 
 // pyramid rows of one contact: jar_r = base +- w1 / w2
@@ -253,19 +253,20 @@ __device__ __forceinline__ void rows4(const float* w, float c0, float* jar) {
   jar[0] = b + w[1]; jar[1] = b - w[1]; jar[2] = b + w[2]; jar[3] = b - w[2];
 }
 
-// contact forces for the current jar: accumulates the world wrench about the COM (ang, lin) into Wc,
-// optionally the contact-augmentation A = X' W X (21 packed) into A, returns the active-row bitmask
-__device__ __forceinline__ int contact_forces(const Contact& c, float mu, float* Wc, float* A, float* fn_out) {
+// contact forces for the current jar: accumulates the world wrench about the COM (ang, lin) into Wc and, when WITH_A,
+// the contact augmentation A += X' W X (21 packed).  Branch-free (inactive slots have D = 0).
+template <bool WITH_A>
+__device__ __forceinline__ void contact_forces(const Contact& c, float mu, float* Wc, float* A, float* fn_out) {
   float jar[4]; rows4(c.w, c.c0, jar);
-  float a[4], f[4]; int bits = 0;
+  float a[4], f[4];
 #pragma unroll
-  for (int r = 0; r < 4; r++) { a[r] = jar[r] < 0.f ? 1.f : 0.f; f[r] = -c.D * fminf(jar[r], 0.f); bits |= (jar[r] < 0.f) << r; }
+  for (int r = 0; r < 4; r++) { a[r] = jar[r] < 0.f ? 1.f : 0.f; f[r] = -c.D * fminf(jar[r], 0.f); }
   float fn = f[0] + f[1] + f[2] + f[3], f1 = mu * (f[0] - f[1]), f2 = mu * (f[2] - f[3]);
   float F[3] = {f1 * c.cx - f2 * c.cy, f1 * c.cy + f2 * c.cx, fn};
   float T[3]; cross3(c.r, F, T);
   Wc[0] += T[0]; Wc[1] += T[1]; Wc[2] += T[2]; Wc[3] += F[0]; Wc[4] += F[1]; Wc[5] += F[2];
   if (fn_out) *fn_out = fn;
-  if (A && bits) {
+  if (WITH_A) {
     float s1 = a[0] + a[1], s2 = a[2] + a[3], d1 = a[0] - a[1], d2 = a[2] - a[3], m2 = mu * mu;
     float W[9];
     W[0] = c.D * m2 * (s1 * c.cx * c.cx + s2 * c.cy * c.cy);
@@ -291,7 +292,6 @@ __device__ __forceinline__ int contact_forces(const Contact& c, float mu, float*
     }
     A[s6(3, 3)] += W[0]; A[s6(3, 4)] += W[1]; A[s6(3, 5)] += W[2]; A[s6(4, 4)] += W[4]; A[s6(4, 5)] += W[5]; A[s6(5, 5)] += W[8];
   }
-  return bits;
 }
 
 // line-search partial sums of one contact at step alpha: d0 += D x jv, d1 += D jv^2 over rows with x < 0
@@ -300,7 +300,8 @@ __device__ __forceinline__ void ls_eval(const Contact& c, float alpha, float& d0
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     float x = jar[r] + alpha * jv[r];
-    if (x < 0.f) { d0 += c.D * x * jv[r]; d1 += c.D * jv[r] * jv[r]; }
+    float on = x < 0.f ? c.D : 0.f;
+    d0 += on * x * jv[r]; d1 += on * jv[r] * jv[r];
     nchanged += ((x < 0.f) != (jar[r] < 0.f)) ? 1.f : 0.f;   // rows whose state differs from the one the Hessian was built for
   }
 }
@@ -311,16 +312,17 @@ __device__ __forceinline__ void ls_eval(const Contact& c, float alpha, float& d0
 // geoms (lane 48 additionally carries the hub's inertia).  Every chain scan therefore runs
 // convergently on all lanes with the full warp mask; hub-specific work (the six free-joint
 // DoFs and the 6x6 Schur block) is smem-only code executed by the hub lanes afterwards.
+// Lane-dependent conditionals in the chain code are written as selects / predicated stores so
+// that warps do not diverge (divergence doubles the issue cost and slows every *_sync collective).
 constexpr int NGROUP = 8;
 constexpr int SM_STATE = 0;                         // S_STRIDE
 constexpr int SM_CDOF = SM_STATE + S_STRIDE;        // NV * 8
 constexpr int SM_FS = SM_CDOF + NV * 8;             // qfrc_smooth
 constexpr int SM_GRAD = SM_FS + NV;                 // gradient / rhs
 constexpr int SM_X = SM_GRAD + NV;                  // search direction / solve result
-constexpr int SM_FC = SM_X + NV;                    // qfrc_constraint
-constexpr int SM_HS = SM_FC + NV;                   // row staging NGROUP * 184 (reused as pose buffer in the epilogue)
-constexpr int HS_STRIDE = 184;
-constexpr int SM_ROOT = SM_HS + NGROUP * HS_STRIDE; // per-group root publications
+constexpr int SM_U = SM_X + NV;                     // u_i = P cdof_i of every chain DoF: NGROUP * 11 * 8 (reused as pose buffer)
+constexpr int U_STRIDE = NLEGDOF * 8;
+constexpr int SM_ROOT = SM_U + NGROUP * U_STRIDE;   // per-group root publications
 constexpr int ROOT_STRIDE = 40;                     // [0..5] wrench, [6..15] crb / fc wrench, [16..36] A-hat
 constexpr int SM_BASE = SM_ROOT + NGROUP * ROOT_STRIDE;  // NLEG*21 Schur contributions, then NLEG*6 rhs contributions
 constexpr int SM_HBB = SM_BASE + 168;               // 21 hub block + 6 xb + 6 S_h
@@ -330,32 +332,36 @@ constexpr int SM_TOTAL = SM_RED + 32;
 constexpr int HU_CVEL = 0, HU_CACC = 6;
 constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27;
 
-// rows of the (contact-augmented) joint-space inertia for this lane's DoFs -> staging
-__device__ __forceinline__ void build_rows(const float* P, const float* s_cdof, float* hs, int grp, int dof0, int ldof0, int ndof,
-                                           const float* diag_add) {
-  for (int j = 0; j < 3; j++) if (j < ndof) {
-    int li = ldof0 + j; float u[6]; sym6_mul(P, s_cdof + 8 * (dof0 + j), u);
-    for (int c = 0; c < 6; c++) hs[li * 16 + c] = dot6(s_cdof + 8 * c, u);
-    for (int jj = 0; jj <= li; jj++) {
-      float v = dot6(s_cdof + 8 * (6 + NLEGDOF * grp + jj), u);
-      if (jj == li) v += diag_add[j];
-      if (li == 10 && jj == 10) hs[176] = v; else hs[li * 16 + 6 + jj] = v;
-    }
+// Lane-constant description of the two matrix columns (of 16) + the shared last one a lane holds.
+struct Cols {
+  const float *cd0, *cd1, *cd10;   // cdof of column t, column 8+t (leg dof t+2), leg dof 10
+  float add0, add1, add10;         // diagonal additions (armature [+ dt damping]) of those DoFs
+};
+
+// H columns of this lane from the staged u_i = P_i cdof_i :  H[i][c] = cdof_c . u_i   (c <= 6 + i)
+__device__ __forceinline__ void load_columns(const float* su, const Cols& cl, int t, float* hk0, float* hk1, float& d10) {
+  float c0[6], c1[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { c0[i] = cl.cd0[i]; c1[i] = cl.cd1[i]; }
+#pragma unroll
+  for (int i = 0; i < NLEGDOF; i++) {
+    const float* u = su + 8 * i;
+    float u6[6] = {u[0], u[1], u[2], u[3], u[4], u[5]};
+    float v0 = dot6(c0, u6), v1 = dot6(c1, u6);
+    hk0[i] = (t <= 6 + i) ? v0 : 0.f;
+    hk1[i] = (t + 2 <= i) ? v1 : 0.f;
+    if (6 + i == t) hk0[i] += cl.add0;
+    if (i == t + 2) hk1[i] += cl.add1;
   }
+  d10 = dot6(cl.cd10, su + 8 * 10) + cl.add10;
 }
 
 // L'DL of the 11x11 chain block + its 11x6 border, one matrix column per lane (columns t and 8+t of 16; the last
 // diagonal entry d10 is held by every lane).  Leaves L (unit lower, scaled rows) in hk0/hk1, the inverse pivots of
 // the lane's own DoFs in i0own/i1own/i10 and this chain's Schur contribution to the hub block in contrib[3].
-__device__ __forceinline__ void chain_factor(float* hk0, float* hk1, float d10, int t, float& i0own, float& i1own, float& i10,
-                                             float* contrib) {
-  int pb[3], pc[3];
-#pragma unroll
-  for (int s = 0; s < 3; s++) {  // pair (b >= c) number t + 8 s of the 21 lower-triangular hub entries
-    int idx = t + 8 * s, b = 0; while ((b + 1) * (b + 2) / 2 <= idx) b++;
-    pb[s] = b; pc[s] = idx - b * (b + 1) / 2; if (idx >= 21) { pb[s] = 0; pc[s] = 0; }
-    contrib[s] = 0.f;
-  }
+__device__ __forceinline__ void chain_factor(float* hk0, float* hk1, float d10, int t, const int* pb, const int* pc, float& i0own, float& i1own,
+                                             float& i10, float* contrib) {
+  contrib[0] = contrib[1] = contrib[2] = 0.f;
 #pragma unroll
   for (int kk = NLEGDOF - 1; kk >= 0; kk--) {
     float dk;
@@ -393,14 +399,14 @@ __device__ __forceinline__ void chain_solve_up(const float* hk0, const float* hk
 // x <- L^-1 D^-1 x given the hub solution xb (lanes t < 6)
 __device__ __forceinline__ void chain_solve_down(const float* hk0, const float* hk1, int t, float xb, float i0own, float i1own,
                                                  float i10, float& x0, float& x1, float& x10) {
-  if (t >= 6) x0 *= i0own;
+  x0 = t >= 6 ? x0 * i0own : x0;
   x1 *= i1own; x10 *= i10;
 #pragma unroll
   for (int kk = 0; kk < NLEGDOF; kk++) {
     float part = (t < 6 ? hk0[kk] * xb : (t - 6 < kk ? hk0[kk] * x0 : 0.f)) + (t + 2 < kk ? hk1[kk] * x1 : 0.f);
     part += __shfl_xor_sync(NMF_FULL, part, 1, 8); part += __shfl_xor_sync(NMF_FULL, part, 2, 8); part += __shfl_xor_sync(NMF_FULL, part, 4, 8);
-    if (6 + kk == t) x0 -= part;
-    if (kk == t + 2) x1 -= part;
+    x0 = (6 + kk == t) ? x0 - part : x0;
+    x1 = (kk == t + 2) ? x1 - part : x1;
     if (kk == 10) x10 -= part;
   }
 }
@@ -434,6 +440,42 @@ __device__ __forceinline__ void hub_solve(float* sm, float* xb) {
     for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
 }
 
+// factor + solve of the arrowhead system  H x = -rhs(SM_GRAD), H given by the staged u vectors (chains) and SM_HBB (hub);
+// the result is written to SM_X.  WITH_SH: lane 48 also publishes the hub part of the spatial acceleration of x.
+__device__ __forceinline__ void arrowhead_solve(float* sm, const float* s_cdof, const Cols& cl, int grp, int t, bool is_leg, int hl, int lbase,
+                                                const int* pb, const int* pc, float* dbg_rows) {
+  float hk0[NLEGDOF], hk1[NLEGDOF], d10, i0own = 0.f, i1own = 0.f, i10 = 0.f, contrib[3];
+  load_columns(sm + SM_U + grp * U_STRIDE, cl, t, hk0, hk1, d10);
+  if (dbg_rows) {
+#pragma unroll
+    for (int i = 0; i < NLEGDOF; i++) { dbg_rows[i * 16 + t] = hk0[i]; dbg_rows[i * 16 + 8 + t] = hk1[i]; }
+    dbg_rows[176] = d10;
+  }
+  chain_factor(hk0, hk1, d10, t, pb, pc, i0own, i1own, i10, contrib);
+#pragma unroll
+  for (int s = 0; s < 3; s++) if (is_leg && t + 8 * s < 21) sm[SM_BASE + grp * 21 + t + 8 * s] = contrib[s];
+  float x0 = (is_leg && t >= 6) ? -sm[SM_GRAD + lbase + t - 6] : 0.f, x1 = is_leg ? -sm[SM_GRAD + lbase + t + 2] : 0.f,
+        x10 = is_leg ? -sm[SM_GRAD + lbase + 10] : 0.f;
+  chain_solve_up(hk0, hk1, t, x0, x1, x10);
+  if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
+  block_sync();
+  if (!is_leg && hl == 0) {
+    float xb[6]; hub_solve(sm, xb);
+    float Sh[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < 6; b++) {
+      sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b];
+      const float* cd = s_cdof + 8 * b; for (int i = 0; i < 6; i++) Sh[i] += cd[i] * xb[b];
+    }
+    for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
+  }
+  block_sync();
+  chain_solve_down(hk0, hk1, t, t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f, i0own, i1own, i10, x0, x1, x10);
+  float* sx = sm + SM_X + lbase;
+  if (is_leg && t >= 6) sx[t - 6] = x0;
+  if (is_leg) sx[t + 2] = x1;
+  if (is_leg && t == 0) sx[10] = x10;
+}
+
 // ------------------------------------------------------------------ the step
 __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   const int tid = threadIdx.x;
@@ -447,20 +489,17 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   float* s_cdof = sm + SM_CDOF;
   float* s_hub = sm + SM_HUB;
   float* s_red = sm + SM_RED;
-  float* hs = sm + SM_HS + grp * HS_STRIDE;
+  float* su = sm + SM_U + grp * U_STRIDE;
   float* rt = sm + SM_ROOT + grp * ROOT_STRIDE;
   int parity = 0;
 
-  // ---- load the state record (coalesced; 304 floats), clear the row staging
+  // ---- load the state record (coalesced; 304 floats), clear the u staging (hub chains keep u = 0)
   {
     const float* g = p.state + (size_t)fly * S_STRIDE;
     for (int i = tid; i < S_STRIDE; i += CTA) st[i] = g[i];
-    for (int i = tid; i < NGROUP * HS_STRIDE; i += CTA) sm[SM_HS + i] = 0.f;
+    for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = 0.f;
   }
   block_sync();
-  if (!is_leg) {  // hub chains carry no DoFs: unit pivots keep their (unused) factorisation finite
-    if (t == 0) { for (int i = 0; i < 10; i++) hs[i * 16 + 6 + i] = 1.f; hs[176] = 1.f; }
-  }
 
   // per-lane constants that stay in registers for the whole launch
   const int ndof = __float_as_int(role[RF_NDOF * CTA + tid]);                 // 0 on hub lanes
@@ -469,9 +508,29 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   const int lbase = is_leg ? 6 + NLEGDOF * grp : 6;                           // first global dof of this chain
   const float mass = role[RF_MASS * CTA + tid];
   const float invw = role[RF_INVW * CTA + tid];
-  float armv[3], dampv[3];
+  float armv[3], dampv[3], msk[3];          // per own-dof constants; msk[j] = 1 if the lane owns a j-th dof
+  int dj[3];                                // global dof index of own dof j (clamped to a valid one when masked)
 #pragma unroll
-  for (int j = 0; j < 3; j++) { armv[j] = role[(RF_ARM + j) * CTA + tid]; dampv[j] = role[(RF_DAMP + j) * CTA + tid]; }
+  for (int j = 0; j < 3; j++) {
+    armv[j] = role[(RF_ARM + j) * CTA + tid]; dampv[j] = role[(RF_DAMP + j) * CTA + tid];
+    msk[j] = j < ndof ? 1.f : 0.f; dj[j] = j < ndof ? dof0 + j : dof0;
+  }
+  Cols cl, cle;   // Newton (armature) and Euler (armature + dt damping) column descriptions
+  {
+    const int g0 = t < 6 ? t : lbase + t - 6;
+    cl.cd0 = s_cdof + 8 * g0; cl.cd1 = s_cdof + 8 * (lbase + t + 2); cl.cd10 = s_cdof + 8 * (lbase + 10);
+    cl.add0 = role[(RF_CARM + 0) * CTA + tid]; cl.add1 = role[(RF_CARM + 1) * CTA + tid]; cl.add10 = role[(RF_CARM + 2) * CTA + tid];
+    cle = cl;
+    cle.add0 += p.dt * role[(RF_CDMP + 0) * CTA + tid]; cle.add1 += p.dt * role[(RF_CDMP + 1) * CTA + tid]; cle.add10 += p.dt * role[(RF_CDMP + 2) * CTA + tid];
+  }
+  int pb[3], pc[3];   // (b >= c) pairs number t, t+8, t+16 of the 21 lower-triangular hub entries
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    int idx = t + 8 * s, b = 0;
+#pragma unroll
+    for (int bb = 1; bb < 6; bb++) b += (bb * (bb + 1) / 2 <= idx) ? 1 : 0;
+    pb[s] = idx < 21 ? b : 0; pc[s] = idx < 21 ? idx - b * (b + 1) / 2 : 0;
+  }
 
   for (int step = 0; step < p.nsteps; step++) {
     // ---- controls for this step
@@ -495,34 +554,37 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int j = 0; j < 3; j++) {
         float ax[3] = {role[(RF_AXIS + 3 * j) * CTA + tid], role[(RF_AXIS + 3 * j + 1) * CTA + tid], role[(RF_AXIS + 3 * j + 2) * CTA + tid]};
         qrot(q, ax, laxis + 3 * j);
-        if (j < ndof) {
-          float ang = st[S_QPOS + 1 + dof0 + j], sn, cs; sincosf(0.5f * ang, &sn, &cs);
-          float ql[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, nq[4];
-          qmul(q, ql, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
-        }
+        float ang = msk[j] * st[S_QPOS + 1 + dj[j]], sn, cs; sincosf(0.5f * ang, &sn, &cs);   // masked dof: identity rotation
+        float ql[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, nq[4];
+        qmul(q, ql, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
       }
-      if (k == 0) {  // seed the chain with the hub pose
-        float t3[3]; qrot(qh, pp, t3); pp[0] = xh[0] + t3[0]; pp[1] = xh[1] + t3[1]; pp[2] = xh[2] + t3[2];
-        float nq[4]; qmul(qh, q, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+      {  // seed the chain root with the hub pose
+        float t3[3], nq[4]; qrot(qh, pp, t3); qmul(qh, q, nq);
+        const bool root = k == 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) pp[i] = root ? xh[i] + t3[i] : pp[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = root ? nq[i] : q[i];
       }
 #pragma unroll
       for (int off = 1; off < 8; off <<= 1) {
-        float uq[4], up[3];
+        float uq[4], up[3], t3[3], nq[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) uq[i] = __shfl_up_sync(NMF_FULL, q[i], off, 8);
 #pragma unroll
         for (int i = 0; i < 3; i++) up[i] = __shfl_up_sync(NMF_FULL, pp[i], off, 8);
-        if (k >= off) {
-          float t3[3]; qrot(uq, pp, t3); pp[0] = up[0] + t3[0]; pp[1] = up[1] + t3[1]; pp[2] = up[2] + t3[2];
-          float nq[4]; qmul(uq, q, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
-        }
+        qrot(uq, pp, t3); qmul(uq, q, nq);
+        const bool on = k >= off;
+#pragma unroll
+        for (int i = 0; i < 3; i++) pp[i] = on ? up[i] + t3[i] : pp[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = on ? nq[i] : q[i];
       }
       qnormalize(q);
       {  // parent world orientation -> world hinge axes
-        float pq[4], qpar[4] = {qh[0], qh[1], qh[2], qh[3]};
+        float qpar[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) pq[i] = __shfl_up_sync(NMF_FULL, q[i], 1, 8);
-        if (k > 0) { qpar[0] = pq[0]; qpar[1] = pq[1]; qpar[2] = pq[2]; qpar[3] = pq[3]; }
+        for (int i = 0; i < 4; i++) { float pq = __shfl_up_sync(NMF_FULL, q[i], 1, 8); qpar[i] = k > 0 ? pq : qh[i]; }
 #pragma unroll
         for (int j = 0; j < 3; j++) { float w[3]; qrot(qpar, laxis + 3 * j, w); laxis[3 * j] = w[0]; laxis[3 * j + 1] = w[1]; laxis[3 * j + 2] = w[2]; }
       }
@@ -534,6 +596,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     float xipos[3];
     {
       float ip[3] = {role[(RF_IPOS + 0) * CTA + tid], role[(RF_IPOS + 1) * CTA + tid], role[(RF_IPOS + 2) * CTA + tid]};
+#pragma unroll
       for (int i = 0; i < 3; i++) xipos[i] = xpos[i] + R[3 * i] * ip[0] + R[3 * i + 1] * ip[1] + R[3 * i + 2] * ip[2];
     }
     float com[3];
@@ -548,25 +611,43 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
 #pragma unroll
       for (int i = 0; i < 6; i++) ib[i] = role[(RF_IB + i) * CTA + tid];
       float Ib[9] = {ib[0], ib[3], ib[4], ib[3], ib[1], ib[5], ib[4], ib[5], ib[2]}, T[9], G[9];
-      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Ib[j] + R[3 * i + 1] * Ib[3 + j] + R[3 * i + 2] * Ib[6 + j];
-      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) G[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Ib[j] + R[3 * i + 1] * Ib[3 + j] + R[3 * i + 2] * Ib[6 + j];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++) G[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
       float off[3] = {xipos[0] - com[0], xipos[1] - com[1], xipos[2] - com[2]};
       float o2 = dot3(off, off);
       cinert[0] = G[0] + mass * (o2 - off[0] * off[0]); cinert[1] = G[4] + mass * (o2 - off[1] * off[1]); cinert[2] = G[8] + mass * (o2 - off[2] * off[2]);
       cinert[3] = G[1] - mass * off[0] * off[1]; cinert[4] = G[2] - mass * off[0] * off[2]; cinert[5] = G[5] - mass * off[1] * off[2];
       cinert[6] = mass * off[0]; cinert[7] = mass * off[1]; cinert[8] = mass * off[2]; cinert[9] = mass;
     }
-    // cdof of own dofs -> shared; hub lanes 0..5 own the free-joint dofs
+    // cdof of own dofs -> shared (predicated stores); hub lanes 0..5 own the free-joint dofs
+    float cdo[3][6];   // own cdof, kept in registers
     {
       float off[3] = {com[0] - xpos[0], com[1] - xpos[1], com[2] - xpos[2]};
-      for (int j = 0; j < ndof; j++) {
-        float* cd = s_cdof + 8 * (dof0 + j); float l[3]; cross3(laxis + 3 * j, off, l);
-        cd[0] = laxis[3 * j]; cd[1] = laxis[3 * j + 1]; cd[2] = laxis[3 * j + 2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float l[3]; cross3(laxis + 3 * j, off, l);
+        cdo[j][0] = laxis[3 * j]; cdo[j][1] = laxis[3 * j + 1]; cdo[j][2] = laxis[3 * j + 2]; cdo[j][3] = l[0]; cdo[j][4] = l[1]; cdo[j][5] = l[2];
+        if (j < ndof) {
+          float* cd = s_cdof + 8 * dj[j];
+#pragma unroll
+          for (int i = 0; i < 6; i++) cd[i] = cdo[j][i];
+        }
       }
       if (hubdof) {
         float* cd = s_cdof + 8 * hl;
-        if (hl < 3) { cd[0] = cd[1] = cd[2] = 0.f; cd[3] = hl == 0; cd[4] = hl == 1; cd[5] = hl == 2; }
-        else { int a = hl - 3; float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l); cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2]; }
+        const int a = hl < 3 ? 0 : hl - 3;
+        float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
+        const bool tr = hl < 3;
+        cd[0] = tr ? 0.f : ax[0]; cd[1] = tr ? 0.f : ax[1]; cd[2] = tr ? 0.f : ax[2];
+        cd[3] = tr ? (hl == 0 ? 1.f : 0.f) : l[0]; cd[4] = tr ? (hl == 1 ? 1.f : 0.f) : l[1]; cd[5] = tr ? (hl == 2 ? 1.f : 0.f) : l[2];
+#pragma unroll
+        for (int i = 0; i < 6; i++) cdo[0][i] = cd[i];
       }
       if (!is_leg && hl == 0) {
         // hub velocity / bias acceleration (free joint: translations first, rotations against the updated velocity)
@@ -575,13 +656,16 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         float cacc[6] = {0.f, 0.f, 0.f, -p.gx, -p.gy, -p.gz};
         float cvel[6] = {cv0[0], cv0[1], cv0[2], cv0[3], cv0[4], cv0[5]};
         float Sh[6] = {0, 0, 0, st[S_WARM], st[S_WARM + 1], st[S_WARM + 2]};
+#pragma unroll
         for (int a = 0; a < 3; a++) {
           float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
           float cd[6] = {ax[0], ax[1], ax[2], l[0], l[1], l[2]}, cdd[6];
           cross_motion(cv0, cd, cdd);
           float qa = st[S_WARM + 3 + a];
+#pragma unroll
           for (int i = 0; i < 6; i++) { cacc[i] += cdd[i] * wl[a]; cvel[i] += cd[i] * wl[a]; Sh[i] += cd[i] * qa; }
         }
+#pragma unroll
         for (int i = 0; i < 6; i++) { s_hub[HU_CVEL + i] = cvel[i]; s_hub[HU_CACC + i] = cacc[i]; sm[SM_HBB + HB_SH + i] = Sh[i]; }
       }
     }
@@ -595,68 +679,87 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     float fs_own[3] = {0.f, 0.f, 0.f};
     float actf[3] = {0.f, 0.f, 0.f}, adhf = 0.f;
     {
-      float loc[6] = {0, 0, 0, 0, 0, 0};
-      for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); float qv = st[S_QVEL + dof0 + j]; for (int i = 0; i < 6; i++) loc[i] += cd[i] * qv; }
+      float qv[3], loc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        qv[j] = msk[j] * st[S_QVEL + dj[j]];
+#pragma unroll
+        for (int i = 0; i < 6; i++) loc[i] += cdo[j][i] * qv[j];
+      }
       float pre[6] = {loc[0], loc[1], loc[2], loc[3], loc[4], loc[5]};
       chain_prefix<6>(pre, NMF_FULL, k);
       float cv[6], ad[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
       for (int i = 0; i < 6; i++) cv[i] = pre[i] - loc[i] + s_hub[HU_CVEL + i];
-      for (int j = 0; j < ndof; j++) {
-        const float* cd = s_cdof + 8 * (dof0 + j); float qv = st[S_QVEL + dof0 + j], cdd[6];
-        cross_motion(cv, cd, cdd);
-        for (int i = 0; i < 6; i++) { ad[i] += cdd[i] * qv; cv[i] += cd[i] * qv; }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float cdd[6]; cross_motion(cv, cdo[j], cdd);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { ad[i] += cdd[i] * qv[j]; cv[i] += cdo[j][i] * qv[j]; }
       }
+#pragma unroll
       for (int i = 0; i < 6; i++) cvel[i] = cv[i];
       chain_prefix<6>(ad, NMF_FULL, k);
       float cacc[6];
+#pragma unroll
       for (int i = 0; i < 6; i++) cacc[i] = ad[i] + s_hub[HU_CACC + i];
       // body wrench  W = -(I a + v x* I v)  (+ adhesion below)
       float t1[6], t2[6], t3[6], W[6];
       mul_inert(cinert, cacc, t1); mul_inert(cinert, cvel, t2); cross_force(cvel, t2, t3);
+#pragma unroll
       for (int i = 0; i < 6; i++) W[i] = -(t1[i] + t3[i]);
       // composite inertia
+#pragma unroll
       for (int i = 0; i < 10; i++) crb[i] = cinert[i];
       chain_suffix<10>(crb, NMF_FULL, k);
       // collision for this body's geom
       collide(p, role, tid, xpos, R, com, cvel, invw, con);
       // adhesion (body transmission): force pulls the body onto the plane along each contact normal
-      const int acidx = __float_as_int(role[RF_ADH_CIDX * CTA + tid]);
-      if (acidx >= 0) {
-        float c = fminf(role[RF_ADH_HI * CTA + tid], fmaxf(role[RF_ADH_LO * CTA + tid], st[S_CTRL + acidx]));
-        adhf = role[RF_ADH_GAIN * CTA + tid] * c;
+      {
+        const int acidx = __float_as_int(role[RF_ADH_CIDX * CTA + tid]);
+        float c = fminf(role[RF_ADH_HI * CTA + tid], fmaxf(role[RF_ADH_LO * CTA + tid], st[S_CTRL + (acidx >= 0 ? acidx : 0)]));
+        adhf = role[RF_ADH_GAIN * CTA + tid] * c;     // gain = 0 on lanes without an adhesion actuator
         float n = con[0].active + con[1].active;
-        if (n > 0.f) {
-          float fz = -adhf / n;
-          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { W[0] += con[s].r[1] * fz; W[1] += -con[s].r[0] * fz; W[5] += fz; }
-        }
+        float fz = n > 0.f ? -adhf / n : 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; s++) { float f = con[s].active * fz; W[0] += con[s].r[1] * f; W[1] -= con[s].r[0] * f; W[5] += f; }
       }
       chain_suffix<6>(W, NMF_FULL, k);
       // joint-space smooth force of own dofs: passive + actuator + C'W
-      for (int j = 0; j < 3; j++) if (j < ndof) {
-        int d = dof0 + j; const float* cd = s_cdof + 8 * d;
-        float q = st[S_QPOS + 1 + d], qv = st[S_QVEL + d];
-        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - dampv[j] * qv;
-        int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]);
-        if (ci >= 0) {
-          float kp = role[(RF_KP + j) * CTA + tid], kv = role[(RF_KV + j) * CTA + tid];
-          float af = kp * st[S_CTRL + ci] - kp * q - kv * qv;
-          af = fminf(role[(RF_FHI + j) * CTA + tid], fmaxf(role[(RF_FLO + j) * CTA + tid], af));
-          actf[j] = af; f += af;
-        }
-        f += dot6(cd, W);
-        fs_own[j] = f; sm[SM_FS + d] = f;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int d = dj[j];
+        float q = st[S_QPOS + 1 + d], qvj = st[S_QVEL + d];
+        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - dampv[j] * qvj;
+        const int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]);
+        float kp = role[(RF_KP + j) * CTA + tid], kv = role[(RF_KV + j) * CTA + tid];     // 0 without an actuator
+        float af = kp * st[S_CTRL + (ci >= 0 ? ci : 0)] - kp * q - kv * qvj;
+        af = fminf(role[(RF_FHI + j) * CTA + tid], fmaxf(role[(RF_FLO + j) * CTA + tid], af));
+        actf[j] = af;
+        f += af + dot6(cdo[j], W);
+        fs_own[j] = f;
+        if (j < ndof) sm[SM_FS + d] = f;
       }
       if (k == 0) {
+#pragma unroll
         for (int i = 0; i < 6; i++) rt[i] = W[i];
+#pragma unroll
         for (int i = 0; i < 10; i++) rt[6 + i] = crb[i];
       }
       // spatial acceleration of this body generated by the warm-start qacc
       float sl[6] = {0, 0, 0, 0, 0, 0};
-      for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); float qa = st[S_WARM + dof0 + j]; for (int i = 0; i < 6; i++) sl[i] += cd[i] * qa; }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float qa = msk[j] * st[S_WARM + dj[j]];
+#pragma unroll
+        for (int i = 0; i < 6; i++) sl[i] += cdo[j][i] * qa;
+      }
       chain_prefix<6>(sl, NMF_FULL, k);
+#pragma unroll
       for (int i = 0; i < 6; i++) Sa[i] = sl[i] + sm[SM_HBB + HB_SH + i];
       // contact rows at the warm-start acceleration
-      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) {
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
         float ap[3]; project_point(con[s], Sa, p.mu, ap);
         con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
       }
@@ -667,7 +770,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       float W[6];
       for (int i = 0; i < 10; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + 6 + i]; crbh[i] = s; }
       for (int i = 0; i < 6; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; W[i] = s; }
-      fs_own[0] = dot6(s_cdof + 8 * hl, W); sm[SM_FS + hl] = fs_own[0];
+      fs_own[0] = dot6(cdo[0], W); sm[SM_FS + hl] = fs_own[0];
     }
     block_sync();   // roots consumed before the solver overwrites them
 
@@ -678,112 +781,104 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     // =====================================================================
     float* qacc = st + S_WARM;      // qacc lives in the warm-start slot of the record
     int niter = 0, nls_total = 0, nchanged_last = 0;
-    float hk0[NLEGDOF], hk1[NLEGDOF];   // column-distributed L'DL factor of this chain
-    float i0own = 0.f, i1own = 0.f, i10 = 0.f;
+    // One loop body serves every Newton iteration AND the final implicit-damping (Euler) solve, so the large unrolled
+    // factorisation exists once in the instruction stream (the kernel is I-cache sensitive):
+    //   pass `iter`:  forces(qacc) -> gradient/fc -> [converged? euler : newton] system -> arrowhead solve -> (line search, move)
     for (int iter = 0;; iter++) {
-      const bool last = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
+      const bool euler = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
       // ---- forces, active set, contact augmentation
       float Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
 #pragma unroll
       for (int i = 0; i < 21; i++) A[i] = 0.f;
-      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) contact_forces(con[s], p.mu, Wc, last ? nullptr : A, nullptr);
+      contact_forces<true>(con[0], p.mu, Wc, A, nullptr); contact_forces<true>(con[1], p.mu, Wc, A, nullptr);
       // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
       float y[12];
       {
         float t6[6]; mul_inert(cinert, Sa, t6);
+#pragma unroll
         for (int i = 0; i < 6; i++) { y[i] = t6[i] - Wc[i]; y[6 + i] = Wc[i]; }
       }
       float gown[3] = {0.f, 0.f, 0.f};
       chain_suffix<12>(y, NMF_FULL, k);
-      if (!last) chain_suffix<21>(A, NMF_FULL, k);
-      for (int j = 0; j < 3; j++) if (j < ndof) {
-        int d = dof0 + j; const float* cd = s_cdof + 8 * d;
-        float g = dot6(cd, y) + armv[j] * qacc[d] - fs_own[j];
-        gown[j] = g; sm[SM_GRAD + d] = g; sm[SM_FC + d] = dot6(cd, y + 6);
+      chain_suffix<21>(A, NMF_FULL, k);
+      const float am = euler ? 0.f : 1.f;     // the Euler system uses the plain inertia (no contact augmentation)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int d = dj[j];
+        float fc = dot6(cdo[j], y + 6);
+        float g = dot6(cdo[j], y) + armv[j] * qacc[d] - fs_own[j];
+        gown[j] = msk[j] * g;
+        if (j < ndof) sm[SM_GRAD + d] = euler ? -(fs_own[j] + fc) : g;   // right-hand side is -(this slot)
       }
       if (k == 0) {
+#pragma unroll
         for (int i = 0; i < 12; i++) rt[i] = y[i];
-        if (!last) for (int i = 0; i < 21; i++) rt[16 + i] = A[i];
+#pragma unroll
+        for (int i = 0; i < 21; i++) rt[16 + i] = am * A[i];
       }
       block_sync();
-      float Ah[21];
-      if (hubdof) {
-        float yh[12];
-        for (int i = 0; i < 12; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; yh[i] = s; }
-        const float* cd = s_cdof + 8 * hl;
-        float g = dot6(cd, yh) - fs_own[0];
-        gown[0] = g; sm[SM_GRAD + hl] = g; sm[SM_FC + hl] = dot6(cd, yh + 6);
-        if (!last) for (int i = 0; i < 21; i++) { float s = 0.f; for (int gg = 0; gg < NGROUP; gg++) s += sm[SM_ROOT + gg * ROOT_STRIDE + 16 + i]; Ah[i] = s; }
-      }
-      if (last) { niter = iter; break; }
-
-      // ---- Hessian rows  H = C'(crb + A-hat)C + armature, staged in shared, then column-distributed
       {
         float P[21];
         if (hubdof) {
+          float yh[12];
+          for (int i = 0; i < 12; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; yh[i] = s; }
+          float fc = dot6(cdo[0], yh + 6), g = dot6(cdo[0], yh) - fs_own[0];
+          gown[0] = g; sm[SM_GRAD + hl] = euler ? -(fs_own[0] + fc) : g;
           expand_inert(crbh, P);
-#pragma unroll
-          for (int i = 0; i < 21; i++) P[i] += Ah[i];
-          float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
+          for (int i = 0; i < 21; i++) { float s = 0.f; for (int gg = 0; gg < NGROUP; gg++) s += sm[SM_ROOT + gg * ROOT_STRIDE + 16 + i]; P[i] += s; }
+          float u[6]; sym6_mul(P, cdo[0], u);
           for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
-        } else {
-          expand_inert(crb, P);
+        }
+        __syncwarp(NMF_FULL);
+        // ---- system matrix  H = C'(crb + A-hat)C + diag : each DoF owner stages u = P cdof, columns are formed by the factoriser
+        expand_inert(crb, P);
 #pragma unroll
-          for (int i = 0; i < 21; i++) P[i] += A[i];
-          build_rows(P, s_cdof, hs, grp, dof0, ldof0, ndof, armv);
+        for (int i = 0; i < 21; i++) P[i] += am * A[i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          float u[6]; sym6_mul(P, cdo[j], u);
+          if (j < ndof) {
+            float* up = su + 8 * (ldof0 + j);
+#pragma unroll
+            for (int i = 0; i < 6; i++) up[i] = u[i];
+          }
         }
       }
       __syncwarp(NMF_FULL);
-#pragma unroll
-      for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
-      float contrib[3];
-      chain_factor(hk0, hk1, hs[176], t, i0own, i1own, i10, contrib);
-      if (is_leg) {
-#pragma unroll
-        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) sm[SM_BASE + grp * 21 + t + 8 * s] = contrib[s];
+      {
+        Cols c = cl;
+        c.add0 = euler ? cle.add0 : cl.add0; c.add1 = euler ? cle.add1 : cl.add1; c.add10 = euler ? cle.add10 : cl.add10;
+        float* dbg_rows = (euler && p.dbg && is_leg) ? p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + grp * 177 : nullptr;
+        arrowhead_solve(sm, s_cdof, c, grp, t, is_leg, hl, lbase, pb, pc, dbg_rows);
       }
-      // ---- solve H x = -g
-      float x0 = (is_leg && t >= 6) ? -sm[SM_GRAD + lbase + t - 6] : 0.f, x1 = is_leg ? -sm[SM_GRAD + lbase + t + 2] : 0.f, x10 = is_leg ? -sm[SM_GRAD + lbase + 10] : 0.f;
-      chain_solve_up(hk0, hk1, t, x0, x1, x10);
-      if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
-      block_sync();
-      if (!is_leg && hl == 0) {
-        float xb[6]; hub_solve(sm, xb);
-        float Sh[6] = {0, 0, 0, 0, 0, 0};
-        for (int b = 0; b < 6; b++) { sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b]; const float* cd = s_cdof + 8 * b; for (int i = 0; i < 6; i++) Sh[i] += cd[i] * xb[b]; }
-        for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
-      }
-      block_sync();
-      chain_solve_down(hk0, hk1, t, t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f, i0own, i1own, i10, x0, x1, x10);
-      if (is_leg) {
-        float* sx = sm + SM_X + lbase;
-        if (t >= 6) sx[t - 6] = x0;
-        sx[t + 2] = x1;
-        if (t == 0) sx[10] = x10;
-      }
+      if (euler) { niter = iter; break; }
       __syncwarp(NMF_FULL);
-      float sown[3] = {0.f, 0.f, 0.f};
-      for (int j = 0; j < 3; j++) if (j < ndof) sown[j] = sm[SM_X + dof0 + j];
+      float sown[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) sown[j] = msk[j] * sm[SM_X + dj[j]];
       if (hubdof) sown[0] = sm[SM_X + hl];
 
       // ---- spatial acceleration of the search direction, row directions, quadratic terms
       float Ss[6];
       {
         float sl[6] = {0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < ndof; j++) { const float* cd = s_cdof + 8 * (dof0 + j); for (int i = 0; i < 6; i++) sl[i] += cd[i] * sown[j]; }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+          for (int i = 0; i < 6; i++) sl[i] += (is_leg ? cdo[j][i] : 0.f) * sown[j];
         chain_prefix<6>(sl, NMF_FULL, k);
+#pragma unroll
         for (int i = 0; i < 6; i++) Ss[i] = sl[i] + sm[SM_HBB + HB_SH + i];
       }
       float red[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // s.g , s'Ms , d0 rows(0), d1 rows(0), |s|^2
       {
         float t6[6]; mul_inert(cinert, Ss, t6);
         red[1] += dot6(Ss, t6);
-        for (int j = 0; j < 3; j++) {
-          bool own = (j < ndof) || (j == 0 && hubdof);
-          if (own) { red[0] += sown[j] * gown[j]; red[1] += (hubdof ? 0.f : armv[j]) * sown[j] * sown[j]; red[4] += sown[j] * sown[j]; }
-        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) { red[0] += sown[j] * gown[j]; red[1] += (is_leg ? armv[j] : 0.f) * sown[j] * sown[j]; red[4] += sown[j] * sown[j]; }
         float dummy = 0.f;
-        for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { project_point(con[s], Ss, p.mu, con[s].s); ls_eval(con[s], 0.f, red[2], red[3], dummy); }
+#pragma unroll
+        for (int s = 0; s < 2; s++) { project_point(con[s], Ss, p.mu, con[s].s); ls_eval(con[s], 0.f, red[2], red[3], dummy); }
       }
       cta_reduce<5>(red, s_red, parity, tid);
       // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
@@ -800,7 +895,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
           if (nx <= lo || nx >= hi) nx = (hi > 1.0e38f) ? 2.f * fmaxf(alpha, 1.f) : 0.5f * (lo + hi);
           alpha = nx;
           float e[3] = {0.f, 0.f, 0.f};
-          for (int s = 0; s < 2; s++) if (con[s].active > 0.f) ls_eval(con[s], alpha, e[0], e[1], e[2]);
+          ls_eval(con[0], alpha, e[0], e[1], e[2]); ls_eval(con[1], alpha, e[0], e[1], e[2]);
           cta_reduce<3>(e, s_red, parity, tid);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
           nchanged_last = (int)e[2];
@@ -808,60 +903,14 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         }
       }
       // ---- move
-      for (int j = 0; j < 3; j++) {
-        bool own = (j < ndof) || (j == 0 && hubdof);
-        if (own) qacc[dof0 + j] += alpha * sown[j];
-      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) if (j < ndof || (j == 0 && hubdof)) qacc[dj[j]] += alpha * sown[j];
+#pragma unroll
       for (int i = 0; i < 6; i++) Sa[i] += alpha * Ss[i];
-      for (int s = 0; s < 2; s++) if (con[s].active > 0.f) { con[s].w[0] += alpha * con[s].s[0]; con[s].w[1] += alpha * con[s].s[1]; con[s].w[2] += alpha * con[s].s[2]; }
-    }
-
-    // =====================================================================
-    // D. semi-implicit Euler with implicit joint damping:
-    //    (M + dt diag(damping)) a' = qfrc_smooth + qfrc_constraint ; v += dt a' ; q integrates with the new v
-    // =====================================================================
-    block_sync();
-    {
-      float P[21];
-      if (hubdof) {
-        expand_inert(crbh, P);
-        float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
-        for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
-        sm[SM_GRAD + hl] = -(fs_own[0] + sm[SM_FC + hl]);
-      } else {
-        expand_inert(crb, P);
-        float dadd[3] = {armv[0] + p.dt * dampv[0], armv[1] + p.dt * dampv[1], armv[2] + p.dt * dampv[2]};
-        build_rows(P, s_cdof, hs, grp, dof0, ldof0, ndof, dadd);
-        for (int j = 0; j < 3; j++) if (j < ndof) sm[SM_GRAD + dof0 + j] = -(fs_own[j] + sm[SM_FC + dof0 + j]);   // rhs = -(grad slot)
-      }
-      __syncwarp(NMF_FULL);
 #pragma unroll
-      for (int i = 0; i < NLEGDOF; i++) { hk0[i] = hs[i * 16 + t]; hk1[i] = hs[i * 16 + 8 + t]; }
-      if (p.dbg && is_leg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + grp * 177; for (int i = t; i < 177; i += 8) dg[i] = hs[i]; }
-      float contrib[3];
-      chain_factor(hk0, hk1, hs[176], t, i0own, i1own, i10, contrib);
-      if (is_leg) {
-#pragma unroll
-        for (int s = 0; s < 3; s++) if (t + 8 * s < 21) sm[SM_BASE + grp * 21 + t + 8 * s] = contrib[s];
-      }
-      float x0 = (is_leg && t >= 6) ? -sm[SM_GRAD + lbase + t - 6] : 0.f, x1 = is_leg ? -sm[SM_GRAD + lbase + t + 2] : 0.f, x10 = is_leg ? -sm[SM_GRAD + lbase + 10] : 0.f;
-      chain_solve_up(hk0, hk1, t, x0, x1, x10);
-      if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
-      block_sync();
-      if (!is_leg && hl == 0) {
-        if (p.dbg) { float* dg = p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + NLEG * 177; for (int i = 0; i < 21; i++) dg[i] = sm[SM_HBB + HB_S + i]; }
-        float xb[6]; hub_solve(sm, xb);
-        for (int b = 0; b < 6; b++) { sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b]; }
-      }
-      block_sync();
-      chain_solve_down(hk0, hk1, t, t < 6 ? sm[SM_HBB + HB_XB + t] : 0.f, i0own, i1own, i10, x0, x1, x10);
-      if (is_leg) {
-        float* sx = sm + SM_X + lbase;
-        if (t >= 6) sx[t - 6] = x0;
-        sx[t + 2] = x1;
-        if (t == 0) sx[10] = x10;
-      }
+      for (int s = 0; s < 2; s++) { con[s].w[0] += alpha * con[s].s[0]; con[s].w[1] += alpha * con[s].s[1]; con[s].w[2] += alpha * con[s].s[2]; }
     }
+    // SM_X now holds the implicit-damping (Euler) acceleration  (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
     block_sync();
 
     // ---- optional outputs of this step (derived quantities belong to the pre-integration state, as in mj_step)
@@ -870,13 +919,14 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       if (p.dbg) {
         float* dg = p.dbg + (size_t)fly * DBG_STRIDE;
         if (tid == 0) { dg[DBG_NITER] = (float)niter; dg[DBG_NLS] = (float)nls_total; dg[DBG_NCHG] = (float)nchanged_last; }
-        for (int i = tid; i < NV; i += CTA) { dg[DBG_FS + i] = sm[SM_FS + i]; dg[DBG_QACC + i] = qacc[i]; dg[DBG_FC + i] = sm[SM_FC + i]; dg[DBG_QACCE + i] = sm[SM_X + i]; }
+        for (int i = tid; i < NV; i += CTA) { dg[DBG_FS + i] = sm[SM_FS + i]; dg[DBG_QACC + i] = qacc[i]; dg[DBG_FC + i] = -sm[SM_GRAD + i] - sm[SM_FS + i]; dg[DBG_QACCE + i] = sm[SM_X + i]; }
+        if (tid < 21) dg[DBG_HROWS + NLEG * 177 + tid] = sm[SM_HBB + HB_S + tid];
         for (int s = 0; s < 2; s++) {
           float* c = dg + DBG_CON + (tid * 2 + s) * 6; float fn = 0.f, Wt[6] = {0, 0, 0, 0, 0, 0};
-          if (con[s].active > 0.f) contact_forces(con[s], p.mu, Wt, nullptr, &fn);
-          c[0] = con[s].active; c[1] = con[s].active > 0.f ? con[s].dist : 0.f;
-          c[2] = con[s].active > 0.f ? con[s].r[0] + com[0] : 0.f; c[3] = con[s].active > 0.f ? con[s].r[1] + com[1] : 0.f;
-          c[4] = con[s].active > 0.f ? con[s].r[2] + com[2] : 0.f; c[5] = fn;
+          contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
+          c[0] = con[s].active; c[1] = con[s].active * con[s].dist;
+          c[2] = con[s].active * (con[s].r[0] + com[0]); c[3] = con[s].active * (con[s].r[1] + com[1]);
+          c[4] = con[s].active * (con[s].r[2] + com[2]); c[5] = fn;
         }
         for (int i = 0; i < 3; i++) dg[DBG_XPOS + tid * 3 + i] = xpos[i];
         for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[8 * (i / 6) + i % 6];
@@ -886,37 +936,44 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       }
       if (p.out_actf) {
         float* o = p.out_actf + (size_t)fly * (p.nu_pos + p.nu_adh);
-        for (int j = 0; j < 3; j++) if (j < ndof) { int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]); if (ci >= 0) o[ci] = actf[j]; }
+#pragma unroll
+        for (int j = 0; j < 3; j++) { int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]); if (j < ndof && ci >= 0) o[ci] = actf[j]; }
         int ai = __float_as_int(role[RF_ADH_CIDX * CTA + tid]); if (ai >= 0) o[ai] = adhf;
       }
       if (p.out_sensor) {
         // per-leg contact sensor (world.py:311-331), reduce="netforce": found, force, torque, pos, normal, tangent
-        const bool sens = is_leg && __float_as_int(role[RF_LEGSENSOR * CTA + tid]) != 0;
+        const float sens = (is_leg && __float_as_int(role[RF_LEGSENSOR * CTA + tid]) != 0) ? 1.f : 0.f;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // F(3), fn-weighted pos(3), fn sum, count
-        float Fc[2][3], fnv[2] = {0.f, 0.f}, plain[3] = {0, 0, 0};
+        float Fc[2][3], plain[3] = {0, 0, 0};
+#pragma unroll
         for (int s = 0; s < 2; s++) {
-          Fc[s][0] = Fc[s][1] = Fc[s][2] = 0.f;
-          if (sens && con[s].active > 0.f) {
-            float Wt[6] = {0, 0, 0, 0, 0, 0}; contact_forces(con[s], p.mu, Wt, nullptr, &fnv[s]);
-            Fc[s][0] = Wt[3]; Fc[s][1] = Wt[4]; Fc[s][2] = Wt[5];
-            for (int i = 0; i < 3; i++) { acc[i] += Fc[s][i]; acc[3 + i] += fnv[s] * (con[s].r[i] + com[i]); plain[i] += con[s].r[i] + com[i]; }
-            acc[6] += fnv[s]; acc[7] += 1.f;
-          }
+          float Wt[6] = {0, 0, 0, 0, 0, 0}, fn = 0.f; contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
+          const float on = sens * con[s].active;
+          Fc[s][0] = on * Wt[3]; Fc[s][1] = on * Wt[4]; Fc[s][2] = on * Wt[5];
+#pragma unroll
+          for (int i = 0; i < 3; i++) { acc[i] += Fc[s][i]; acc[3 + i] += on * fn * (con[s].r[i] + com[i]); plain[i] += on * (con[s].r[i] + com[i]); }
+          acc[6] += on * fn; acc[7] += on;
         }
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
           for (int i = 0; i < 8; i++) acc[i] += __shfl_xor_sync(NMF_FULL, acc[i], off, 8);
+#pragma unroll
           for (int i = 0; i < 3; i++) plain[i] += __shfl_xor_sync(NMF_FULL, plain[i], off, 8);
         }
         float P3[3] = {0, 0, 0};
         if (acc[7] > 0.f) for (int i = 0; i < 3; i++) P3[i] = acc[6] > NMF_MINVAL ? acc[3 + i] / acc[6] : plain[i] / acc[7];
         float T[3] = {0, 0, 0};
-        for (int s = 0; s < 2; s++) if (sens && con[s].active > 0.f) {
-          float rr[3] = {con[s].r[0] + com[0] - P3[0], con[s].r[1] + com[1] - P3[1], con[s].r[2] + com[2] - P3[2]}, tt[3];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const float on = sens * con[s].active;
+          float rr[3] = {on * (con[s].r[0] + com[0] - P3[0]), on * (con[s].r[1] + com[1] - P3[1]), on * (con[s].r[2] + com[2] - P3[2])}, tt[3];
           cross3(rr, Fc[s], tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
         }
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) for (int i = 0; i < 3; i++) T[i] += __shfl_xor_sync(NMF_FULL, T[i], off, 8);
+        for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+          for (int i = 0; i < 3; i++) T[i] += __shfl_xor_sync(NMF_FULL, T[i], off, 8);
         if (is_leg && k == 0) {
           float* o = p.out_sensor + ((size_t)fly * NLEG + grp) * 16;
           o[0] = acc[7];
@@ -925,21 +982,19 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         }
       }
       if (p.out_xpos || p.out_xquat) {
-        block_sync();   // the row staging is free again: reuse it as the pose exchange buffer
-        float* ps = sm + SM_HS + tid * 8;
+        block_sync();   // the u staging is free again: reuse it as the pose exchange buffer
+        float* ps = sm + SM_U + tid * 8;
         ps[0] = xpos[0]; ps[1] = xpos[1]; ps[2] = xpos[2]; ps[3] = xq[0]; ps[4] = xq[1]; ps[5] = xq[2]; ps[6] = xq[3];
         block_sync();
         for (int sgi = tid; sgi < p.nseg; sgi += CTA) {
-          const float* tb = p.seg_tab + sgi * 8; const float* bp = sm + SM_HS + __float_as_int(tb[0]) * 8;
+          const float* tb = p.seg_tab + sgi * 8; const float* bp = sm + SM_U + __float_as_int(tb[0]) * 8;
           float lp[3] = {tb[1], tb[2], tb[3]}, lq[4] = {tb[4], tb[5], tb[6], tb[7]}, w[3], wq[4];
           qrot(bp + 3, lp, w); qmul(bp + 3, lq, wq);
           if (p.out_xpos) { float* o = p.out_xpos + ((size_t)fly * p.nseg + sgi) * 3; o[0] = bp[0] + w[0]; o[1] = bp[1] + w[1]; o[2] = bp[2] + w[2]; }
           if (p.out_xquat) { float* o = p.out_xquat + ((size_t)fly * p.nseg + sgi) * 4; o[0] = wq[0]; o[1] = wq[1]; o[2] = wq[2]; o[3] = wq[3]; }
         }
         block_sync();
-        for (int i = tid; i < NGROUP * HS_STRIDE; i += CTA) sm[SM_HS + i] = 0.f;   // restore the staging invariants
-        block_sync();
-        if (!is_leg && t == 0) { for (int i = 0; i < 10; i++) hs[i * 16 + 6 + i] = 1.f; hs[176] = 1.f; }
+        for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = 0.f;   // restore the staging invariant (hub chains: u = 0)
       }
     }
 
