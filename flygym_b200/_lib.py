@@ -87,6 +87,17 @@ def load() -> ctypes.CDLL:
     for fn in ("nmf_create", "nmf_destroy", "nmf_model_info", "nmf_bind", "nmf_reset", "nmf_step", "nmf_scatter_ctrl",
                "nmf_gather_state", "nmf_step_host", "nmf_set_solver"):
         getattr(lib, fn).restype = ci
+    lib.nmf_retina_create.argtypes = [vp, vp, ci, ci, ci, ci, ctypes.POINTER(vp)]
+    lib.nmf_retina_destroy.argtypes = [vp]
+    lib.nmf_retina_last_error.argtypes = [vp]
+    lib.nmf_retina_last_error.restype = ctypes.c_char_p
+    lib.nmf_retina_launch_count.argtypes = [vp]
+    lib.nmf_retina_launch_count.restype = ctypes.c_int64
+    lib.nmf_retina_forward.argtypes = [vp, vp, ci, vp, vp]
+    lib.nmf_retina_forward_host.argtypes = [vp, vp, ci, vp, vp]
+    lib.nmf_odor_intensity.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, ci, ci, vp, vp]
+    for fn in ("nmf_retina_create", "nmf_retina_destroy", "nmf_retina_forward", "nmf_retina_forward_host", "nmf_odor_intensity"):
+        getattr(lib, fn).restype = ci
     _LIB = lib
     return lib
 
@@ -95,5 +106,6 @@ def load() -> ctypes.CDLL:
 DECLARED_SYMBOLS = [
     "nmf_create", "nmf_destroy", "nmf_model_info", "nmf_last_error", "nmf_bind", "nmf_reset", "nmf_step",
     "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_launch_count",
-    "nmf_retina_create", "nmf_retina_destroy", "nmf_retina_forward", "nmf_retina_forward_host", "nmf_odor_intensity",
+    "nmf_retina_create", "nmf_retina_destroy", "nmf_retina_last_error", "nmf_retina_launch_count", "nmf_retina_forward",
+    "nmf_retina_forward_host", "nmf_odor_intensity",
 ]

@@ -81,6 +81,30 @@ int nmf_set_solver(nmf_handle* h, int max_newton_iterations, int max_linesearch_
 /* Number of kernels this library has launched on behalf of the handle (bench.py's gpu_launches). */
 int64_t nmf_launch_count(const nmf_handle* h);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Retina transform and odor-intensity sensor.  FlyGym 2.0.1 ships no implementation (only the v1 parameter block at
+ * src/flygym/assets/model/legacy/flygym1_config.yaml:141-200); these entry points are what a re-added
+ * `flygym.vision.Retina.raw_image_to_hex_pxls` / odor observation would bind.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct nmf_retina nmf_retina;
+
+/* pixcode HOST int16 [2 eyes][H*W]: 0 = pixel outside every ommatidium, else 2*bin + (channel==blue), bin in 1..n_omm.
+ * inv_norm HOST float [2 eyes][n_omm+1][2]: 1/(255*pixel_count) in the channel slot the ommatidium reads, 0 elsewhere. */
+int nmf_retina_create(const int16_t* pixcode, const float* inv_norm, int H, int W, int n_omm, int device, nmf_retina** out);
+int nmf_retina_destroy(nmf_retina* r);
+const char* nmf_retina_last_error(const nmf_retina* r);
+int64_t nmf_retina_launch_count(const nmf_retina* r);
+/* images DEVICE uint8 [n_flies][2][H][W][3] (16-byte aligned) -> out DEVICE float [n_flies][2][n_omm][2] */
+int nmf_retina_forward(nmf_retina* r, const uint8_t* images, int n_flies, float* out, void* cuda_stream);
+/* same with HOST buffers (H2D, kernel, D2H, synchronises) */
+int nmf_retina_forward_host(nmf_retina* r, const uint8_t* images_host, int n_flies, float* out_host, void* cuda_stream);
+
+/* odor intensity at the 4 sensor sites: out DEVICE float [n_flies][D][4];  all pointers DEVICE.
+ * seg_xpos / seg_xquat are the buffers bound with nmf_bind (segment poses of the last step). */
+int nmf_odor_intensity(const float* seg_xpos, const float* seg_xquat, int n_flies, int nseg, const int32_t* sensor_seg /*[4]*/,
+                       const float* sensor_relpos /*[4][3]*/, const float* src_pos /*[nsrc][3]*/, const float* src_peak /*[nsrc][D]*/,
+                       int nsrc, int D, float* out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
