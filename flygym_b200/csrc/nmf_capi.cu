@@ -14,7 +14,7 @@ using namespace nmf;
 
 // ------------------------------------------------------------------ kernels
 #ifndef NMF_MINBLOCKS
-#define NMF_MINBLOCKS 12   // <= 80 registers/thread: best measured trade-off between occupancy and spills (profiles/)
+#define NMF_MINBLOCKS 16   // <= 64 registers/thread: best measured trade-off between occupancy and spills (profiles/)
 #endif
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) {
   __shared__ __align__(16) float sm[SM_TOTAL];

@@ -64,6 +64,20 @@ __device__ __forceinline__ void qnormalize(float* q) {
   float s = rsqrtf(n2);
   q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s;
 }
+// sin/cos with a 2-term Cody-Waite reduction and cephes-style minimax polynomials (|err| ~ 1 ulp for |x| < ~1e3):
+// replaces sincosf, whose inlined slow path bloated the instruction footprint of an I-cache-bound kernel.
+__device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
+  const float kf = rintf(x * 0.63661977236758134f);
+  float r = fmaf(-kf, 1.5707962512969971f, x);
+  r = fmaf(-kf, 7.5497894158615964e-8f, r);
+  const int q = (int)kf;
+  const float r2 = r * r;
+  const float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f) * r2, r, r);
+  const float pc = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f) * r2, r2, fmaf(-0.5f, r2, 1.0f));
+  const float s0 = (q & 1) ? pc : ps, c0 = (q & 1) ? ps : pc;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
 __device__ __forceinline__ void cross3(const float* a, const float* b, float* r) {
   float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
@@ -326,11 +340,11 @@ constexpr int SM_ROOT = SM_U + NGROUP * U_STRIDE;   // per-group root publicatio
 constexpr int ROOT_STRIDE = 40;                     // [0..5] wrench, [6..15] crb / fc wrench, [16..36] A-hat
 constexpr int SM_BASE = SM_ROOT + NGROUP * ROOT_STRIDE;  // NLEG*21 Schur contributions, then NLEG*6 rhs contributions
 constexpr int SM_HBB = SM_BASE + 168;               // 21 hub block + 6 xb + 6 S_h
-constexpr int SM_HUB = SM_HBB + 48;                 // hub uniforms
+constexpr int SM_HUB = SM_HBB + 112;                // hub uniforms
 constexpr int SM_RED = SM_HUB + 64;                 // 32
 constexpr int SM_TOTAL = SM_RED + 32;
 constexpr int HU_CVEL = 0, HU_CACC = 6;
-constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27;
+constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27, HB_TOT = 33, HB_SR = 72;   // TOT: 37 root totals; SR: assembled Schur block (21) + rhs (6)
 
 // Lane-constant description of the two matrix columns (of 16) + the shared last one a lane holds.
 struct Cols {
@@ -410,11 +424,22 @@ __device__ __forceinline__ void chain_solve_down(const float* hk0, const float* 
     if (kk == 10) x10 -= part;
   }
 }
+// sum of entries [lo, lo+n) of the 8 chain-root records, computed cooperatively by the 16 hub lanes into SM_HBB + HB_TOT
+__device__ __forceinline__ void hub_root_totals(float* sm, int hl, int lo, int n) {
+  for (int i = hl; i < n; i += NHUBLANE) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + lo + i];
+    sm[SM_HBB + HB_TOT + i] = s;
+  }
+}
 // hub 6x6 block: S = Hbb - sum(chain contributions); solve S xb = rhs (dense L'DL, serial, one lane)
 __device__ __forceinline__ void hub_solve(float* sm, float* xb) {
   float S[21];
-  for (int i = 0; i < 21; i++) { float s = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) s -= sm[SM_BASE + l * 21 + i]; S[i] = s; }
-  for (int b = 0; b < 6; b++) { float s = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) s += sm[SM_BASE + NLEG * 21 + l * 6 + b]; xb[b] = s; }
+#pragma unroll
+  for (int i = 0; i < 21; i++) S[i] = sm[SM_HBB + HB_SR + i];
+#pragma unroll
+  for (int b = 0; b < 6; b++) xb[b] = sm[SM_HBB + HB_SR + 21 + b];
   float dinv[6];
 #pragma unroll
   for (int kk = 5; kk >= 0; kk--) {
@@ -459,6 +484,15 @@ __device__ __forceinline__ void arrowhead_solve(float* sm, const float* s_cdof, 
   chain_solve_up(hk0, hk1, t, x0, x1, x10);
   if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
   block_sync();
+  if (!is_leg) {   // Schur block and hub right-hand side assembled by the 16 hub lanes, then solved by lane 48
+    for (int i = hl; i < 27; i += NHUBLANE) {
+      float v;
+      if (i < 21) { v = sm[SM_HBB + HB_S + i]; for (int l = 0; l < NLEG; l++) v -= sm[SM_BASE + l * 21 + i]; }
+      else { const int b = i - 21; v = -sm[SM_GRAD + b]; for (int l = 0; l < NLEG; l++) v += sm[SM_BASE + NLEG * 21 + l * 6 + b]; }
+      sm[SM_HBB + HB_SR + i] = v;
+    }
+  }
+  __syncwarp(NMF_FULL);
   if (!is_leg && hl == 0) {
     float xb[6]; hub_solve(sm, xb);
     float Sh[6] = {0, 0, 0, 0, 0, 0};
@@ -554,7 +588,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int j = 0; j < 3; j++) {
         float ax[3] = {role[(RF_AXIS + 3 * j) * CTA + tid], role[(RF_AXIS + 3 * j + 1) * CTA + tid], role[(RF_AXIS + 3 * j + 2) * CTA + tid]};
         qrot(q, ax, laxis + 3 * j);
-        float ang = msk[j] * st[S_QPOS + 1 + dj[j]], sn, cs; sincosf(0.5f * ang, &sn, &cs);   // masked dof: identity rotation
+        float ang = msk[j] * st[S_QPOS + 1 + dj[j]], sn, cs; sincos_small(0.5f * ang, &sn, &cs);   // masked dof: identity rotation
         float ql[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, nq[4];
         qmul(q, ql, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
       }
@@ -764,12 +798,17 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
       }
     }
+    const bool any0 = __any_sync(NMF_FULL, con[0].active > 0.f), any1 = __any_sync(NMF_FULL, con[1].active > 0.f);
     block_sync();   // chain roots (wrench, crb) visible to the hub lanes
     float crbh[10];    // hub-dof lanes: composite inertia of the whole fly
+    if (!is_leg) hub_root_totals(sm, hl, 0, 16);
+    __syncwarp(NMF_FULL);
     if (hubdof) {
       float W[6];
-      for (int i = 0; i < 10; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + 6 + i]; crbh[i] = s; }
-      for (int i = 0; i < 6; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; W[i] = s; }
+#pragma unroll
+      for (int i = 0; i < 10; i++) crbh[i] = sm[SM_HBB + HB_TOT + 6 + i];
+#pragma unroll
+      for (int i = 0; i < 6; i++) W[i] = sm[SM_HBB + HB_TOT + i];
       fs_own[0] = dot6(cdo[0], W); sm[SM_FS + hl] = fs_own[0];
     }
     block_sync();   // roots consumed before the solver overwrites them
@@ -790,7 +829,8 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       float Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
 #pragma unroll
       for (int i = 0; i < 21; i++) A[i] = 0.f;
-      contact_forces<true>(con[0], p.mu, Wc, A, nullptr); contact_forces<true>(con[1], p.mu, Wc, A, nullptr);
+      if (any0) contact_forces<true>(con[0], p.mu, Wc, A, nullptr);    // warp-uniform skips: most lanes have no contact
+      if (any1) contact_forces<true>(con[1], p.mu, Wc, A, nullptr);
       // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
       float y[12];
       {
@@ -800,7 +840,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       }
       float gown[3] = {0.f, 0.f, 0.f};
       chain_suffix<12>(y, NMF_FULL, k);
-      chain_suffix<21>(A, NMF_FULL, k);
+      if (!euler) chain_suffix<21>(A, NMF_FULL, k);
       const float am = euler ? 0.f : 1.f;     // the Euler system uses the plain inertia (no contact augmentation)
 #pragma unroll
       for (int j = 0; j < 3; j++) {
@@ -819,13 +859,17 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       block_sync();
       {
         float P[21];
+        if (!is_leg) hub_root_totals(sm, hl, 0, 37);
+        __syncwarp(NMF_FULL);
         if (hubdof) {
           float yh[12];
-          for (int i = 0; i < 12; i++) { float s = 0.f; for (int g = 0; g < NGROUP; g++) s += sm[SM_ROOT + g * ROOT_STRIDE + i]; yh[i] = s; }
+#pragma unroll
+          for (int i = 0; i < 12; i++) yh[i] = sm[SM_HBB + HB_TOT + i];
           float fc = dot6(cdo[0], yh + 6), g = dot6(cdo[0], yh) - fs_own[0];
           gown[0] = g; sm[SM_GRAD + hl] = euler ? -(fs_own[0] + fc) : g;
           expand_inert(crbh, P);
-          for (int i = 0; i < 21; i++) { float s = 0.f; for (int gg = 0; gg < NGROUP; gg++) s += sm[SM_ROOT + gg * ROOT_STRIDE + 16 + i]; P[i] += s; }
+#pragma unroll
+          for (int i = 0; i < 21; i++) P[i] += sm[SM_HBB + HB_TOT + 16 + i];
           float u[6]; sym6_mul(P, cdo[0], u);
           for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
         }
@@ -878,7 +922,8 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         for (int j = 0; j < 3; j++) { red[0] += sown[j] * gown[j]; red[1] += (is_leg ? armv[j] : 0.f) * sown[j] * sown[j]; red[4] += sown[j] * sown[j]; }
         float dummy = 0.f;
 #pragma unroll
-        for (int s = 0; s < 2; s++) { project_point(con[s], Ss, p.mu, con[s].s); ls_eval(con[s], 0.f, red[2], red[3], dummy); }
+        if (any0) { project_point(con[0], Ss, p.mu, con[0].s); ls_eval(con[0], 0.f, red[2], red[3], dummy); }
+        if (any1) { project_point(con[1], Ss, p.mu, con[1].s); ls_eval(con[1], 0.f, red[2], red[3], dummy); }
       }
       cta_reduce<5>(red, s_red, parity, tid);
       // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
@@ -895,7 +940,8 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
           if (nx <= lo || nx >= hi) nx = (hi > 1.0e38f) ? 2.f * fmaxf(alpha, 1.f) : 0.5f * (lo + hi);
           alpha = nx;
           float e[3] = {0.f, 0.f, 0.f};
-          ls_eval(con[0], alpha, e[0], e[1], e[2]); ls_eval(con[1], alpha, e[0], e[1], e[2]);
+          if (any0) ls_eval(con[0], alpha, e[0], e[1], e[2]);
+          if (any1) ls_eval(con[1], alpha, e[0], e[1], e[2]);
           cta_reduce<3>(e, s_red, parity, tid);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
           nchanged_last = (int)e[2];
@@ -1009,7 +1055,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       float n = sqrtf(dot3(w, w));
       float q[4] = {st[S_QPOS + 3], st[S_QPOS + 4], st[S_QPOS + 5], st[S_QPOS + 6]};
       if (n > NMF_MINVAL) {
-        float sn, cs; sincosf(0.5f * p.dt * n, &sn, &cs);
+        float sn, cs; sincos_small(0.5f * p.dt * n, &sn, &cs);
         float dq[4] = {cs, w[0] / n * sn, w[1] / n * sn, w[2] / n * sn}, nq[4];
         qmul(q, dq, nq); q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
       }
