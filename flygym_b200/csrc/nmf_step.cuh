@@ -164,16 +164,14 @@ __device__ __forceinline__ void cta_reduce(float* v, float* s_red, int& parity, 
 
 // ------------------------------------------------------------------ contact slot (kept in registers)
 // Branch-free convention: an inactive slot has D = c0 = w = s = 0, so it contributes nothing anywhere.
-struct Contact {
-  float active;      // 1 if dist < margin
+struct Contact {     // 10 registers per slot; "active" <=> D > 0; signed distance = 2 (r[2] + com_z) (the point sits midway)
   float r[3];        // contact position relative to the subtree COM
   float cx, cy;      // first tangent (cx, cy, 0); second = (-cy, cx, 0); normal = +z
-  float D;           // 1/R of the four pyramid rows
+  float D;           // 1/R of the four pyramid rows (0 when the slot is inactive)
   float c0;          // K * imp * (dist - margin)
   float w[3];        // (n, mu t1, mu t2) . (a_p + B v_p)  for the current qacc
-  float s[3];        // (n, mu t1, mu t2) . a_p(search)
-  float dist;
 };
+__device__ __forceinline__ float con_on(const Contact& c) { return c.D > 0.f ? 1.f : 0.f; }
 
 __device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
   const float d0 = p.solimp[0], d1 = p.solimp[1], width = p.solimp[2], mid = p.solimp[3], power = p.solimp[4];
@@ -189,7 +187,6 @@ __device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
 // finishes a candidate contact: solver parameters and the B*velocity part of the rows
 __device__ __forceinline__ void finish_contact(const StepParams& p, Contact& c, float active, float dist, const float* pos, float hx, float hy,
                                                const float* com, const float* cvel, float invw) {
-  c.active = active; c.dist = dist;
   c.r[0] = pos[0] - com[0]; c.r[1] = pos[1] - com[1]; c.r[2] = pos[2] - com[2];
   c.cx = hx; c.cy = hy;
   float imp = impedance(p, fabsf(dist - p.margin));
@@ -201,13 +198,12 @@ __device__ __forceinline__ void finish_contact(const StepParams& p, Contact& c, 
   c.w[0] = active * p.cB * vp[2];
   c.w[1] = active * p.cB * p.mu * (c.cx * vp[0] + c.cy * vp[1]);
   c.w[2] = active * p.cB * p.mu * (-c.cy * vp[0] + c.cx * vp[1]);
-  c.s[0] = c.s[1] = c.s[2] = 0.f;
 }
 
 // geom-vs-ground-plane narrow phase for the geom carried by this lane's body
 // (plane z = 0, normal +z: reference world.py:251-260).  Fills two slots.
-__device__ __forceinline__ void collide(const StepParams& p, const float* role, int tid, const float* xpos, const float* R,
-                                        const float* com, const float* cvel, float invw, Contact* con) {
+__device__ __forceinline__ float collide(const StepParams& p, const float* role, int tid, const float* xpos, const float* R,
+                                         const float* com, const float* cvel, float invw, Contact* con) {
   const int gtype = __float_as_int(role[RF_GTYPE * CTA + tid]);
   float pos0[3] = {0.f, 0.f, 0.f}, pos1[3] = {0.f, 0.f, 0.f}, d0 = 1.f, d1 = 1.f, a0 = 0.f, a1 = 0.f, hx = 0.f, hy = 1.f;
   {  // capsule: two sphere-plane tests, frame aligned with the capsule axis (evaluated on every lane, masked by type)
@@ -251,6 +247,7 @@ __device__ __forceinline__ void collide(const StepParams& p, const float* role, 
   __syncwarp(NMF_FULL);
   finish_contact(p, con[0], a0, d0, pos0, hx, hy, com, cvel, invw);
   finish_contact(p, con[1], a1, d1, pos1, hx, hy, com, cvel, invw);
+  return a0 + a1;   // number of contacts of this geom (adhesion transmission divides by it)
 }
 
 // point "acceleration" of a contact for a body spatial vector S (ang, lin), projected on (n, mu t1, mu t2)
@@ -258,7 +255,8 @@ __device__ __forceinline__ void project_point(const Contact& c, const float* S, 
   float ax = S[3] + S[1] * c.r[2] - S[2] * c.r[1];
   float ay = S[4] + S[2] * c.r[0] - S[0] * c.r[2];
   float az = S[5] + S[0] * c.r[1] - S[1] * c.r[0];
-  out[0] = c.active * az; out[1] = c.active * mu * (c.cx * ax + c.cy * ay); out[2] = c.active * mu * (-c.cy * ax + c.cx * ay);
+  const float on = con_on(c);
+  out[0] = on * az; out[1] = on * mu * (c.cx * ax + c.cy * ay); out[2] = on * mu * (-c.cy * ax + c.cx * ay);
 }
 
 // pyramid rows of one contact: jar_r = base +- w1 / w2
@@ -309,8 +307,8 @@ __device__ __forceinline__ void contact_forces(const Contact& c, float mu, float
 }
 
 // line-search partial sums of one contact at step alpha: d0 += D x jv, d1 += D jv^2 over rows with x < 0
-__device__ __forceinline__ void ls_eval(const Contact& c, float alpha, float& d0, float& d1, float& nchanged) {
-  float jar[4], jv[4]; rows4(c.w, c.c0, jar); rows4(c.s, 0.f, jv);
+__device__ __forceinline__ void ls_eval(const Contact& c, const float* sv, float alpha, float& d0, float& d1, float& nchanged) {
+  float jar[4], jv[4]; rows4(c.w, c.c0, jar); rows4(sv, 0.f, jv);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     float x = jar[r] + alpha * jv[r];
@@ -542,19 +540,20 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   const int lbase = is_leg ? 6 + NLEGDOF * grp : 6;                           // first global dof of this chain
   const float mass = role[RF_MASS * CTA + tid];
   const float invw = role[RF_INVW * CTA + tid];
-  float armv[3], dampv[3], msk[3];          // per own-dof constants; msk[j] = 1 if the lane owns a j-th dof
+  float armv[3], msk[3];          // per own-dof constants; msk[j] = 1 if the lane owns a j-th dof
   int dj[3];                                // global dof index of own dof j (clamped to a valid one when masked)
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    armv[j] = role[(RF_ARM + j) * CTA + tid]; dampv[j] = role[(RF_DAMP + j) * CTA + tid];
+    armv[j] = role[(RF_ARM + j) * CTA + tid];
     msk[j] = j < ndof ? 1.f : 0.f; dj[j] = j < ndof ? dof0 + j : dof0;
   }
+#define CDO(j) (s_cdof + 8 * dj[j])   /* cdof of own dof j (a valid, masked address when the lane has fewer dofs) */
   Cols cl, cle;   // Newton (armature) and Euler (armature + dt damping) column descriptions
   {
     const int g0 = t < 6 ? t : lbase + t - 6;
     cl.cd0 = s_cdof + 8 * g0; cl.cd1 = s_cdof + 8 * (lbase + t + 2); cl.cd10 = s_cdof + 8 * (lbase + 10);
     cl.add0 = role[(RF_CARM + 0) * CTA + tid]; cl.add1 = role[(RF_CARM + 1) * CTA + tid]; cl.add10 = role[(RF_CARM + 2) * CTA + tid];
-    cle = cl;
+    cle = cl;   // (only the three diagonal additions differ; the compiler keeps one copy of the pointers)
     cle.add0 += p.dt * role[(RF_CDMP + 0) * CTA + tid]; cle.add1 += p.dt * role[(RF_CDMP + 1) * CTA + tid]; cle.add10 += p.dt * role[(RF_CDMP + 2) * CTA + tid];
   }
   int pb[3], pc[3];   // (b >= c) pairs number t, t+8, t+16 of the 21 lower-triangular hub entries
@@ -660,17 +659,15 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       cinert[6] = mass * off[0]; cinert[7] = mass * off[1]; cinert[8] = mass * off[2]; cinert[9] = mass;
     }
     // cdof of own dofs -> shared (predicated stores); hub lanes 0..5 own the free-joint dofs
-    float cdo[3][6];   // own cdof, kept in registers
+    // own cdof live in shared memory (s_cdof + 8*dj[j]); hub-dof lanes use s_cdof + 8*hl
     {
       float off[3] = {com[0] - xpos[0], com[1] - xpos[1], com[2] - xpos[2]};
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         float l[3]; cross3(laxis + 3 * j, off, l);
-        cdo[j][0] = laxis[3 * j]; cdo[j][1] = laxis[3 * j + 1]; cdo[j][2] = laxis[3 * j + 2]; cdo[j][3] = l[0]; cdo[j][4] = l[1]; cdo[j][5] = l[2];
         if (j < ndof) {
           float* cd = s_cdof + 8 * dj[j];
-#pragma unroll
-          for (int i = 0; i < 6; i++) cd[i] = cdo[j][i];
+          cd[0] = laxis[3 * j]; cd[1] = laxis[3 * j + 1]; cd[2] = laxis[3 * j + 2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
         }
       }
       if (hubdof) {
@@ -680,8 +677,6 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         const bool tr = hl < 3;
         cd[0] = tr ? 0.f : ax[0]; cd[1] = tr ? 0.f : ax[1]; cd[2] = tr ? 0.f : ax[2];
         cd[3] = tr ? (hl == 0 ? 1.f : 0.f) : l[0]; cd[4] = tr ? (hl == 1 ? 1.f : 0.f) : l[1]; cd[5] = tr ? (hl == 2 ? 1.f : 0.f) : l[2];
-#pragma unroll
-        for (int i = 0; i < 6; i++) cdo[0][i] = cd[i];
       }
       if (!is_leg && hl == 0) {
         // hub velocity / bias acceleration (free joint: translations first, rotations against the updated velocity)
@@ -718,7 +713,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int j = 0; j < 3; j++) {
         qv[j] = msk[j] * st[S_QVEL + dj[j]];
 #pragma unroll
-        for (int i = 0; i < 6; i++) loc[i] += cdo[j][i] * qv[j];
+        for (int i = 0; i < 6; i++) loc[i] += CDO(j)[i] * qv[j];
       }
       float pre[6] = {loc[0], loc[1], loc[2], loc[3], loc[4], loc[5]};
       chain_prefix<6>(pre, NMF_FULL, k);
@@ -727,9 +722,9 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int i = 0; i < 6; i++) cv[i] = pre[i] - loc[i] + s_hub[HU_CVEL + i];
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        float cdd[6]; cross_motion(cv, cdo[j], cdd);
+        float cdd[6]; cross_motion(cv, CDO(j), cdd);
 #pragma unroll
-        for (int i = 0; i < 6; i++) { ad[i] += cdd[i] * qv[j]; cv[i] += cdo[j][i] * qv[j]; }
+        for (int i = 0; i < 6; i++) { ad[i] += cdd[i] * qv[j]; cv[i] += CDO(j)[i] * qv[j]; }
       }
 #pragma unroll
       for (int i = 0; i < 6; i++) cvel[i] = cv[i];
@@ -747,16 +742,15 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int i = 0; i < 10; i++) crb[i] = cinert[i];
       chain_suffix<10>(crb, NMF_FULL, k);
       // collision for this body's geom
-      collide(p, role, tid, xpos, R, com, cvel, invw, con);
+      const float ncon_lane = collide(p, role, tid, xpos, R, com, cvel, invw, con);
       // adhesion (body transmission): force pulls the body onto the plane along each contact normal
       {
         const int acidx = __float_as_int(role[RF_ADH_CIDX * CTA + tid]);
         float c = fminf(role[RF_ADH_HI * CTA + tid], fmaxf(role[RF_ADH_LO * CTA + tid], st[S_CTRL + (acidx >= 0 ? acidx : 0)]));
         adhf = role[RF_ADH_GAIN * CTA + tid] * c;     // gain = 0 on lanes without an adhesion actuator
-        float n = con[0].active + con[1].active;
-        float fz = n > 0.f ? -adhf / n : 0.f;
+        float fz = ncon_lane > 0.f ? -adhf / ncon_lane : 0.f;
 #pragma unroll
-        for (int s = 0; s < 2; s++) { float f = con[s].active * fz; W[0] += con[s].r[1] * f; W[1] -= con[s].r[0] * f; W[5] += f; }
+        for (int s = 0; s < 2; s++) { float f = con_on(con[s]) * fz; W[0] += con[s].r[1] * f; W[1] -= con[s].r[0] * f; W[5] += f; }
       }
       chain_suffix<6>(W, NMF_FULL, k);
       // joint-space smooth force of own dofs: passive + actuator + C'W
@@ -764,13 +758,13 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int j = 0; j < 3; j++) {
         const int d = dj[j];
         float q = st[S_QPOS + 1 + d], qvj = st[S_QVEL + d];
-        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - dampv[j] * qvj;
+        float f = -role[(RF_STIFF + j) * CTA + tid] * (q - role[(RF_SREF + j) * CTA + tid]) - role[(RF_DAMP + j) * CTA + tid] * qvj;
         const int ci = __float_as_int(role[(RF_CIDX + j) * CTA + tid]);
         float kp = role[(RF_KP + j) * CTA + tid], kv = role[(RF_KV + j) * CTA + tid];     // 0 without an actuator
         float af = kp * st[S_CTRL + (ci >= 0 ? ci : 0)] - kp * q - kv * qvj;
         af = fminf(role[(RF_FHI + j) * CTA + tid], fmaxf(role[(RF_FLO + j) * CTA + tid], af));
         actf[j] = af;
-        f += af + dot6(cdo[j], W);
+        f += af + dot6(CDO(j), W);
         fs_own[j] = f;
         if (j < ndof) sm[SM_FS + d] = f;
       }
@@ -786,7 +780,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int j = 0; j < 3; j++) {
         float qa = msk[j] * st[S_WARM + dj[j]];
 #pragma unroll
-        for (int i = 0; i < 6; i++) sl[i] += cdo[j][i] * qa;
+        for (int i = 0; i < 6; i++) sl[i] += CDO(j)[i] * qa;
       }
       chain_prefix<6>(sl, NMF_FULL, k);
 #pragma unroll
@@ -798,7 +792,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
       }
     }
-    const bool any0 = __any_sync(NMF_FULL, con[0].active > 0.f), any1 = __any_sync(NMF_FULL, con[1].active > 0.f);
+    const bool any0 = __any_sync(NMF_FULL, con[0].D > 0.f), any1 = __any_sync(NMF_FULL, con[1].D > 0.f);
     block_sync();   // chain roots (wrench, crb) visible to the hub lanes
     float crbh[10];    // hub-dof lanes: composite inertia of the whole fly
     if (!is_leg) hub_root_totals(sm, hl, 0, 16);
@@ -809,7 +803,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int i = 0; i < 10; i++) crbh[i] = sm[SM_HBB + HB_TOT + 6 + i];
 #pragma unroll
       for (int i = 0; i < 6; i++) W[i] = sm[SM_HBB + HB_TOT + i];
-      fs_own[0] = dot6(cdo[0], W); sm[SM_FS + hl] = fs_own[0];
+      fs_own[0] = dot6(s_cdof + 8 * hl, W); sm[SM_FS + hl] = fs_own[0];
     }
     block_sync();   // roots consumed before the solver overwrites them
 
@@ -845,8 +839,8 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         const int d = dj[j];
-        float fc = dot6(cdo[j], y + 6);
-        float g = dot6(cdo[j], y) + armv[j] * qacc[d] - fs_own[j];
+        float fc = dot6(CDO(j), y + 6);
+        float g = dot6(CDO(j), y) + armv[j] * qacc[d] - fs_own[j];
         gown[j] = msk[j] * g;
         if (j < ndof) sm[SM_GRAD + d] = euler ? -(fs_own[j] + fc) : g;   // right-hand side is -(this slot)
       }
@@ -865,12 +859,12 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
           float yh[12];
 #pragma unroll
           for (int i = 0; i < 12; i++) yh[i] = sm[SM_HBB + HB_TOT + i];
-          float fc = dot6(cdo[0], yh + 6), g = dot6(cdo[0], yh) - fs_own[0];
+          float fc = dot6(s_cdof + 8 * hl, yh + 6), g = dot6(s_cdof + 8 * hl, yh) - fs_own[0];
           gown[0] = g; sm[SM_GRAD + hl] = euler ? -(fs_own[0] + fc) : g;
           expand_inert(crbh, P);
 #pragma unroll
           for (int i = 0; i < 21; i++) P[i] += sm[SM_HBB + HB_TOT + 16 + i];
-          float u[6]; sym6_mul(P, cdo[0], u);
+          float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
           for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
         }
         __syncwarp(NMF_FULL);
@@ -880,7 +874,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         for (int i = 0; i < 21; i++) P[i] += am * A[i];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          float u[6]; sym6_mul(P, cdo[j], u);
+          float u[6]; sym6_mul(P, CDO(j), u);
           if (j < ndof) {
             float* up = su + 8 * (ldof0 + j);
 #pragma unroll
@@ -909,21 +903,21 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
-          for (int i = 0; i < 6; i++) sl[i] += (is_leg ? cdo[j][i] : 0.f) * sown[j];
+          for (int i = 0; i < 6; i++) sl[i] += (is_leg ? CDO(j)[i] : 0.f) * sown[j];
         chain_prefix<6>(sl, NMF_FULL, k);
 #pragma unroll
         for (int i = 0; i < 6; i++) Ss[i] = sl[i] + sm[SM_HBB + HB_SH + i];
       }
       float red[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // s.g , s'Ms , d0 rows(0), d1 rows(0), |s|^2
+      float sv0[3] = {0.f, 0.f, 0.f}, sv1[3] = {0.f, 0.f, 0.f};   // row directions of the two contact slots along the search vector
       {
         float t6[6]; mul_inert(cinert, Ss, t6);
         red[1] += dot6(Ss, t6);
 #pragma unroll
         for (int j = 0; j < 3; j++) { red[0] += sown[j] * gown[j]; red[1] += (is_leg ? armv[j] : 0.f) * sown[j] * sown[j]; red[4] += sown[j] * sown[j]; }
         float dummy = 0.f;
-#pragma unroll
-        if (any0) { project_point(con[0], Ss, p.mu, con[0].s); ls_eval(con[0], 0.f, red[2], red[3], dummy); }
-        if (any1) { project_point(con[1], Ss, p.mu, con[1].s); ls_eval(con[1], 0.f, red[2], red[3], dummy); }
+        if (any0) { project_point(con[0], Ss, p.mu, sv0); ls_eval(con[0], sv0, 0.f, red[2], red[3], dummy); }
+        if (any1) { project_point(con[1], Ss, p.mu, sv1); ls_eval(con[1], sv1, 0.f, red[2], red[3], dummy); }
       }
       cta_reduce<5>(red, s_red, parity, tid);
       // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
@@ -940,8 +934,8 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
           if (nx <= lo || nx >= hi) nx = (hi > 1.0e38f) ? 2.f * fmaxf(alpha, 1.f) : 0.5f * (lo + hi);
           alpha = nx;
           float e[3] = {0.f, 0.f, 0.f};
-          if (any0) ls_eval(con[0], alpha, e[0], e[1], e[2]);
-          if (any1) ls_eval(con[1], alpha, e[0], e[1], e[2]);
+          if (any0) ls_eval(con[0], sv0, alpha, e[0], e[1], e[2]);
+          if (any1) ls_eval(con[1], sv1, alpha, e[0], e[1], e[2]);
           cta_reduce<3>(e, s_red, parity, tid);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
           nchanged_last = (int)e[2];
@@ -954,7 +948,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
 #pragma unroll
       for (int i = 0; i < 6; i++) Sa[i] += alpha * Ss[i];
 #pragma unroll
-      for (int s = 0; s < 2; s++) { con[s].w[0] += alpha * con[s].s[0]; con[s].w[1] += alpha * con[s].s[1]; con[s].w[2] += alpha * con[s].s[2]; }
+      for (int i = 0; i < 3; i++) { con[0].w[i] += alpha * sv0[i]; con[1].w[i] += alpha * sv1[i]; }
     }
     // SM_X now holds the implicit-damping (Euler) acceleration  (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
     block_sync();
@@ -970,13 +964,14 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         for (int s = 0; s < 2; s++) {
           float* c = dg + DBG_CON + (tid * 2 + s) * 6; float fn = 0.f, Wt[6] = {0, 0, 0, 0, 0, 0};
           contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
-          c[0] = con[s].active; c[1] = con[s].active * con[s].dist;
-          c[2] = con[s].active * (con[s].r[0] + com[0]); c[3] = con[s].active * (con[s].r[1] + com[1]);
-          c[4] = con[s].active * (con[s].r[2] + com[2]); c[5] = fn;
+          const float on = con_on(con[s]);
+          c[0] = on; c[1] = on * 2.f * (con[s].r[2] + com[2]);
+          c[2] = on * (con[s].r[0] + com[0]); c[3] = on * (con[s].r[1] + com[1]);
+          c[4] = on * (con[s].r[2] + com[2]); c[5] = fn;
         }
         for (int i = 0; i < 3; i++) dg[DBG_XPOS + tid * 3 + i] = xpos[i];
         for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[8 * (i / 6) + i % 6];
-        float nc[1] = {con[0].active + con[1].active};
+        float nc[1] = {con_on(con[0]) + con_on(con[1])};
         cta_reduce<1>(nc, s_red, parity, tid);
         if (tid == 0) dg[DBG_NCON] = nc[0];
       }
@@ -994,7 +989,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
           float Wt[6] = {0, 0, 0, 0, 0, 0}, fn = 0.f; contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
-          const float on = sens * con[s].active;
+          const float on = sens * con_on(con[s]);
           Fc[s][0] = on * Wt[3]; Fc[s][1] = on * Wt[4]; Fc[s][2] = on * Wt[5];
 #pragma unroll
           for (int i = 0; i < 3; i++) { acc[i] += Fc[s][i]; acc[3 + i] += on * fn * (con[s].r[i] + com[i]); plain[i] += on * (con[s].r[i] + com[i]); }
@@ -1012,7 +1007,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
         float T[3] = {0, 0, 0};
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-          const float on = sens * con[s].active;
+          const float on = sens * con_on(con[s]);
           float rr[3] = {on * (con[s].r[0] + com[0] - P3[0]), on * (con[s].r[1] + com[1] - P3[1]), on * (con[s].r[2] + com[2] - P3[2])}, tt[3];
           cross3(rr, Fc[s], tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
         }
