@@ -176,11 +176,11 @@ def bake(
             radius, half = G.fit_capsule(box)
             I_seg = ax @ np.diag(G.capsule_inertia(mass, radius, half)) @ ax.T
             seg_geom[s] = dict(type=GEOM_CAPSULE, pos=com, quat=G.mat_to_quat(ax), size=(radius, half),
-                               verts=np.zeros((0, 3)))
+                               verts=np.zeros((0, 3)), nbrs=[])
         else:
             I_seg = I_unit * (mass / V)
-            seg_geom[s] = dict(type=GEOM_HULL, pos=com, quat=G.mat_to_quat(ax), size=(0.0, 0.0),
-                               verts=G.convex_hull_vertices(tris.reshape(-1, 3)))
+            hv, hn = G.convex_hull_vertices(tris.reshape(-1, 3))
+            seg_geom[s] = dict(type=GEOM_HULL, pos=com, quat=G.mat_to_quat(ax), size=(0.0, 0.0), verts=hv, nbrs=hn)
         seg_mass[s], seg_com[s], seg_inertia[s] = mass, com, I_seg
 
     # ---- fuse static segments into their owner, then bound mass/inertia ----
@@ -264,6 +264,7 @@ def bake(
     # ---- contact geoms ------------------------------------------------------
     geom_body, geom_type, geom_pos, geom_quat, geom_size = [], [], [], [], []
     geom_vertadr, geom_vertnum, hull = [], [], []
+    nbr_adr, nbr = [0], []          # CSR adjacency of the hull vertices (indices local to the geom)
     nvert = 0
     for s in contact_segs:
         g = seg_geom[s]
@@ -277,6 +278,9 @@ def bake(
         geom_vertadr.append(nvert)
         geom_vertnum.append(len(v))
         hull.append(v)
+        for lst in g["nbrs"]:
+            nbr.extend(lst)
+            nbr_adr.append(len(nbr))
         nvert += len(v)
     hull_vert = np.concatenate(hull) if nvert else np.zeros((0, 3))
 
@@ -322,7 +326,7 @@ def bake(
         geom_body=np.array(geom_body, np.int32), geom_type=np.array(geom_type, np.int32),
         geom_pos=np.array(geom_pos), geom_quat=np.array(geom_quat), geom_size=np.array(geom_size),
         geom_vertadr=np.array(geom_vertadr, np.int32), geom_vertnum=np.array(geom_vertnum, np.int32),
-        hull_vert=hull_vert,
+        hull_vert=hull_vert, hull_nbr_adr=np.array(nbr_adr, np.int32), hull_nbr=np.array(nbr if nbr else [0], np.int32),
         site_body=site_body, site_pos=site_pos, seg_body=seg_body, seg_pos=seg_pos, seg_quat=seg_quat,
         leg_rootbody=leg_rootbody, key_qpos=key_qpos, key_ctrl=key_ctrl,
     )

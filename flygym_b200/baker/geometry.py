@@ -163,9 +163,16 @@ def capsule_inertia(mass: float, radius: float, half: float) -> np.ndarray:
     return np.array([ixx, ixx, izz])
 
 
-def convex_hull_vertices(points: np.ndarray) -> np.ndarray:
+def convex_hull_vertices(points: np.ndarray):
+    """Hull vertices (sorted by original index) and their adjacency lists (edges of the triangulated hull facets)."""
     from scipy.spatial import ConvexHull
 
     up = np.unique(points, axis=0)
     hull = ConvexHull(up)
-    return up[np.sort(hull.vertices)]
+    order = np.sort(hull.vertices)
+    remap = {int(v): i for i, v in enumerate(order)}
+    nbrs = [set() for _ in order]
+    for tri in hull.simplices:
+        a, b, c = (remap[int(t)] for t in tri)
+        nbrs[a].update((b, c)); nbrs[b].update((a, c)); nbrs[c].update((a, b))
+    return up[order], [sorted(n) for n in nbrs]

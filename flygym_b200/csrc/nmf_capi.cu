@@ -46,6 +46,7 @@ struct nmf_handle {
   HostModel hm;
   int n_flies = 0, device = 0;
   float *d_role = nullptr, *d_hull = nullptr, *d_seg = nullptr, *d_key = nullptr;
+  int *d_nbr_adr = nullptr, *d_nbr = nullptr;
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   nmf_buffers buf{};
   bool bound = false;
@@ -76,12 +77,16 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   if ((rc = upload(h, &h->d_hull, h->hm.hull))) return rc;
   if ((rc = upload(h, &h->d_seg, h->hm.seg_tab))) return rc;
   if ((rc = upload(h, &h->d_key, h->hm.key_state))) return rc;
+  CK(cudaMalloc(&h->d_nbr_adr, sizeof(int) * h->hm.hull_nbr_adr.size()));
+  CK(cudaMemcpy(h->d_nbr_adr, h->hm.hull_nbr_adr.data(), sizeof(int) * h->hm.hull_nbr_adr.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_nbr, sizeof(int) * h->hm.hull_nbr.size()));
+  CK(cudaMemcpy(h->d_nbr, h->hm.hull_nbr.data(), sizeof(int) * h->hm.hull_nbr.size(), cudaMemcpyHostToDevice));
   return NMF_OK;
 }
 
 extern "C" int nmf_destroy(nmf_handle* h) {
   if (!h) return NMF_OK;
-  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_act); cudaFree(h->d_qpos);
+  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos);
   delete h;
   return NMF_OK;
 }
@@ -125,7 +130,7 @@ extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table
   if (nsteps <= 0) return NMF_OK;
   if (table && table_T <= 0) { h->err = "nmf_step: action table needs table_T > 0"; return NMF_EINVAL; }
   StepParams p = h->hm.par;
-  p.state = h->buf.state; p.role = h->d_role; p.hull = h->d_hull; p.seg_tab = h->d_seg;
+  p.state = h->buf.state; p.role = h->d_role; p.hull = h->d_hull; p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
   p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
   p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps;

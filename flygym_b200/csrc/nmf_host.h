@@ -45,6 +45,7 @@ inline float i2f(int v) { float f; memcpy(&f, &v, 4); return f; }
 struct HostModel {
   std::vector<float> role;     // RF_COUNT * CTA
   std::vector<float> hull;     // 3 * nhullvert
+  std::vector<int32_t> hull_nbr_adr, hull_nbr;   // CSR adjacency of the hull vertices
   std::vector<float> seg_tab;  // nseg * 8
   std::vector<float> key_state;  // S_STRIDE, the neutral keyframe as a state record
   StepParams par{};            // pointer members left null
@@ -151,6 +152,13 @@ struct HostModel {
     }
     hull.assign((size_t)3 * (nhv > 0 ? nhv : 1), 0.f);
     for (int i = 0; i < 3 * nhv; i++) hull[i] = (float)hv[i];
+    {
+      int na = 0, nn = 0; const int32_t* adr = b.get<int32_t>("hull_nbr_adr", &na); const int32_t* nb = b.get<int32_t>("hull_nbr", &nn);
+      if (nhv > 0 && (!adr || !nb || na != nhv + 1)) { err = "blob has no hull adjacency (re-bake the model)"; return false; }
+      hull_nbr_adr.assign(adr ? adr : nullptr, adr ? adr + na : nullptr); hull_nbr.assign(nb ? nb : nullptr, nb ? nb + nn : nullptr);
+      if (hull_nbr_adr.empty()) hull_nbr_adr.push_back(0);
+      if (hull_nbr.empty()) hull_nbr.push_back(0);
+    }
     seg_tab.assign((size_t)nseg * 8, 0.f);
     for (int s = 0; s < nseg; s++) {
       seg_tab[8 * s] = i2f(lane_of_body(seg_body[s]));

@@ -87,7 +87,8 @@ struct StepParams {
   float* out_actf;           // optional [n_flies][nu]
   float* out_sensor;         // optional [n_flies][NLEG*16]
   float* dbg;                // optional [n_flies][DBG_STRIDE]
-  const int* seg_lane;       // [nseg] thread id whose body carries the segment
+  const int* hull_nbr_adr;   // CSR adjacency of the hull vertices: neighbours of vertex v are hull_nbr[hull_nbr_adr[v] .. hull_nbr_adr[v+1])
+  const int* hull_nbr;       //   (indices local to the geom)
   int n_flies, nsteps, table_T, table_t0;
   int nu_pos, nu_adh, nseg, nhubgeom;
   float dt, gx, gy, gz, inv_total_mass;

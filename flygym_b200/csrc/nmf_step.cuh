@@ -203,7 +203,7 @@ __device__ __forceinline__ void finish_contact(const StepParams& p, Contact& c, 
 // geom-vs-ground-plane narrow phase for the geom carried by this lane's body
 // (plane z = 0, normal +z: reference world.py:251-260).  Fills two slots.
 __device__ __forceinline__ float collide(const StepParams& p, const float* role, int tid, const float* xpos, const float* R,
-                                         const float* com, const float* cvel, float invw, Contact* con) {
+                                         const float* com, const float* cvel, float invw, Contact* con, int& hullv) {
   const int gtype = __float_as_int(role[RF_GTYPE * CTA + tid]);
   float pos0[3] = {0.f, 0.f, 0.f}, pos1[3] = {0.f, 0.f, 0.f}, d0 = 1.f, d1 = 1.f, a0 = 0.f, a1 = 0.f, hx = 0.f, hy = 1.f;
   {  // capsule: two sphere-plane tests, frame aligned with the capsule axis (evaluated on every lane, masked by type)
@@ -228,14 +228,27 @@ __device__ __forceinline__ float collide(const StepParams& p, const float* role,
       a0 = (e0 <= p.margin + rad) ? 1.f : 0.f; a1 = (e1 <= p.margin + rad) ? 1.f : 0.f;
     }
   }
-  if (gtype == 1) {  // convex hull: deepest vertex (lane-dependent trip count: the caller reconverges afterwards)
+  if (gtype == 1) {
+    // convex hull: deepest vertex = support point along -z.  Steepest-descent walk on the hull's vertex graph, warm-started
+    // from the previous step's support vertex (exact: on a convex polytope a vertex with no lower neighbour is the global
+    // minimum of a linear function).  Lane-dependent trip count: the warp reconverges below.
     const int adr = __float_as_int(role[RF_GVADR * CTA + tid]), num = __float_as_int(role[RF_GVNUM * CTA + tid]);
-    float best = 3.0e38f; int bi = 0;
-    for (int v = 0; v < num; v++) {
-      const float* hv = p.hull + 3 * (adr + v);
-      float z = R[6] * __ldg(hv) + R[7] * __ldg(hv + 1) + R[8] * __ldg(hv + 2);
-      if (z < best) { best = z; bi = v; }
+    int bi = hullv < num ? hullv : 0;
+    float best = 3.0e38f;
+    if (num > 0) { const float* hv = p.hull + 3 * (adr + bi); best = R[6] * __ldg(hv) + R[7] * __ldg(hv + 1) + R[8] * __ldg(hv + 2); }
+    for (int moved = num > 0; moved;) {
+      moved = 0;
+      const int n0 = __ldg(p.hull_nbr_adr + adr + bi), n1 = __ldg(p.hull_nbr_adr + adr + bi + 1);
+      int cand = bi;
+      for (int e = n0; e < n1; e++) {
+        const int v = __ldg(p.hull_nbr + e);
+        const float* hv = p.hull + 3 * (adr + v);
+        float z = R[6] * __ldg(hv) + R[7] * __ldg(hv + 1) + R[8] * __ldg(hv + 2);
+        if (z < best) { best = z; cand = v; moved = 1; }
+      }
+      bi = cand;
     }
+    hullv = bi;
     const float* hv = p.hull + 3 * (adr + bi);
     float h0 = __ldg(hv), h1 = __ldg(hv + 1), h2 = __ldg(hv + 2);
     d0 = best + xpos[2];
@@ -340,7 +353,8 @@ constexpr int SM_BASE = SM_ROOT + NGROUP * ROOT_STRIDE;  // NLEG*21 Schur contri
 constexpr int SM_HBB = SM_BASE + 168;               // 21 hub block + 6 xb + 6 S_h
 constexpr int SM_HUB = SM_HBB + 112;                // hub uniforms
 constexpr int SM_RED = SM_HUB + 64;                 // 32
-constexpr int SM_TOTAL = SM_RED + 32;
+constexpr int SM_MBAR = SM_RED + 32;                // 8-byte mbarrier for the TMA record load (16-byte slot)
+constexpr int SM_TOTAL = SM_MBAR + 4;
 constexpr int HU_CVEL = 0, HU_CACC = 6;
 constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27, HB_TOT = 33, HB_SR = 72;   // TOT: 37 root totals; SR: assembled Schur block (21) + rhs (6)
 
@@ -508,6 +522,49 @@ __device__ __forceinline__ void arrowhead_solve(float* sm, const float* s_cdof, 
   if (is_leg && t == 0) sx[10] = x10;
 }
 
+// ------------------------------------------------------------------ TMA (bulk async copy) staging of the state record
+// One elected thread moves the whole 1216-byte record HBM <-> shared memory with cp.async.bulk (SASS: UBLKCP); the block
+// waits on an mbarrier.  Under the SIMT emulator the same copies are plain loops.
+#ifndef NMF_SIMT_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_record(float* dst_smem, const float* src_gmem, unsigned long long* mbar, int tid) {
+  const unsigned bar = smem_u32(mbar), dst = smem_u32(dst_smem);
+  constexpr unsigned bytes = S_STRIDE * sizeof(float);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  block_sync();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* src_smem, int tid) {
+  block_sync();                                                      // all generic-proxy writes to the record are done
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // make them visible to the async (TMA) proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"((unsigned)(S_STRIDE * sizeof(float))) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until the copy has read it
+  }
+}
+#else
+__device__ __forceinline__ void tma_load_record(float* dst_smem, const float* src_gmem, unsigned long long*, int tid) {
+  for (int i = tid; i < S_STRIDE; i += CTA) dst_smem[i] = src_gmem[i];
+  block_sync();
+}
+__device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* src_smem, int tid) {
+  block_sync();
+  for (int i = tid; i < S_STRIDE; i += CTA) dst_gmem[i] = src_smem[i];
+}
+#endif
+
 // ------------------------------------------------------------------ the step
 __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   const int tid = threadIdx.x;
@@ -525,12 +582,9 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   float* rt = sm + SM_ROOT + grp * ROOT_STRIDE;
   int parity = 0;
 
-  // ---- load the state record (coalesced; 304 floats), clear the u staging (hub chains keep u = 0)
-  {
-    const float* g = p.state + (size_t)fly * S_STRIDE;
-    for (int i = tid; i < S_STRIDE; i += CTA) st[i] = g[i];
-    for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = 0.f;
-  }
+  // ---- load the state record (one TMA bulk copy of 1216 B), clear the u staging (hub chains keep u = 0)
+  for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = 0.f;
+  tma_load_record(st, p.state + (size_t)fly * S_STRIDE, reinterpret_cast<unsigned long long*>(sm + SM_MBAR), tid);
   block_sync();
 
   // per-lane constants that stay in registers for the whole launch
@@ -556,6 +610,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     cle = cl;   // (only the three diagonal additions differ; the compiler keeps one copy of the pointers)
     cle.add0 += p.dt * role[(RF_CDMP + 0) * CTA + tid]; cle.add1 += p.dt * role[(RF_CDMP + 1) * CTA + tid]; cle.add10 += p.dt * role[(RF_CDMP + 2) * CTA + tid];
   }
+  int hullv = 0;      // support vertex of this lane's hull geom, carried from step to step as the warm start of the hill climb
   int pb[3], pc[3];   // (b >= c) pairs number t, t+8, t+16 of the 21 lower-triangular hub entries
 #pragma unroll
   for (int s = 0; s < 3; s++) {
@@ -742,7 +797,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int i = 0; i < 10; i++) crb[i] = cinert[i];
       chain_suffix<10>(crb, NMF_FULL, k);
       // collision for this body's geom
-      const float ncon_lane = collide(p, role, tid, xpos, R, com, cvel, invw, con);
+      const float ncon_lane = collide(p, role, tid, xpos, R, com, cvel, invw, con, hullv);
       // adhesion (body transmission): force pulls the body onto the plane along each contact normal
       {
         const int acidx = __float_as_int(role[RF_ADH_CIDX * CTA + tid]);
@@ -1061,11 +1116,8 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     block_sync();
   }
 
-  // ---- write the record back
-  {
-    float* g = p.state + (size_t)fly * S_STRIDE;
-    for (int i = tid; i < S_STRIDE; i += CTA) g[i] = st[i];
-  }
+  // ---- write the record back (TMA bulk store)
+  tma_store_record(p.state + (size_t)fly * S_STRIDE, st, tid);
 }
 
 }  // namespace nmf

@@ -46,7 +46,7 @@ _I32 = [
     "dof_body", "dof_parent",
     "act_dof", "adh_body",
     "geom_body", "geom_type", "geom_vertadr", "geom_vertnum",
-    "site_body", "seg_body", "leg_rootbody",
+    "site_body", "seg_body", "leg_rootbody", "hull_nbr_adr", "hull_nbr",
 ]
 DIM_FIELDS = ["nbody", "nq", "nv", "nu_pos", "nu_adh", "ngeom", "nsite", "nseg", "nleg", "nhullvert"]
 OPT_FIELDS = ["timestep", "gx", "gy", "gz", "iterations", "tolerance", "ls_iterations",

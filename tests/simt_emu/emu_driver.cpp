@@ -19,7 +19,7 @@ extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_fli
   nmf::HostModel hm;
   if (!hm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", hm.err.c_str()); return -1; }
   nmf::StepParams p = hm.par;
-  p.state = state; p.role = hm.role.data(); p.hull = hm.hull.data(); p.seg_tab = hm.seg_tab.data();
+  p.state = state; p.role = hm.role.data(); p.hull = hm.hull.data(); p.seg_tab = hm.seg_tab.data(); p.hull_nbr_adr = hm.hull_nbr_adr.data(); p.hull_nbr = hm.hull_nbr.data();
   p.act_table = act_table; p.table_T = table_T; p.table_t0 = table_t0;
   p.out_xpos = out_xpos; p.out_xquat = out_xquat; p.out_actf = out_actf; p.out_sensor = out_sensor; p.dbg = dbg;
   p.n_flies = n_flies; p.nsteps = nsteps;
