@@ -341,8 +341,9 @@ __device__ __forceinline__ void ls_eval(const Contact& c, const float* sv, float
 // that warps do not diverge (divergence doubles the issue cost and slows every *_sync collective).
 constexpr int NGROUP = 8;
 constexpr int SM_STATE = 0;                         // S_STRIDE
-constexpr int SM_CDOF = SM_STATE + S_STRIDE;        // NV * 8
-constexpr int SM_FS = SM_CDOF + NV * 8;             // qfrc_smooth
+constexpr int CDS = 12;                             // floats per cdof slot: 48-byte stride keeps the 8 lanes of a chain on distinct banks for 16-byte loads
+constexpr int SM_CDOF = SM_STATE + S_STRIDE;        // NV * CDS
+constexpr int SM_FS = SM_CDOF + NV * CDS;           // qfrc_smooth
 constexpr int SM_GRAD = SM_FS + NV;                 // gradient / rhs
 constexpr int SM_X = SM_GRAD + NV;                  // search direction / solve result
 constexpr int SM_U = SM_X + NV;                     // u_i = P cdof_i of every chain DoF: NGROUP * 11 * 8 (reused as pose buffer)
@@ -510,7 +511,7 @@ __device__ __forceinline__ void arrowhead_solve(float* sm, const float* s_cdof, 
     float Sh[6] = {0, 0, 0, 0, 0, 0};
     for (int b = 0; b < 6; b++) {
       sm[SM_HBB + HB_XB + b] = xb[b]; sm[SM_X + b] = xb[b];
-      const float* cd = s_cdof + 8 * b; for (int i = 0; i < 6; i++) Sh[i] += cd[i] * xb[b];
+      const float* cd = s_cdof + CDS * b; for (int i = 0; i < 6; i++) Sh[i] += cd[i] * xb[b];
     }
     for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
   }
@@ -601,11 +602,11 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     armv[j] = role[(RF_ARM + j) * CTA + tid];
     msk[j] = j < ndof ? 1.f : 0.f; dj[j] = j < ndof ? dof0 + j : dof0;
   }
-#define CDO(j) (s_cdof + 8 * dj[j])   /* cdof of own dof j (a valid, masked address when the lane has fewer dofs) */
+#define CDO(j) (s_cdof + CDS * dj[j])   /* cdof of own dof j (a valid, masked address when the lane has fewer dofs) */
   Cols cl, cle;   // Newton (armature) and Euler (armature + dt damping) column descriptions
   {
     const int g0 = t < 6 ? t : lbase + t - 6;
-    cl.cd0 = s_cdof + 8 * g0; cl.cd1 = s_cdof + 8 * (lbase + t + 2); cl.cd10 = s_cdof + 8 * (lbase + 10);
+    cl.cd0 = s_cdof + CDS * g0; cl.cd1 = s_cdof + CDS * (lbase + t + 2); cl.cd10 = s_cdof + CDS * (lbase + 10);
     cl.add0 = role[(RF_CARM + 0) * CTA + tid]; cl.add1 = role[(RF_CARM + 1) * CTA + tid]; cl.add10 = role[(RF_CARM + 2) * CTA + tid];
     cle = cl;   // (only the three diagonal additions differ; the compiler keeps one copy of the pointers)
     cle.add0 += p.dt * role[(RF_CDMP + 0) * CTA + tid]; cle.add1 += p.dt * role[(RF_CDMP + 1) * CTA + tid]; cle.add10 += p.dt * role[(RF_CDMP + 2) * CTA + tid];
@@ -721,12 +722,12 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int j = 0; j < 3; j++) {
         float l[3]; cross3(laxis + 3 * j, off, l);
         if (j < ndof) {
-          float* cd = s_cdof + 8 * dj[j];
+          float* cd = s_cdof + CDS * dj[j];
           cd[0] = laxis[3 * j]; cd[1] = laxis[3 * j + 1]; cd[2] = laxis[3 * j + 2]; cd[3] = l[0]; cd[4] = l[1]; cd[5] = l[2];
         }
       }
       if (hubdof) {
-        float* cd = s_cdof + 8 * hl;
+        float* cd = s_cdof + CDS * hl;
         const int a = hl < 3 ? 0 : hl - 3;
         float ax[3] = {R[a], R[3 + a], R[6 + a]}, l[3]; cross3(ax, off, l);
         const bool tr = hl < 3;
@@ -858,7 +859,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
       for (int i = 0; i < 10; i++) crbh[i] = sm[SM_HBB + HB_TOT + 6 + i];
 #pragma unroll
       for (int i = 0; i < 6; i++) W[i] = sm[SM_HBB + HB_TOT + i];
-      fs_own[0] = dot6(s_cdof + 8 * hl, W); sm[SM_FS + hl] = fs_own[0];
+      fs_own[0] = dot6(s_cdof + CDS * hl, W); sm[SM_FS + hl] = fs_own[0];
     }
     block_sync();   // roots consumed before the solver overwrites them
 
@@ -914,13 +915,13 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
           float yh[12];
 #pragma unroll
           for (int i = 0; i < 12; i++) yh[i] = sm[SM_HBB + HB_TOT + i];
-          float fc = dot6(s_cdof + 8 * hl, yh + 6), g = dot6(s_cdof + 8 * hl, yh) - fs_own[0];
+          float fc = dot6(s_cdof + CDS * hl, yh + 6), g = dot6(s_cdof + CDS * hl, yh) - fs_own[0];
           gown[0] = g; sm[SM_GRAD + hl] = euler ? -(fs_own[0] + fc) : g;
           expand_inert(crbh, P);
 #pragma unroll
           for (int i = 0; i < 21; i++) P[i] += sm[SM_HBB + HB_TOT + 16 + i];
-          float u[6]; sym6_mul(P, s_cdof + 8 * hl, u);
-          for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + 8 * c, u);
+          float u[6]; sym6_mul(P, s_cdof + CDS * hl, u);
+          for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + CDS * c, u);
         }
         __syncwarp(NMF_FULL);
         // ---- system matrix  H = C'(crb + A-hat)C + diag : each DoF owner stages u = P cdof, columns are formed by the factoriser
@@ -1025,7 +1026,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
           c[4] = on * (con[s].r[2] + com[2]); c[5] = fn;
         }
         for (int i = 0; i < 3; i++) dg[DBG_XPOS + tid * 3 + i] = xpos[i];
-        for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[8 * (i / 6) + i % 6];
+        for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[CDS * (i / 6) + i % 6];
         float nc[1] = {con_on(con[0]) + con_on(con[1])};
         cta_reduce<1>(nc, s_red, parity, tid);
         if (tid == 0) dg[DBG_NCON] = nc[0];
