@@ -154,7 +154,12 @@ def run_ours(args, rank, world, local_rank):
     simplify = not args.mesh
     model = NMFModel.bench(simplify_geom=simplify)
     sim = B200Simulation(model, n_worlds=n, device=dev, outputs=False)
-    table_np = cpg_table(model, n, TABLE_T, fly_offset=rank * n, n_flies_total=world * n)
+    if args.actions == "replay":
+        from flygym_b200.actions import replay_table
+        table_np = replay_table(model, n, 1000, fly_offset=rank * n)      # sim_steps = 1000 as run_gpu_benchmark.py
+    else:
+        table_np = cpg_table(model, n, TABLE_T, fly_offset=rank * n, n_flies_total=world * n)
+    table_T = table_np.shape[1]
     table = torch.from_numpy(table_np).to(dev)
     sim.set_leg_adhesion_states("nmf", np.ones((n, 6), np.float32))     # as the reference benchmark (time_gpu_simulation.py:130)
     sim.warmup()                                                        # 500 steps at the neutral pose
@@ -162,7 +167,7 @@ def run_ours(args, rank, world, local_rank):
     t0 = 0
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for _ in range(max(3, args.warmup)):
-        sim.step(chunk, table, t0); t0 = (t0 + chunk) % TABLE_T
+        sim.step(chunk, table, t0); t0 = (t0 + chunk) % table_T
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -184,7 +189,7 @@ def run_ours(args, rank, world, local_rank):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); sim.step(c, table, t0); b.record()
-        ev.append((a, b, c)); t0 = (t0 + c) % TABLE_T; done += c
+        ev.append((a, b, c)); t0 = (t0 + c) % table_T; done += c
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -238,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(n, chunk, simplify),
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(n, chunk, simplify), actions=args.actions),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * model.dim("nu_pos") * 4),
                     "d2h_bytes_per_step": int(n * model.nq * 4), "steps": e2e_steps},
@@ -264,6 +269,7 @@ def main():
     ap.add_argument("--n-flies", type=int, default=N_FLIES_PER_GPU)
     ap.add_argument("--chunk", type=int, default=100, help="physics steps fused per kernel launch")
     ap.add_argument("--mesh", action="store_true", help="mesh-hull collision geoms (simplify_geom=False)")
+    ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -45,3 +45,36 @@ def cpg_table(model, n_flies: int, n_steps: int, *, freq_hz: float = 12.0, fly_o
     psi = 2 * np.pi * (np.arange(n_flies) + fly_offset) / total
     arg = 2 * np.pi * freq_hz * t[None, :, None] + phase[None, None, :] + psi[:, None, None]
     return (neutral[None, None, :] + amp[None, None, :] * np.sin(arg)).astype(dtype)
+
+
+def replay_angles(model, timestep: float | None = None) -> np.ndarray:
+    """The reference's only shipped action source: the recorded walking clip, Savitzky-Golay filtered (done offline,
+    ``assets/replay_clip_filtered.npz``; generator in ``tests/golden/make_golden.py``) and cubic-interpolated onto the
+    simulation time grid exactly as ``MotionSnippet.get_joint_angles`` does
+    (reference ``src/flygym_demo/spotlight_data/preprocessing.py:80-142``).  Returns ``(n_steps, n_position_actuators)``."""
+    from scipy.interpolate import interp1d
+    from .model import ASSETS_DIR
+    with np.load(ASSETS_DIR / "replay_clip_filtered.npz") as z:
+        filt, fps, names = z["angles"].astype(np.float64), int(z["fps"]), [str(s) for s in z["actuators"]]
+    if names != list(model.names["actuated_position"]):
+        raise ValueError("replay clip was baked for a different actuator order")
+    dt = model.timestep if timestep is None else timestep
+    n = filt.shape[0]
+    src = np.arange(n) / fps
+    out_t = np.arange(0, n / fps, dt)
+    f = interp1d(src, filt, kind="cubic", axis=0, bounds_error=False, fill_value=(filt[0], filt[-1]))
+    return f(out_t)
+
+
+def replay_table(model, n_flies: int, n_steps: int, *, fly_offset: int = 0, dtype=np.float32) -> np.ndarray:
+    """``ReplayTargetData.make_target_angles_all_worlds`` (reference ``time_gpu_simulation.py:73-86``): world k replays
+    partition ``k % n_partitions`` of the clip."""
+    ang = replay_angles(model)
+    n_part = ang.shape[0] // n_steps
+    if n_part < 1:
+        raise ValueError("clip shorter than the requested number of steps")
+    out = np.empty((n_flies, n_steps, ang.shape[1]), dtype=dtype)
+    for k in range(n_flies):
+        p = (k + fly_offset) % n_part
+        out[k] = ang[p * n_steps:(p + 1) * n_steps]
+    return out

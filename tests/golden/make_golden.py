@@ -38,4 +38,14 @@ img = np.random.default_rng(0).integers(0, 256, (1, 2, 512, 450, 3), dtype=np.ui
 g = dict(id_map_sha256=hashlib.sha256(idm.tobytes()).hexdigest(), pale_mask_sha256=hashlib.sha256(np.packbits(pale).tobytes()).hexdigest(),
          oracle_seed0_sha256=hashlib.sha256(retina_oracle(img, idm, pale).tobytes()).hexdigest())
 (HERE / "retina_golden.json").write_text(json.dumps(g, indent=1))
-print("golden written", len(segs), len(dofs), len(act), len(contact))
+
+# ---- replay clip: run the reference's own MotionSnippet resampler (scipy only) and keep sample rows
+demo = types.ModuleType("flygym_demo"); demo.__path__ = [str(REF.parent / "flygym_demo")]; sys.modules["flygym_demo"] = demo
+sd = types.ModuleType("flygym_demo.spotlight_data"); sd.__path__ = [str(REF.parent / "flygym_demo/spotlight_data")]; sys.modules["flygym_demo.spotlight_data"] = sd
+spec = importlib.util.spec_from_file_location("flygym_demo.spotlight_data.preprocessing", REF.parent / "flygym_demo/spotlight_data/preprocessing.py")
+pre = importlib.util.module_from_spec(spec); spec.loader.exec_module(pre)
+snip = pre.MotionSnippet(data_path=REF.parent / "flygym_demo/spotlight_data/assets/spotlight_behavior_clip.npz")
+ref_angles = snip.get_joint_angles(1e-4, act)
+rows = [0, 1, 777, 5000, 12345, 19999]
+np.savez_compressed(HERE / "replay_golden.npz", rows=np.array(rows), angles=ref_angles[rows], shape=np.array(ref_angles.shape))
+print("golden written", len(segs), len(dofs), len(act), len(contact), ref_angles.shape)

@@ -145,3 +145,68 @@ def test_api_shapes_and_time():
     sim.reset()
     assert sim.time == 0.0
     assert float(sim.qvel.abs().max()) == 0.0
+
+
+def test_control_changes_angles_and_input_types():
+    """Mirrors tests/warp/test_simulation.py:254-297 of the reference: numpy and device inputs are accepted,
+    and different controls give different joint angles after 50 steps."""
+    import torch
+    from flygym_b200 import B200Simulation, ActuatorType
+    n = 3
+    sim = B200Simulation(None, n_worlds=n)
+    sim.warmup(0.005)
+    a0 = sim.get_joint_angles("nmf").clone()
+    sim.set_actuator_inputs("nmf", ActuatorType.POSITION, np.zeros((n, 42), dtype=np.float32))          # numpy
+    sim.step(50)
+    a1 = sim.get_joint_angles("nmf").clone()
+    sim.set_actuator_inputs("nmf", ActuatorType.POSITION, torch.full((n, 42), 0.5, device="cuda"))        # device tensor
+    sim.step(50)
+    a2 = sim.get_joint_angles("nmf")
+    assert (a1 - a0).abs().max() > 1e-3 and (a2 - a1).abs().max() > 1e-3
+    assert isinstance(a2, torch.Tensor) and a2.dtype == torch.float32 and a2.shape == (n, 66)
+    f = sim.get_actuator_forces("nmf", ActuatorType.POSITION)
+    assert float(f.abs().max()) <= 30.0 + 1e-4            # forcerange (-30, 30), fly.py:305-306
+    adh = sim.get_actuator_forces("nmf", ActuatorType.ADHESION)
+    assert adh.shape == (n, 6) and float(adh.min()) >= 1.0 - 1e-6   # ctrlrange (1, 100) clamps 0 -> 1
+
+
+def test_masked_reset_and_site_positions():
+    import torch
+    from flygym_b200 import B200Simulation
+    n = 4
+    sim = B200Simulation(None, n_worlds=n)
+    sim.step(30)
+    before = sim.qpos.clone()
+    sim.reset(mask=[True, False, True, False])
+    key = torch.as_tensor(sim.model.arrays["key_qpos"], dtype=torch.float32, device="cuda")
+    assert torch.equal(sim.qpos[0], key) and torch.equal(sim.qpos[2], key)
+    assert torch.equal(sim.qpos[1], before[1]) and torch.equal(sim.qpos[3], before[3])
+    assert sim.time == 0.0        # world 0 was reset
+    sim.step(1)
+    sites = sim.get_site_positions("nmf")
+    bodies = sim.get_body_positions("nmf")
+    segs, names = sim.model.names["segments"], sim.model.names["sites"]
+    idx = [segs.index(s.split("-")[1]) for s in names]
+    assert torch.equal(sites, bodies[:, idx])       # sites sit at the child-segment origins (fly.py:371-405)
+
+
+def test_step_is_cuda_graph_capturable():
+    """The reference benchmark replays the step as a CUDA graph (time_gpu_simulation.py:137-150): the C ABI must not
+    allocate, synchronise or touch the default stream."""
+    import torch
+    from flygym_b200 import B200Simulation
+    sim = B200Simulation(None, n_worlds=8, outputs=False)
+    ref = B200Simulation(None, n_worlds=8, outputs=False)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        sim.step(1)
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            sim.step(5)
+        for _ in range(4):
+            g.replay()
+    torch.cuda.synchronize()
+    ref.step(1 + 5 + 4 * 5)
+    torch.cuda.synchronize()
+    assert torch.equal(sim.state, ref.state)
