@@ -59,6 +59,12 @@ class NmfBuffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("state", "seg_xpos", "seg_xquat", "act_force", "sensordata", "debug")]
 
 
+class NmfEyeParams(ctypes.Structure):
+    _fields_ = [("eye_seg", ctypes.c_int32 * 2), ("rel_pos", ctypes.c_float * 6), ("R_local", ctypes.c_float * 18),
+                ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("inv_f", ctypes.c_float), ("inv_check", ctypes.c_float),
+                ("ground_lo", ctypes.c_uint32), ("ground_hi", ctypes.c_uint32), ("sky_g", ctypes.c_uint32), ("sky_b", ctypes.c_uint32)]
+
+
 _LIB = None
 
 
@@ -96,6 +102,10 @@ def load() -> ctypes.CDLL:
     lib.nmf_retina_forward.argtypes = [vp, vp, ci, vp, vp]
     lib.nmf_retina_forward_host.argtypes = [vp, vp, ci, vp, vp]
     lib.nmf_odor_intensity.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, ci, ci, vp, vp]
+    lib.nmf_eye_render.argtypes = [vp, ctypes.POINTER(NmfEyeParams), vp, vp, ci, ci, vp, vp]
+    lib.nmf_eye_retina.argtypes = [vp, ctypes.POINTER(NmfEyeParams), vp, vp, ci, ci, vp, vp]
+    lib.nmf_eye_render.restype = ci
+    lib.nmf_eye_retina.restype = ci
     for fn in ("nmf_retina_create", "nmf_retina_destroy", "nmf_retina_forward", "nmf_retina_forward_host", "nmf_odor_intensity"):
         getattr(lib, fn).restype = ci
     _LIB = lib
@@ -107,5 +117,5 @@ DECLARED_SYMBOLS = [
     "nmf_create", "nmf_destroy", "nmf_model_info", "nmf_last_error", "nmf_bind", "nmf_reset", "nmf_step",
     "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_launch_count",
     "nmf_retina_create", "nmf_retina_destroy", "nmf_retina_last_error", "nmf_retina_launch_count", "nmf_retina_forward",
-    "nmf_retina_forward_host", "nmf_odor_intensity",
+    "nmf_retina_forward_host", "nmf_odor_intensity", "nmf_eye_render", "nmf_eye_retina",
 ]

@@ -180,3 +180,76 @@ class OdorSensor:
         if rc != 0:
             raise RuntimeError(f"nmf_odor_intensity failed (status {rc})")
         return out
+
+
+# ------------------------------------------------------------------------------------------------ eye cameras
+FOVY_DEG = 157.0                                   # flygym1_config.yaml:142
+EYE_CAMERAS = [("l_eye", (-0.03, 0.38, 0.0), (1.57, 0.00, -0.47)),      # flygym1_config.yaml:163-174 (parent, rel_pos, euler)
+               ("r_eye", (-0.03, -0.38, 0.0), (-1.57, 3.14, 0.47))]
+CHECKER_MM = 4.0                                   # world.py:233-250: 2000 mm plane, texrepeat 250, 2x2 builtin checker
+GROUND_U8, SKY_GB_U8 = (77, 102), (178, 229)       # rgb1 = 0.3, rgb2 = 0.4 (world.py:240-241); uniform light-blue sky
+
+
+def euler_xyz_to_mat(e) -> np.ndarray:
+    """Intrinsic x-y-z Euler angles -> rotation matrix (own convention, documented in DESIGN.md)."""
+    a, b, c = e
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return Rx @ Ry @ Rz
+
+
+def eye_params(segments: list[str], H: int = RAW_H, W: int = RAW_W) -> dict:
+    """Plain-number camera description shared by the CUDA kernels and the numpy oracle (all float32)."""
+    f = (H / 2.0) / np.tan(np.deg2rad(FOVY_DEG) / 2.0)
+    return dict(
+        eye_seg=np.array([segments.index(s) for s, _, _ in EYE_CAMERAS], dtype=np.int32),
+        rel_pos=np.array([p for _, p, _ in EYE_CAMERAS], dtype=np.float32),
+        R_local=np.array([euler_xyz_to_mat(e) for _, _, e in EYE_CAMERAS]).astype(np.float32),
+        cx=np.float32((W - 1) / 2.0), cy=np.float32((H - 1) / 2.0), inv_f=np.float32(1.0 / f),
+        inv_check=np.float32(1.0 / CHECKER_MM), ground=GROUND_U8, sky=SKY_GB_U8)
+
+
+class EyeCameras:
+    """Image formation for the two compound-eye cameras on top of a :class:`B200Simulation` (segment poses of the last
+    step): ``render()`` gives the raw buffers ``(n, 2, 512, 450, 3) uint8``; ``retina()`` is the fused
+    render + Retina path that never materialises them.  The two are bit-identical by construction
+    (``retina() == Retina()(render())``)."""
+
+    def __init__(self, sim, retina: Retina | None = None):
+        self.sim = sim
+        self.ret = retina if retina is not None else Retina(device=sim.device)
+        self.params = eye_params(sim.model.names["segments"], self.ret.H, self.ret.W)
+        p = self.params
+        c = _lib.NmfEyeParams()
+        c.eye_seg[:] = [int(v) for v in p["eye_seg"]]
+        c.rel_pos[:] = [float(v) for v in p["rel_pos"].ravel()]
+        c.R_local[:] = [float(v) for v in p["R_local"].ravel()]
+        c.cx, c.cy, c.inv_f, c.inv_check = float(p["cx"]), float(p["cy"]), float(p["inv_f"]), float(p["inv_check"])
+        c.ground_lo, c.ground_hi = p["ground"]
+        c.sky_g, c.sky_b = p["sky"]
+        self._c = c
+        self._lib = _lib.load()
+
+    def _args(self):
+        sim = self.sim
+        if sim.seg_xpos is None:
+            raise RuntimeError("the simulation was created with outputs=False")
+        return (self.ret._h, ctypes.byref(self._c), ctypes.c_void_p(sim.seg_xpos.data_ptr()), ctypes.c_void_p(sim.seg_xquat.data_ptr()),
+                sim.n_worlds, sim.info.nseg)
+
+    def render(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        sim = self.sim
+        if out is None:
+            out = torch.empty((sim.n_worlds, 2, self.ret.H, self.ret.W, 3), dtype=torch.uint8, device=sim.device)
+        rc = self._lib.nmf_eye_render(*self._args(), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream(sim.device).cuda_stream))
+        self.ret._check(rc)
+        return out
+
+    def retina(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        sim = self.sim
+        if out is None:
+            out = torch.empty((sim.n_worlds, 2, self.ret.n_ommatidia, 2), dtype=torch.float32, device=sim.device)
+        rc = self._lib.nmf_eye_retina(*self._args(), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream(sim.device).cuda_stream))
+        self.ret._check(rc)
+        return out

@@ -99,6 +99,23 @@ int nmf_retina_forward(nmf_retina* r, const uint8_t* images, int n_flies, float*
 /* same with HOST buffers (H2D, kernel, D2H, synchronises) */
 int nmf_retina_forward_host(nmf_retina* r, const uint8_t* images_host, int n_flies, float* out_host, void* cuda_stream);
 
+/* Eye-camera image formation (v1 camera block flygym1_config.yaml:141-174).  Plain-data
+ * parameters, passed by pointer from HOST memory. */
+typedef struct nmf_eye_params {
+  int32_t eye_seg[2];      /* segment index (in the model's segment order) of l_eye, r_eye */
+  float rel_pos[6];        /* camera position in the eye segment frame, per eye */
+  float R_local[18];       /* camera-to-segment rotation (row-major 3x3), per eye; the camera looks along its -z, +y is up */
+  float cx, cy, inv_f;     /* principal point (pixels) and 1/focal length (1/pixels): f = (H/2)/tan(fovy/2) */
+  float inv_check;         /* 1 / checker square size (1/mm) */
+  uint32_t ground_lo, ground_hi, sky_g, sky_b;   /* 8-bit colours: the two checker greys, sky green / blue */
+} nmf_eye_params;
+/* raw eye images DEVICE uint8 [n_flies][2][H][W][3] from the segment poses of the last step */
+int nmf_eye_render(nmf_retina* r, const nmf_eye_params* prm, const float* seg_xpos, const float* seg_xquat, int n_flies, int nseg,
+                   uint8_t* images, void* cuda_stream);
+/* fused image formation + Retina (the images are never materialised): out DEVICE float [n_flies][2][n_omm][2] */
+int nmf_eye_retina(nmf_retina* r, const nmf_eye_params* prm, const float* seg_xpos, const float* seg_xquat, int n_flies, int nseg,
+                   float* out, void* cuda_stream);
+
 /* odor intensity at the 4 sensor sites: out DEVICE float [n_flies][D][4];  all pointers DEVICE.
  * seg_xpos / seg_xquat are the buffers bound with nmf_bind (segment poses of the last step). */
 int nmf_odor_intensity(const float* seg_xpos, const float* seg_xquat, int n_flies, int nseg, const int32_t* sensor_seg /*[4]*/,

@@ -46,3 +46,42 @@ def odor_oracle(seg_xpos, seg_xquat, sensor_seg, sensor_rel, src_pos, src_peak):
             d2 = ((p[None, :] - src_pos) ** 2).sum(axis=1)
             out[i, :, s] = (src_peak / d2[:, None]).sum(axis=0)
     return out
+
+
+def eye_render_oracle(seg_xpos, seg_xquat, prm, H, W):
+    """float32 restatement of csrc/nmf_retina.cu::eye_pixel (same operation order, every op individually rounded):
+    raw eye images (n, 2, H, W, 3) uint8 from float32 segment poses."""
+    f32 = np.float32
+    n = seg_xpos.shape[0]
+    img = np.zeros((n, 2, H, W, 3), dtype=np.uint8)
+    rows, cols = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    dx = (cols - prm["cx"]) * prm["inv_f"]
+    dy = (prm["cy"] - rows) * prm["inv_f"]
+    for i in range(n):
+        for e in range(2):
+            seg = int(prm["eye_seg"][e])
+            xp = seg_xpos[i, seg].astype(f32)
+            w, x, y, z = (f32(v) for v in seg_xquat[i, seg])
+            two, one = f32(2), f32(1)
+            S = np.array([[one - two * (y * y + z * z), two * (x * y - w * z), two * (x * z + w * y)],
+                          [two * (x * y + w * z), one - two * (x * x + z * z), two * (y * z - w * x)],
+                          [two * (x * z - w * y), two * (y * z + w * x), one - two * (x * x + y * y)]], dtype=f32)
+            rel, Rl = prm["rel_pos"][e].astype(f32), prm["R_local"][e].astype(f32)
+            pos = np.array([xp[k] + ((S[k, 0] * rel[0] + S[k, 1] * rel[1]) + S[k, 2] * rel[2]) for k in range(3)], dtype=f32)
+            R = np.array([[(S[k, 0] * Rl[0, j] + S[k, 1] * Rl[1, j]) + S[k, 2] * Rl[2, j] for j in range(3)] for k in range(3)], dtype=f32)
+            wz = (R[2, 0] * dx + R[2, 1] * dy) - R[2, 2]
+            wx = (R[0, 0] * dx + R[0, 1] * dy) - R[0, 2]
+            wy = (R[1, 0] * dx + R[1, 1] * dy) - R[1, 2]
+            hit = (wz < 0) & (pos[2] > 0)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t = pos[2] / (-wz)
+                hx, hy = pos[0] + t * wx, pos[1] + t * wy
+                ix = np.floor(hx * prm["inv_check"]).astype(np.int64)
+                iy = np.floor(hy * prm["inv_check"]).astype(np.int64)
+            v = np.where(((ix + iy) & 1) == 1, prm["ground"][1], prm["ground"][0])
+            g = np.where(hit, v, prm["sky"][0]).astype(np.uint8)
+            b = np.where(hit, v, prm["sky"][1]).astype(np.uint8)
+            img[i, e, :, :, 0] = g
+            img[i, e, :, :, 1] = g
+            img[i, e, :, :, 2] = b
+    return img

@@ -65,3 +65,29 @@ def test_odor_sensor():
                       [segs.index(s) for s, _ in ODOR_SENSORS], [p for _, p in ODOR_SENSORS], src.astype(np.float64), peak.astype(np.float64))
     assert got.shape == (5, 2, 4)
     assert np.allclose(got, ref, rtol=1e-5, atol=0)
+
+
+def test_eye_cameras_bit_exact_and_fused_path():
+    """Eye-camera image formation: raw buffers bit-exact vs the float32 numpy restatement, and the fused
+    render+Retina kernel identical to Retina(render)."""
+    import torch
+    from flygym_b200 import B200Simulation
+    from flygym_b200.retina import EyeCameras
+    from oracle.retina_oracle import eye_render_oracle, retina_oracle
+    n = 3
+    sim = B200Simulation(None, n_worlds=n)
+    q = torch.tensor([1.0, 0.05, -0.1, 0.2]); q = q / q.norm()
+    sim.qpos[1, 3:7] = q.cuda()                       # tilt one fly so that the horizon is not axis-aligned
+    sim.qpos[2, 0:3] = torch.tensor([3.3, -1.7, 2.0]).cuda()
+    sim.step(2)
+    cams = EyeCameras(sim)
+    img = cams.render()
+    ref = eye_render_oracle(sim.seg_xpos.cpu().numpy(), sim.seg_xquat.cpu().numpy(), cams.params, cams.ret.H, cams.ret.W)
+    got = img.cpu().numpy()
+    assert got.shape == (n, 2, 512, 450, 3)
+    assert np.array_equal(got, ref), int((got != ref).sum())
+    assert len(np.unique(got[..., 1])) >= 3              # both checker greys and the sky are visible
+    fused = cams.retina()
+    two_stage = cams.ret(img)
+    assert torch.equal(fused, two_stage)
+    assert np.array_equal(fused.cpu().numpy(), retina_oracle(ref, cams.ret.id_map, cams.ret.pale))

@@ -5,7 +5,7 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from flygym_b200 import B200Simulation, NMFModel
-from flygym_b200.actions import cpg_table
+from flygym_b200.actions import cpg_table, replay_table
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, nargs="+", default=[4096])
@@ -13,12 +13,14 @@ ap.add_argument("--chunk", type=int, default=100)
 ap.add_argument("--steps", type=int, default=300)
 ap.add_argument("--mesh", action="store_true")
 ap.add_argument("--stats", action="store_true")
+ap.add_argument("--actions", default="cpg")
 args = ap.parse_args()
 model = NMFModel.bench(simplify_geom=not args.mesh)
 T = 2500
 for n in args.n:
     sim = B200Simulation(model, n_worlds=n, outputs=False, debug=args.stats)
-    table = torch.from_numpy(cpg_table(model, n, T)).cuda()
+    table = torch.from_numpy(cpg_table(model, n, T) if args.actions == 'cpg' else replay_table(model, n, 1000)).cuda()
+    T = table.shape[1]
     sim.set_leg_adhesion_states("nmf", np.ones((n, 6), np.float32))
     sim.warmup()
     t0 = 0
