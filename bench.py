@@ -3,12 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one physics timestep of every fly of the batch.  Workload at N=1 =
-BASELINE.json configs[1]: 4096 parallel flies, flat terrain, sinusoidal CPG tripod
-actions (flygym_b200/actions.py), adhesion on, no vision.  Multi-GPU (torchrun, one
-rank per GPU): every rank steps its own 4096 flies, no data-path collective (flies
-are independent); NCCL is used for the barrier, the max-over-ranks time and one
-gather of a per-fly metrics slab -> "scaling": "weak".
+A "step" is one physics timestep of every fly of the batch.  Default workload
+(`--workload flat`) = BASELINE.json configs[1]: 4096 parallel flies, flat terrain,
+sinusoidal CPG tripod actions (flygym_b200/actions.py), adhesion on, no vision.
+The other BASELINE configs are selectable and print the same JSON line:
+  --workload terrain    configs[2]: 4096 flies on blocks / gapped terrain, stance-phase adhesion
+  --workload vision     configs[3]: 1024 flies, two eye-camera renders -> Retina every step
+  --workload olfaction  configs[4]: 32768 flies per GPU, flat + odor sensors every step
+Multi-GPU (torchrun, one rank per GPU): every rank steps its own flies, no data-path
+collective (flies are independent); NCCL is used for the barrier, the max-over-ranks
+time and the gathers of a per-fly metrics slab -> "scaling": "weak".
 
 `--impl reference` times the CPU restatement of the reference's mj_step path
 (oracle/, kind "port": real MuJoCo cannot be installed here) on all host cores.
@@ -36,13 +40,31 @@ UNIT = "env-steps/s"
 TABLE_T = 2500                 # 3 exact CPG periods at 12 Hz, dt = 1e-4
 
 
-def workload_config(n_flies, chunk, simplify):
-    return {
-        "workload": f"{n_flies} NeuroMechFly per GPU, flat terrain, CPG tripod gait (12 Hz sinusoids), adhesion on, "
-                    f"{'capsule' if simplify else 'mesh-hull'} collision geoms, no vision",
+ALG_BYTES_OBS = 4940           # the same + the full observation set written every step
+RETINA_ALG_BYTES = 2 * 512 * 450 * 3 + 2 * 721 * 2 * 4   # 1 393 936 B per fly-frame
+ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
+ODOR_PEAKS = [[1.0, 0.0], [0.0, 1.0]]
+
+
+def workload_config(args, n_flies, chunk):
+    geoms = "mesh-hull" if (args.mesh and args.workload != "terrain") else "capsule"
+    what = {
+        "flat": "flat terrain, CPG tripod gait (12 Hz sinusoids), adhesion on, no vision",
+        "terrain": f"{args.terrain} terrain (box columns), CPG tripod gait, adhesion 100 in stance / 1 in swing, no vision",
+        "vision": "flat terrain, CPG tripod gait, adhesion on, two 512x450 eye-camera renders -> 721-ommatidia Retina after EVERY step",
+        "olfaction": "flat terrain, CPG tripod gait, adhesion on, 4 odor sensors x 2 sources x 2 odor dims after every step",
+    }[args.workload]
+    cfg = {
+        "workload": f"{n_flies} NeuroMechFly per GPU, {what}, {geoms} collision geoms",
+        "baseline_config": {"flat": 1, "terrain": 2, "vision": 3, "olfaction": 4}[args.workload],
         "n_flies_per_gpu": n_flies, "nv": 72, "nu": 48, "timestep": 1e-4,
-        "steps_per_launch": chunk, "l2": "flushed (256 MiB write) before every timed launch; action table 1.7 GB > L2",
+        "l2": "flushed (256 MiB write) before every timed launch group; action table > L2",
     }
+    if args.workload in ("flat", "terrain"):
+        cfg["steps_per_launch"] = chunk
+    else:
+        cfg["steps_per_timed_group"] = chunk; cfg["launches_per_step"] = 2
+    return cfg
 
 
 def measured_peak_hbm():
@@ -92,7 +114,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- CPU arm
-def cpu_arm(model, table64, steps_per_thread, threads):
+def cpu_arm(model, table64, steps_per_thread, threads, adhesion=None):
     """Oracle (CPU restatement of mj_step) on `threads` host threads, one fly each, `steps_per_thread` steps
     after a 500-step warm-up (mirrors Simulation.warmup, simulation.py:298-309).  Returns env-steps/s."""
     from oracle.oracle import Oracle
@@ -101,7 +123,11 @@ def cpu_arm(model, table64, steps_per_thread, threads):
         o.ctrl[model.dim("nu_pos"):] = 1.0
         o.step(500)
     def run(k):
-        oracles[k].step_table(table64[k % table64.shape[0], :steps_per_thread])
+        if adhesion is None:
+            oracles[k].step_table(table64[k % table64.shape[0], :steps_per_thread])
+        else:   # per-step adhesion inputs ride in the table's trailing columns
+            oracles[k].step_table_full(np.concatenate([table64[k % table64.shape[0], :steps_per_thread],
+                                                       adhesion[k % adhesion.shape[0], :steps_per_thread]], axis=1))
     ths = [threading.Thread(target=run, args=(k,)) for k in range(threads)]
     t0 = time.perf_counter()
     for t in ths: t.start()
@@ -110,15 +136,37 @@ def cpu_arm(model, table64, steps_per_thread, threads):
     return threads * steps_per_thread / dt, dt
 
 
+def cpu_baseline_leg(model, n_total, target_s=12.0):
+    """cpu_baseline: the oracle on every host core, sized to ~target_s seconds of CPU work from a short pilot run."""
+    from flygym_b200.actions import cpg_table
+    cores = os.cpu_count() or 1
+    pilot = 200
+    tb = cpg_table(model, cores, pilot, n_flies_total=n_total).astype(np.float64)
+    v0, _ = cpu_arm(model, tb, pilot, cores)
+    cs = int(min(50000, max(500, target_s * v0 / cores)))
+    tb = cpg_table(model, cores, cs, n_flies_total=n_total).astype(np.float64)
+    v, dt = cpu_arm(model, tb, cs, cores)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} threads x 1 fly x {cs} CPG steps after a 500-step warm-up (oracle/nmf_oracle.c, fp64 restatement of "
+                      f"mj_step), {dt:.1f} s"}
+
+
+def bench_model(args):
+    from flygym_b200.model import NMFModel
+    if args.workload == "terrain":
+        return NMFModel.bench(simplify_geom=True, terrain=args.terrain)
+    return NMFModel.bench(simplify_geom=not args.mesh)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from flygym_b200.actions import cpg_table
-    from flygym_b200.model import NMFModel
-    model = NMFModel.bench(simplify_geom=not args.mesh)
+    model = bench_model(args)
     cores = os.cpu_count() or 1
     sample_steps = 200                      # per thread per "step" of this arm: bounded sample of the workload
-    table = cpg_table(model, cores, sample_steps, n_flies_total=N_FLIES_PER_GPU).astype(np.float64)
+    n = args.n_flies
+    table = cpg_table(model, cores, sample_steps, n_flies_total=n).astype(np.float64)
     for _ in range(args.warmup):
         cpu_arm(model, table, 50, cores)
     vals, tot = [], 0.0
@@ -131,43 +179,94 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(N_FLIES_PER_GPU, 1, not args.mesh),
+        "config": workload_config(args, n, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU fp64 restatement of the reference's mujoco.mj_step path (oracle/nmf_oracle.c); real MuJoCo 3.6.0 is not installable here",
+        "note": "CPU fp64 restatement of the reference's mujoco.mj_step path (oracle/nmf_oracle.c); real MuJoCo 3.6.0 is not installable "
+                "here.  Physics only: the CPU arm has no vision / olfaction leg",
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------- GPU arm
+def device_cpg_table(torch, model, n, T, dev, fly_offset, n_total, adhesion_stance=False):
+    """cpg_table (flygym_b200/actions.py) evaluated on the device in fp64, in slabs (the 32768-fly table is 13.8 GB).
+    With adhesion_stance the table gets 6 extra columns: adhesion ctrl 100 during the stance half-cycle of each leg
+    (sin < 0 of the leg's coxa-pitch phase), 1 during swing."""
+    from flygym_b200.actions import cpg_parameters, TRIPOD_PHASE
+    neutral, amp, phase = cpg_parameters(model)
+    ncol = len(neutral) + (6 if adhesion_stance else 0)
+    out = torch.empty((n, T, ncol), dtype=torch.float32, device=dev)
+    tt = torch.arange(T, dtype=torch.float64, device=dev) * model.timestep
+    ne, am, ph = (torch.as_tensor(a, dtype=torch.float64, device=dev) for a in (neutral, amp, phase))
+    legph = torch.as_tensor([TRIPOD_PHASE[l] for l in model.names["legs"]], dtype=torch.float64, device=dev)
+    slab = max(1, (1 << 26) // (T * ncol))
+    for lo in range(0, n, slab):
+        hi = min(n, lo + slab)
+        psi = 2 * np.pi * (torch.arange(lo, hi, dtype=torch.float64, device=dev) + fly_offset) / n_total
+        base = 2 * np.pi * 12.0 * tt[None, :, None] + psi[:, None, None]
+        out[lo:hi, :, :len(neutral)] = (ne + am * torch.sin(base + ph)).float()
+        if adhesion_stance:
+            out[lo:hi, :, len(neutral):] = torch.where(torch.sin(base + legph) < 0, 100.0, 1.0).float()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from flygym_b200 import B200Simulation, NMFModel
-    from flygym_b200.actions import cpg_table
+    from flygym_b200 import B200Simulation
+    from flygym_b200.anatomy import ActuatorType
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
     n = args.n_flies
-    simplify = not args.mesh
-    model = NMFModel.bench(simplify_geom=simplify)
-    sim = B200Simulation(model, n_worlds=n, device=dev, outputs=False)
+    model = bench_model(args)
+    nu_pos = model.dim("nu_pos")
+    per_step = wl in ("vision", "olfaction")          # sensors are evaluated after every physics step
+    sim = B200Simulation(model, n_worlds=n, device=dev, outputs=per_step)
     if args.actions == "replay":
         from flygym_b200.actions import replay_table
-        table_np = replay_table(model, n, 1000, fly_offset=rank * n)      # sim_steps = 1000 as run_gpu_benchmark.py
+        table = torch.from_numpy(replay_table(model, n, 1000, fly_offset=rank * n)).to(dev)   # sim_steps = 1000 as run_gpu_benchmark.py
     else:
-        table_np = cpg_table(model, n, TABLE_T, fly_offset=rank * n, n_flies_total=world * n)
-    table_T = table_np.shape[1]
-    table = torch.from_numpy(table_np).to(dev)
+        table = device_cpg_table(torch, model, n, TABLE_T, dev, rank * n, world * n, adhesion_stance=(wl == "terrain"))
+    table_T = table.shape[1]
     sim.set_leg_adhesion_states("nmf", np.ones((n, 6), np.float32))     # as the reference benchmark (time_gpu_simulation.py:130)
     sim.warmup()                                                        # 500 steps at the neutral pose
     chunk = max(1, min(args.chunk, args.steps))
-    t0 = 0
+
+    # ---- the sensors of the workload
+    eyes = odor = sens_out = None
+    if wl == "vision":
+        from flygym_b200.retina import EyeCameras
+        eyes = EyeCameras(sim)
+        sens_out = torch.empty((n, 2, eyes.ret.n_ommatidia, 2), dtype=torch.float32, device=dev)
+    elif wl == "olfaction":
+        from flygym_b200.retina import OdorSensor
+        odor = OdorSensor(sim, ODOR_SOURCES, ODOR_PEAKS)
+
+    state = {"t0": 0, "launches": 0}
+
+    def advance(c):
+        """c physics steps (+ the workload's sensors after every step); returns nothing, counts our kernel launches"""
+        if not per_step:
+            sim.step(c, table, state["t0"]); state["launches"] += 1
+            state["t0"] = (state["t0"] + c) % table_T
+            return
+        for _ in range(c):
+            sim.step(1, table, state["t0"]); state["launches"] += 1
+            state["t0"] = (state["t0"] + 1) % table_T
+            if eyes is not None:
+                eyes.retina(sens_out)
+            else:
+                state["odor"] = odor()
+            state["launches"] += 1
+
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for _ in range(max(3, args.warmup)):
-        sim.step(chunk, table, t0); t0 = (t0 + chunk) % table_T
+        advance(chunk)
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -175,8 +274,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream around every launch
-    launches0 = sim.launch_count
+    def max_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream around every launch group
+    state["launches"] = 0
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -184,39 +289,87 @@ def run_ours(args, rank, world, local_rank):
     wall0 = time.perf_counter()
     ev = []
     done = 0
+    gathered_slabs = 0
     while done < args.steps:
         c = min(chunk, args.steps - done)
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); sim.step(c, table, t0); b.record()
-        ev.append((a, b, c)); t0 = (t0 + c) % table_T; done += c
+        a.record(); advance(c); b.record()
+        ev.append((a, b, c)); done += c
+        if wl == "olfaction" and world > 1 and done % 100 == 0:      # config 5: metrics slab over NCCL every 100 steps
+            slab = torch.cat([sim.qpos[:, :3], sim.qvel[:, :1], state["odor"].reshape(n, -1)[:, :4]], dim=1).contiguous()
+            outl = [torch.empty_like(slab) for _ in range(world)]
+            dist.all_gather(outl, slab); gathered_slabs += 1
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
     kernel_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
-    n_launch = sim.launch_count - launches0
-    t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    n_launch = state["launches"]
+    ms_total = max_ranks(kernel_ms)
     value = world * n * args.steps / (ms_total * 1e-3)
 
-    # ---- end-to-end through the public API with HOST buffers, every step: H2D actions, step, D2H qpos
+    # ---- dominant-kernel time for the roofline (per launch, CUDA events around that kernel alone)
+    roof = {}
+    if wl == "vision":
+        imgs = [eyes.render() for _ in range(2)]       # two 1.4 GB buffer sets alternated: no launch finds its input in L2
+        for i in range(3):
+            eyes.ret(imgs[i % 2], sens_out)
+        tms = []
+        for i in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eyes.ret(imgs[i % 2], sens_out); b.record(); tms.append((a, b))
+        fms = []
+        for i in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eyes.retina(sens_out); b.record(); fms.append((a, b))
+        torch.cuda.synchronize(dev)
+        ret_ms = float(np.mean([a.elapsed_time(b) for a, b in tms])); fused_ms = float(np.mean([a.elapsed_time(b) for a, b in fms]))
+        alg = n * RETINA_ALG_BYTES
+        roof = {"kernel": "nmf_retina_kernel (eye buffers in HBM -> ommatidia)", "ms": ret_ms, "alg_bytes": alg,
+                "fused_eye_retina_ms": fused_ms,
+                "note": f"Retina over materialised eye buffers is HBM-bound ({RETINA_ALG_BYTES} B per fly-frame, SURVEY.md 8d); the timed "
+                        "region uses the fused render+Retina kernel, which never materialises them (bit-identical output)"}
+        del imgs
+    else:
+        per_launch_steps = 1 if per_step else chunk
+        if per_step:
+            tms = []
+            for i in range(20):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); sim.step(1, table, state["t0"]); b.record(); tms.append((a, b))
+            torch.cuda.synchronize(dev)
+            step_ms = float(np.mean([a.elapsed_time(b) for a, b in tms]))
+        else:
+            step_ms = kernel_ms / max(1, len(ev))
+        per_fly = ALG_BYTES_OBS if per_step else ALG_BYTES_CORE
+        roof = {"kernel": "nmf_step_kernel", "ms": step_ms, "alg_bytes": per_fly * n * per_launch_steps,
+                "note": "the fused step is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); algorithmic bytes "
+                        f"= {per_fly} B per fly-step"}
+
+    # ---- end-to-end through the public API with HOST buffers, every step: H2D actions, step (+ sensors), D2H result
     e2e_steps = min(args.steps, 200)
-    act_host = torch.from_numpy(np.ascontiguousarray(table_np[:, :e2e_steps].transpose(1, 0, 2))).pin_memory()
-    qpos_host = torch.empty((n, model.nq), dtype=torch.float32).pin_memory()
+    act_host = table[:, :e2e_steps, :nu_pos].permute(1, 0, 2).contiguous().cpu().pin_memory()
+    if not per_step:
+        res_host = torch.empty((n, model.nq), dtype=torch.float32).pin_memory()
+        def e2e_step(s):
+            sim.step_host(act_host[s].numpy(), 1, res_host.numpy())
+    else:
+        res_dev = sens_out if eyes is not None else state["odor"]
+        res_host = torch.empty(res_dev.shape, dtype=torch.float32).pin_memory()
+        def e2e_step(s):
+            sim.set_actuator_inputs("nmf", ActuatorType.POSITION, act_host[s])     # H2D inside
+            sim.step()
+            r = eyes.retina(sens_out) if eyes is not None else odor()
+            res_host.copy_(r, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
     for s in range(3):
-        sim.step_host(act_host[s].numpy(), 1, qpos_host.numpy())
+        e2e_step(s)
     barrier()
     w0 = time.perf_counter()
     for s in range(e2e_steps):
-        sim.step_host(act_host[s].numpy(), 1, qpos_host.numpy())
+        e2e_step(s)
     barrier()
-    e2e_s = time.perf_counter() - w0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t.item())
+    e2e_value = world * n * e2e_steps / max_ranks(time.perf_counter() - w0)
 
     # ---- metrics slab gathered over NCCL (the only collective of the path)
     slab = torch.stack([sim.qpos[:, 0], sim.qpos[:, 1], sim.qpos[:, 2], sim.qvel[:, 0]], dim=1).contiguous()
@@ -229,49 +382,56 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
-        per_launch_steps = chunk
-        avg_launch_ms = kernel_ms / max(1, len(ev))
-        achieved = ALG_BYTES_CORE * n * per_launch_steps / (avg_launch_ms * 1e-3) / 1e9
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            cs = 10000
-            tb = cpg_table(model, cores, cs, n_flies_total=n).astype(np.float64)
-            v, dt = cpu_arm(model, tb, cs, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} threads x 1 fly x {cs} CPG steps (oracle/nmf_oracle.c, fp64), {dt:.1f} s"}
+        achieved = roof["alg_bytes"] / (roof["ms"] * 1e-3) / 1e9
+        cpu = cpu_baseline_leg(model, n) if (world == 1 and not args.no_cpu) else None
+        cfg = dict(workload_config(args, n, chunk), actions=args.actions)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(n, chunk, simplify), actions=args.actions),
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * model.dim("nu_pos") * 4),
-                    "d2h_bytes_per_step": int(n * model.nq * 4), "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * nu_pos * 4),
+                    "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps},
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind,
-                         "note": "the fused step is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); algorithmic bytes "
-                                 f"= {ALG_BYTES_CORE} B per fly-step"},
+                         "traffic": None, "peak_kind": peak_kind, "kernel": roof["kernel"], "kernel_ms_per_launch": roof["ms"],
+                         "note": roof["note"]},
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall, "state_finite": finite,
         }
+        if "fused_eye_retina_ms" in roof:
+            line["roofline"]["fused_eye_retina_ms_per_launch"] = roof["fused_eye_retina_ms"]
+        if gathered_slabs:
+            line["nccl_all_gathers_in_timed_region"] = gathered_slabs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+DEFAULT_FLIES = {"flat": 4096, "terrain": 4096, "vision": 1024, "olfaction": 32768}
+DEFAULT_CHUNK = {"flat": 100, "terrain": 100, "vision": 10, "olfaction": 10}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-flies", type=int, default=N_FLIES_PER_GPU)
-    ap.add_argument("--chunk", type=int, default=100, help="physics steps fused per kernel launch")
+    ap.add_argument("--workload", default="flat", choices=list(DEFAULT_FLIES), help="BASELINE.json configs[1..4]")
+    ap.add_argument("--terrain", default="blocks", choices=["blocks", "gapped"], help="terrain of --workload terrain")
+    ap.add_argument("--n-flies", type=int, default=None, help="flies per GPU (default: the BASELINE config's)")
+    ap.add_argument("--chunk", type=int, default=None, help="physics steps per timed launch group (fused into one launch when no sensors run)")
     ap.add_argument("--mesh", action="store_true", help="mesh-hull collision geoms (simplify_geom=False)")
     ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.n_flies is None:
+        args.n_flies = DEFAULT_FLIES[args.workload]
+    if args.chunk is None:
+        args.chunk = DEFAULT_CHUNK[args.workload]
+    if args.steps is None:
+        args.steps = 1000 if args.impl == "ours" and args.workload in ("flat", "terrain") else (200 if args.impl == "ours" else 5)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
