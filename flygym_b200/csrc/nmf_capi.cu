@@ -3,6 +3,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -16,9 +18,57 @@ using namespace nmf;
 #ifndef NMF_MINBLOCKS
 #define NMF_MINBLOCKS 16   // <= 64 registers/thread: best measured trade-off between occupancy and spills (profiles/)
 #endif
+// Two schedules, one call site of the (large) step body:
+//  * p.queue == nullptr: block b advances fly b by all p.nsteps steps (grid = n_flies);
+//  * work queue: the launch is cut into items (fly, sub-chunk of p.sub_steps steps) served to a grid that just fills the
+//    GPU.  n_flies is rarely a multiple of the 148 x 16 resident blocks, and this latency-bound kernel slows down in
+//    proportion to the empty slots of a partial last wave; with items a launch is many waves long instead of one or two.
+//    The queue is a FIFO of READY flies: entries 0..n-1 are implicit (every fly's first sub-chunk), and a block that has
+//    written a fly's record back appends the fly again (release) unless that was its last sub-chunk.  Entry i >= n is
+//    therefore filled by the (i-n)-th completion; when a block pops it at most `grid` items are still running, i.e. at
+//    least i - grid >= i - n have completed (the queue is only used when n_flies >= grid), so pops do not wait.
+//    queue[0] = pop counter, queue[1] = push counter, queue[2 + f] = sub-chunks of fly f done, queue[2 + n + j] = ring entry j.
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) {
   __shared__ __align__(16) float sm[SM_TOTAL];
-  step_block(p, sm);
+  __shared__ int s_fly, s_chunk;
+  const int tid = threadIdx.x;
+  for (;;) {
+    int fly = blockIdx.x, step0 = 0, nsub = p.nsteps;
+    if (p.queue) {
+      if (tid == 0) {
+        const int i = atomicAdd(p.queue, 1);
+        int f = -1;
+        if (i < p.n_flies) f = i;
+        else if (i < p.n_items) {
+          const int* slot = p.queue + 2 + p.n_flies + (i - p.n_flies);
+          int v = 0;
+          for (unsigned spins = 0; spins < (1u << 24); spins++) {      // bounded: a scheduling bug must not hang the GPU
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+            if (v) break;
+            __nanosleep(64);
+          }
+          f = v - 1;
+          asm volatile("fence.proxy.async;" ::: "memory");            // the record is read through the async proxy (TMA) next
+        }
+        s_fly = f; s_chunk = f >= 0 ? p.queue[2 + f] : 0;
+      }
+      block_sync();
+      fly = s_fly;
+      if (fly < 0) return;
+      step0 = s_chunk * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
+    }
+    step_block(p, sm, fly, step0, nsub, p.queue != nullptr);
+    if (!p.queue) return;
+    if (tid == 0) {   // the TMA store of the record has completed (tma_store_record waited for it): hand the fly on
+      const int done = step0 / p.sub_steps + 1;
+      p.queue[2 + fly] = done;
+      if (done * p.sub_steps < p.nsteps) {
+        __threadfence();
+        const int j = atomicAdd(p.queue + 1, 1);
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.queue + 2 + p.n_flies + j), "r"(fly + 1) : "memory");
+      }
+    }
+  }
 }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
@@ -48,11 +98,16 @@ struct nmf_handle {
   float *d_role = nullptr, *d_hull = nullptr, *d_seg = nullptr, *d_key = nullptr;
   int *d_nbr_adr = nullptr, *d_nbr = nullptr;
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
+  int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
+  int resident_blocks = 0;                     // blocks of the step kernel the device holds at once
+  int sub_steps = -1;                          // steps per work item: -1 = chosen per launch, 0 = never use the queue
   nmf_buffers buf{};
   bool bound = false;
   int64_t launches = 0;
   std::string err;
 };
+
+constexpr int QUEUE_MAX_CHUNKS = 16;   // sub-chunks per fly and launch the queue buffer is sized for
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return NMF_ECUDA; } } while (0)
 
@@ -81,12 +136,20 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   CK(cudaMemcpy(h->d_nbr_adr, h->hm.hull_nbr_adr.data(), sizeof(int) * h->hm.hull_nbr_adr.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_nbr, sizeof(int) * h->hm.hull_nbr.size()));
   CK(cudaMemcpy(h->d_nbr, h->hm.hull_nbr.data(), sizeof(int) * h->hm.hull_nbr.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_queue, sizeof(int) * ((size_t)n_flies * QUEUE_MAX_CHUNKS + 2)));
+  {
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_kernel, CTA, 0));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    h->resident_blocks = per_sm * sms;
+  }
+  if (const char* e = getenv("NMF_QUEUE_SUBSTEPS")) h->sub_steps = atoi(e);
   return NMF_OK;
 }
 
 extern "C" int nmf_destroy(nmf_handle* h) {
   if (!h) return NMF_OK;
-  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos);
+  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue);
   delete h;
   return NMF_OK;
 }
@@ -124,17 +187,42 @@ extern "C" int nmf_reset(nmf_handle* h, const uint8_t* mask, void* stream) {
   return NMF_OK;
 }
 
-extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, void* stream) {
+extern "C" int nmf_set_schedule(nmf_handle* h, int sub_steps) {
+  if (!h || sub_steps < -1) return NMF_EINVAL;
+  h->sub_steps = sub_steps;
+  return NMF_OK;
+}
+
+extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, void* stream) {
   if (!h) return NMF_EINVAL;
   if (!h->bound) { h->err = "nmf_step: not bound"; return NMF_ENOTBOUND; }
   if (nsteps <= 0) return NMF_OK;
   if (table && table_T <= 0) { h->err = "nmf_step: action table needs table_T > 0"; return NMF_EINVAL; }
+  if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
+    h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
+  }
   StepParams p = h->hm.par;
   p.state = h->buf.state; p.role = h->d_role; p.hull = h->d_hull; p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
-  p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0;
+  p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
   p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps;
-  nmf_step_kernel<<<h->n_flies, CTA, 0, (cudaStream_t)stream>>>(p);
+  int grid = h->n_flies;
+  p.queue = nullptr; p.sub_steps = nsteps; p.n_items = h->n_flies;
+  int sub = h->sub_steps;
+  if (sub < 0) {
+    // ~25 steps per item: measured on B200 (profiles/queue_sweep_r01.txt) an item costs ~0.6 step of fixed overhead (its
+    // set-up code and constants are cold in the instruction / L1 caches), while items of 50+ steps leave a visible tail
+    const int k = (nsteps + 12) / 25;
+    sub = k >= 2 ? (nsteps + k - 1) / k : 0;
+  }
+  if (sub > 0 && h->n_flies > h->resident_blocks && nsteps >= 2 * sub) {   // more flies than resident blocks: work queue
+    if (sub * QUEUE_MAX_CHUNKS < nsteps) sub = (nsteps + QUEUE_MAX_CHUNKS - 1) / QUEUE_MAX_CHUNKS;
+    const int nchunk = (nsteps + sub - 1) / sub;
+    p.queue = h->d_queue; p.sub_steps = sub; p.n_items = nchunk * h->n_flies;
+    grid = h->resident_blocks;
+    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)h->n_flies * nchunk + 2), (cudaStream_t)stream));
+  }
+  nmf_step_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
   h->launches++;
   CK(cudaGetLastError());
   return NMF_OK;
@@ -168,7 +256,7 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int nstep
   if (!h->d_act) { CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n * nu_pos)); CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n * NQ)); }
   CK(cudaMemcpyAsync(h->d_act, actions_host, sizeof(float) * (size_t)n * nu_pos, cudaMemcpyHostToDevice, stream));
   // the action block doubles as a 1-row action table: ctrl[0:nu_pos] <- actions (position actuators are ctrl 0..nu_pos-1)
-  int rc = nmf_step(h, nsteps, h->d_act, 1, 0, stream);
+  int rc = nmf_step(h, nsteps, h->d_act, 1, 0, nu_pos, stream);
   if (rc) return rc;
   rc = nmf_gather_state(h, S_QPOS, nullptr, NQ, h->d_qpos, stream);
   if (rc) return rc;

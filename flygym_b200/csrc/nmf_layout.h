@@ -80,7 +80,7 @@ struct StepParams {
   float* state;              // [n_flies][S_STRIDE]
   const float* role;         // [RF_COUNT][CTA]
   const float* hull;         // hull vertices (xyz) in body frames
-  const float* act_table;    // optional [n_flies][table_T][nu_pos]; nullptr = use ctrl in state
+  const float* act_table;    // optional [n_flies][table_T][table_cols] -> ctrl[0:table_cols]; nullptr = use ctrl in state
   const float* seg_tab;      // [nseg][8]: body lane (as float), pos xyz, quat wxyz  (static segments on the hub)
   float* out_xpos;           // optional [n_flies][nseg][3]
   float* out_xquat;          // optional [n_flies][nseg][4]
@@ -89,12 +89,16 @@ struct StepParams {
   float* dbg;                // optional [n_flies][DBG_STRIDE]
   const int* hull_nbr_adr;   // CSR adjacency of the hull vertices: neighbours of vertex v are hull_nbr[hull_nbr_adr[v] .. hull_nbr_adr[v+1])
   const int* hull_nbr;       //   (indices local to the geom)
-  int n_flies, nsteps, table_T, table_t0;
+  int n_flies, nsteps, table_T, table_t0, table_cols;
   int nu_pos, nu_adh, nseg, nhubgeom;
   float dt, gx, gy, gz, inv_total_mass;
   float mu, cK, cB, margin, impratio;
   float solimp[5];           // sanitised: d0, dmax, width, midpoint, power
   int max_newton, max_ls;
+  // work-queue scheduling (nullptr = one block per fly for the whole launch): queue[0] = next work item,
+  // queue[1 + fly] = number of sub-chunks of that fly already written back
+  int* queue;
+  int sub_steps, n_items;
 };
 
 }  // namespace nmf

@@ -545,14 +545,19 @@ __device__ __forceinline__ void tma_load_record(float* dst_smem, const float* sr
   while (!done) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
   }
+  block_sync();
+  if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");   // the slot is re-initialised by the next work item
 }
-__device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* src_smem, int tid) {
+// `published`: the caller hands the record to another block afterwards (work-queue scheduling), so wait until the
+// global writes have completed, not only until shared memory has been read.
+__device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* src_smem, int tid, bool published) {
   block_sync();                                                      // all generic-proxy writes to the record are done
   if (tid == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // make them visible to the async (TMA) proxy
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"((unsigned)(S_STRIDE * sizeof(float))) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until the copy has read it
+    if (published) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until the copy has read it
   }
 }
 #else
@@ -560,16 +565,17 @@ __device__ __forceinline__ void tma_load_record(float* dst_smem, const float* sr
   for (int i = tid; i < S_STRIDE; i += CTA) dst_smem[i] = src_gmem[i];
   block_sync();
 }
-__device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* src_smem, int tid) {
+__device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* src_smem, int tid, bool) {
   block_sync();
   for (int i = tid; i < S_STRIDE; i += CTA) dst_gmem[i] = src_smem[i];
 }
 #endif
 
 // ------------------------------------------------------------------ the step
-__device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
+// Advances fly `fly` by steps [step0, step0 + nsub) of the launch's p.nsteps (one work item of the launch: the whole
+// launch when flies map 1:1 to blocks, a sub-chunk under work-queue scheduling).
+__device__ __forceinline__ void step_block(const StepParams& p, float* sm, const int fly, const int step0, const int nsub, const bool published) {
   const int tid = threadIdx.x;
-  const int fly = blockIdx.x;
   const int grp = tid >> 3, k = tid & 7, t = k;
   const bool is_leg = grp < NLEG;
   const int hl = tid - NLEG * NLINK;          // hub lane index (valid when !is_leg)
@@ -621,11 +627,11 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
     pb[s] = idx < 21 ? b : 0; pc[s] = idx < 21 ? idx - b * (b + 1) / 2 : 0;
   }
 
-  for (int step = 0; step < p.nsteps; step++) {
+  for (int step = step0; step < step0 + nsub; step++) {
     // ---- controls for this step
     if (p.act_table) {
-      const float* row = p.act_table + ((size_t)fly * p.table_T + (size_t)((p.table_t0 + step) % p.table_T)) * p.nu_pos;
-      for (int i = tid; i < p.nu_pos; i += CTA) st[S_CTRL + i] = row[i];
+      const float* row = p.act_table + ((size_t)fly * p.table_T + (size_t)((p.table_t0 + step) % p.table_T)) * p.table_cols;
+      for (int i = tid; i < p.table_cols; i += CTA) st[S_CTRL + i] = row[i];
       block_sync();
     }
 
@@ -1118,7 +1124,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm) {
   }
 
   // ---- write the record back (TMA bulk store)
-  tma_store_record(p.state + (size_t)fly * S_STRIDE, st, tid);
+  tma_store_record(p.state + (size_t)fly * S_STRIDE, st, tid, published);
 }
 
 }  // namespace nmf

@@ -188,16 +188,18 @@ class B200Simulation:
 
         ``action_table`` (device float32 ``(n_worlds, T, n_position_actuators)``), when
         given, supplies the position-actuator inputs of step ``s`` from row
-        ``(table_t0 + s) % T`` (the reference benchmark's replay protocol)."""
+        ``(table_t0 + s) % T`` (the reference benchmark's replay protocol); with
+        ``n_position_actuators + 6`` columns the trailing six are the leg adhesion inputs."""
         if action_table is None:
-            self._check(self._lib.nmf_step(self._h, int(n), None, 0, 0, self._stream()))
+            self._check(self._lib.nmf_step(self._h, int(n), None, 0, 0, 0, self._stream()))
         else:
             if action_table.dtype != torch.float32 or not action_table.is_cuda or not action_table.is_contiguous():
                 raise ValueError("action_table must be a contiguous float32 CUDA tensor")
-            if action_table.shape[0] != self.n_worlds or action_table.shape[2] != self.info.nu_pos:
-                raise ValueError("action_table must have shape (n_worlds, T, n_position_actuators)")
+            if action_table.ndim != 3 or action_table.shape[0] != self.n_worlds or \
+                    action_table.shape[2] not in (self.info.nu_pos, self.info.nu_pos + self.info.nu_adh):
+                raise ValueError("action_table must have shape (n_worlds, T, n_position_actuators [+ 6 adhesion inputs])")
             self._check(self._lib.nmf_step(self._h, int(n), ctypes.c_void_p(action_table.data_ptr()),
-                                           int(action_table.shape[1]), int(table_t0), self._stream()))
+                                           int(action_table.shape[1]), int(table_t0), int(action_table.shape[2]), self._stream()))
 
     def step_with_profile(self) -> None:
         t0 = perf_counter_ns()
@@ -314,6 +316,10 @@ class B200Simulation:
 
     def set_solver(self, max_newton: int = 8, max_linesearch: int = 8) -> None:
         self._check(self._lib.nmf_set_solver(self._h, int(max_newton), int(max_linesearch)))
+
+    def set_schedule(self, sub_steps: int = -1) -> None:
+        """Steps per work item of multi-step launches (0 = one block per fly for the whole launch, -1 = automatic)."""
+        self._check(self._lib.nmf_set_schedule(self._h, int(sub_steps)))
 
     @property
     def launch_count(self) -> int:

@@ -61,9 +61,16 @@ int nmf_bind(nmf_handle* h, const nmf_buffers* buffers);
 int nmf_reset(nmf_handle* h, const uint8_t* mask_or_null, void* cuda_stream);
 
 /* GPUSimulation.step (warp/simulation.py:260-263), `nsteps` times inside one launch.  With an action table
- * (DEVICE [n_flies][table_T][nu_pos], as the reference benchmark keeps it: time_gpu_simulation.py:89-98,133-146)
- * step s uses row (table_t0 + s) % table_T as the position-actuator inputs; NULL = use ctrl in the state. */
-int nmf_step(nmf_handle* h, int nsteps, const float* action_table_or_null, int table_T, int table_t0, void* cuda_stream);
+ * (DEVICE [n_flies][table_T][table_cols], as the reference benchmark keeps it: time_gpu_simulation.py:89-98,133-146)
+ * step s copies row (table_t0 + s) % table_T into ctrl[0:table_cols]; table_cols = nu_pos (position targets only, the
+ * reference's table) or nu_pos + nu_adh (position targets followed by the six adhesion inputs); NULL = use ctrl in the state. */
+int nmf_step(nmf_handle* h, int nsteps, const float* action_table_or_null, int table_T, int table_t0, int table_cols, void* cuda_stream);
+
+/* Scheduling of multi-step launches: with more flies than the GPU holds resident blocks, a launch of nsteps >= 2*sub_steps
+ * is cut into (fly, sub_steps-step) work items served from a device-side queue (results are identical; only the order in
+ * which flies advance changes).  sub_steps = 0 disables the queue (one block per fly for the whole launch); -1 (default)
+ * lets the library pick the sub-chunk length that fills whole waves of resident blocks best. */
+int nmf_set_schedule(nmf_handle* h, int sub_steps);
 
 /* set_actuator_inputs / set_leg_adhesion_states (warp/simulation.py:213-258; kernel warp/utils.py:84-104):
  * state.ctrl[:, cols[k]] = src[:, k]   (src DEVICE [n_flies][ncols], cols DEVICE int32[ncols]) */

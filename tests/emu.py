@@ -54,8 +54,9 @@ def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0,
     oa = np.zeros((n, nu), np.float32) if outputs else None
     os_ = np.zeros((n, 96), np.float32) if outputs else None
     T = 0 if act_table is None else act_table.shape[1]
+    cols = 0 if act_table is None else act_table.shape[2]
     rc = lib().emu_step(blob, ctypes.c_size_t(len(blob)), _p(state), n, nsteps, _p(d), _p(ox), _p(oq), _p(oa), _p(os_),
-                        _p(act_table), T, t0, max_newton, max_ls)
+                        _p(act_table), T, t0, cols, max_newton, max_ls)
     assert rc == 0
     res.update(dbg=d, xpos=ox, xquat=oq, actf=oa, sensor=os_)
     return res

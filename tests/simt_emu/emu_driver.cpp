@@ -14,17 +14,17 @@ extern "C" int emu_key_state(const void* blob, size_t nbytes, float* out) {
 }
 
 extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_flies, int nsteps, float* dbg, float* out_xpos,
-                        float* out_xquat, float* out_actf, float* out_sensor, const float* act_table, int table_T, int table_t0,
+                        float* out_xquat, float* out_actf, float* out_sensor, const float* act_table, int table_T, int table_t0, int table_cols,
                         int max_newton, int max_ls) {
   nmf::HostModel hm;
   if (!hm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", hm.err.c_str()); return -1; }
   nmf::StepParams p = hm.par;
   p.state = state; p.role = hm.role.data(); p.hull = hm.hull.data(); p.seg_tab = hm.seg_tab.data(); p.hull_nbr_adr = hm.hull_nbr_adr.data(); p.hull_nbr = hm.hull_nbr.data();
-  p.act_table = act_table; p.table_T = table_T; p.table_t0 = table_t0;
+  p.act_table = act_table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table_cols;
   p.out_xpos = out_xpos; p.out_xquat = out_xquat; p.out_actf = out_actf; p.out_sensor = out_sensor; p.dbg = dbg;
   p.n_flies = n_flies; p.nsteps = nsteps;
   if (max_newton > 0) p.max_newton = max_newton;
   if (max_ls > 0) p.max_ls = max_ls;
-  for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() { nmf::step_block(p, g_sm); });
+  for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() { nmf::step_block(p, g_sm, f, 0, p.nsteps, false); });
   return 0;
 }

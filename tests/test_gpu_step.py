@@ -210,3 +210,29 @@ def test_step_is_cuda_graph_capturable():
     ref.step(1 + 4 * 5)      # the captured launch itself does not execute during capture
     torch.cuda.synchronize()
     assert torch.equal(sim.state, ref.state)
+
+
+def test_work_queue_schedule_is_bit_identical():
+    """Multi-step launches of more flies than the GPU holds resident blocks are served from a device-side work queue
+    (sub-chunks of `sub_steps` steps); the schedule must not change a single bit of any fly's trajectory."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    m = NMFModel.bench(simplify_geom=True)
+    n = 3001                                         # > 148 SMs x 16 resident blocks, and not a multiple of anything
+    table = torch.from_numpy(cpg_table(m, n, 64)).cuda()
+    finals = []
+    for sub in (0, 10, 7):
+        sim = B200Simulation(m, n_worlds=n, outputs=True)
+        sim.set_schedule(sub)
+        sim.qpos[:, 2] = -0.15                       # feet on the ground
+        sim.qpos[:, 0] += torch.linspace(0, 1, n, device="cuda")     # distinct flies
+        sim.step(45, table, 3)
+        sim.step(1, table, 48)                       # a 1-step launch (never queued) on top
+        torch.cuda.synchronize()
+        finals.append((sim.state.clone(), sim.seg_xpos.clone(), sim.sensordata.clone()))
+    for other in finals[1:]:
+        for a, b in zip(finals[0], other):
+            assert torch.equal(a, b)
+    assert torch.isfinite(finals[0][0]).all()
+    assert abs(float(finals[0][0][0, 300]) - 46e-4) < 1e-6      # time advanced by 46 steps
