@@ -136,16 +136,26 @@ def cpu_arm(model, table64, steps_per_thread, threads, adhesion=None):
     return threads * steps_per_thread / dt, dt
 
 
-def cpu_baseline_leg(model, n_total, target_s=12.0):
+def host_adhesion_table(model, n_flies, n_steps, n_total):
+    """stance-phase adhesion inputs of the terrain workload (same definition as device_cpg_table)"""
+    from flygym_b200.actions import TRIPOD_PHASE
+    t = np.arange(n_steps) * model.timestep
+    psi = 2 * np.pi * np.arange(n_flies) / n_total
+    legph = np.array([TRIPOD_PHASE[l] for l in model.names["legs"]])
+    return np.where(np.sin(2 * np.pi * 12.0 * t[None, :, None] + psi[:, None, None] + legph[None, None, :]) < 0, 100.0, 1.0)
+
+
+def cpu_baseline_leg(model, n_total, target_s=12.0, stance_adhesion=False):
     """cpu_baseline: the oracle on every host core, sized to ~target_s seconds of CPU work from a short pilot run."""
     from flygym_b200.actions import cpg_table
     cores = os.cpu_count() or 1
     pilot = 200
+    adh = (lambda k: host_adhesion_table(model, cores, k, n_total)) if stance_adhesion else (lambda k: None)
     tb = cpg_table(model, cores, pilot, n_flies_total=n_total).astype(np.float64)
-    v0, _ = cpu_arm(model, tb, pilot, cores)
+    v0, _ = cpu_arm(model, tb, pilot, cores, adh(pilot))
     cs = int(min(50000, max(500, target_s * v0 / cores)))
     tb = cpg_table(model, cores, cs, n_flies_total=n_total).astype(np.float64)
-    v, dt = cpu_arm(model, tb, cs, cores)
+    v, dt = cpu_arm(model, tb, cs, cores, adh(cs))
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{cores} threads x 1 fly x {cs} CPG steps after a 500-step warm-up (oracle/nmf_oracle.c, fp64 restatement of "
                       f"mj_step), {dt:.1f} s"}
@@ -167,11 +177,12 @@ def run_reference(args, rank, world):
     sample_steps = 200                      # per thread per "step" of this arm: bounded sample of the workload
     n = args.n_flies
     table = cpg_table(model, cores, sample_steps, n_flies_total=n).astype(np.float64)
+    adh = host_adhesion_table(model, cores, sample_steps, n) if args.workload == "terrain" else None
     for _ in range(args.warmup):
-        cpu_arm(model, table, 50, cores)
+        cpu_arm(model, table, 50, cores, adh)
     vals, tot = [], 0.0
     for _ in range(args.steps):
-        v, dt = cpu_arm(model, table, sample_steps, cores)
+        v, dt = cpu_arm(model, table, sample_steps, cores, adh)
         vals.append(v); tot += dt
     value = float(np.mean(vals))
     sample = f"{cores} threads x 1 fly x {sample_steps} steps per timed step (CPG actions, after 500 warm-up steps)"
@@ -342,13 +353,14 @@ def run_ours(args, rank, world, local_rank):
         else:
             step_ms = kernel_ms / max(1, len(ev))
         per_fly = ALG_BYTES_OBS if per_step else ALG_BYTES_CORE
-        roof = {"kernel": "nmf_step_kernel", "ms": step_ms, "alg_bytes": per_fly * n * per_launch_steps,
+        roof = {"kernel": "nmf_step_terrain_kernel" if wl == "terrain" else "nmf_step_kernel", "ms": step_ms, "alg_bytes": per_fly * n * per_launch_steps,
                 "note": "the fused step is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); algorithmic bytes "
                         f"= {per_fly} B per fly-step"}
 
     # ---- end-to-end through the public API with HOST buffers, every step: H2D actions, step (+ sensors), D2H result
     e2e_steps = min(args.steps, 200)
-    act_host = table[:, :e2e_steps, :nu_pos].permute(1, 0, 2).contiguous().cpu().pin_memory()
+    act_cols = table.shape[2] if wl == "terrain" else nu_pos        # terrain: the six adhesion inputs travel with the position targets
+    act_host = table[:, :e2e_steps, :act_cols].permute(1, 0, 2).contiguous().cpu().pin_memory()
     if not per_step:
         res_host = torch.empty((n, model.nq), dtype=torch.float32).pin_memory()
         def e2e_step(s):
@@ -383,14 +395,14 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
         achieved = roof["alg_bytes"] / (roof["ms"] * 1e-3) / 1e9
-        cpu = cpu_baseline_leg(model, n) if (world == 1 and not args.no_cpu) else None
+        cpu = cpu_baseline_leg(model, n, stance_adhesion=(wl == "terrain")) if (world == 1 and not args.no_cpu) else None
         cfg = dict(workload_config(args, n, chunk), actions=args.actions)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * nu_pos * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * act_cols * 4),
                     "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps},
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -87,7 +87,7 @@ def load() -> ctypes.CDLL:
     lib.nmf_set_schedule.argtypes = [vp, ci]
     lib.nmf_scatter_ctrl.argtypes = [vp, vp, vp, ci, vp]
     lib.nmf_gather_state.argtypes = [vp, ci, vp, ci, vp, vp]
-    lib.nmf_step_host.argtypes = [vp, vp, ci, vp, vp]
+    lib.nmf_step_host.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.nmf_set_solver.argtypes = [vp, ci, ci]
     lib.nmf_launch_count.argtypes = [vp]
     lib.nmf_launch_count.restype = ctypes.c_int64

@@ -28,7 +28,8 @@ using namespace nmf;
 //    therefore filled by the (i-n)-th completion; when a block pops it at most `grid` items are still running, i.e. at
 //    least i - grid >= i - n have completed (the queue is only used when n_flies >= grid), so pops do not wait.
 //    queue[0] = pop counter, queue[1] = push counter, queue[2 + f] = sub-chunks of fly f done, queue[2 + n + j] = ring entry j.
-extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) {
+template <bool TERRAIN>
+__device__ __forceinline__ void step_entry(const StepParams& p) {
   __shared__ __align__(16) float sm[SM_TOTAL];
   __shared__ int s_fly, s_chunk;
   const int tid = threadIdx.x;
@@ -57,7 +58,7 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel
       if (fly < 0) return;
       step0 = s_chunk * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
     }
-    step_block(p, sm, fly, step0, nsub, p.queue != nullptr);
+    step_block<TERRAIN>(p, sm, fly, step0, nsub, p.queue != nullptr);
     if (!p.queue) return;
     if (tid == 0) {   // the TMA store of the record has completed (tma_store_record waited for it): hand the fly on
       const int done = step0 / p.sub_steps + 1;
@@ -70,6 +71,13 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel
     }
   }
 }
+
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) { step_entry<false>(p); }
+// terrain worlds (box columns: BASELINE config 3): general contact frames need 8 more registers per lane
+#ifndef NMF_MINBLOCKS_TERRAIN
+#define NMF_MINBLOCKS_TERRAIN 12
+#endif
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_step_terrain_kernel(const StepParams p) { step_entry<true>(p); }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
   int fly = blockIdx.x;
@@ -99,7 +107,7 @@ struct nmf_handle {
   int *d_nbr_adr = nullptr, *d_nbr = nullptr;
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
-  int resident_blocks = 0;                     // blocks of the step kernel the device holds at once
+  int resident_blocks = 0;                     // blocks of the step kernel (the model's variant) the device holds at once
   int sub_steps = -1;                          // steps per work item: -1 = chosen per launch, 0 = never use the queue
   nmf_buffers buf{};
   bool bound = false;
@@ -139,7 +147,8 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   CK(cudaMalloc(&h->d_queue, sizeof(int) * ((size_t)n_flies * QUEUE_MAX_CHUNKS + 2)));
   {
     int per_sm = 0, sms = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_kernel, CTA, 0));
+    if (h->hm.par.terrain) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_terrain_kernel, CTA, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_kernel, CTA, 0));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     h->resident_blocks = per_sm * sms;
   }
@@ -222,7 +231,8 @@ extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table
     grid = h->resident_blocks;
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)h->n_flies * nchunk + 2), (cudaStream_t)stream));
   }
-  nmf_step_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
+  if (p.terrain) nmf_step_terrain_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
+  else nmf_step_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
   h->launches++;
   CK(cudaGetLastError());
   return NMF_OK;
@@ -248,15 +258,16 @@ extern "C" int nmf_gather_state(nmf_handle* h, int off, const int32_t* cols, int
   return NMF_OK;
 }
 
-extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int nsteps, float* qpos_host, void* stream_) {
+extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, void* stream_) {
   if (!h || !actions_host || !qpos_host) return NMF_EINVAL;
   if (!h->bound) return NMF_ENOTBOUND;
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int nu_pos = h->hm.par.nu_pos, n = h->n_flies;
-  if (!h->d_act) { CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n * nu_pos)); CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n * NQ)); }
-  CK(cudaMemcpyAsync(h->d_act, actions_host, sizeof(float) * (size_t)n * nu_pos, cudaMemcpyHostToDevice, stream));
-  // the action block doubles as a 1-row action table: ctrl[0:nu_pos] <- actions (position actuators are ctrl 0..nu_pos-1)
-  int rc = nmf_step(h, nsteps, h->d_act, 1, 0, nu_pos, stream);
+  const int nu = h->hm.par.nu_pos + h->hm.par.nu_adh, n = h->n_flies;
+  if (action_cols != h->hm.par.nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
+  if (!h->d_act) { CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n * nu)); CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n * NQ)); }
+  CK(cudaMemcpyAsync(h->d_act, actions_host, sizeof(float) * (size_t)n * action_cols, cudaMemcpyHostToDevice, stream));
+  // the action block doubles as a 1-row action table: ctrl[0:action_cols] <- actions (position actuators first, then adhesion)
+  int rc = nmf_step(h, nsteps, h->d_act, 1, 0, action_cols, stream);
   if (rc) return rc;
   rc = nmf_gather_state(h, S_QPOS, nullptr, NQ, h->d_qpos, stream);
   if (rc) return rc;

@@ -184,6 +184,17 @@ struct HostModel {
     par.max_newton = (int)opt[4]; par.max_ls = (int)opt[6]; par.nsteps = 1;   // reference: iterations=100 (mujoco_globals.yaml:14), ls_iterations=50 (MuJoCo default)
     if (par.max_newton < 1) par.max_newton = 100;
     if (par.max_ls < 1) par.max_ls = 50;
+    {  // optional terrain section: {type, Px, Py, hx, hy, top_even, top_odd, z_floor}
+      int nt = 0; const double* terr = b.get<double>("terrain", &nt);
+      if (terr && nt >= 8 && terr[0] != 0.0) {
+        if (terr[0] != 1.0 || !(terr[1] > 0) || !(terr[2] > 0) || !(terr[3] > 0) || !(terr[4] > 0) || terr[3] > 0.5 * terr[1] * (1 + 1e-9) || terr[4] > 0.5 * terr[2] * (1 + 1e-9)) {
+          err = "unsupported terrain description"; return false;
+        }
+        for (int g = 0; g < ngeom; g++) if (geom_type[g] != 0) { err = "terrain worlds need capsule collision geoms (simplify_geom=True)"; return false; }
+        par.terrain = 1;
+        for (int i = 0; i < 7; i++) par.terr[i] = (float)terr[1 + i];
+      }
+    }
     (void)body_parent;
     return true;
   }

@@ -95,6 +95,10 @@ struct StepParams {
   float mu, cK, cB, margin, impratio;
   float solimp[5];           // sanitised: d0, dmax, width, midpoint, power
   int max_newton, max_ls;
+  // terrain: 0 = ground plane z = 0 (FlatGroundWorld); 1 = floor plane + grid of box columns, terr = {Px, Py, hx, hy, top_even,
+  // top_odd, z_floor, 0}: column (i, j) covers |x - i Px| <= hx, |y - j Py| <= hy, z <= top_{(i+j)&1}
+  int terrain;
+  float terr[8];
   // work-queue scheduling (nullptr = one block per fly for the whole launch): queue[0] = next work item,
   // queue[1 + fly] = number of sub-chunks of that fly already written back
   int* queue;

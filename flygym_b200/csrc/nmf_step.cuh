@@ -25,6 +25,8 @@
 // (NMF_SIMT_EMU) so it can be exercised without a GPU; that is test
 // infrastructure, not a fallback: the shipped library only contains the nvcc build.
 #pragma once
+#include <type_traits>
+
 #include "nmf_layout.h"
 
 namespace nmf {
@@ -320,7 +322,8 @@ __device__ __forceinline__ void contact_forces(const Contact& c, float mu, float
 }
 
 // line-search partial sums of one contact at step alpha: d0 += D x jv, d1 += D jv^2 over rows with x < 0
-__device__ __forceinline__ void ls_eval(const Contact& c, const float* sv, float alpha, float& d0, float& d1, float& nchanged) {
+template <class Con>
+__device__ __forceinline__ void ls_eval(const Con& c, const float* sv, float alpha, float& d0, float& d1, float& nchanged) {
   float jar[4], jv[4]; rows4(c.w, c.c0, jar); rows4(sv, 0.f, jv);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
@@ -330,6 +333,158 @@ __device__ __forceinline__ void ls_eval(const Contact& c, const float* sv, float
     nchanged += ((x < 0.f) != (jar[r] < 0.f)) ? 1.f : 0.f;   // rows whose state differs from the one the Hessian was built for
   }
 }
+
+// ------------------------------------------------------------------ general-frame contact slot (terrain worlds)
+// Same conventions as Contact, but the contact normal is arbitrary (box-column terrain has walls and edges):
+// frame = (n, t1, t2 = n x t1).  Used by the TERRAIN instantiation of the step only; the flat-ground kernel keeps the
+// cheaper z-normal slot above.
+struct ContactG {    // 14 registers per slot
+  float r[3];        // contact position relative to the subtree COM
+  float n[3], t[3];  // normal, first tangent
+  float D, c0;
+  float w[3];
+};
+__device__ __forceinline__ float con_on(const ContactG& c) { return c.D > 0.f ? 1.f : 0.f; }
+
+__device__ __forceinline__ void finish_contact(const StepParams& p, ContactG& c, float active, float dist, const float* pos, const float* nrm,
+                                               const float* hint, const float* com, const float* cvel, float invw) {
+  c.r[0] = pos[0] - com[0]; c.r[1] = pos[1] - com[1]; c.r[2] = pos[2] - com[2];
+  c.n[0] = nrm[0]; c.n[1] = nrm[1]; c.n[2] = nrm[2];
+  {  // first tangent: the hint (capsule axis) orthogonalised against the normal; world x (or y) when they are parallel
+    float hn = dot3(hint, nrm), t[3] = {hint[0] - hn * nrm[0], hint[1] - hn * nrm[1], hint[2] - hn * nrm[2]};
+    float t2 = dot3(t, t);
+    if (t2 < 1e-12f) {
+      const bool usex = fabsf(nrm[0]) < 0.9f;
+      const float e[3] = {usex ? 1.f : 0.f, usex ? 0.f : 1.f, 0.f};
+      hn = dot3(e, nrm); t[0] = e[0] - hn * nrm[0]; t[1] = e[1] - hn * nrm[1]; t[2] = e[2] - hn * nrm[2]; t2 = dot3(t, t);
+    }
+    const float inv = rsqrtf(t2);
+    c.t[0] = t[0] * inv; c.t[1] = t[1] * inv; c.t[2] = t[2] * inv;
+  }
+  float imp = impedance(p, fabsf(dist - p.margin));
+  float R0 = fmaxf(NMF_MINVAL, (1.f - imp) * invw * (1.f + p.mu * p.mu) / imp);
+  c.D = active / (2.f * (p.mu * p.mu / p.impratio) * R0);
+  c.c0 = active * p.cK * imp * (dist - p.margin);
+  float vp[3] = {cvel[3] + cvel[1] * c.r[2] - cvel[2] * c.r[1], cvel[4] + cvel[2] * c.r[0] - cvel[0] * c.r[2],
+                 cvel[5] + cvel[0] * c.r[1] - cvel[1] * c.r[0]};
+  float t2v[3]; cross3(c.n, c.t, t2v);
+  c.w[0] = active * p.cB * dot3(c.n, vp);
+  c.w[1] = active * p.cB * p.mu * dot3(c.t, vp);
+  c.w[2] = active * p.cB * p.mu * dot3(t2v, vp);
+}
+
+// one sphere (centre c, radius rad) against the terrain solid = floor plane + grid of box columns: the closest point of
+// the solid decides normal and distance (ONE contact per sphere).  Column (i, j) covers |x - i Px| <= hx, |y - j Py| <= hy,
+// z <= top(i, j), top = terr[4 + ((i + j) & 1)].  A centre inside a column is pushed out through the top face.
+__device__ __forceinline__ void sphere_terrain(const StepParams& p, const float* c, float rad, float* nrm, float& dist) {
+  const float Px = p.terr[0], Py = p.terr[1], hx = p.terr[2], hy = p.terr[3];
+  nrm[0] = 0.f; nrm[1] = 0.f; nrm[2] = 1.f; dist = c[2] - p.terr[6] - rad;      // floor plane
+  const float fi = rintf(c[0] / Px), fj = rintf(c[1] / Py);
+  const int i0 = (int)fi, j0 = (int)fj;
+  const int sx = c[0] >= fi * Px ? 1 : -1, sy = c[1] >= fj * Py ? 1 : -1;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int i = i0 + ((q & 1) ? sx : 0), j = j0 + ((q & 2) ? sy : 0);
+    const float cx = (float)i * Px, cy = (float)j * Py, top = ((i + j) & 1) ? p.terr[5] : p.terr[4];
+    const float qx = fminf(fmaxf(c[0], cx - hx), cx + hx), qy = fminf(fmaxf(c[1], cy - hy), cy + hy), qz = fminf(c[2], top);
+    const float dx = c[0] - qx, dy = c[1] - qy, dz = c[2] - qz, d2 = dx * dx + dy * dy + dz * dz;
+    float d, n0, n1, n2;
+    if (d2 > 0.f) { const float inv = rsqrtf(d2); d = d2 * inv - rad; n0 = dx * inv; n1 = dy * inv; n2 = dz * inv; }
+    else { d = c[2] - top - rad; n0 = 0.f; n1 = 0.f; n2 = 1.f; }
+    if (d < dist) { dist = d; nrm[0] = n0; nrm[1] = n1; nrm[2] = n2; }
+  }
+}
+
+// capsule-vs-terrain narrow phase for the geom carried by this lane's body: the two end spheres, one contact each
+__device__ __forceinline__ float collide(const StepParams& p, const float* role, int tid, const float* xpos, const float* R,
+                                         const float* com, const float* cvel, float invw, ContactG* con, int&) {
+  const int gtype = __float_as_int(role[RF_GTYPE * CTA + tid]);
+  float gp[3] = {role[(RF_GPOS + 0) * CTA + tid], role[(RF_GPOS + 1) * CTA + tid], role[(RF_GPOS + 2) * CTA + tid]};
+  float ga[3] = {role[(RF_GAXIS + 0) * CTA + tid], role[(RF_GAXIS + 1) * CTA + tid], role[(RF_GAXIS + 2) * CTA + tid]};
+  const float rad = role[RF_GRAD * CTA + tid], half = role[RF_GHALF * CTA + tid];
+  float c[3], a[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    c[i] = xpos[i] + R[3 * i] * gp[0] + R[3 * i + 1] * gp[1] + R[3 * i + 2] * gp[2];
+    a[i] = R[3 * i] * ga[0] + R[3 * i + 1] * ga[1] + R[3 * i + 2] * ga[2];
+  }
+  float total = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const float sg = s == 0 ? half : -half;
+    float e[3] = {c[0] + sg * a[0], c[1] + sg * a[1], c[2] + sg * a[2]}, nrm[3], dist;
+    sphere_terrain(p, e, rad, nrm, dist);
+    const float act = (gtype == 0 && dist <= p.margin) ? 1.f : 0.f;
+    const float back = rad + 0.5f * dist;
+    float pos[3] = {e[0] - back * nrm[0], e[1] - back * nrm[1], e[2] - back * nrm[2]};
+    finish_contact(p, con[s], act, dist, pos, nrm, a, com, cvel, invw);
+    total += act;
+  }
+  return total;
+}
+
+__device__ __forceinline__ void project_point(const ContactG& c, const float* S, float mu, float* out) {
+  float a[3] = {S[3] + S[1] * c.r[2] - S[2] * c.r[1], S[4] + S[2] * c.r[0] - S[0] * c.r[2], S[5] + S[0] * c.r[1] - S[1] * c.r[0]};
+  float t2[3]; cross3(c.n, c.t, t2);
+  const float on = con_on(c);
+  out[0] = on * dot3(c.n, a); out[1] = on * mu * dot3(c.t, a); out[2] = on * mu * dot3(t2, a);
+}
+
+template <bool WITH_A>
+__device__ __forceinline__ void contact_forces(const ContactG& c, float mu, float* Wc, float* A, float* fn_out) {
+  float jar[4]; rows4(c.w, c.c0, jar);
+  float a[4], f[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) { a[r] = jar[r] < 0.f ? 1.f : 0.f; f[r] = -c.D * fminf(jar[r], 0.f); }
+  float fn = f[0] + f[1] + f[2] + f[3], f1 = mu * (f[0] - f[1]), f2 = mu * (f[2] - f[3]);
+  float t2[3]; cross3(c.n, c.t, t2);
+  float F[3] = {fn * c.n[0] + f1 * c.t[0] + f2 * t2[0], fn * c.n[1] + f1 * c.t[1] + f2 * t2[1], fn * c.n[2] + f1 * c.t[2] + f2 * t2[2]};
+  float T[3]; cross3(c.r, F, T);
+  Wc[0] += T[0]; Wc[1] += T[1]; Wc[2] += T[2]; Wc[3] += F[0]; Wc[4] += F[1]; Wc[5] += F[2];
+  if (fn_out) *fn_out = fn;
+  if (WITH_A) {
+    // W = D sum_r a_r d_r d_r',  d = n +- mu t1 | n +- mu t2
+    const float s1 = a[0] + a[1], s2 = a[2] + a[3], d1 = mu * (a[0] - a[1]), d2 = mu * (a[2] - a[3]), m2 = mu * mu;
+    float u[3] = {d1 * c.t[0] + d2 * t2[0], d1 * c.t[1] + d2 * t2[1], d1 * c.t[2] + d2 * t2[2]};   // n u' + u n' carries the cross terms
+    float W[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = i; j < 3; j++) {
+        float v = (s1 + s2) * c.n[i] * c.n[j] + c.n[i] * u[j] + u[i] * c.n[j] + m2 * (s1 * c.t[i] * c.t[j] + s2 * t2[i] * t2[j]);
+        W[3 * i + j] = W[3 * j + i] = c.D * v;
+      }
+    float Tm[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float col[3] = {W[j], W[3 + j], W[6 + j]}, t[3]; cross3(c.r, col, t);
+      Tm[j] = t[0]; Tm[3 + j] = t[1]; Tm[6 + j] = t[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float row[3] = {Tm[3 * i], Tm[3 * i + 1], Tm[3 * i + 2]}, t[3]; cross3(c.r, row, t);
+#pragma unroll
+      for (int j = i; j < 3; j++) A[s6(i, j)] += t[j];
+#pragma unroll
+      for (int j = 0; j < 3; j++) A[s6(i, 3 + j)] += Tm[3 * i + j];
+    }
+    A[s6(3, 3)] += W[0]; A[s6(3, 4)] += W[1]; A[s6(3, 5)] += W[2]; A[s6(4, 4)] += W[4]; A[s6(4, 5)] += W[5]; A[s6(5, 5)] += W[8];
+  }
+}
+
+// adhesion pull f (>= 0 towards the surface) of one contact: wrench of -f n at the contact point
+__device__ __forceinline__ void adhesion_wrench(const Contact& c, float f, float* W) {
+  const float fz = -con_on(c) * f;
+  W[0] += c.r[1] * fz; W[1] -= c.r[0] * fz; W[5] += fz;
+}
+__device__ __forceinline__ void adhesion_wrench(const ContactG& c, float f, float* W) {
+  const float s = -con_on(c) * f;
+  float F[3] = {s * c.n[0], s * c.n[1], s * c.n[2]}, T[3]; cross3(c.r, F, T);
+  W[0] += T[0]; W[1] += T[1]; W[2] += T[2]; W[3] += F[0]; W[4] += F[1]; W[5] += F[2];
+}
+// signed distance of an active slot (debug dump only)
+__device__ __forceinline__ float con_dist(const Contact& c, const float* com) { return 2.f * (c.r[2] + com[2]); }
+__device__ __forceinline__ float con_dist(const ContactG&, const float*) { return 0.f; }
 
 // ------------------------------------------------------------------ shared-memory plan (floats)
 // The 64 lanes form 8 shuffle groups of 8: groups 0..5 are the leg chains, groups 6..7 are
@@ -574,7 +729,10 @@ __device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* s
 // ------------------------------------------------------------------ the step
 // Advances fly `fly` by steps [step0, step0 + nsub) of the launch's p.nsteps (one work item of the launch: the whole
 // launch when flies map 1:1 to blocks, a sub-chunk under work-queue scheduling).
+// TERRAIN selects the general-frame contact slot and the capsule-vs-box-column narrow phase (separate kernel instantiation).
+template <bool TERRAIN>
 __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const int fly, const int step0, const int nsub, const bool published) {
+  using Con = typename std::conditional<TERRAIN, ContactG, Contact>::type;
   const int tid = threadIdx.x;
   const int grp = tid >> 3, k = tid & 7, t = k;
   const bool is_leg = grp < NLEG;
@@ -766,7 +924,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
     // B. velocities, composite inertia, collision, bias + actuator forces (all lanes, convergent)
     // =====================================================================
     float crb[10], cvel[6], Sa[6];
-    Contact con[2];
+    Con con[2];
     float fs_own[3] = {0.f, 0.f, 0.f};
     float actf[3] = {0.f, 0.f, 0.f}, adhf = 0.f;
     {
@@ -810,9 +968,9 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
         const int acidx = __float_as_int(role[RF_ADH_CIDX * CTA + tid]);
         float c = fminf(role[RF_ADH_HI * CTA + tid], fmaxf(role[RF_ADH_LO * CTA + tid], st[S_CTRL + (acidx >= 0 ? acidx : 0)]));
         adhf = role[RF_ADH_GAIN * CTA + tid] * c;     // gain = 0 on lanes without an adhesion actuator
-        float fz = ncon_lane > 0.f ? -adhf / ncon_lane : 0.f;
+        const float pull = ncon_lane > 0.f ? adhf / ncon_lane : 0.f;
 #pragma unroll
-        for (int s = 0; s < 2; s++) { float f = con_on(con[s]) * fz; W[0] += con[s].r[1] * f; W[1] -= con[s].r[0] * f; W[5] += f; }
+        for (int s = 0; s < 2; s++) adhesion_wrench(con[s], pull, W);
       }
       chain_suffix<6>(W, NMF_FULL, k);
       // joint-space smooth force of own dofs: passive + actuator + C'W
@@ -1027,7 +1185,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
           float* c = dg + DBG_CON + (tid * 2 + s) * 6; float fn = 0.f, Wt[6] = {0, 0, 0, 0, 0, 0};
           contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
           const float on = con_on(con[s]);
-          c[0] = on; c[1] = on * 2.f * (con[s].r[2] + com[2]);
+          c[0] = on; c[1] = on * con_dist(con[s], com);
           c[2] = on * (con[s].r[0] + com[0]); c[3] = on * (con[s].r[1] + com[1]);
           c[4] = on * (con[s].r[2] + com[2]); c[5] = fn;
         }

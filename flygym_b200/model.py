@@ -39,6 +39,7 @@ _F64 = [
     "key_qpos", "key_ctrl",
     "opt",  # see OPT_FIELDS
     "contact",  # see CONTACT_FIELDS
+    "terrain",  # see TERRAIN_FIELDS (optional: all zeros = the reference's flat ground plane)
 ]
 _I32 = [
     "dims",  # see DIM_FIELDS
@@ -53,6 +54,17 @@ OPT_FIELDS = ["timestep", "gx", "gy", "gz", "iterations", "tolerance", "ls_itera
               "ls_tolerance", "noslip_iterations", "meaninertia", "impratio"]
 CONTACT_FIELDS = ["mu", "solref0", "solref1", "solimp0", "solimp1", "solimp2", "solimp3",
                   "solimp4", "margin", "gap"]
+TERRAIN_FIELDS = ["type", "period_x", "period_y", "half_x", "half_y", "top_even", "top_odd", "z_floor"]
+# Terrain worlds.  FlyGym 2.0.1 ships only FlatGroundWorld / TetheredWorld (reference src/flygym/compose/world.py:229-366);
+# BASELINE.json config 3 asks for the v1-style "blocks" and "gapped" arenas, defined here as a floor plane plus a grid of
+# axis-aligned box columns ([PRIOR] v1 defaults): column (i, j) covers |x - i*period_x| <= half_x,
+# |y - j*period_y| <= half_y, z <= top_even / top_odd by the parity of i + j.
+TERRAINS = {
+    # 1.0 mm blocks separated by 0.4 mm gaps that are 2 mm deep, running across the walking direction (infinite in y)
+    "gapped": [1.0, 1.4, 1.0e6, 0.5, 0.5e6, 0.0, 0.0, -2.0],
+    # 1.3 mm square tiles, every other one raised by 0.2 mm (checkerboard)
+    "blocks": [1.0, 1.3, 1.3, 0.65, 0.65, 0.0, 0.2, -1.0],
+}
 GEOM_CAPSULE = 0
 GEOM_HULL = 1
 
@@ -100,12 +112,26 @@ class NMFModel:
         return cls(arrays, names, meta)
 
     @classmethod
-    def bench(cls, simplify_geom: bool = True) -> "NMFModel":
-        """The reference benchmark model (``time_gpu_simulation.py:21-64``)."""
-        return cls.load(ASSETS_DIR / ("nmf_bench_capsule.npz" if simplify_geom else "nmf_bench_mesh.npz"))
+    def bench(cls, simplify_geom: bool = True, terrain: str | None = None) -> "NMFModel":
+        """The reference benchmark model (``time_gpu_simulation.py:21-64``); ``terrain`` = ``"blocks"`` / ``"gapped"``
+        replaces the flat ground plane by a box-column terrain (capsule geoms only)."""
+        m = cls.load(ASSETS_DIR / ("nmf_bench_capsule.npz" if simplify_geom else "nmf_bench_mesh.npz"))
+        return m if terrain in (None, "flat") else m.with_terrain(terrain)
+
+    def with_terrain(self, terrain) -> "NMFModel":
+        """Copy of the model standing on a box-column terrain: a name from ``TERRAINS`` or the 8 ``TERRAIN_FIELDS`` values."""
+        spec = TERRAINS[terrain] if isinstance(terrain, str) else list(terrain)
+        if len(spec) != len(TERRAIN_FIELDS):
+            raise ValueError(f"terrain needs {len(TERRAIN_FIELDS)} values: {TERRAIN_FIELDS}")
+        if (self.arrays["geom_type"] != GEOM_CAPSULE).any():
+            raise ValueError("terrain worlds need capsule collision geoms (simplify_geom=True)")
+        arrays = dict(self.arrays)
+        arrays["terrain"] = np.asarray(spec, dtype=np.float64)
+        return NMFModel(arrays, self.names, dict(self.meta, terrain=terrain if isinstance(terrain, str) else "custom"))
 
     def to_blob(self) -> bytes:
-        secs = [(n, 0, np.ascontiguousarray(self.arrays[n], dtype=np.float64).ravel()) for n in _F64]
+        arrays = self.arrays if "terrain" in self.arrays else dict(self.arrays, terrain=np.zeros(len(TERRAIN_FIELDS)))
+        secs = [(n, 0, np.ascontiguousarray(arrays[n], dtype=np.float64).ravel()) for n in _F64]
         secs += [(n, 1, np.ascontiguousarray(self.arrays[n], dtype=np.int32).ravel()) for n in _I32]
         header_size = 8 + 8 + len(secs) * (24 + 4 + 4 + 8)
         off = (header_size + 7) // 8 * 8

@@ -309,9 +309,10 @@ class B200Simulation:
 
     def step_host(self, actions_host: np.ndarray, nsteps: int, qpos_host: np.ndarray) -> None:
         """End-to-end call with HOST buffers (H2D actions, ``nsteps`` steps, D2H qpos); synchronous."""
-        assert actions_host.dtype == np.float32 and actions_host.shape == (self.n_worlds, self.info.nu_pos)
+        assert actions_host.dtype == np.float32 and actions_host.ndim == 2 and actions_host.shape[0] == self.n_worlds
+        assert actions_host.shape[1] in (self.info.nu_pos, self.info.nu_pos + self.info.nu_adh) and actions_host.flags.c_contiguous
         assert qpos_host.dtype == np.float32 and qpos_host.shape == (self.n_worlds, self.info.nq)
-        self._check(self._lib.nmf_step_host(self._h, actions_host.ctypes.data_as(ctypes.c_void_p), int(nsteps),
+        self._check(self._lib.nmf_step_host(self._h, actions_host.ctypes.data_as(ctypes.c_void_p), int(actions_host.shape[1]), int(nsteps),
                                             qpos_host.ctypes.data_as(ctypes.c_void_p), self._stream()))
 
     def set_solver(self, max_newton: int = 8, max_linesearch: int = 8) -> None:

@@ -43,7 +43,7 @@ typedef struct {
   const double *dof_axis, *dof_stiffness, *dof_damping, *dof_armature, *dof_springref;
   const double *act_kp, *act_kv, *act_frcrange, *adh_gain, *adh_ctrlrange;
   const double *geom_pos, *geom_quat, *geom_size, *hull_vert, *site_pos, *seg_pos, *seg_quat;
-  const double *key_qpos, *key_ctrl, *opt, *contact;
+  const double *key_qpos, *key_ctrl, *opt, *contact, *terrain;   /* terrain: optional section, NULL or type 0 = flat */
   const int32_t *body_parent, *body_dofadr, *body_dofnum, *body_leg, *dof_body, *dof_parent;
   const int32_t *act_dof, *adh_body, *geom_body, *geom_type, *geom_vertadr, *geom_vertnum;
   const int32_t *site_body, *seg_body, *leg_rootbody;
@@ -182,6 +182,7 @@ nmfo* nmfo_create(const void* blob, size_t nbytes) {
   SEC(adh_ctrlrange, "adh_ctrlrange"); SEC(geom_pos, "geom_pos"); SEC(geom_quat, "geom_quat");
   SEC(geom_size, "geom_size"); SEC(hull_vert, "hull_vert"); SEC(site_pos, "site_pos"); SEC(seg_pos, "seg_pos");
   SEC(seg_quat, "seg_quat"); SEC(key_qpos, "key_qpos"); SEC(key_ctrl, "key_ctrl"); SEC(opt, "opt"); SEC(contact, "contact");
+  o->terrain = find_section(o->blob, "terrain", NULL);
   SEC(body_parent, "body_parent"); SEC(body_dofadr, "body_dofadr"); SEC(body_dofnum, "body_dofnum");
   SEC(body_leg, "body_leg"); SEC(dof_body, "dof_body"); SEC(dof_parent, "dof_parent"); SEC(act_dof, "act_dof");
   SEC(adh_body, "adh_body"); SEC(geom_body, "geom_body"); SEC(geom_type, "geom_type");
@@ -345,6 +346,37 @@ static void jac_point(const nmfo* o, double* jacp, int b, const double* point) {
 }
 
 /* collision: explicit geom-plane pairs only (world.py:292-309); plane z=0, normal +z */
+static void add_contact_n(nmfo* o, int g, double dist, const double* pos, const double* nrm, const double* hint) {
+  /* general normal (terrain worlds): tangent = hint orthogonalised against the normal, world x (or y) if they are parallel */
+  if (o->ncon >= o->maxcon) return;
+  int c = o->ncon++; double* f = o->con_frame + 9 * c;
+  o->con_dist[c] = dist; memcpy(o->con_pos + 3 * c, pos, 24); o->con_geom[c] = g;
+  memcpy(f, nrm, 24);
+  double t = dot3(hint, nrm), y[3] = {hint[0] - t * nrm[0], hint[1] - t * nrm[1], hint[2] - t * nrm[2]};
+  if (dot3(y, y) < 1e-12) {
+    double e[3] = {fabs(nrm[0]) < 0.9 ? 1.0 : 0.0, fabs(nrm[0]) < 0.9 ? 0.0 : 1.0, 0.0};
+    t = dot3(e, nrm); for (int k = 0; k < 3; k++) y[k] = e[k] - t * nrm[k];
+  }
+  double n = sqrt(dot3(y, y)); for (int k = 0; k < 3; k++) y[k] /= n;
+  memcpy(f + 3, y, 24); cross3(f + 6, f, y);
+}
+/* sphere vs terrain solid (floor plane + grid of box columns): closest point of the solid -> one contact candidate.
+ * terrain = {type, Px, Py, hx, hy, top_even, top_odd, z_floor} (flygym_b200/model.py TERRAIN_FIELDS) */
+static void sphere_terrain(const nmfo* o, const double* c, double rad, double* nrm, double* dist) {
+  const double* T = o->terrain; double Px = T[1], Py = T[2], hx = T[3], hy = T[4];
+  nrm[0] = 0; nrm[1] = 0; nrm[2] = 1; *dist = c[2] - T[7] - rad;
+  double fi = nearbyint(c[0] / Px), fj = nearbyint(c[1] / Py);
+  int i0 = (int)fi, j0 = (int)fj, sx = c[0] >= fi * Px ? 1 : -1, sy = c[1] >= fj * Py ? 1 : -1;
+  for (int q = 0; q < 4; q++) {
+    int i = i0 + ((q & 1) ? sx : 0), j = j0 + ((q & 2) ? sy : 0);
+    double cx = i * Px, cy = j * Py, top = ((i + j) & 1) ? T[6] : T[5];
+    double qx = fmin(fmax(c[0], cx - hx), cx + hx), qy = fmin(fmax(c[1], cy - hy), cy + hy), qz = fmin(c[2], top);
+    double d[3] = {c[0] - qx, c[1] - qy, c[2] - qz}, d2 = dot3(d, d), dd, n[3] = {0, 0, 1};
+    if (d2 > 0) { double l = sqrt(d2); dd = l - rad; for (int k = 0; k < 3; k++) n[k] = d[k] / l; }
+    else dd = c[2] - top - rad;   /* centre inside the column: out through the top face */
+    if (dd < *dist) { *dist = dd; memcpy(nrm, n, 24); }
+  }
+}
 static void add_contact(nmfo* o, int g, double dist, const double* pos, const double* hint) {
   if (o->ncon >= o->maxcon) return;
   int c = o->ncon++; double* f = o->con_frame + 9 * c;
@@ -368,6 +400,13 @@ static void collision(nmfo* o) {
       for (int s = 0; s < 2; s++) {
         double sg = s == 0 ? 1.0 : -1.0, c[3];
         for (int k = 0; k < 3; k++) c[k] = gp[k] + sg * h * axis[k];
+        if (o->terrain && o->terrain[0] != 0) {   /* terrain world: each end sphere against the terrain solid */
+          double nrm[3], dist; sphere_terrain(o, c, r, nrm, &dist);
+          if (dist > o->margin) continue;
+          double pos[3]; for (int k = 0; k < 3; k++) pos[k] = c[k] - (r + dist / 2) * nrm[k];
+          add_contact_n(o, g, dist, pos, nrm, axis);
+          continue;
+        }
         double cdist = c[2];
         if (cdist > o->margin + r) continue;
         double dist = cdist - r, pos[3] = {c[0], c[1], c[2] - (r + dist / 2)};
@@ -660,6 +699,10 @@ void nmfo_step(nmfo* o) {
 }
 
 void nmfo_step_n(nmfo* o, int n) { for (int i = 0; i < n; i++) nmfo_step(o); }
+/* n steps with a per-step table [n][cols] written into ctrl[0:cols] (cols = nu_pos, or nu for position + adhesion inputs) */
+void nmfo_step_table_cols(nmfo* o, const double* table, int n, int cols) {
+  for (int i = 0; i < n; i++) { memcpy(o->ctrl, table + (size_t)i * cols, sizeof(double) * cols); nmfo_step(o); }
+}
 /* n steps with a per-step action table [n][nu_pos] written into ctrl[0:nu_pos] */
 void nmfo_step_table(nmfo* o, const double* table, int n) {
   for (int i = 0; i < n; i++) { memcpy(o->ctrl, table + (size_t)i * o->nu_pos, sizeof(double) * o->nu_pos); nmfo_step(o); }

@@ -37,6 +37,7 @@ def _lib():
         lib.nmfo_step.argtypes = [ctypes.c_void_p]
         lib.nmfo_step_n.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.nmfo_step_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.nmfo_step_table_cols.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         lib.nmfo_dim.restype = ctypes.c_int
         lib.nmfo_dim.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         lib.nmfo_array.restype = ctypes.POINTER(ctypes.c_double)
@@ -102,6 +103,11 @@ class Oracle:
         """One step per row of ``table`` (float64 ``[n][nu_pos]``) used as position-actuator inputs."""
         table = np.ascontiguousarray(table, dtype=np.float64)
         self._lib.nmfo_step_table(self._h, table.ctypes.data_as(ctypes.c_void_p), int(table.shape[0]))
+
+    def step_table_full(self, table):
+        """One step per row of ``table`` (float64 ``[n][cols]``) copied into ``ctrl[0:cols]`` (position targets, then adhesion)."""
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        self._lib.nmfo_step_table_cols(self._h, table.ctypes.data_as(ctypes.c_void_p), int(table.shape[0]), int(table.shape[1]))
 
     def error(self) -> str:
         return self._lib.nmfo_last_error(self._h).decode()

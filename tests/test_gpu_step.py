@@ -236,3 +236,52 @@ def test_work_queue_schedule_is_bit_identical():
             assert torch.equal(a, b)
     assert torch.isfinite(finals[0][0]).all()
     assert abs(float(finals[0][0][0, 300]) - 46e-4) < 1e-6      # time advanced by 46 steps
+
+
+@pytest.mark.parametrize("terrain", ["blocks", "gapped"])
+def test_terrain_walking_parity(terrain):
+    """BASELINE config 3: CPG gait with stance-phase adhesion (ctrl 100 in stance, 1 in swing) on box-column terrain,
+    flies spread over the tile / gap pattern.  Contact dynamics over edges are more chaotic than on the plane (a foot
+    sliding off a tile edge switches contact normal): 1e-6 after one step and 1e-4 up to 100 steps for every fly, median
+    below 1e-4 (max 5e-2) at 300 steps (measured on B200: median 1.2e-5, one fly 8e-3 after an edge event)."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_parameters, TRIPOD_PHASE
+    from oracle.oracle import Oracle
+    model = NMFModel.bench(simplify_geom=True, terrain=terrain)
+    n, T, nu_pos = 8, 300, model.dim("nu_pos")
+    neutral, amp, phase = cpg_parameters(model)
+    t = np.arange(T) * model.timestep
+    tab = np.zeros((n, T, nu_pos + 6))
+    legph = np.array([TRIPOD_PHASE[l] for l in model.names["legs"]])
+    for k in range(n):
+        base = 2 * np.pi * 12.0 * t[:, None] + 2 * np.pi * k / n
+        tab[k, :, :nu_pos] = neutral + amp * np.sin(base + phase)
+        tab[k, :, nu_pos:] = np.where(np.sin(base + legph) < 0, 100.0, 1.0)
+    tab32 = tab.astype(np.float32)
+    sim = B200Simulation(model, n_worlds=n, outputs=True)
+    q0 = np.tile(model.arrays["key_qpos"], (n, 1))
+    q0[:, 2] = -0.15 if terrain == "blocks" else -0.17
+    q0[:, 0] += np.linspace(0.0, 1.4, n)                     # different phases relative to the tile / gap pattern
+    q0[:, 1] += np.linspace(0.0, 0.9, n)
+    sim.qpos.copy_(torch.as_tensor(q0, dtype=torch.float32))
+    tabd = torch.from_numpy(tab32).cuda()
+    got, done = {}, 0
+    for cp in (1, 100, 300):
+        sim.step(cp - done, tabd, done); done = cp
+        got[cp] = sim.qpos.cpu().numpy().astype(np.float64)
+    found = sim.get_ground_contact_info("nmf")[0].cpu().numpy()
+    errs = {cp: [] for cp in got}
+    ncon_total = 0
+    for k in range(n):
+        o = Oracle(model); o.reset(); o.qpos[:] = q0[k]
+        done = 0
+        for cp in (1, 100, 300):
+            o.step_table_full(tab32[k, done:cp].astype(np.float64)); done = cp
+            errs[cp].append(float(np.abs(got[cp][k] - o.qpos).max() / np.abs(o.qpos).max()))
+        ncon_total += o.dim("ncon")
+    print(terrain, "qpos rel Linf:", {k: ["%.1e" % e for e in v] for k, v in errs.items()})
+    assert ncon_total > 0 and found.sum() > 0
+    assert max(errs[1]) < 1e-6 and max(errs[100]) < 1e-4
+    assert np.median(errs[300]) < 1e-4 and max(errs[300]) < 5e-2
+    assert torch.isfinite(sim.state).all()
