@@ -28,7 +28,7 @@ using namespace nmf;
 //    therefore filled by the (i-n)-th completion; when a block pops it at most `grid` items are still running, i.e. at
 //    least i - grid >= i - n have completed (the queue is only used when n_flies >= grid), so pops do not wait.
 //    queue[0] = pop counter, queue[1] = push counter, queue[2 + f] = sub-chunks of fly f done, queue[2 + n + j] = ring entry j.
-template <bool TERRAIN>
+template <int WORLD>
 __device__ __forceinline__ void step_entry(const StepParams& p) {
   __shared__ __align__(16) float sm[SM_TOTAL];
   __shared__ int s_fly, s_chunk;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void step_entry(const StepParams& p) {
       if (fly < 0) return;
       step0 = s_chunk * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
     }
-    step_block<TERRAIN>(p, sm, fly, step0, nsub, p.queue != nullptr);
+    step_block<WORLD>(p, sm, fly, step0, nsub, p.queue != nullptr);
     if (!p.queue) return;
     if (tid == 0) {   // the TMA store of the record has completed (tma_store_record waited for it): hand the fly on
       const int done = step0 / p.sub_steps + 1;
@@ -72,12 +72,14 @@ __device__ __forceinline__ void step_entry(const StepParams& p) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) { step_entry<false>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) { step_entry<W_FLAT>(p); }
 // terrain worlds (box columns: BASELINE config 3): general contact frames need 8 more registers per lane
 #ifndef NMF_MINBLOCKS_TERRAIN
 #define NMF_MINBLOCKS_TERRAIN 12
 #endif
-extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_step_terrain_kernel(const StepParams p) { step_entry<true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_step_terrain_kernel(const StepParams p) { step_entry<W_TERRAIN>(p); }
+// TetheredWorld (reference world.py:334-366): no ground contacts, six weld rows on the free body
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether_kernel(const StepParams p) { step_entry<W_TETHER>(p); }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
   int fly = blockIdx.x;
@@ -147,7 +149,8 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   CK(cudaMalloc(&h->d_queue, sizeof(int) * ((size_t)n_flies * QUEUE_MAX_CHUNKS + 2)));
   {
     int per_sm = 0, sms = 0;
-    if (h->hm.par.terrain) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_terrain_kernel, CTA, 0));
+    if (h->hm.par.weld) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_tether_kernel, CTA, 0));
+    else if (h->hm.par.terrain) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_terrain_kernel, CTA, 0));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_kernel, CTA, 0));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     h->resident_blocks = per_sm * sms;
@@ -231,7 +234,8 @@ extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table
     grid = h->resident_blocks;
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)h->n_flies * nchunk + 2), (cudaStream_t)stream));
   }
-  if (p.terrain) nmf_step_terrain_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
+  if (p.weld) nmf_step_tether_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
+  else if (p.terrain) nmf_step_terrain_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
   else nmf_step_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
   h->launches++;
   CK(cudaGetLastError());

@@ -184,6 +184,20 @@ struct HostModel {
     par.max_newton = (int)opt[4]; par.max_ls = (int)opt[6]; par.nsteps = 1;   // reference: iterations=100 (mujoco_globals.yaml:14), ls_iterations=50 (MuJoCo default)
     if (par.max_newton < 1) par.max_newton = 100;
     if (par.max_ls < 1) par.max_ls = 50;
+    {  // optional weld section (TetheredWorld): see flygym_b200/model.py WELD_FIELDS
+      int nw = 0; const double* wd = b.get<double>("weld", &nw);
+      if (wd && nw >= 18 && wd[0] != 0.0) {
+        if (ngeom != 0) { err = "a tethered (welded) world cannot have ground-contact geoms"; return false; }
+        par.weld = 1;
+        for (int i = 0; i < 3; i++) par.weld_a[i] = (float)wd[1 + i];
+        for (int i = 0; i < 4; i++) par.weld_q[i] = (float)wd[4 + i];
+        const double wtc = std::fmax(wd[8], 2 * opt[0]), wdmax = clampimp(wd[11]);
+        par.weld_K = (float)(1.0 / (wdmax * wdmax * wtc * wtc * wd[9] * wd[9])); par.weld_B = (float)(2.0 / (wdmax * wtc));
+        par.weld_imp[0] = (float)clampimp(wd[10]); par.weld_imp[1] = (float)wdmax; par.weld_imp[2] = (float)std::fmax(0.0, wd[12]);
+        par.weld_imp[3] = (float)clampimp(wd[13]); par.weld_imp[4] = (float)std::fmax(1.0, wd[14]);
+        par.weld_ts = (float)wd[15]; par.weld_invw[0] = (float)wd[16]; par.weld_invw[1] = (float)wd[17];
+      }
+    }
     {  // optional terrain section: {type, Px, Py, hx, hy, top_even, top_odd, z_floor}
       int nt = 0; const double* terr = b.get<double>("terrain", &nt);
       if (terr && nt >= 8 && terr[0] != 0.0) {

@@ -99,6 +99,10 @@ struct StepParams {
   // top_odd, z_floor, 0}: column (i, j) covers |x - i Px| <= hx, |y - j Py| <= hy, z <= top_{(i+j)&1}
   int terrain;
   float terr[8];
+  // TetheredWorld weld (reference world.py:350-366): the hub-frame point weld_a is pulled onto the world origin and
+  // q_hub * weld_q onto the identity by six always-active (equality) rows with their own solref / solimp
+  int weld;
+  float weld_a[3], weld_q[4], weld_K, weld_B, weld_imp[5], weld_ts, weld_invw[2];
   // work-queue scheduling (nullptr = one block per fly for the whole launch): queue[0] = next work item,
   // queue[1 + fly] = number of sub-chunks of that fly already written back
   int* queue;

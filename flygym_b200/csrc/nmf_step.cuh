@@ -175,8 +175,8 @@ struct Contact {     // 10 registers per slot; "active" <=> D > 0; signed distan
 };
 __device__ __forceinline__ float con_on(const Contact& c) { return c.D > 0.f ? 1.f : 0.f; }
 
-__device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
-  const float d0 = p.solimp[0], d1 = p.solimp[1], width = p.solimp[2], mid = p.solimp[3], power = p.solimp[4];
+__device__ __forceinline__ float impedance_of(const float* solimp, float x_abs) {
+  const float d0 = solimp[0], d1 = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (d0 == d1 || width <= NMF_MINVAL) return 0.5f * (d0 + d1);   // (uniform branch)
   float x = fminf(x_abs / width, 1.f);
   float y;
@@ -185,6 +185,8 @@ __device__ __forceinline__ float impedance(const StepParams& p, float x_abs) {
   else y = (x <= mid) ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
   return d0 + y * (d1 - d0);
 }
+
+__device__ __forceinline__ float impedance(const StepParams& p, float x_abs) { return impedance_of(p.solimp, x_abs); }
 
 // finishes a candidate contact: solver parameters and the B*velocity part of the rows
 __device__ __forceinline__ void finish_contact(const StepParams& p, Contact& c, float active, float dist, const float* pos, float hx, float hy,
@@ -486,6 +488,76 @@ __device__ __forceinline__ void adhesion_wrench(const ContactG& c, float f, floa
 __device__ __forceinline__ float con_dist(const Contact& c, const float* com) { return 2.f * (c.r[2] + com[2]); }
 __device__ __forceinline__ float con_dist(const ContactG&, const float*) { return 0.f; }
 
+// ------------------------------------------------------------------ weld equality of the TetheredWorld (hub lane only)
+// Six always-active rows on the free body: rows 0-2 = world position of the hub-frame point weld_a, rows 3-5 =
+// torquescale * vec(q_hub * weld_q) with Jacobian G w = 0.5 ts vec((0, w) * q) (w = world angular velocity).  They only touch
+// the hub's 6x6 block, so they enter exactly like a contact on the hub: a wrench in the gradient and an X'WX augmentation
+// of the hub's spatial inertia.  State lives in shared memory (one lane uses it): r[3] G[9] D[6] c0[6] w[6] sv[6].
+constexpr int WL_R = 0, WL_G = 3, WL_D = 12, WL_C0 = 18, WL_W = 24, WL_SV = 30, WL_COUNT = 36;
+
+__device__ __forceinline__ void point_and_rot(const float* sw, const float* S, float* out) {   // J * (spatial vector of the hub)
+  const float* r = sw + WL_R; const float* G = sw + WL_G;
+  out[0] = S[3] + S[1] * r[2] - S[2] * r[1]; out[1] = S[4] + S[2] * r[0] - S[0] * r[2]; out[2] = S[5] + S[0] * r[1] - S[1] * r[0];
+#pragma unroll
+  for (int i = 0; i < 3; i++) out[3 + i] = G[3 * i] * S[0] + G[3 * i + 1] * S[1] + G[3 * i + 2] * S[2];
+}
+__device__ __forceinline__ void weld_setup(const StepParams& p, float* sw, const float* qh, const float* xh, const float* com,
+                                           const float* cvel, const float* Sa) {
+  float a[3], q[4], pos[6];
+  qrot(qh, p.weld_a, a); qmul(qh, p.weld_q, q);
+  const float h = 0.5f * p.weld_ts;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { pos[i] = xh[i] + a[i]; sw[WL_R + i] = pos[i] - com[i]; pos[3 + i] = p.weld_ts * q[1 + i]; }
+  float* G = sw + WL_G;
+  G[0] = h * q[0]; G[1] = h * q[3]; G[2] = -h * q[2];
+  G[3] = -h * q[3]; G[4] = h * q[0]; G[5] = h * q[1];
+  G[6] = h * q[2]; G[7] = -h * q[1]; G[8] = h * q[0];
+  float jv[6], ja[6];
+  point_and_rot(sw, cvel, jv); point_and_rot(sw, Sa, ja);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float imp = impedance_of(p.weld_imp, fabsf(pos[i]));
+    const float Rr = fmaxf(NMF_MINVAL, (1.f - imp) * p.weld_invw[i >= 3 ? 1 : 0] / imp);
+    sw[WL_D + i] = 1.f / Rr;
+    sw[WL_C0 + i] = p.weld_K * imp * pos[i];
+    sw[WL_W + i] = p.weld_B * jv[i] + ja[i];
+  }
+}
+// forces of the six rows for the current acceleration: wrench about the COM into Wc, Hessian augmentation into A
+__device__ __forceinline__ void weld_forces(const float* sw, float* Wc, float* A) {
+  const float* r = sw + WL_R; const float* G = sw + WL_G; const float* D = sw + WL_D;
+  float f[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) f[i] = -D[i] * (sw[WL_W + i] + sw[WL_C0 + i]);
+  float T[3]; cross3(r, f, T);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { Wc[i] += T[i] + G[i] * f[3] + G[3 + i] * f[4] + G[6 + i] * f[5]; Wc[3 + i] += f[i]; }
+  // position rows: W = diag(D0, D1, D2) at the point r  ->  X' W X ; rotation rows: G' diag(D3..5) G on the angular block
+  float Tm[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float col[3] = {j == 0 ? D[0] : 0.f, j == 1 ? D[1] : 0.f, j == 2 ? D[2] : 0.f}, t[3]; cross3(r, col, t);
+    Tm[j] = t[0]; Tm[3 + j] = t[1]; Tm[6 + j] = t[2];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float row[3] = {Tm[3 * i], Tm[3 * i + 1], Tm[3 * i + 2]}, t[3]; cross3(r, row, t);
+#pragma unroll
+    for (int j = i; j < 3; j++) A[s6(i, j)] += t[j] + G[i] * D[3] * G[j] + G[3 + i] * D[4] * G[3 + j] + G[6 + i] * D[5] * G[6 + j];
+#pragma unroll
+    for (int j = 0; j < 3; j++) A[s6(i, 3 + j)] += Tm[3 * i + j];
+  }
+  A[s6(3, 3)] += D[0]; A[s6(4, 4)] += D[1]; A[s6(5, 5)] += D[2];
+}
+// line-search sums of the (always active) rows at step alpha
+__device__ __forceinline__ void weld_ls(const float* sw, float alpha, float& d0, float& d1) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float jv = sw[WL_SV + i], x = sw[WL_W + i] + sw[WL_C0 + i] + alpha * jv;
+    d0 += sw[WL_D + i] * x * jv; d1 += sw[WL_D + i] * jv * jv;
+  }
+}
+
 // ------------------------------------------------------------------ shared-memory plan (floats)
 // The 64 lanes form 8 shuffle groups of 8: groups 0..5 are the leg chains, groups 6..7 are
 // "hub chains": massless, joint-less bodies welded to the hub that carry the hub's contact
@@ -510,7 +582,8 @@ constexpr int SM_HBB = SM_BASE + 168;               // 21 hub block + 6 xb + 6 S
 constexpr int SM_HUB = SM_HBB + 112;                // hub uniforms
 constexpr int SM_RED = SM_HUB + 64;                 // 32
 constexpr int SM_MBAR = SM_RED + 32;                // 8-byte mbarrier for the TMA record load (16-byte slot)
-constexpr int SM_TOTAL = SM_MBAR + 4;
+constexpr int SM_WELD = SM_MBAR + 4;                // weld rows of the tethered world (WL_COUNT)
+constexpr int SM_TOTAL = SM_WELD + WL_COUNT;
 constexpr int HU_CVEL = 0, HU_CACC = 6;
 constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27, HB_TOT = 33, HB_SR = 72;   // TOT: 37 root totals; SR: assembled Schur block (21) + rhs (6)
 
@@ -729,11 +802,16 @@ __device__ __forceinline__ void tma_store_record(float* dst_gmem, const float* s
 // ------------------------------------------------------------------ the step
 // Advances fly `fly` by steps [step0, step0 + nsub) of the launch's p.nsteps (one work item of the launch: the whole
 // launch when flies map 1:1 to blocks, a sub-chunk under work-queue scheduling).
-// TERRAIN selects the general-frame contact slot and the capsule-vs-box-column narrow phase (separate kernel instantiation).
-template <bool TERRAIN>
+// WORLD selects the kernel instantiation: W_FLAT = the reference's FlatGroundWorld; W_TERRAIN = general-frame contact
+// slots + capsule-vs-box-column narrow phase; W_TETHER = TetheredWorld (no ground, weld equality on the hub).
+constexpr int W_FLAT = 0, W_TERRAIN = 1, W_TETHER = 2;
+template <int WORLD>
 __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const int fly, const int step0, const int nsub, const bool published) {
-  using Con = typename std::conditional<TERRAIN, ContactG, Contact>::type;
+  using Con = typename std::conditional<WORLD == W_TERRAIN, ContactG, Contact>::type;
+  constexpr bool TETHER = WORLD == W_TETHER;
+  float* sw = sm + SM_WELD;
   const int tid = threadIdx.x;
+  const bool weld_lane = TETHER && tid == NLEG * NLINK;
   const int grp = tid >> 3, k = tid & 7, t = k;
   const bool is_leg = grp < NLEG;
   const int hl = tid - NLEG * NLINK;          // hub lane index (valid when !is_leg)
@@ -1011,6 +1089,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
         float ap[3]; project_point(con[s], Sa, p.mu, ap);
         con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
       }
+      if (TETHER && weld_lane) weld_setup(p, sw, qh, xh, com, s_hub + HU_CVEL, Sa);
     }
     const bool any0 = __any_sync(NMF_FULL, con[0].D > 0.f), any1 = __any_sync(NMF_FULL, con[1].D > 0.f);
     block_sync();   // chain roots (wrench, crb) visible to the hub lanes
@@ -1045,6 +1124,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
       for (int i = 0; i < 21; i++) A[i] = 0.f;
       if (any0) contact_forces<true>(con[0], p.mu, Wc, A, nullptr);    // warp-uniform skips: most lanes have no contact
       if (any1) contact_forces<true>(con[1], p.mu, Wc, A, nullptr);
+      if (TETHER && weld_lane) weld_forces(sw, Wc, A);
       // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
       float y[12];
       {
@@ -1138,6 +1218,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
         float dummy = 0.f;
         if (any0) { project_point(con[0], Ss, p.mu, sv0); ls_eval(con[0], sv0, 0.f, red[2], red[3], dummy); }
         if (any1) { project_point(con[1], Ss, p.mu, sv1); ls_eval(con[1], sv1, 0.f, red[2], red[3], dummy); }
+        if (TETHER && weld_lane) { point_and_rot(sw, Ss, sw + WL_SV); weld_ls(sw, 0.f, red[2], red[3]); }
       }
       cta_reduce<5>(red, s_red, parity, tid);
       // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
@@ -1156,6 +1237,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
           float e[3] = {0.f, 0.f, 0.f};
           if (any0) ls_eval(con[0], sv0, alpha, e[0], e[1], e[2]);
           if (any1) ls_eval(con[1], sv1, alpha, e[0], e[1], e[2]);
+          if (TETHER && weld_lane) weld_ls(sw, alpha, e[0], e[1]);
           cta_reduce<3>(e, s_red, parity, tid);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
           nchanged_last = (int)e[2];
@@ -1169,6 +1251,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
       for (int i = 0; i < 6; i++) Sa[i] += alpha * Ss[i];
 #pragma unroll
       for (int i = 0; i < 3; i++) { con[0].w[i] += alpha * sv0[i]; con[1].w[i] += alpha * sv1[i]; }
+      if (TETHER && weld_lane) for (int i = 0; i < 6; i++) sw[WL_W + i] += alpha * sw[WL_SV + i];
     }
     // SM_X now holds the implicit-damping (Euler) acceleration  (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
     block_sync();

@@ -40,6 +40,7 @@ _F64 = [
     "opt",  # see OPT_FIELDS
     "contact",  # see CONTACT_FIELDS
     "terrain",  # see TERRAIN_FIELDS (optional: all zeros = the reference's flat ground plane)
+    "weld",  # see WELD_FIELDS (optional: all zeros = no weld; TetheredWorld sets it)
 ]
 _I32 = [
     "dims",  # see DIM_FIELDS
@@ -65,8 +66,23 @@ TERRAINS = {
     # 1.3 mm square tiles, every other one raised by 0.2 mm (checkerboard)
     "blocks": [1.0, 1.3, 1.3, 0.65, 0.65, 0.0, 0.2, -1.0],
 }
+# TetheredWorld's weld(body1=c_thorax, body2=world) (reference src/flygym/compose/world.py:350-366), reduced to what the
+# step needs: the body-1 anchor point and the orientation offset in the frame of the free ("hub") body, the constraint's
+# own solref / solimp, torquescale, and the hub's translational / rotational inverse weights (diagApprox of the six rows).
+WELD_FIELDS = ["enabled", "anchor_x", "anchor_y", "anchor_z", "quat_w", "quat_x", "quat_y", "quat_z", "solref0", "solref1",
+               "solimp0", "solimp1", "solimp2", "solimp3", "solimp4", "torquescale", "invweight_tran", "invweight_rot"]
 GEOM_CAPSULE = 0
 GEOM_HULL = 1
+
+
+def _quat_mul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def _quat_rotate(q, v):
+    t = 2.0 * np.cross(q[1:], v)
+    return v + q[0] * t + np.cross(q[1:], t)
 
 
 @dataclass
@@ -118,6 +134,36 @@ class NMFModel:
         m = cls.load(ASSETS_DIR / ("nmf_bench_capsule.npz" if simplify_geom else "nmf_bench_mesh.npz"))
         return m if terrain in (None, "flat") else m.with_terrain(terrain)
 
+    @classmethod
+    def tethered(cls, spawn_position=(0.0, 0.0, 1.5), spawn_quat=(1.0, 0.0, 0.0, 0.0)) -> "NMFModel":
+        """The same fly in the reference's ``TetheredWorld`` (``world.py:334-366``, the world behind the reference's own
+        ``tests/core/test_simulation.py`` fixtures): no ground, no contact pairs, and a soft weld
+        ``weld(body1=c_thorax, body2=world, relpose=(*spawn_position, *spawn_rotation), solref=(2e-4, 1),
+        solimp=(0.98, 0.99, 1e-5, 0.5, 3))``.  MuJoCo reads ``relpose`` as the pose of body 2 in the frame of body 1, so the
+        constraint pulls the thorax-frame point ``spawn_position`` onto the world origin and ``q_thorax * spawn_quat`` onto
+        the identity ([PRIOR] mjEQ_WELD semantics); that effective behaviour is what is reproduced."""
+        m = cls.load(ASSETS_DIR / "nmf_bench_capsule.npz")
+        a = dict(m.arrays)
+        dims = a["dims"].copy(); dims[DIM_FIELDS.index("ngeom")] = 0; dims[DIM_FIELDS.index("nhullvert")] = 0
+        a["dims"] = dims
+        for k, w in (("geom_pos", 3), ("geom_quat", 4), ("geom_size", 2)):
+            a[k] = np.zeros((0, w))
+        for k in ("geom_body", "geom_type", "geom_vertadr", "geom_vertnum"):
+            a[k] = np.zeros(0, np.int32)
+        a["hull_vert"] = np.zeros((0, 3)); a["hull_nbr_adr"] = np.zeros(1, np.int32); a["hull_nbr"] = np.zeros(0, np.int32)
+        key = a["key_qpos"].copy(); key[0:3] = spawn_position; key[3:7] = spawn_quat
+        a["key_qpos"] = key
+        seg = m.names["segments"].index("c_thorax")
+        if int(a["seg_body"][seg]) != 0:
+            raise ValueError("c_thorax is not part of the free body")
+        sp, sq = a["seg_pos"].reshape(-1, 3)[seg], a["seg_quat"].reshape(-1, 4)[seg]
+        anchor = sp + _quat_rotate(sq, np.asarray(spawn_position, dtype=np.float64))
+        quat = _quat_mul(sq, np.asarray(spawn_quat, dtype=np.float64))
+        invw = a["body_invweight0"].reshape(-1, 2)[0]
+        a["weld"] = np.array([1.0, *anchor, *quat, 2e-4, 1.0, 0.98, 0.99, 1e-5, 0.5, 3.0, 1.0, invw[0], invw[1]])
+        names = dict(m.names, contact_geoms=[])
+        return NMFModel(a, names, dict(m.meta, world="tethered", contact_preset=None))
+
     def with_terrain(self, terrain) -> "NMFModel":
         """Copy of the model standing on a box-column terrain: a name from ``TERRAINS`` or the 8 ``TERRAIN_FIELDS`` values."""
         spec = TERRAINS[terrain] if isinstance(terrain, str) else list(terrain)
@@ -130,7 +176,9 @@ class NMFModel:
         return NMFModel(arrays, self.names, dict(self.meta, terrain=terrain if isinstance(terrain, str) else "custom"))
 
     def to_blob(self) -> bytes:
-        arrays = self.arrays if "terrain" in self.arrays else dict(self.arrays, terrain=np.zeros(len(TERRAIN_FIELDS)))
+        arrays = dict(self.arrays)
+        arrays.setdefault("terrain", np.zeros(len(TERRAIN_FIELDS)))
+        arrays.setdefault("weld", np.zeros(len(WELD_FIELDS)))
         secs = [(n, 0, np.ascontiguousarray(arrays[n], dtype=np.float64).ravel()) for n in _F64]
         secs += [(n, 1, np.ascontiguousarray(self.arrays[n], dtype=np.int32).ravel()) for n in _I32]
         header_size = 8 + 8 + len(secs) * (24 + 4 + 4 + 8)

@@ -44,6 +44,8 @@ typedef struct {
   const double *act_kp, *act_kv, *act_frcrange, *adh_gain, *adh_ctrlrange;
   const double *geom_pos, *geom_quat, *geom_size, *hull_vert, *site_pos, *seg_pos, *seg_quat;
   const double *key_qpos, *key_ctrl, *opt, *contact, *terrain;   /* terrain: optional section, NULL or type 0 = flat */
+  const double* weld;   /* optional section (TetheredWorld): enabled, anchor[3], quat[4], solref[2], solimp[5], torquescale, invweight tran/rot */
+  int neq;              /* equality rows at the head of the efc arrays (6 with a weld) */
   const int32_t *body_parent, *body_dofadr, *body_dofnum, *body_leg, *dof_body, *dof_parent;
   const int32_t *act_dof, *adh_body, *geom_body, *geom_type, *geom_vertadr, *geom_vertnum;
   const int32_t *site_body, *seg_body, *leg_rootbody;
@@ -183,6 +185,8 @@ nmfo* nmfo_create(const void* blob, size_t nbytes) {
   SEC(geom_size, "geom_size"); SEC(hull_vert, "hull_vert"); SEC(site_pos, "site_pos"); SEC(seg_pos, "seg_pos");
   SEC(seg_quat, "seg_quat"); SEC(key_qpos, "key_qpos"); SEC(key_ctrl, "key_ctrl"); SEC(opt, "opt"); SEC(contact, "contact");
   o->terrain = find_section(o->blob, "terrain", NULL);
+  o->weld = find_section(o->blob, "weld", NULL);
+  if (o->weld && o->weld[0] == 0) o->weld = NULL;
   SEC(body_parent, "body_parent"); SEC(body_dofadr, "body_dofadr"); SEC(body_dofnum, "body_dofnum");
   SEC(body_leg, "body_leg"); SEC(dof_body, "dof_body"); SEC(dof_parent, "dof_parent"); SEC(act_dof, "act_dof");
   SEC(adh_body, "adh_body"); SEC(geom_body, "geom_body"); SEC(geom_type, "geom_type");
@@ -209,7 +213,7 @@ nmfo* nmfo_create(const void* blob, size_t nbytes) {
   o->maxcon = 4 * o->ngeom;
   o->con_dist = dalloc(o->maxcon); o->con_pos = dalloc(3 * o->maxcon); o->con_frame = dalloc(9 * o->maxcon);
   o->con_geom = (int*)calloc(o->maxcon, sizeof(int));
-  int maxefc = 4 * o->maxcon;
+  int maxefc = 4 * o->maxcon + 6;
   o->efc_J = dalloc((size_t)maxefc * nv); o->efc_pos = dalloc(maxefc); o->efc_D = dalloc(maxefc);
   o->efc_R = dalloc(maxefc); o->efc_aref = dalloc(maxefc); o->efc_vel = dalloc(maxefc);
   o->efc_force = dalloc(maxefc); o->efc_jar = dalloc(maxefc); o->efc_active = (int*)calloc(maxefc, sizeof(int));
@@ -428,9 +432,9 @@ static void collision(nmfo* o) {
 }
 
 /* impedance d(r) — getimpedance with sanitised solimp */
-static double impedance(const nmfo* o, double pos_minus_margin) {
-  double d0 = fmin(MAXIMP, fmax(MINIMP, o->solimp[0])), d1 = fmin(MAXIMP, fmax(MINIMP, o->solimp[1]));
-  double width = fmax(0, o->solimp[2]), mid = fmin(MAXIMP, fmax(MINIMP, o->solimp[3])), power = fmax(1, o->solimp[4]);
+static double impedance_of(const double* solimp, double pos_minus_margin) {
+  double d0 = fmin(MAXIMP, fmax(MINIMP, solimp[0])), d1 = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
+  double width = fmax(0, solimp[2]), mid = fmin(MAXIMP, fmax(MINIMP, solimp[3])), power = fmax(1, solimp[4]);
   if (d0 == d1 || width <= MINVAL) return 0.5 * (d0 + d1);
   double x = fabs(pos_minus_margin) / width;
   if (x >= 1) return d1;
@@ -442,9 +446,40 @@ static double impedance(const nmfo* o, double pos_minus_margin) {
   return d0 + y * (d1 - d0);
 }
 
-/* mj_makeConstraint (contacts, pyramidal condim 3) + mj_makeImpedance + reference acceleration */
+static double impedance(const nmfo* o, double pos_minus_margin) { return impedance_of(o->solimp, pos_minus_margin); }
+
+/* weld equality (TetheredWorld, reference world.py:350-366): [PRIOR] mj_instantiateEquality, mjEQ_WELD with body2 = world.
+ * Rows 0-2: position of the body-1 point `anchor` (the weld's relpose position, in the hub frame here) minus the world
+ * origin; rows 3-5: torquescale * vector part of  q_body1 * relquat;  Jacobian of the rotation rows = 0.5 * vec((0, w) * q).
+ * Equality rows are active on both sides (quadratic cost).  diagApprox = body_invweight0 (translational | rotational). */
+static void make_weld(nmfo* o) {
+  int nv = o->nv; const double* W = o->weld;
+  const double *anchor = W + 1, *qfix = W + 4, *solref = W + 8, *solimp = W + 10; double ts = W[15], invw[2] = {W[16], W[17]};
+  double p[3], t[3]; mat_vec(t, o->xmat, anchor); for (int k = 0; k < 3; k++) p[k] = o->xpos[k] + t[k];
+  double q[4]; quat_mul(q, o->xquat, qfix);
+  double cpos[6] = {p[0], p[1], p[2], ts * q[1], ts * q[2], ts * q[3]};
+  double* jacp = dalloc(3 * nv); jac_point(o, jacp, 0, p);
+  double tc = fmax(solref[0], 2 * o->dt), dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
+  double K = 1.0 / (dmax * dmax * tc * tc * solref[1] * solref[1]), B = 2.0 / (dmax * tc);
+  for (int r = 0; r < 6; r++) {
+    int e = o->nefc++; double* J = o->efc_J + (size_t)e * nv; memset(J, 0, sizeof(double) * nv);
+    if (r < 3) memcpy(J, jacp + r * nv, sizeof(double) * nv);
+    else for (int d = 0; d < o->body_dofnum[0]; d++) {       /* only the free joint's dofs rotate body 0 */
+      const double* w = o->cdof + 6 * d; double c[3]; cross3(c, w, q + 1);
+      J[d] = 0.5 * ts * (q[0] * w[r - 3] + c[r - 3]);
+    }
+    double imp = impedance_of(solimp, cpos[r]);
+    o->efc_pos[e] = cpos[r]; o->efc_R[e] = fmax(MINVAL, (1 - imp) * invw[r >= 3] / imp); o->efc_D[e] = 1.0 / o->efc_R[e];
+    o->efc_vel[e] = dotn(J, o->qvel, nv);
+    o->efc_aref[e] = -B * o->efc_vel[e] - K * imp * cpos[r];
+  }
+  free(jacp);
+}
+
+/* mj_makeConstraint (equality first, then contacts, pyramidal condim 3) + mj_makeImpedance + reference acceleration */
 static void make_constraint(nmfo* o) {
-  int nv = o->nv; o->nefc = 0;
+  int nv = o->nv; o->nefc = 0; o->neq = 0;
+  if (o->weld) { make_weld(o); o->neq = o->nefc; }
   double* jacp = dalloc(3 * nv);
   double tc = fmax(o->solref[0], 2 * o->dt), dampratio = o->solref[1];
   double dmax = fmin(MAXIMP, fmax(MINIMP, o->solimp[1]));
@@ -556,7 +591,7 @@ static void actuation(nmfo* o) {
 static double constraint_update(nmfo* o, const double* jar, double* force, int* active) {
   double cost = 0;
   for (int e = 0; e < o->nefc; e++) {
-    if (jar[e] < 0) { force[e] = -o->efc_D[e] * jar[e]; cost += 0.5 * o->efc_D[e] * jar[e] * jar[e]; if (active) active[e] = 1; }
+    if (jar[e] < 0 || e < o->neq) { force[e] = -o->efc_D[e] * jar[e]; cost += 0.5 * o->efc_D[e] * jar[e] * jar[e]; if (active) active[e] = 1; }
     else { force[e] = 0; if (active) active[e] = 0; }
   }
   return cost;
@@ -615,7 +650,7 @@ static void solve_constraints(nmfo* o) {
     double lo = 0, hi = INFINITY, alpha = 0;
     for (int it = 0; it < o->ls_iterations; it++) {
       double d0 = q1 + alpha * q2, d1 = q2;
-      for (int e = 0; e < ne; e++) { double x = jar[e] + alpha * jv[e]; if (x < 0) { d0 += o->efc_D[e] * x * jv[e]; d1 += o->efc_D[e] * jv[e] * jv[e]; } }
+      for (int e = 0; e < ne; e++) { double x = jar[e] + alpha * jv[e]; if (x < 0 || e < o->neq) { d0 += o->efc_D[e] * x * jv[e]; d1 += o->efc_D[e] * jv[e] * jv[e]; } }
       if (fabs(d0) < gtol) break;
       if (d0 < 0) lo = alpha; else hi = alpha;
       double nx = alpha - d0 / d1;
@@ -639,7 +674,7 @@ static void sensors(nmfo* o) {
     double* s = o->sensordata + 16 * l; double F[3] = {0, 0, 0}, P[3] = {0, 0, 0}, wsum = 0; int found = 0;
     for (int c = 0; c < o->ncon; c++) {
       if (o->body_leg[o->geom_body[o->con_geom[c]]] != l) continue;
-      const double* f = o->con_frame + 9 * c; const double* ef = o->efc_force + 4 * c; double fc[3];
+      const double* f = o->con_frame + 9 * c; const double* ef = o->efc_force + o->neq + 4 * c; double fc[3];
       double fn = ef[0] + ef[1] + ef[2] + ef[3], f1 = o->mu * (ef[0] - ef[1]), f2 = o->mu * (ef[2] - ef[3]);
       for (int k = 0; k < 3; k++) fc[k] = fn * f[k] + f1 * f[3 + k] + f2 * f[6 + k];
       for (int k = 0; k < 3; k++) { F[k] += fc[k]; P[k] += fn * o->con_pos[3 * c + k]; }
@@ -652,7 +687,7 @@ static void sensors(nmfo* o) {
     double T[3] = {0, 0, 0};
     for (int c = 0; c < o->ncon; c++) {
       if (o->body_leg[o->geom_body[o->con_geom[c]]] != l) continue;
-      const double* f = o->con_frame + 9 * c; const double* ef = o->efc_force + 4 * c; double fc[3], r[3], t[3];
+      const double* f = o->con_frame + 9 * c; const double* ef = o->efc_force + o->neq + 4 * c; double fc[3], r[3], t[3];
       double fn = ef[0] + ef[1] + ef[2] + ef[3], f1 = o->mu * (ef[0] - ef[1]), f2 = o->mu * (ef[2] - ef[3]);
       for (int k = 0; k < 3; k++) { fc[k] = fn * f[k] + f1 * f[3 + k] + f2 * f[6 + k]; r[k] = o->con_pos[3 * c + k] - P[k]; }
       cross3(t, r, fc); for (int k = 0; k < 3; k++) T[k] += t[k];

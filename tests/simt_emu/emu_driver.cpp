@@ -25,6 +25,6 @@ extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_fli
   p.n_flies = n_flies; p.nsteps = nsteps;
   if (max_newton > 0) p.max_newton = max_newton;
   if (max_ls > 0) p.max_ls = max_ls;
-  for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() { if (p.terrain) nmf::step_block<true>(p, g_sm, f, 0, p.nsteps, false); else nmf::step_block<false>(p, g_sm, f, 0, p.nsteps, false); });
+  for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() { if (p.weld) nmf::step_block<nmf::W_TETHER>(p, g_sm, f, 0, p.nsteps, false); else if (p.terrain) nmf::step_block<nmf::W_TERRAIN>(p, g_sm, f, 0, p.nsteps, false); else nmf::step_block<nmf::W_FLAT>(p, g_sm, f, 0, p.nsteps, false); });
   return 0;
 }

@@ -1,0 +1,167 @@
+"""The reference's own Simulation test-suite (reference tests/core/test_simulation.py, whose fixture world is a
+TetheredWorld with the LEGS_ONLY / YAW_PITCH_ROLL / kp = 50 / adhesion fly at spawn (0, 0, 1.5): tests/conftest.py:74-152),
+restated against B200Simulation.  Batched getters return (n_worlds, ...) like the reference's GPUSimulation, so the
+single-world assertions are applied to every world."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = 3
+
+
+@pytest.fixture(scope="module")
+def model():
+    from flygym_b200 import NMFModel
+    return NMFModel.tethered(spawn_position=(0.0, 0.0, 1.5))
+
+
+@pytest.fixture(scope="module")
+def simulation(model):
+    from flygym_b200 import B200Simulation
+    sim = B200Simulation(model, n_worlds=N, fly_name="sim_fly")
+    sim.reset()
+    return sim
+
+
+class TestSimulationConstruction:
+    def test_construction_succeeds(self, simulation):
+        assert simulation is not None
+
+    def test_world_empty_raises(self, model):
+        from flygym_b200 import B200Simulation
+        from flygym_b200.simulation import WorldView
+        w = WorldView(model); w.fly_lookup.clear()
+        with pytest.raises(ValueError):
+            B200Simulation(w)
+
+    def test_time_starts_at_zero_after_reset(self, simulation):
+        simulation.reset()
+        assert simulation.time == pytest.approx(0.0)
+
+
+class TestSimulationStep:
+    def test_step_advances_time(self, simulation):
+        simulation.reset()
+        simulation.step()
+        assert simulation.time == pytest.approx(simulation.timestep, rel=1e-6)
+
+    def test_multiple_steps(self, simulation):
+        simulation.reset()
+        for _ in range(10):
+            simulation.step()
+        assert simulation.time == pytest.approx(10 * simulation.timestep, rel=1e-6)
+
+    def test_reset_resets_time(self, simulation):
+        simulation.reset()
+        for _ in range(5):
+            simulation.step()
+        simulation.reset()
+        assert simulation.time == pytest.approx(0.0)
+
+
+class TestGetters:
+    def test_joint_angles_length_and_neutral_pose(self, simulation, model):
+        simulation.reset()
+        angles = simulation.get_joint_angles("sim_fly").cpu().numpy()
+        order = simulation.world.fly_lookup["sim_fly"].get_jointdofs_order()
+        assert angles.shape == (N, len(order)) and len(order) == 66
+        neutral = model.arrays["dof_springref"][6:]                # springref = neutral angle (fly.py:285-295)
+        assert np.abs(angles - neutral[None]).max() < 0.2
+
+    def test_velocities_near_zero_at_reset(self, simulation):
+        simulation.reset()
+        vels = simulation.get_joint_velocities("sim_fly").cpu().numpy()
+        assert vels.shape == (N, 66)
+        np.testing.assert_allclose(vels, 0.0, atol=1e-8)
+
+    def test_body_positions_and_unit_quaternions(self, simulation):
+        simulation.reset()
+        simulation.step()
+        pos = simulation.get_body_positions("sim_fly").cpu().numpy()
+        quat = simulation.get_body_rotations("sim_fly").cpu().numpy()
+        nseg = len(simulation.world.fly_lookup["sim_fly"].get_bodysegs_order())
+        assert pos.shape == (N, nseg, 3) and quat.shape == (N, nseg, 4) and nseg == 69
+        np.testing.assert_allclose(np.linalg.norm(quat, axis=-1), 1.0, atol=1e-5)
+
+
+class TestActuatorIO:
+    def test_set_and_get_actuator_forces(self, simulation):
+        from flygym_b200.anatomy import ActuatorType
+        simulation.reset()
+        n_act = len(simulation.world.fly_lookup["sim_fly"].get_actuated_jointdofs_order(ActuatorType.POSITION))
+        simulation.set_actuator_inputs("sim_fly", ActuatorType.POSITION, np.zeros(n_act))
+        simulation.step()
+        forces = simulation.get_actuator_forces("sim_fly", ActuatorType.POSITION).cpu().numpy()
+        assert forces.shape == (N, n_act) and n_act == 42 and np.isfinite(forces).all() and np.abs(forces).max() > 0
+
+    def test_set_actuator_inputs_wrong_length_raises(self, simulation):
+        from flygym_b200.anatomy import ActuatorType
+        simulation.reset()
+        with pytest.raises(ValueError):
+            simulation.set_actuator_inputs("sim_fly", ActuatorType.POSITION, np.zeros(42 + 5))
+
+
+class TestLegAdhesion:
+    def test_set_all_adhesion_on_and_off(self, simulation):
+        simulation.reset()
+        simulation.set_leg_adhesion_states("sim_fly", np.ones(6, dtype=bool))
+        simulation.step()
+        simulation.set_leg_adhesion_states("sim_fly", np.zeros(6, dtype=bool))
+        simulation.step()
+        assert np.isfinite(simulation.state.cpu().numpy()).all()
+
+    def test_set_adhesion_wrong_length_raises(self, simulation):
+        simulation.reset()
+        with pytest.raises(ValueError):
+            simulation.set_leg_adhesion_states("sim_fly", np.ones(5, dtype=bool))
+
+
+class TestWarmupAndProfiling:
+    def test_warmup_advances_time(self, simulation):
+        simulation.reset()
+        simulation.warmup(duration_s=0.001)
+        assert simulation.time > 0.0
+
+    def test_warmup_zero_duration_does_not_change_time(self, simulation):
+        simulation.reset()
+        simulation.warmup(duration_s=0.0)
+        assert simulation.time == pytest.approx(0.0)
+
+    def test_step_with_profile(self, simulation, capsys):
+        simulation.reset()
+        simulation.step_with_profile()
+        assert simulation.time == pytest.approx(simulation.timestep, rel=1e-6)
+        assert simulation._curr_step == 1 and simulation._total_physics_time_ns > 0
+        simulation.print_performance_report()
+        assert "physics" in capsys.readouterr().out
+        simulation.reset()
+        assert simulation._curr_step == 0 and simulation._total_physics_time_ns == 0
+
+
+def test_tethered_parity_with_oracle(model):
+    """Legs driven by the CPG targets while the thorax hangs on the weld: no contacts, so the fp32 trajectory must stay
+    within the north_star tolerance (1e-4 rel) of the fp64 oracle over 1000 steps."""
+    import torch
+    from flygym_b200 import B200Simulation
+    from flygym_b200.actions import cpg_table
+    from oracle.oracle import Oracle
+    n, T = 4, 1000
+    tab = cpg_table(model, n, T)
+    sim = B200Simulation(model, n_worlds=n, outputs=True)
+    tabd = torch.from_numpy(tab).cuda()
+    got, done = {}, 0
+    for cp in (1, 10, 100, 1000):
+        sim.step(cp - done, tabd, done); done = cp
+        got[cp] = sim.qpos.cpu().numpy().astype(np.float64)
+    errs = {cp: [] for cp in got}
+    for k in range(n):
+        o = Oracle(model); o.reset(); done = 0
+        for cp in (1, 10, 100, 1000):
+            o.step_table(tab[k, done:cp].astype(np.float64)); done = cp
+            errs[cp].append(float(np.abs(got[cp][k] - o.qpos).max() / np.abs(o.qpos).max()))
+    print("tethered qpos rel Linf:", {k: ["%.1e" % e for e in v] for k, v in errs.items()})
+    assert max(errs[1]) < 1e-4 and max(errs[10]) < 1e-4 and max(errs[100]) < 1e-4 and max(errs[1000]) < 1e-4
+    thorax = sim.model.names["segments"].index("c_thorax")
+    assert (sim.get_body_positions("nmf")[:, thorax].cpu() - torch.tensor([0.0, 0.0, -1.5])).abs().max() < 5e-3
+    found = sim.get_ground_contact_info("nmf")[0]
+    assert float(found.abs().sum()) == 0.0        # no ground in the tethered world
