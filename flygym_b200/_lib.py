@@ -72,9 +72,10 @@ def load() -> ctypes.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    if needs_build():
+    override = os.environ.get("NMF_LIB_PATH")      # kernel-tuning experiments: load an alternative build of the same sources
+    if override is None and needs_build():
         build()
-    lib = ctypes.CDLL(str(SO_PATH))
+    lib = ctypes.CDLL(override or str(SO_PATH))
     vp, ci = ctypes.c_void_p, ctypes.c_int
     lib.nmf_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ci, ci, ctypes.POINTER(vp)]
     lib.nmf_destroy.argtypes = [vp]

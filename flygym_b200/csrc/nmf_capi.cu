@@ -30,7 +30,7 @@ using namespace nmf;
 //    queue[0] = pop counter, queue[1] = push counter, queue[2 + f] = sub-chunks of fly f done, queue[2 + n + j] = ring entry j.
 template <int WORLD>
 __device__ __forceinline__ void step_entry(const StepParams& p) {
-  __shared__ __align__(16) float sm[SM_TOTAL];
+  __shared__ __align__(16) float sm[WORLD == W_TETHER ? SM_TOTAL : SM_WELD];   // only the tethered world keeps weld rows
   __shared__ int s_fly, s_chunk;
   const int tid = threadIdx.x;
   for (;;) {
