@@ -42,6 +42,13 @@ TABLE_T = 2500                 # 3 exact CPG periods at 12 Hz, dt = 1e-4
 
 ALG_BYTES_OBS = 4940           # the same + the full observation set written every step
 RETINA_ALG_BYTES = 2 * 512 * 450 * 3 + 2 * 721 * 2 * 4   # 1 393 936 B per fly-frame
+# DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture on
+# B200, profiles/ncu_*_summary.txt), keyed by (workload, flies, steps per launch); None for configurations not captured
+NCU_TRAFFIC = {
+    ("flat", 4096, 100): (0.1176e9 + 2.7727e9, "profiles/ncu_step_r01i_summary.txt: 0.118 GB read + 2.77 GB written (local-memory spill lines "
+                                               "evicted from L2) vs 0.79 GB algorithmic"),
+    ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt: 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
+}
 ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
 ODOR_PEAKS = [[1.0, 0.0], [0.0, 1.0]]
 
@@ -397,6 +404,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = roof["alg_bytes"] / (roof["ms"] * 1e-3) / 1e9
         cpu = cpu_baseline_leg(model, n, stance_adhesion=(wl == "terrain")) if (world == 1 and not args.no_cpu) else None
         cfg = dict(workload_config(args, n, chunk), actions=args.actions)
+        traffic = NCU_TRAFFIC.get((wl, n, chunk), (None, None)) if args.actions == "cpg" and not args.mesh else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -406,7 +414,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps},
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": roof["kernel"], "kernel_ms_per_launch": roof["ms"],
+                         "traffic": traffic[0], "traffic_source": traffic[1], "peak_kind": peak_kind, "kernel": roof["kernel"], "kernel_ms_per_launch": roof["ms"],
                          "note": roof["note"]},
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall, "state_finite": finite,
