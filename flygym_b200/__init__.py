@@ -14,6 +14,9 @@ def __getattr__(name):
     if name == "B200Simulation":
         from .simulation import B200Simulation
         return B200Simulation
+    if name == "NMFVectorEnv":
+        from .vecenv import NMFVectorEnv
+        return NMFVectorEnv
     if name in ("Retina",):
         from .retina import Retina
         return Retina

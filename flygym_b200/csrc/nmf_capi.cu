@@ -205,7 +205,15 @@ extern "C" int nmf_set_schedule(nmf_handle* h, int sub_steps) {
   return NMF_OK;
 }
 
+static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream);
+
 extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, void* stream) {
+  return launch_steps(h, nsteps, table, table_T, table_t0, table_cols, false, stream);
+}
+
+extern "C" int nmf_forward(nmf_handle* h, void* stream) { return launch_steps(h, 1, nullptr, 0, 0, 0, true, stream); }
+
+static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream) {
   if (!h) return NMF_EINVAL;
   if (!h->bound) { h->err = "nmf_step: not bound"; return NMF_ENOTBOUND; }
   if (nsteps <= 0) return NMF_OK;
@@ -217,7 +225,7 @@ extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table
   p.state = h->buf.state; p.role = h->d_role; p.hull = h->d_hull; p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
   p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
-  p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps;
+  p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps; p.forward_only = forward_only ? 1 : 0;
   int grid = h->n_flies;
   p.queue = nullptr; p.sub_steps = nsteps; p.n_items = h->n_flies;
   int sub = h->sub_steps;

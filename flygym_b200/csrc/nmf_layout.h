@@ -90,6 +90,7 @@ struct StepParams {
   const int* hull_nbr_adr;   // CSR adjacency of the hull vertices: neighbours of vertex v are hull_nbr[hull_nbr_adr[v] .. hull_nbr_adr[v+1])
   const int* hull_nbr;       //   (indices local to the geom)
   int n_flies, nsteps, table_T, table_t0, table_cols;
+  int forward_only;          // 1: evaluate the current state (outputs) without advancing it (mj_forward)
   int nu_pos, nu_adh, nseg, nhubgeom;
   float dt, gx, gy, gz, inv_total_mass;
   float mu, cK, cB, margin, impratio;

@@ -1367,7 +1367,7 @@ __device__ __forceinline__ void step_block(const StepParams& p, float* sm, const
   }
 
   // ---- write the record back (TMA bulk store)
-  tma_store_record(p.state + (size_t)fly * S_STRIDE, st, tid, published);
+  if (!p.forward_only) tma_store_record(p.state + (size_t)fly * S_STRIDE, st, tid, published);
 }
 
 }  // namespace nmf

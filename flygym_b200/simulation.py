@@ -201,6 +201,11 @@ class B200Simulation:
             self._check(self._lib.nmf_step(self._h, int(n), ctypes.c_void_p(action_table.data_ptr()),
                                            int(action_table.shape[1]), int(table_t0), int(action_table.shape[2]), self._stream()))
 
+    def forward(self) -> None:
+        """``mj_forward`` for every world: refresh body poses, actuator forces and contact sensors from the current state
+        without advancing it (e.g. right after ``reset`` or after writing ``qpos`` directly)."""
+        self._check(self._lib.nmf_forward(self._h, self._stream()))
+
     def step_with_profile(self) -> None:
         t0 = perf_counter_ns()
         self.step()

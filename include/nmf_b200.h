@@ -66,6 +66,11 @@ int nmf_reset(nmf_handle* h, const uint8_t* mask_or_null, void* cuda_stream);
  * reference's table) or nu_pos + nu_adh (position targets followed by the six adhesion inputs); NULL = use ctrl in the state. */
 int nmf_step(nmf_handle* h, int nsteps, const float* action_table_or_null, int table_T, int table_t0, int table_cols, void* cuda_stream);
 
+/* mj_forward for every fly: evaluates the current state (segment poses, actuator forces, contact sensors into the bound
+ * observation buffers) without advancing it.  The reference reaches this through mj_data after mj_forward / the first step
+ * following Simulation.reset (simulation.py:59-72 resets without forward). */
+int nmf_forward(nmf_handle* h, void* cuda_stream);
+
 /* Scheduling of multi-step launches: with more flies than the GPU holds resident blocks, a launch of nsteps >= 2*sub_steps
  * is cut into (fly, sub_steps-step) work items served from a device-side queue (results are identical; only the order in
  * which flies advance changes).  sub_steps = 0 disables the queue (one block per fly for the whole launch); -1 (default)

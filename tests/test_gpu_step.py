@@ -285,3 +285,38 @@ def test_terrain_walking_parity(terrain):
     assert max(errs[1]) < 1e-6 and max(errs[100]) < 1e-4
     assert np.median(errs[300]) < 1e-4 and max(errs[300]) < 5e-2
     assert torch.isfinite(sim.state).all()
+
+
+def test_full_size_properties():
+    """BASELINE full sizes (4096 and 32768 flies per GPU) through size-independent properties: flies that start from the same
+    state with the same actions end bit-identically wherever they sit in the batch (scheduling independence, work queue on),
+    time = n dt, unit quaternions, finite state; and the C ABI rejects ragged action tables."""
+    import ctypes
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    m = NMFModel.bench(simplify_geom=True)
+    base = torch.from_numpy(cpg_table(m, 4, 64))                     # 4 distinct action sequences
+    for n in (4096, 32768):
+        table = base.repeat(n // 4, 1, 1).contiguous().cuda()        # fly k follows sequence k % 4
+        sim = B200Simulation(m, n_worlds=n, outputs=False)
+        sim.qpos[:, 2] = -0.15
+        sim.step(60, table, 0)
+        torch.cuda.synchronize()
+        st = sim.state.view(n // 4, 4, -1)
+        assert torch.equal(st, st[:1].expand_as(st))                 # every replica of a sequence is bit-identical
+        assert not torch.equal(st[0, 0], st[0, 1])                   # ... and the sequences differ
+        assert torch.isfinite(sim.state).all()
+        assert torch.allclose(sim.state[:, sim.info.off_time], torch.full((n,), 60e-4, device="cuda"), rtol=1e-5)
+        q = sim.qpos[:, 3:7]
+        assert torch.allclose(q.norm(dim=1), torch.ones(n, device="cuda"), atol=1e-5)
+        # ragged / mistyped tables are refused, by the Python class and by the C ABI itself
+        with pytest.raises(ValueError):
+            sim.step(1, table[:, :, :41].contiguous(), 0)
+        with pytest.raises(ValueError):
+            sim.step(1, table[: n - 1], 0)
+        rc = sim._lib.nmf_step(sim._h, 1, ctypes.c_void_p(table.data_ptr()), 64, 0, 41, sim._stream())
+        assert rc == -1 and b"action table" in sim._lib.nmf_last_error(sim._h)
+        rc = sim._lib.nmf_step(sim._h, 1, ctypes.c_void_p(table.data_ptr()), 0, 0, 42, sim._stream())
+        assert rc == -1
+        del sim, table

@@ -1,0 +1,64 @@
+"""Vector-env wrapper and nmf_forward (mj_forward semantics) on the GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_forward_refreshes_outputs_without_advancing():
+    import torch
+    from flygym_b200 import B200Simulation
+    sim = B200Simulation(None, n_worlds=3)
+    sim.step(5)
+    before = sim.state.clone()
+    sim.qpos[1, 0] += 2.5                      # move one fly by hand: poses are stale until forward()
+    moved = sim.state.clone()
+    stale = sim.get_body_positions("nmf").clone()
+    sim.forward()
+    torch.cuda.synchronize()
+    assert torch.equal(sim.state, moved)        # nothing advanced (time, qpos, qvel, warm start untouched)
+    fresh = sim.get_body_positions("nmf")
+    assert torch.allclose(fresh[1, :, 0], stale[1, :, 0] + 2.5, atol=1e-3)
+    assert not torch.equal(before, moved)
+    # forward after reset gives the keyframe poses; a subsequent step starts from the same state as without forward
+    a, b = B200Simulation(None, n_worlds=2), B200Simulation(None, n_worlds=2)
+    a.forward(); a.step(3); b.step(3)
+    assert torch.equal(a.state, b.state)
+
+
+def test_vector_env_loop_and_masked_autoreset():
+    import torch
+    from flygym_b200 import NMFVectorEnv, NMFModel
+    from flygym_b200.actions import cpg_table
+    n = 64
+    env = NMFVectorEnv(NMFModel.bench(True), n_envs=n, physics_steps_per_action=10, episode_steps=7,
+                       odor=([[12.0, 4.0, 1.5]], [[1.0]]), vision=True)
+    obs, info = env.reset()
+    assert obs["joint_angles"].shape == (n, 66) and obs["vision"].shape == (n, 2, 721, 2) and obs["odor"].shape == (n, 1, 4)
+    assert obs["thorax_position"].shape == (n, 3) and float(obs["thorax_position"][:, 2].min()) > 1.0   # spawned above ground
+    acts = torch.from_numpy(cpg_table(env.sim.model, n, 200)).cuda()
+    env.sim.qpos[:, 2] = -0.15
+    total = torch.zeros(n, device="cuda")
+    resets = 0
+    for t in range(20):
+        a = acts[:, 10 * t]
+        if t % 2:                                    # alternate the 42- and the 48-column action forms
+            a = torch.cat([a, torch.ones(n, 6, device="cuda")], dim=1)
+        obs, rew, term, trunc, info = env.step(a)
+        assert rew.shape == (n,) and term.dtype == torch.bool and trunc.dtype == torch.bool
+        total += rew
+        resets += int(info["reset_mask"].sum())
+        if t == 6:
+            assert bool(trunc.all())                 # episode_steps = 7
+            assert abs(env.sim.time) < 1e-9          # ... and every fly was reset on the device
+    assert resets >= 2 * n and torch.isfinite(total).all()
+    assert torch.isfinite(obs["vision"]).all() and float(obs["vision"].max()) <= 1.0 + 1e-6
+    with pytest.raises(ValueError):
+        env.step(np.zeros((n, 40), np.float32))
+    # masked reset leaves the other flies alone
+    env.step(acts[:, 0])
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda"); mask[::2] = True
+    t_before = env.sim.state[:, env.sim.info.off_time].clone()
+    env.reset(mask)
+    t_after = env.sim.state[:, env.sim.info.off_time]
+    assert bool((t_after[::2] == 0).all()) and torch.equal(t_after[1::2], t_before[1::2])
