@@ -364,7 +364,11 @@ def kinematics_qpos0(model: NMFModel):
 def set_const(model: NMFModel) -> None:
     """[PRIOR] ``mj_setConst`` subset: ``body_invweight0`` (mean translational /
     rotational diagonal of J M^-1 J^T at each body's COM, at qpos0) and
-    ``stat.meaninertia`` (mean diagonal of M at qpos0)."""
+    ``stat.meaninertia`` (mean diagonal of M at qpos0).
+
+    Locked DoFs (``model.arrays['locked_dofs']``, see ``NMFModel.with_locked_dofs``) stand for rigid attachments: the
+    bodies they connect are treated as ONE body, as the MuJoCo compiler would see them after fusing -- the inverse weight is
+    evaluated at the group's common COM and shared by its members, and ``meaninertia`` averages over the free DoFs only."""
     a = model.arrays
     nb, nv = model.nbody, model.nv
     xpos, xquat = kinematics_qpos0(model)
@@ -395,14 +399,72 @@ def set_const(model: NMFModel) -> None:
         Iw = Rw @ np.diag(a["body_inertia"][b]) @ Rw.T
         M += a["body_mass"][b] * J[0:3].T @ J[0:3] + J[3:6].T @ Iw @ J[3:6]
     Minv = np.linalg.inv(M)
+    locked = set(int(d) for d in a.get("locked_dofs", []))
+    group = list(range(nb))                 # representative (most proximal member) of each rigid group
+    for b in range(1, nb):
+        adr, num = int(a["body_dofadr"][b]), int(a["body_dofnum"][b])
+        if num > 0 and all(d in locked for d in range(adr, adr + num)):
+            group[b] = group[int(a["body_parent"][b])]
     inv = np.zeros((nb, 2))
-    for b in range(nb):
-        J = jac(b, xipos[b])
+    for g in sorted(set(group)):
+        members = [b for b in range(nb) if group[b] == g]
+        mass = a["body_mass"][members]
+        com = xipos[members[0]] if len(members) == 1 else (mass[:, None] * xipos[members]).sum(0) / mass.sum()
+        J = jac(g, com)
         Ab = J @ Minv @ J.T
-        inv[b, 0] = np.trace(Ab[0:3, 0:3]) / 3
-        inv[b, 1] = np.trace(Ab[3:6, 3:6]) / 3
+        inv[members, 0] = np.trace(Ab[0:3, 0:3]) / 3
+        inv[members, 1] = np.trace(Ab[3:6, 3:6]) / 3
     a["body_invweight0"] = inv
-    a["opt"][OPT_FIELDS.index("meaninertia")] = np.trace(M) / nv
+    free = [d for d in range(nv) if d not in locked]
+    opt = a["opt"].copy(); opt[OPT_FIELDS.index("meaninertia")] = np.trace(M[np.ix_(free, free)]) / len(free); a["opt"] = opt
+
+
+LOCK_ARMATURE = NMFModel.LOCK_ARMATURE
+
+
+def bake_kernel_layout(reference_root, joint_preset: str = "legs_active_only", **kw) -> NMFModel:
+    """A joint preset with fewer leg DoFs, laid out for the sm_100a kernels (hub + 6 chains of 8 links, 11 DoFs each).
+
+    The MuJoCo compiler fuses links without joints into their parent (and applies ``boundmass`` / ``boundinertia`` to the
+    FUSED body, ``mujoco_globals.yaml:6-7``), so the reduced model is baked for real first; its bodies are then spread back
+    over the LEGS_ONLY lanes: a link that kept its joint carries the fused body's inertia, the links fused into it become
+    massless lanes whose DoFs are locked (armature ``LOCK_ARMATURE``, no spring / damper, keyframe angle 0 -- a rigid
+    attachment is the infinite-armature limit) and share its inverse weight.  Geoms keep their own lanes."""
+    true = bake(reference_root, joint_preset=joint_preset, **kw)
+    full = bake(reference_root, joint_preset="legs_only", **kw)
+    a, t = dict(full.arrays), true.arrays
+    tb = {n: i for i, n in enumerate(true.names["bodies"])}
+    nb = full.nbody
+    mass, ipos, iquat, inertia, invw = (a[k].copy() for k in ("body_mass", "body_ipos", "body_iquat", "body_inertia", "body_invweight0"))
+    ipos, iquat, inertia, invw = ipos.reshape(nb, 3), iquat.reshape(nb, 4), inertia.reshape(nb, 3), invw.reshape(nb, 2)
+    tt = {k: t[k].reshape(true.nbody, -1) for k in ("body_ipos", "body_iquat", "body_inertia", "body_invweight0")}
+    locked = []
+    for b, name in enumerate(full.names["bodies"]):
+        if name in tb:
+            i = tb[name]
+            mass[b] = t["body_mass"][i]; ipos[b] = tt["body_ipos"][i]; iquat[b] = tt["body_iquat"][i]
+            inertia[b] = tt["body_inertia"][i]; invw[b] = tt["body_invweight0"][i]
+        else:                                   # fused into the nearest ancestor that kept a joint
+            anc = int(a["body_parent"][b])
+            while full.names["bodies"][anc] not in tb:
+                anc = int(a["body_parent"][anc])
+            mass[b] = 0.0; ipos[b] = 0.0; iquat[b] = (1.0, 0.0, 0.0, 0.0); inertia[b] = 0.0
+            invw[b] = tt["body_invweight0"][tb[full.names["bodies"][anc]]]
+            locked += list(range(int(a["body_dofadr"][b]), int(a["body_dofadr"][b]) + int(a["body_dofnum"][b])))
+    a.update(body_mass=mass, body_ipos=ipos, body_iquat=iquat, body_inertia=inertia, body_invweight0=invw)
+    locked = np.array(sorted(locked), dtype=np.int32)
+    for key, v in (("dof_stiffness", 0.0), ("dof_damping", 0.0), ("dof_armature", LOCK_ARMATURE), ("dof_springref", 0.0)):
+        arr = a[key].copy(); arr[locked] = v; a[key] = arr
+    key = a["key_qpos"].copy(); key[locked + 1] = 0.0; a["key_qpos"] = key
+    a["locked_dofs"] = locked
+    opt = a["opt"].copy(); opt[OPT_FIELDS.index("meaninertia")] = true.opt("meaninertia"); a["opt"] = opt
+    if true.names["actuated_position"] != full.names["actuated_position"]:
+        raise ValueError("the reduced preset changes the actuator set; not representable in the kernel layout")
+    lockset = set(int(d) - 6 for d in locked)
+    names = dict(full.names, jointdofs=list(true.names["jointdofs"]),
+                 locked_jointdofs=[nm for j, nm in enumerate(full.names["jointdofs"]) if j in lockset])
+    assert names["jointdofs"] == [nm for j, nm in enumerate(full.names["jointdofs"]) if j not in lockset]
+    return NMFModel(a, names, dict(true.meta, kernel_layout="legs_only lanes, fused links massless + locked"))
 
 
 def main():
@@ -417,6 +479,9 @@ def main():
         m.save(out / name)
         print(name, {k: m.dim(k) for k in DIM_FIELDS}, "mass", m.arrays["body_mass"].sum(),
               "meaninertia", m.opt("meaninertia"))
+    m = bake_kernel_layout(args.reference, "legs_active_only", simplify_geom=True)
+    m.save(out / "nmf_bench_capsule_legs_active_only.npz")
+    print("nmf_bench_capsule_legs_active_only.npz", {k: m.dim(k) for k in DIM_FIELDS}, "free hinge DoFs", len(m.names["jointdofs"]))
 
 
 if __name__ == "__main__":

@@ -128,10 +128,19 @@ class NMFModel:
         return cls(arrays, names, meta)
 
     @classmethod
-    def bench(cls, simplify_geom: bool = True, terrain: str | None = None) -> "NMFModel":
+    def bench(cls, simplify_geom: bool = True, terrain: str | None = None, joint_preset: str = "legs_only") -> "NMFModel":
         """The reference benchmark model (``time_gpu_simulation.py:21-64``); ``terrain`` = ``"blocks"`` / ``"gapped"``
-        replaces the flat ground plane by a box-column terrain (capsule geoms only)."""
+        replaces the flat ground plane by a box-column terrain (capsule geoms only); ``joint_preset="legs_active_only"``
+        (reference ``anatomy.py:402-409``: no passive tarsal joints, 42 hinge DoFs) is baked in the kernels' chain layout with
+        the tarsus2-5 links massless and their DoFs locked (``baker.bake.bake_kernel_layout``)."""
+        if joint_preset == "legs_active_only":
+            if not simplify_geom:
+                raise ValueError("the LEGS_ACTIVE_ONLY preset is baked with capsule geoms only")
+            m = cls.load(ASSETS_DIR / "nmf_bench_capsule_legs_active_only.npz")    # flygym_b200.baker.bake.bake_kernel_layout
+            return m if terrain in (None, "flat") else m.with_terrain(terrain)
         m = cls.load(ASSETS_DIR / ("nmf_bench_capsule.npz" if simplify_geom else "nmf_bench_mesh.npz"))
+        if joint_preset != "legs_only":
+            raise ValueError("the sm_100a kernels handle the LEGS_ONLY chain layout (and LEGS_ACTIVE_ONLY by DoF locking)")
         return m if terrain in (None, "flat") else m.with_terrain(terrain)
 
     @classmethod
@@ -163,6 +172,87 @@ class NMFModel:
         a["weld"] = np.array([1.0, *anchor, *quat, 2e-4, 1.0, 0.98, 0.99, 1e-5, 0.5, 3.0, 1.0, invw[0], invw[1]])
         names = dict(m.names, contact_geoms=[])
         return NMFModel(a, names, dict(m.meta, world="tethered", contact_preset=None))
+
+    # ---- model variants the reference composes through Fly / World keyword arguments ----------------------------------
+    def with_contact_bodies(self, preset: str) -> "NMFModel":
+        """Keep only the ground-contact pairs of a ``ContactBodiesPreset`` (reference ``anatomy.py:501-562``, applied in
+        ``world.py:292-309``): ``"legs_thorax_abdomen_head"`` (the baked default), ``"legs_only"``, ``"tibia_tarsus_only"``.
+        The per-leg contact sensor follows: its subtree starts at the most proximal remaining contact segment of the leg
+        (``world.py:311-331``)."""
+        from . import anatomy as A
+        keep_names = set(A.contact_bodies(preset))
+        geoms = self.names["contact_geoms"]
+        keep = np.array([g in keep_names for g in geoms], dtype=bool)
+        if keep.sum() == 0 or not keep_names.issubset(set(geoms)):
+            raise ValueError(f"contact preset {preset!r} is not a subset of the baked contact geoms")
+        a = dict(self.arrays)
+        for k, w in (("geom_pos", 3), ("geom_quat", 4), ("geom_size", 2)):
+            a[k] = a[k].reshape(-1, w)[keep]
+        for k in ("geom_body", "geom_type", "geom_vertadr", "geom_vertnum"):
+            a[k] = a[k][keep]            # hull vertex storage is shared and indexed by (adr, num): nothing to repack
+        dims = a["dims"].copy(); dims[DIM_FIELDS.index("ngeom")] = int(keep.sum()); a["dims"] = dims
+        root = np.full(self.dim("nleg"), -1, np.int32)
+        body_leg = a["body_leg"]
+        for b in sorted(set(int(x) for x in a["geom_body"])):
+            l = int(body_leg[b])
+            if l >= 0 and root[l] < 0:
+                root[l] = b                   # bodies of a leg are numbered proximal -> distal
+        a["leg_rootbody"] = root
+        names = dict(self.names, contact_geoms=[g for g, k in zip(geoms, keep) if k])
+        return NMFModel(a, names, dict(self.meta, contact_preset=preset))
+
+    def with_actuator_gains(self, kp: float | None = None, kv: float | None = None, forcerange=None) -> "NMFModel":
+        """``Fly.add_actuators(..., kp=, kv=, forcerange=)`` (reference ``fly.py:301-369``; tutorial 2 uses kp = 150)."""
+        a = dict(self.arrays)
+        n = self.dim("nu_pos")
+        if kp is not None: a["act_kp"] = np.full(n, float(kp))
+        if kv is not None: a["act_kv"] = np.full(n, float(kv))
+        if forcerange is not None: a["act_frcrange"] = np.tile(np.asarray(forcerange, dtype=np.float64), (n, 1))
+        return NMFModel(a, self.names, dict(self.meta, position_gain=float(a["act_kp"][0])))
+
+    def with_joint_params(self, stiffness: float | None = None, damping: float | None = None, armature: float | None = None) -> "NMFModel":
+        """``Fly.add_joints(..., stiffness=, damping=, armature=)`` (reference ``fly.py:221-299``) for every hinge DoF that is
+        not locked."""
+        a = dict(self.arrays)
+        free = np.ones(self.nv, bool); free[:6] = False
+        if "locked_dofs" in a: free[a["locked_dofs"]] = False
+        for key, v in (("dof_stiffness", stiffness), ("dof_damping", damping), ("dof_armature", armature)):
+            if v is not None:
+                arr = a[key].copy(); arr[free] = float(v); a[key] = arr
+        return NMFModel(a, self.names, dict(self.meta))
+
+    LOCK_ARMATURE = 1.0e6     # g mm^2: ~1e12 x the tarsal inertias; a locked DoF accelerates by < 1e-5 rad/s^2 under walking loads
+
+    def with_locked_dofs(self, locked_names) -> "NMFModel":
+        """Hold the named hinge DoFs at angle 0 (they disappear from every ordering the API exposes).  This is how joint
+        presets with fewer DoFs run on kernels written for the LEGS_ONLY chain layout: a rigid attachment is the limit of a
+        DoF with infinite armature, so the DoF keeps its lane but gets armature ``LOCK_ARMATURE``, no spring, no damper, no
+        actuator and a zero keyframe angle."""
+        locked_names = set(locked_names)
+        all_dofs = self.names["jointdofs"]
+        idx = np.array([6 + j for j, nm in enumerate(all_dofs) if nm in locked_names], dtype=np.int32)
+        if len(idx) != len(locked_names):
+            raise ValueError("unknown DoF names: " + ", ".join(sorted(locked_names - set(all_dofs))))
+        act = set(int(d) for d in self.arrays["act_dof"])
+        if act & set(int(i) for i in idx):
+            raise ValueError("cannot lock an actuated DoF")
+        a = dict(self.arrays)
+        for key, v in (("dof_stiffness", 0.0), ("dof_damping", 0.0), ("dof_armature", self.LOCK_ARMATURE), ("dof_springref", 0.0)):
+            arr = a[key].copy(); arr[idx] = v; a[key] = arr
+        key = a["key_qpos"].copy(); key[idx + 1] = 0.0; a["key_qpos"] = key
+        a["locked_dofs"] = np.union1d(a.get("locked_dofs", np.zeros(0, np.int32)), idx).astype(np.int32)
+        names = dict(self.names, jointdofs=[nm for nm in all_dofs if nm not in locked_names],
+                     locked_jointdofs=self.names.get("locked_jointdofs", []) + [nm for nm in all_dofs if nm in locked_names])
+        out = NMFModel(a, names, dict(self.meta))
+        from .baker.bake import set_const       # inverse weights / meaninertia of the model with the rigid groups fused
+        set_const(out)
+        return out
+
+    def exposed_hinge_dofs(self) -> np.ndarray:
+        """Indices (0-based among the hinge DoFs of the kernel layout) of the DoFs in ``names['jointdofs']`` order."""
+        n_h = self.nv - 6
+        locked = set(int(i) - 6 for i in self.arrays.get("locked_dofs", []))
+        return np.array([j for j in range(n_h) if j not in locked], dtype=np.int64)
 
     def with_terrain(self, terrain) -> "NMFModel":
         """Copy of the model standing on a box-column terrain: a name from ``TERRAINS`` or the 8 ``TERRAIN_FIELDS`` values."""

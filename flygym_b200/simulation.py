@@ -130,11 +130,12 @@ class B200Simulation:
         """Name -> index tables (reference ``_map_internal_*``, simulation.py:311-448)."""
         m, dev = self.model, self.device
         names = m.names
-        nhinge = len(names["jointdofs"])
         self._fly_names = list(self.world.fly_lookup.keys())
-        # hinge DoF j lives at qpos[7 + j] / qvel[6 + j]
-        self._qpos_cols = torch.arange(7, 7 + nhinge, dtype=torch.int32, device=dev)
-        self._qvel_cols = torch.arange(6, 6 + nhinge, dtype=torch.int32, device=dev)
+        # hinge DoF j of the kernel layout lives at qpos[7 + j] / qvel[6 + j]; locked DoFs (joint presets with fewer DoFs) are not exposed
+        exposed = torch.as_tensor(m.exposed_hinge_dofs(), dtype=torch.int32, device=dev)
+        assert exposed.numel() == len(names["jointdofs"])
+        self._qpos_cols = (7 + exposed).contiguous()
+        self._qvel_cols = (6 + exposed).contiguous()
         self._act_cols = {ActuatorType.POSITION: torch.arange(0, m.dim("nu_pos"), dtype=torch.int32, device=dev)}
         self._adh_cols = torch.arange(m.dim("nu_pos"), m.nu, dtype=torch.int32, device=dev)
         seg_index = {s: k for k, s in enumerate(names["segments"])}

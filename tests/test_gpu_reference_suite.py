@@ -165,3 +165,42 @@ def test_tethered_parity_with_oracle(model):
     assert (sim.get_body_positions("nmf")[:, thorax].cpu() - torch.tensor([0.0, 0.0, -1.5])).abs().max() < 5e-3
     found = sim.get_ground_contact_info("nmf")[0]
     assert float(found.abs().sum()) == 0.0        # no ground in the tethered world
+
+
+def test_joint_and_contact_presets_on_gpu():
+    """JointPreset.LEGS_ACTIVE_ONLY (42 hinge DoFs; reference tests/core/test_compose.py:74-76,178-183 count joints = len(iter_jointdofs))
+    and the ContactBodiesPreset variants through the public API, each against the oracle on the same blob."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    from oracle.oracle import Oracle
+    base = NMFModel.bench(True)
+    variants = {
+        "legs_active_only": NMFModel.bench(True, joint_preset="legs_active_only"),
+        "contacts_legs_only": base.with_contact_bodies("legs_only"),
+        "contacts_tibia_tarsus": base.with_contact_bodies("tibia_tarsus_only"),
+        "kp150": base.with_actuator_gains(kp=150.0),
+    }
+    for name, model in variants.items():
+        n, T = 3, 200
+        tab = cpg_table(model, n, T)
+        sim = B200Simulation(model, n_worlds=n)
+        sim.qpos[:, 2] = -0.17
+        sim.set_leg_adhesion_states("nmf", np.ones(6, dtype=bool))
+        ndof = len(sim.world.fly_lookup["nmf"].get_jointdofs_order())
+        assert sim.get_joint_angles("nmf").shape == (n, ndof) and ndof == (42 if name == "legs_active_only" else 66)
+        sim.step(T, torch.from_numpy(tab).cuda(), 0)
+        got = sim.qpos.cpu().numpy().astype(np.float64)
+        errs = []
+        for k in range(n):
+            o = Oracle(model); o.reset(); o.qpos[2] = -0.17; o.ctrl[42:] = 1.0
+            o.step_table(tab[k].astype(np.float64))
+            errs.append(float(np.abs(got[k] - o.qpos).max() / np.abs(o.qpos).max()))
+        print(name, ["%.1e" % e for e in errs])
+        assert np.median(errs) < 1e-4 and max(errs) < 1e-2, (name, errs)
+        ang = sim.get_joint_angles("nmf").cpu().numpy()
+        ex = model.exposed_hinge_dofs()
+        assert np.allclose(ang, got[:, 7 + ex], atol=1e-6)
+        if name == "legs_active_only":
+            locked = np.delete(got[:, 7:], ex, axis=1)
+            assert np.abs(locked).max() < 1e-6
