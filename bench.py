@@ -121,26 +121,32 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- CPU arm
-def cpu_arm(model, table64, steps_per_thread, threads, adhesion=None):
-    """Oracle (CPU restatement of mj_step) on `threads` host threads, one fly each, `steps_per_thread` steps
-    after a 500-step warm-up (mirrors Simulation.warmup, simulation.py:298-309).  Returns env-steps/s."""
-    from oracle.oracle import Oracle
-    oracles = [Oracle(model) for _ in range(threads)]
-    for k, o in enumerate(oracles):
-        o.ctrl[model.dim("nu_pos"):] = 1.0
-        o.step(500)
-    def run(k):
-        if adhesion is None:
-            oracles[k].step_table(table64[k % table64.shape[0], :steps_per_thread])
-        else:   # per-step adhesion inputs ride in the table's trailing columns
-            oracles[k].step_table_full(np.concatenate([table64[k % table64.shape[0], :steps_per_thread],
-                                                       adhesion[k % adhesion.shape[0], :steps_per_thread]], axis=1))
-    ths = [threading.Thread(target=run, args=(k,)) for k in range(threads)]
-    t0 = time.perf_counter()
-    for t in ths: t.start()
-    for t in ths: t.join()
-    dt = time.perf_counter() - t0
-    return threads * steps_per_thread / dt, dt
+class CpuArm:
+    """Oracle (CPU restatement of mj_step) on `threads` host threads, one fly each.  Built once (500-step warm-up per fly,
+    mirroring Simulation.warmup, simulation.py:298-309); every run() advances each fly by `steps_per_thread` more steps."""
+
+    def __init__(self, model, threads):
+        from oracle.oracle import Oracle
+        self.model, self.threads = model, threads
+        self.oracles = [Oracle(model) for _ in range(threads)]
+        for o in self.oracles:
+            o.ctrl[model.dim("nu_pos"):] = 1.0
+            o.step(500)
+
+    def run(self, table64, steps_per_thread, adhesion=None):
+        """Returns (env-steps/s, seconds)."""
+        def work(k):
+            tb = table64[k % table64.shape[0], :steps_per_thread]
+            if adhesion is None:
+                self.oracles[k].step_table(tb)
+            else:   # per-step adhesion inputs ride in the table's trailing columns
+                self.oracles[k].step_table_full(np.concatenate([tb, adhesion[k % adhesion.shape[0], :steps_per_thread]], axis=1))
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(self.threads)]
+        t0 = time.perf_counter()
+        for t in ths: t.start()
+        for t in ths: t.join()
+        dt = time.perf_counter() - t0
+        return self.threads * steps_per_thread / dt, dt
 
 
 def host_adhesion_table(model, n_flies, n_steps, n_total):
@@ -152,17 +158,18 @@ def host_adhesion_table(model, n_flies, n_steps, n_total):
     return np.where(np.sin(2 * np.pi * 12.0 * t[None, :, None] + psi[:, None, None] + legph[None, None, :]) < 0, 100.0, 1.0)
 
 
-def cpu_baseline_leg(model, n_total, target_s=12.0, stance_adhesion=False):
+def cpu_baseline_leg(model, n_total, target_s=20.0, stance_adhesion=False):
     """cpu_baseline: the oracle on every host core, sized to ~target_s seconds of CPU work from a short pilot run."""
     from flygym_b200.actions import cpg_table
     cores = os.cpu_count() or 1
     pilot = 200
     adh = (lambda k: host_adhesion_table(model, cores, k, n_total)) if stance_adhesion else (lambda k: None)
+    arm = CpuArm(model, cores)
     tb = cpg_table(model, cores, pilot, n_flies_total=n_total).astype(np.float64)
-    v0, _ = cpu_arm(model, tb, pilot, cores, adh(pilot))
-    cs = int(min(50000, max(500, target_s * v0 / cores)))
+    v0, _ = arm.run(tb, pilot, adh(pilot))
+    cs = int(min(100000, max(500, target_s * v0 / cores)))
     tb = cpg_table(model, cores, cs, n_flies_total=n_total).astype(np.float64)
-    v, dt = cpu_arm(model, tb, cs, cores, adh(cs))
+    v, dt = arm.run(tb, cs, adh(cs))
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{cores} threads x 1 fly x {cs} CPG steps after a 500-step warm-up (oracle/nmf_oracle.c, fp64 restatement of "
                       f"mj_step), {dt:.1f} s"}
@@ -185,11 +192,12 @@ def run_reference(args, rank, world):
     n = args.n_flies
     table = cpg_table(model, cores, sample_steps, n_flies_total=n).astype(np.float64)
     adh = host_adhesion_table(model, cores, sample_steps, n) if args.workload == "terrain" else None
+    arm = CpuArm(model, cores)
     for _ in range(args.warmup):
-        cpu_arm(model, table, 50, cores, adh)
+        arm.run(table, 50, adh)
     vals, tot = [], 0.0
     for _ in range(args.steps):
-        v, dt = cpu_arm(model, table, sample_steps, cores, adh)
+        v, dt = arm.run(table, sample_steps, adh)
         vals.append(v); tot += dt
     value = float(np.mean(vals))
     sample = f"{cores} threads x 1 fly x {sample_steps} steps per timed step (CPG actions, after 500 warm-up steps)"

@@ -210,6 +210,24 @@ def test_step_is_cuda_graph_capturable():
     ref.step(1 + 4 * 5)      # the captured launch itself does not execute during capture
     torch.cuda.synchronize()
     assert torch.equal(sim.state, ref.state)
+    # the work-queue launch (more flies than resident blocks; counters cleared by a captured memset node) replays as well
+    n = 2500
+    big, big_ref = B200Simulation(None, n_worlds=n, outputs=False), B200Simulation(None, n_worlds=n, outputs=False)
+    for b in (big, big_ref):
+        b.qpos[:, 2] = -0.15
+    with torch.cuda.stream(s):
+        big.step(1)
+        g2 = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g2, stream=s):
+            big.step(50)
+        for _ in range(3):
+            g2.replay()
+    torch.cuda.synchronize()
+    big_ref.set_schedule(0)
+    big_ref.step(1 + 3 * 50)
+    torch.cuda.synchronize()
+    assert torch.equal(big.state, big_ref.state)
 
 
 def test_work_queue_schedule_is_bit_identical():
