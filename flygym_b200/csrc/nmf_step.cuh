@@ -175,6 +175,16 @@ struct Contact {     // 10 registers per slot; "active" <=> D > 0; signed distan
 };
 __device__ __forceinline__ float con_on(const Contact& c) { return c.D > 0.f ? 1.f : 0.f; }
 
+// general-exponent branch of the impedance sigmoid: kept out of line (four inlined powf bodies per call site are ~18 KB of
+// SASS that the reference's power-2 / power-1 settings never execute, in an instruction-fetch-bound kernel)
+#ifdef NMF_SIMT_EMU
+#define NMF_COLD
+#else
+#define NMF_COLD __noinline__
+#endif
+__device__ NMF_COLD float impedance_general(float x, float mid, float power) {
+  return (x <= mid) ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
 __device__ __forceinline__ float impedance_of(const float* solimp, float x_abs) {
   const float d0 = solimp[0], d1 = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (d0 == d1 || width <= NMF_MINVAL) return 0.5f * (d0 + d1);   // (uniform branch)
@@ -182,7 +192,7 @@ __device__ __forceinline__ float impedance_of(const float* solimp, float x_abs) 
   float y;
   if (power == 1.f) y = x;
   else if (power == 2.f) y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-  else y = (x <= mid) ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  else y = impedance_general(x, mid, power);
   return d0 + y * (d1 - d0);
 }
 
