@@ -338,3 +338,31 @@ def test_full_size_properties():
         rc = sim._lib.nmf_step(sim._h, 1, ctypes.c_void_p(table.data_ptr()), 0, 0, 42, sim._stream())
         assert rc == -1
         del sim, table
+
+
+def test_step_host_pipelined_slices_match_device_path():
+    """nmf_step_host cuts the batch into slices pipelined over private streams; the result must equal the plain device path
+    bit for bit (42- and 48-column action forms, odd batch size)."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    m = NMFModel.bench(simplify_geom=True)
+    n = 2051
+    tab = cpg_table(m, n, 6)
+    adh = np.where(np.arange(n * 6).reshape(n, 6) % 3 == 0, 50.0, 1.0).astype(np.float32)
+    a, b = B200Simulation(m, n_worlds=n, outputs=True), B200Simulation(m, n_worlds=n, outputs=True)
+    for s in (a, b):
+        s.qpos[:, 2] = -0.15
+    qh = np.empty((n, m.nq), np.float32)
+    for t in range(6):
+        if t % 2 == 0:
+            act = np.ascontiguousarray(tab[:, t])
+            b.ctrl[:, :42] = torch.from_numpy(act).cuda()
+        else:
+            act = np.ascontiguousarray(np.concatenate([tab[:, t], adh], axis=1))
+            b.ctrl[:, :48] = torch.from_numpy(act).cuda()
+        a.step_host(act, 1, qh)
+        b.step(1)
+        torch.cuda.synchronize()
+        assert np.array_equal(qh, b.qpos.cpu().numpy())
+    assert torch.equal(a.state, b.state) and torch.equal(a.seg_xpos, b.seg_xpos) and torch.equal(a.sensordata, b.sensordata)
