@@ -62,3 +62,47 @@ def test_vector_env_loop_and_masked_autoreset():
     env.reset(mask)
     t_after = env.sim.state[:, env.sim.info.off_time]
     assert bool((t_after[::2] == 0).all()) and torch.equal(t_after[1::2], t_before[1::2])
+
+
+def test_several_flies_per_world():
+    """BaseWorld.add_fly called twice (reference compose/world.py:95-150): flies never collide with each other, so each fly of a
+    two-fly world must follow exactly the single-fly trajectory translated by its spawn offset (the ground is translation
+    invariant), and per-fly setters must only touch their own fly."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.anatomy import ActuatorType
+    from flygym_b200.multifly import B200MultiFlySimulation, B200World
+    from flygym_b200.actions import cpg_table
+    m = NMFModel.bench(True)
+    w = B200World(m)
+    w.add_fly("alice", (0.0, 0.0, 0.8))
+    w.add_fly("bob", (4.0, -3.0, 0.8))
+    with pytest.raises(ValueError):
+        w.add_fly("bob", (1.0, 1.0, 0.8))
+    n = 3
+    multi = B200MultiFlySimulation(w, n_worlds=n)
+    single = B200Simulation(m, n_worlds=n)
+    acts = torch.from_numpy(cpg_table(m, n, 400)).cuda()
+    multi.set_leg_adhesion_states("alice", np.ones(6, dtype=bool)); multi.set_leg_adhesion_states("bob", np.ones(6, dtype=bool))
+    single.set_leg_adhesion_states("nmf", np.ones(6, dtype=bool))
+    for t in range(0, 400, 20):
+        multi.set_actuator_inputs("alice", ActuatorType.POSITION, acts[:, t])
+        multi.set_actuator_inputs("bob", ActuatorType.POSITION, acts[:, t])
+        single.set_actuator_inputs("nmf", ActuatorType.POSITION, acts[:, t])
+        multi.step(20); single.step(20)
+    ref = single.get_body_positions("nmf")
+    a, b = multi.get_body_positions("alice"), multi.get_body_positions("bob")
+    assert a.shape == (n, 69, 3) and torch.equal(a, ref)
+    off = torch.tensor([4.0, -3.0, 0.0], device="cuda")
+    assert torch.allclose(b - off, ref, atol=2e-4)                  # fp32 round-off of the translated coordinates only
+    assert torch.allclose(multi.get_joint_angles("bob"), single.get_joint_angles("nmf"), atol=2e-4)
+    assert float(ref[:, 0, 2].max()) < 2.0 and bool((multi.get_ground_contact_info("bob")[0].sum(dim=1) >= 0).all())
+    # a setter addressed to one fly leaves the other alone
+    multi.set_actuator_inputs("alice", ActuatorType.POSITION, np.zeros(42))
+    multi.step(50); single.step(50)
+    assert not torch.allclose(multi.get_joint_angles("alice"), single.get_joint_angles("nmf"), atol=1e-3)
+    assert torch.allclose(multi.get_joint_angles("bob"), single.get_joint_angles("nmf"), atol=5e-4)
+    with pytest.raises(ValueError):
+        multi.set_actuator_inputs("alice", ActuatorType.POSITION, np.zeros(40))
+    with pytest.raises(KeyError):
+        multi.get_joint_angles("carol")
