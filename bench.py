@@ -254,8 +254,8 @@ def run_ours(args, rank, world, local_rank):
     per_step = wl in ("vision", "olfaction")          # sensors are evaluated after every physics step
     sim = B200Simulation(model, n_worlds=n, device=dev, outputs=per_step)
     if args.actions == "replay":
-        from flygym_b200.actions import replay_table
-        table = torch.from_numpy(replay_table(model, n, 1000, fly_offset=rank * n)).to(dev)   # sim_steps = 1000 as run_gpu_benchmark.py
+        from flygym_b200.actions import replay_table_device
+        table = replay_table_device(model, n, 1000, dev, fly_offset=rank * n)                 # sim_steps = 1000 as run_gpu_benchmark.py
     else:
         table = device_cpg_table(torch, model, n, TABLE_T, dev, rank * n, world * n, adhesion_stance=(wl == "terrain"))
     table_T = table.shape[1]

@@ -78,3 +78,42 @@ def replay_table(model, n_flies: int, n_steps: int, *, fly_offset: int = 0, dtyp
         p = (k + fly_offset) % n_part
         out[k] = ang[p * n_steps:(p + 1) * n_steps]
     return out
+
+
+def replay_spline(model, timestep: float | None = None):
+    """The cubic spline ``MotionSnippet.get_joint_angles`` evaluates (``interp1d(kind="cubic")`` = not-a-knot B-spline through the
+    filtered samples) as piecewise-cubic coefficients on the source grid: ``(coef[4, n_int, A], last[A], fps, n_out_steps)``."""
+    from scipy.interpolate import CubicSpline
+    from .model import ASSETS_DIR
+    with np.load(ASSETS_DIR / "replay_clip_filtered.npz") as z:
+        filt, fps, names = z["angles"].astype(np.float64), int(z["fps"]), [str(s) for s in z["actuators"]]
+    if names != list(model.names["actuated_position"]):
+        raise ValueError("replay clip was baked for a different actuator order")
+    n = filt.shape[0]
+    # the not-a-knot cubic interpolant is unique, so CubicSpline gives the same function as interp1d's B-spline, already as
+    # per-interval polynomials c[4, n - 1, A] (highest power first) in the local variable t - x_i
+    pp = CubicSpline(np.arange(n) / fps, filt, axis=0, bc_type="not-a-knot")
+    dt = model.timestep if timestep is None else timestep
+    n_out = len(np.arange(0, n / fps, dt))
+    return np.ascontiguousarray(pp.c), np.ascontiguousarray(filt[-1]), float(fps), n_out
+
+
+def replay_table_device(model, n_flies: int, n_steps: int, device, *, fly_offset: int = 0):
+    """``replay_table`` evaluated on the GPU (``nmf_replay_table``): only the spline coefficients are uploaded; returns a float32
+    CUDA tensor ``(n_flies, n_steps, n_position_actuators)``."""
+    import ctypes
+    import torch
+    from . import _lib
+    coef, last, fps, n_out = replay_spline(model)
+    n_part = n_out // n_steps
+    if n_part < 1:
+        raise ValueError("clip shorter than the requested number of steps")
+    A = coef.shape[2]
+    out = torch.empty((n_flies, n_steps, A), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        rc = _lib.load().nmf_replay_table(coef.ctypes.data_as(ctypes.c_void_p), last.ctypes.data_as(ctypes.c_void_p), coef.shape[1], A, fps,
+                                          float(model.timestep), n_part, n_steps, n_flies, int(fly_offset), ctypes.c_void_p(out.data_ptr()),
+                                          ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"nmf_replay_table failed (status {rc})")
+    return out

@@ -330,3 +330,48 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
   CK(cudaStreamSynchronize(stream));
   return NMF_OK;
 }
+
+// ------------------------------------------------------------------ action table of the reference benchmark, built on the device
+// MotionSnippet.get_joint_angles (reference src/flygym_demo/spotlight_data/preprocessing.py:80-142) resamples the recorded clip
+// onto the simulation time grid with a cubic spline, and ReplayTargetData.make_target_angles_all_worlds
+// (src/flygym_demo/benchmark/time_gpu_simulation.py:73-86) tiles it: world k replays partition k % n_part.  The reference
+// builds the (n_worlds, T, A) float32 table on the host and uploads it (688 MB at 4096 worlds); here only the spline's
+// piecewise-cubic coefficients travel (n_int * 4 * A doubles) and every table entry is one Horner evaluation.
+__global__ void nmf_replay_table_kernel(const double* __restrict__ coef, const double* __restrict__ last, int n_int, int A, double fps, double dt,
+                                        int n_part, int T, long long total, int fly_offset, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int a = (int)(i % A);
+  const long long ws = i / A;
+  const int s = (int)(ws % T), world = (int)(ws / T);
+  const int part = (world + fly_offset) % n_part;
+  const double t = (double)((long long)part * T + s) * dt;
+  const double x_last = (double)n_int / fps;                  // last source sample; beyond it interp1d returns fill_value = y[-1]
+  double v;
+  if (t > x_last) v = last[a];
+  else {
+    int k = (int)floor(t * fps); k = k < 0 ? 0 : (k >= n_int ? n_int - 1 : k);
+    const double u = t - (double)k / fps;
+    const double* c = coef + (size_t)k * A + a;               // coef[d][k][a], highest power first (scipy PPoly layout)
+    const size_t stride = (size_t)n_int * A;
+    v = ((c[0] * u + c[stride]) * u + c[2 * stride]) * u + c[3 * stride];
+  }
+  out[i] = (float)v;
+}
+
+extern "C" int nmf_replay_table(const double* coef_host, const double* last_host, int n_int, int A, double fps, double dt, int n_part, int T,
+                                int n_worlds, int fly_offset, float* out_dev, void* stream_) {
+  if (!coef_host || !last_host || !out_dev || n_int <= 0 || A <= 0 || n_part <= 0 || T <= 0 || n_worlds <= 0 || !(fps > 0) || !(dt > 0)) return NMF_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  double* d = nullptr;
+  const size_t nc = (size_t)4 * n_int * A;
+  if (cudaMalloc(&d, sizeof(double) * (nc + A)) != cudaSuccess) return NMF_ECUDA;
+  cudaMemcpyAsync(d, coef_host, sizeof(double) * nc, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(d + nc, last_host, sizeof(double) * A, cudaMemcpyHostToDevice, stream);
+  const long long total = (long long)n_worlds * T * A;
+  nmf_replay_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d, d + nc, n_int, A, fps, dt, n_part, T, total, fly_offset, out_dev);
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(stream);      // the pageable host arrays and the scratch buffer must outlive the copies / the kernel
+  cudaFree(d);
+  return e == cudaSuccess ? NMF_OK : NMF_ECUDA;
+}

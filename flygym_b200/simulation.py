@@ -313,6 +313,14 @@ class B200Simulation:
     def timestep(self) -> float:
         return float(self.model.timestep)
 
+    def export_state(self, world_id: int = 0) -> dict:
+        """``qpos`` / ``qvel`` / ``time`` of one world as host arrays: what the reference's CPU renderer pulls out of the batched
+        data before drawing a frame (``mjw.get_data_into``, reference ``warp/rendering.py:357-359``)."""
+        i = self.info
+        rec = self.state[int(world_id)].cpu().numpy().astype(np.float64)
+        return {"qpos": rec[i.off_qpos:i.off_qpos + i.nq].copy(), "qvel": rec[i.off_qvel:i.off_qvel + i.nv].copy(),
+                "time": float(rec[i.off_time])}
+
     def step_host(self, actions_host: np.ndarray, nsteps: int, qpos_host: np.ndarray) -> None:
         """End-to-end call with HOST buffers (H2D actions, ``nsteps`` steps, D2H qpos); synchronous."""
         assert actions_host.dtype == np.float32 and actions_host.ndim == 2 and actions_host.shape[0] == self.n_worlds

@@ -94,6 +94,15 @@ int nmf_set_solver(nmf_handle* h, int max_newton_iterations, int max_linesearch_
 /* Number of kernels this library has launched on behalf of the handle (bench.py's gpu_launches). */
 int64_t nmf_launch_count(const nmf_handle* h);
 
+/* The reference benchmark's action table built on the device: MotionSnippet.get_joint_angles' cubic resampling of the recorded
+ * clip (src/flygym_demo/spotlight_data/preprocessing.py:80-142) tiled per world as ReplayTargetData.make_target_angles_all_worlds
+ * does (src/flygym_demo/benchmark/time_gpu_simulation.py:73-86; world k replays partition (k + fly_offset) % n_part).
+ * coef HOST double[4][n_int][A]: piecewise-cubic coefficients of the spline on the uniform source grid i / fps, highest power
+ * first (scipy PPoly layout); last HOST double[A]: the final source sample (interp1d's fill value beyond the grid);
+ * out DEVICE float[n_worlds][T][A].  Synchronises the stream. */
+int nmf_replay_table(const double* coef, const double* last, int n_int, int A, double fps, double dt, int n_part, int T,
+                     int n_worlds, int fly_offset, float* out, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Retina transform and odor-intensity sensor.  FlyGym 2.0.1 ships no implementation (only the v1 parameter block at
  * src/flygym/assets/model/legacy/flygym1_config.yaml:141-200); these entry points are what a re-added

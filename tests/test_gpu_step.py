@@ -366,3 +366,19 @@ def test_step_host_pipelined_slices_match_device_path():
         torch.cuda.synchronize()
         assert np.array_equal(qh, b.qpos.cpu().numpy())
     assert torch.equal(a.state, b.state) and torch.equal(a.seg_xpos, b.seg_xpos) and torch.equal(a.sensordata, b.sensordata)
+
+
+def test_replay_table_built_on_device():
+    """nmf_replay_table (cubic resampling of the recorded clip + per-world tiling on the GPU) equals the host construction the
+    reference uses (MotionSnippet.get_joint_angles + ReplayTargetData.make_target_angles_all_worlds), incl. the rank offset."""
+    import torch
+    from flygym_b200 import NMFModel
+    from flygym_b200.actions import replay_table, replay_table_device
+    m = NMFModel.bench(True)
+    for n, T, off in ((37, 1000, 0), (8, 1000, 29), (5, 2500, 3)):
+        host = replay_table(m, n, T, fly_offset=off)
+        dev = replay_table_device(m, n, T, "cuda", fly_offset=off).cpu().numpy()
+        assert dev.shape == host.shape == (n, T, 42)
+        assert np.abs(dev - host).max() <= 2.4e-7          # fp64 evaluation, one float32 rounding apart at most
+    with pytest.raises(ValueError):
+        replay_table_device(m, 2, 30000, "cuda")

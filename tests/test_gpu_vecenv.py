@@ -106,3 +106,25 @@ def test_several_flies_per_world():
         multi.set_actuator_inputs("alice", ActuatorType.POSITION, np.zeros(40))
     with pytest.raises(KeyError):
         multi.get_joint_angles("carol")
+
+
+def test_trajectory_recorder_and_state_export(tmp_path):
+    import torch
+    from flygym_b200 import B200Simulation
+    from flygym_b200.trajectory import TrajectoryRecorder
+    sim = B200Simulation(None, n_worlds=5)
+    rec = TrajectoryRecorder(sim, capacity=4, every=2, with_qvel=True)
+    kept = []
+    for t in range(10):
+        sim.step(3)
+        if rec.record():
+            kept.append(sim.qpos.clone())
+    assert rec.count == 4 and len(kept) == 4                       # calls 0, 2, 4, 6; the buffer is full afterwards
+    data = rec.gather()
+    assert data["qpos"].shape == (4, 5, 73) and data["qvel"].shape == (4, 5, 72)
+    assert np.array_equal(data["qpos"][2], kept[2].cpu().numpy())
+    assert np.allclose(data["time"], [3e-4, 9e-4, 15e-4, 21e-4], rtol=1e-5)
+    assert rec.save(tmp_path / "traj.npz") and np.load(tmp_path / "traj.npz")["qpos"].shape == (4, 5, 73)
+    st = sim.export_state(3)
+    assert st["qpos"].shape == (73,) and st["qvel"].shape == (72,) and abs(st["time"] - 30e-4) < 1e-7
+    assert np.array_equal(st["qpos"].astype(np.float32), sim.qpos[3].cpu().numpy())
