@@ -49,6 +49,14 @@ NCU_TRAFFIC = {
                                                "evicted from L2) vs 0.79 GB algorithmic"),
     ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt: 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
 }
+# what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
+NCU_LIMITER = {
+    "flat": {"issue_slots_busy": 0.402, "top_stall": "no_inst (instruction fetch) 46 % of samples", "warp_instructions_per_fly_step": 21200,
+             "source": "profiles/ncu_step_r01i_summary.txt"},
+    "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
+    "vision": {"issue_slots_busy": 0.860, "top_stall": "issue-bound: ~69 thread-instructions per shaded pixel (fused eye + Retina kernel)",
+               "source": "profiles/ncu_vision_r01s2_summary.txt"},
+}
 ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
 ODOR_PEAKS = [[1.0, 0.0], [0.0, 1.0]]
 
@@ -427,6 +435,8 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall, "state_finite": finite,
         }
+        if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh:
+            line["roofline"]["limiter"] = NCU_LIMITER[wl]
         if "fused_eye_retina_ms" in roof:
             line["roofline"]["fused_eye_retina_ms_per_launch"] = roof["fused_eye_retina_ms"]
         if gathered_slabs:
