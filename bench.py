@@ -359,10 +359,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
         ret_ms = float(np.mean([a.elapsed_time(b) for a, b in tms])); fused_ms = float(np.mean([a.elapsed_time(b) for a, b in fms]))
         alg = n * RETINA_ALG_BYTES
-        roof = {"kernel": "nmf_retina_kernel (eye buffers in HBM -> ommatidia)", "ms": ret_ms, "alg_bytes": alg,
-                "fused_eye_retina_ms": fused_ms,
-                "note": f"Retina over materialised eye buffers is HBM-bound ({RETINA_ALG_BYTES} B per fly-frame, SURVEY.md 8d); the timed "
-                        "region uses the fused render+Retina kernel, which never materialises them (bit-identical output)"}
+        roof = {"kernel": "nmf_eye_retina_kernel (fused eye-camera image formation + Retina)", "ms": fused_ms, "alg_bytes": alg,
+                "retina_over_buffers": {"kernel": "nmf_retina_kernel", "ms_per_launch": ret_ms, "achieved": alg / (ret_ms * 1e-3) / 1e9,
+                                        "note": "the HBM-bound form of the operator: eye buffers materialised in HBM (two 1.4 GB sets alternated); a pure "
+                                                "read stream that skips chunks outside the ommatidia hexagon, hence above the copy-measured peak"},
+                "note": f"algorithmic bytes = the Retina operator's {RETINA_ALG_BYTES} B per fly-frame (SURVEY.md 8d); the fused kernel shades "
+                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (86 % busy), not HBM"}
         del imgs
     else:
         per_launch_steps = 1 if per_step else chunk
@@ -437,8 +439,9 @@ def run_ours(args, rank, world, local_rank):
         }
         if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh:
             line["roofline"]["limiter"] = NCU_LIMITER[wl]
-        if "fused_eye_retina_ms" in roof:
-            line["roofline"]["fused_eye_retina_ms_per_launch"] = roof["fused_eye_retina_ms"]
+        if "retina_over_buffers" in roof:
+            rb = dict(roof["retina_over_buffers"]); rb["frac"] = rb["achieved"] / peak
+            line["roofline"]["retina_over_buffers"] = rb
         if gathered_slabs:
             line["nccl_all_gathers_in_timed_region"] = gathered_slabs
         print(json.dumps(line), flush=True)
