@@ -47,14 +47,16 @@ RETINA_ALG_BYTES = 2 * 512 * 450 * 3 + 2 * 721 * 2 * 4   # 1 393 936 B per fly-f
 NCU_TRAFFIC = {
     ("flat", 4096, 100): (0.1176e9 + 2.7727e9, "profiles/ncu_step_r01i_summary.txt: 0.118 GB read + 2.77 GB written (local-memory spill lines "
                                                "evicted from L2) vs 0.79 GB algorithmic"),
-    ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt: 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
+    ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt (80-register build): 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
+    ("vision", 1024, 10): (0.81e6, "profiles/ncu_vision_r01s2_summary.txt: the fused kernel reads 0.81 MB (run table, poses) and never materialises the 1.4 GB of eye buffers"),
 }
+RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.txt: 1.009 GB read + 8.3 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
 # what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
 NCU_LIMITER = {
     "flat": {"issue_slots_busy": 0.402, "top_stall": "no_inst (instruction fetch) 46 % of samples", "warp_instructions_per_fly_step": 21200,
              "source": "profiles/ncu_step_r01i_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
-    "vision": {"issue_slots_busy": 0.860, "top_stall": "issue-bound: ~69 thread-instructions per shaded pixel (fused eye + Retina kernel)",
+    "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
                "source": "profiles/ncu_vision_r01s2_summary.txt"},
 }
 ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
@@ -364,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
                                         "note": "the HBM-bound form of the operator: eye buffers materialised in HBM (two 1.4 GB sets alternated); a pure "
                                                 "read stream that skips chunks outside the ommatidia hexagon, hence above the copy-measured peak"},
                 "note": f"algorithmic bytes = the Retina operator's {RETINA_ALG_BYTES} B per fly-frame (SURVEY.md 8d); the fused kernel shades "
-                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (86 % busy), not HBM"}
+                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (83 % busy), not HBM"}
         del imgs
     else:
         per_launch_steps = 1 if per_step else chunk
@@ -441,6 +443,8 @@ def run_ours(args, rank, world, local_rank):
             line["roofline"]["limiter"] = NCU_LIMITER[wl]
         if "retina_over_buffers" in roof:
             rb = dict(roof["retina_over_buffers"]); rb["frac"] = rb["achieved"] / peak
+            if n == 1024:
+                rb["traffic"], rb["traffic_source"] = RETINA_BUFFERS_TRAFFIC
             line["roofline"]["retina_over_buffers"] = rb
         if gathered_slabs:
             line["nccl_all_gathers_in_timed_region"] = gathered_slabs

@@ -73,12 +73,13 @@ def eye_render_oracle(seg_xpos, seg_xquat, prm, H, W):
             wx = (R[0, 0] * dx + R[0, 1] * dy) - R[0, 2]
             wy = (R[1, 0] * dx + R[1, 1] * dy) - R[1, 2]
             hit = (wz < 0) & (pos[2] > 0)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                t = pos[2] / (-wz)
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                t = pos[2] * (f32(1) / (-wz))                     # correctly rounded reciprocal, then one multiplication
                 hx, hy = pos[0] + t * wx, pos[1] + t * wy
-                ix = np.floor(hx * prm["inv_check"]).astype(np.int64)
-                iy = np.floor(hy * prm["inv_check"]).astype(np.int64)
-            v = np.where(((ix + iy) & 1) == 1, prm["ground"][1], prm["ground"][0])
+                sat = lambda v: np.clip(np.nan_to_num(np.floor(v), nan=0.0), -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)   # float -> int32, round down, saturating
+                ix, iy = sat(hx * prm["inv_check"]), sat(hy * prm["inv_check"])
+                ix, iy = ix.astype(np.int32), iy.astype(np.int32)
+            v = np.where(((ix.astype(np.int64) + iy) & 1) == 1, prm["ground"][1], prm["ground"][0])
             g = np.where(hit, v, prm["sky"][0]).astype(np.uint8)
             b = np.where(hit, v, prm["sky"][1]).astype(np.uint8)
             img[i, e, :, :, 0] = g
