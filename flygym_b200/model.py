@@ -210,6 +210,28 @@ class NMFModel:
         if forcerange is not None: a["act_frcrange"] = np.tile(np.asarray(forcerange, dtype=np.float64), (n, 1))
         return NMFModel(a, self.names, dict(self.meta, position_gain=float(a["act_kp"][0])))
 
+    def with_actuated_dofs(self, preset: str) -> "NMFModel":
+        """Position actuators on the DoFs of an ``ActuatedDOFPreset`` (reference ``anatomy.py:463-498``, applied by
+        ``Fly.add_actuators``, ``fly.py:301-369``): ``"legs_active_only"`` (the baked default, 42 actuators) or ``"legs_only"`` /
+        ``"all"`` (every leg hinge incl. the passive tarsal joints, 66 actuators in the LEGS_ONLY skeleton).  Gains and force range
+        are those of the existing actuators; the neutral input of an actuator is its DoF's neutral (keyframe) angle."""
+        from . import anatomy as A
+        dofs = [A.JointDOF(*nm.split("-")) for nm in self.names["jointdofs"]]
+        chosen = {d.name for d in A.actuated_dofs(dofs, preset)}
+        idx = [j for j, d in enumerate(dofs) if d.name in chosen]
+        if not idx:
+            raise ValueError(f"actuated-DoF preset {preset!r} selects nothing in this skeleton")
+        ex = self.exposed_hinge_dofs()
+        a = dict(self.arrays)
+        n = len(idx)
+        a["act_dof"] = np.array([6 + int(ex[j]) for j in idx], dtype=np.int32)
+        a["act_kp"] = np.full(n, float(self.arrays["act_kp"][0])); a["act_kv"] = np.full(n, float(self.arrays["act_kv"][0]))
+        a["act_frcrange"] = np.tile(self.arrays["act_frcrange"].reshape(-1, 2)[0], (n, 1))
+        a["key_ctrl"] = np.r_[self.arrays["key_qpos"][1 + a["act_dof"]], self.arrays["key_ctrl"][self.dim("nu_pos"):]]
+        dims = a["dims"].copy(); dims[DIM_FIELDS.index("nu_pos")] = n; a["dims"] = dims
+        names = dict(self.names, actuated_position=[dofs[j].name for j in idx])
+        return NMFModel(a, names, dict(self.meta, actuated_preset=preset))
+
     def with_joint_params(self, stiffness: float | None = None, damping: float | None = None, armature: float | None = None) -> "NMFModel":
         """``Fly.add_joints(..., stiffness=, damping=, armature=)`` (reference ``fly.py:221-299``) for every hinge DoF that is
         not locked."""
