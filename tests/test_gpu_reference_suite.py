@@ -204,3 +204,49 @@ def test_joint_and_contact_presets_on_gpu():
         if name == "legs_active_only":
             locked = np.delete(got[:, 7:], ex, axis=1)
             assert np.abs(locked).max() < 1e-6
+
+
+class TestGatherScatterKernels:
+    """The reference checks its indexed gather / scatter kernels against numpy fancy indexing (tests/warp/test_utils.py:26-150:
+    correct columns, a single column, all columns, scatter preserves the other values); same checks through the C ABI
+    (nmf_gather_state / nmf_scatter_ctrl, which stand behind the getters / setters)."""
+
+    @pytest.fixture(scope="class")
+    def sim(self):
+        import torch
+        from flygym_b200 import B200Simulation
+        s = B200Simulation(None, n_worlds=7)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        s.state.copy_(torch.randn(s.state.shape, device="cuda", generator=g))
+        return s
+
+    def _gather(self, sim, off, cols):
+        import ctypes, torch
+        c = torch.tensor(cols, dtype=torch.int32, device="cuda")
+        dst = torch.full((sim.n_worlds, len(cols)), float("nan"), device="cuda")
+        rc = sim._lib.nmf_gather_state(sim._h, off, ctypes.c_void_p(c.data_ptr()), len(cols), ctypes.c_void_p(dst.data_ptr()), sim._stream())
+        assert rc == 0
+        return dst.cpu().numpy()
+
+    @pytest.mark.parametrize("cols", [[3, 0, 17, 65, 9], [41], list(range(72))])
+    def test_gather_matches_numpy_indexing(self, sim, cols):
+        host = sim.state.cpu().numpy()
+        off = sim.info.off_qvel
+        assert np.array_equal(self._gather(sim, off, cols), host[:, off + np.array(cols)])
+
+    def test_scatter_writes_only_the_selected_columns(self, sim):
+        import ctypes, torch
+        before = sim.state.cpu().numpy().copy()
+        cols = [5, 0, 47, 20]
+        src = torch.arange(sim.n_worlds * len(cols), dtype=torch.float32, device="cuda").reshape(sim.n_worlds, len(cols)) + 100
+        c = torch.tensor(cols, dtype=torch.int32, device="cuda")
+        rc = sim._lib.nmf_scatter_ctrl(sim._h, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(c.data_ptr()), len(cols), sim._stream())
+        assert rc == 0
+        after = sim.state.cpu().numpy()
+        off = sim.info.off_ctrl
+        assert np.array_equal(after[:, off + np.array(cols)], src.cpu().numpy())
+        mask = np.ones(after.shape[1], bool); mask[off + np.array(cols)] = False
+        assert np.array_equal(after[:, mask], before[:, mask])
+        # bad arguments are refused with a status, not a fault
+        assert sim._lib.nmf_gather_state(sim._h, 10_000, ctypes.c_void_p(c.data_ptr()), 4, ctypes.c_void_p(src.data_ptr()), sim._stream()) == -1
+        assert sim._lib.nmf_scatter_ctrl(sim._h, None, ctypes.c_void_p(c.data_ptr()), 4, sim._stream()) == -1
