@@ -206,19 +206,20 @@ def test_joint_and_contact_presets_on_gpu():
             assert np.abs(locked).max() < 1e-6
 
 
+@pytest.fixture(scope="module")
+def sim():
+    import torch
+    from flygym_b200 import B200Simulation
+    s = B200Simulation(None, n_worlds=7)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    s.state.copy_(torch.randn(s.state.shape, device="cuda", generator=g))
+    return s
+
+
 class TestGatherScatterKernels:
     """The reference checks its indexed gather / scatter kernels against numpy fancy indexing (tests/warp/test_utils.py:26-150:
     correct columns, a single column, all columns, scatter preserves the other values); same checks through the C ABI
     (nmf_gather_state / nmf_scatter_ctrl, which stand behind the getters / setters)."""
-
-    @pytest.fixture(scope="class")
-    def sim(self):
-        import torch
-        from flygym_b200 import B200Simulation
-        s = B200Simulation(None, n_worlds=7)
-        g = torch.Generator(device="cuda").manual_seed(1)
-        s.state.copy_(torch.randn(s.state.shape, device="cuda", generator=g))
-        return s
 
     def _gather(self, sim, off, cols):
         import ctypes, torch
