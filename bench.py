@@ -54,6 +54,7 @@ RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.tx
 # what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
 NCU_LIMITER = {
     "flat": {"issue_slots_busy": 0.402, "top_stall": "no_inst (instruction fetch) 46 % of samples", "warp_instructions_per_fly_step": 21200,
+             "issue_ceiling_env_steps_per_s": 148 * 4 * 1.965e9 / 21200,
              "source": "profiles/ncu_step_r01i_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
     "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
