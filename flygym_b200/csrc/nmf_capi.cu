@@ -305,6 +305,9 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
   int parts = h->host_parts;
   while (parts > 1 && n < 1024 * parts) parts--;   // at least 1024 flies per slice
   if (parts > 1 && !h->part_stream[0]) {
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != h->device) { h->err = "nmf_step_host: the handle's device is not the current CUDA device"; return NMF_EINVAL; }
     for (int k = 0; k < nmf_handle::MAX_PARTS; k++) {
       CK(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));
