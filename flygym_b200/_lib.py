@@ -86,6 +86,7 @@ def load() -> ctypes.CDLL:
     lib.nmf_reset.argtypes = [vp, vp, vp]
     lib.nmf_step.argtypes = [vp, ci, vp, ci, ci, ci, vp]
     lib.nmf_set_schedule.argtypes = [vp, ci]
+    lib.nmf_set_precision.argtypes = [vp, ci]
     lib.nmf_forward.argtypes = [vp, vp]
     lib.nmf_replay_table.argtypes = [vp, vp, ci, ci, ctypes.c_double, ctypes.c_double, ci, ci, ci, ci, vp, vp]
     lib.nmf_replay_table.restype = ci
@@ -96,7 +97,7 @@ def load() -> ctypes.CDLL:
     lib.nmf_launch_count.argtypes = [vp]
     lib.nmf_launch_count.restype = ctypes.c_int64
     for fn in ("nmf_create", "nmf_destroy", "nmf_model_info", "nmf_bind", "nmf_reset", "nmf_step", "nmf_scatter_ctrl",
-               "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_forward"):
+               "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_forward"):
         getattr(lib, fn).restype = ci
     lib.nmf_retina_create.argtypes = [vp, vp, ci, ci, ci, ci, ctypes.POINTER(vp)]
     lib.nmf_retina_destroy.argtypes = [vp]
@@ -120,7 +121,7 @@ def load() -> ctypes.CDLL:
 # symbols declared in include/nmf_b200.h (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
     "nmf_create", "nmf_destroy", "nmf_model_info", "nmf_last_error", "nmf_bind", "nmf_reset", "nmf_step",
-    "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_forward", "nmf_replay_table", "nmf_launch_count",
+    "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_forward", "nmf_replay_table", "nmf_launch_count",
     "nmf_retina_create", "nmf_retina_destroy", "nmf_retina_last_error", "nmf_retina_launch_count", "nmf_retina_forward",
     "nmf_retina_forward_host", "nmf_odor_intensity", "nmf_eye_render", "nmf_eye_retina",
 ]

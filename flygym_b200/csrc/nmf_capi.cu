@@ -10,7 +10,7 @@
 
 #include "../../include/nmf_b200.h"
 #include "nmf_host.h"
-#include "nmf_step.cuh"
+#include "nmf_step_all.cuh"
 
 using namespace nmf;
 
@@ -18,69 +18,20 @@ using namespace nmf;
 #ifndef NMF_MINBLOCKS
 #define NMF_MINBLOCKS 16   // <= 64 registers/thread: best measured trade-off between occupancy and spills (profiles/)
 #endif
-// Two schedules, one call site of the (large) step body:
-//  * p.queue == nullptr: block b advances fly b by all p.nsteps steps (grid = n_flies);
-//  * work queue: the launch is cut into items (fly, sub-chunk of p.sub_steps steps) served to a grid that just fills the
-//    GPU.  n_flies is rarely a multiple of the 148 x 16 resident blocks, and this latency-bound kernel slows down in
-//    proportion to the empty slots of a partial last wave; with items a launch is many waves long instead of one or two.
-//    The queue is a FIFO of READY flies: entries 0..n-1 are implicit (every fly's first sub-chunk), and a block that has
-//    written a fly's record back appends the fly again (release) unless that was its last sub-chunk.  Entry i >= n is
-//    therefore filled by the (i-n)-th completion; when a block pops it at most `grid` items are still running, i.e. at
-//    least i - grid >= i - n have completed (the queue is only used when n_flies >= grid), so pops do not wait.
-//    queue[0] = pop counter, queue[1] = push counter, queue[2 + f] = sub-chunks of fly f done, queue[2 + n + j] = ring entry j.
-template <int WORLD>
-__device__ __forceinline__ void step_entry(const StepParams& p) {
-  __shared__ __align__(16) float sm[WORLD == W_TETHER ? SM_TOTAL : SM_WELD];   // only the tethered world keeps weld rows
-  __shared__ int s_fly, s_chunk;
-  const int tid = threadIdx.x;
-  for (;;) {
-    int fly = blockIdx.x, step0 = 0, nsub = p.nsteps;
-    if (p.queue) {
-      if (tid == 0) {
-        const int i = atomicAdd(p.queue, 1);
-        int f = -1;
-        if (i < p.n_flies) f = i;
-        else if (i < p.n_items) {
-          const int* slot = p.queue + 2 + p.n_flies + (i - p.n_flies);
-          int v = 0;
-          for (unsigned spins = 0; spins < (1u << 24); spins++) {      // bounded: a scheduling bug must not hang the GPU
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
-            if (v) break;
-            __nanosleep(64);
-          }
-          f = v - 1;
-          asm volatile("fence.proxy.async;" ::: "memory");            // the record is read through the async proxy (TMA) next
-        }
-        s_fly = f; s_chunk = f >= 0 ? p.queue[2 + f] : 0;
-      }
-      block_sync();
-      fly = s_fly;
-      if (fly < 0) return;
-      step0 = s_chunk * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
-    }
-    step_block<WORLD>(p, sm, fly, step0, nsub, p.queue != nullptr);
-    if (!p.queue) return;
-    if (tid == 0) {   // the TMA store of the record has completed (tma_store_record waited for it): hand the fly on
-      const int done = step0 / p.sub_steps + 1;
-      p.queue[2 + fly] = done;
-      if (done * p.sub_steps < p.nsteps) {
-        __threadfence();
-        const int j = atomicAdd(p.queue + 1, 1);
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.queue + 2 + p.n_flies + j), "r"(fly + 1) : "memory");
-      }
-    }
-  }
-}
-
-extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) { step_entry<W_FLAT>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT>(p); }
 // terrain worlds (box columns: BASELINE config 3): general contact frames need 8 more registers per lane; measured on B200 at
 // 12 / 14 / 16 blocks per SM (80 / 72 / 64 registers): 15.8 / 16.8 / 16.8 M env-steps/s -> occupancy wins over spills here too
 #ifndef NMF_MINBLOCKS_TERRAIN
 #define NMF_MINBLOCKS_TERRAIN 16
 #endif
-extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_step_terrain_kernel(const StepParams p) { step_entry<W_TERRAIN>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_step_terrain_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN>(p); }
 // TetheredWorld (reference world.py:334-366): no ground contacts, six weld rows on the free body
-extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether_kernel(const StepParams p) { step_entry<W_TETHER>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether_kernel(const StepParams p) { f32::step_entry<f32::W_TETHER>(p); }
+// fp64 instantiations of the same source: a validation build (nmf_set_precision(h, 64)), not a product path -- every
+// quantity takes two registers, so occupancy is whatever 255 registers leave
+extern "C" __global__ void __launch_bounds__(CTA, 4) nmf_step_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, 4) nmf_step_terrain_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, 4) nmf_step_tether_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER>(p); }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
   int fly = blockIdx.x;
@@ -108,6 +59,8 @@ struct nmf_handle {
   int n_flies = 0, device = 0;
   float *d_role = nullptr, *d_hull = nullptr, *d_seg = nullptr, *d_key = nullptr;
   int *d_nbr_adr = nullptr, *d_nbr = nullptr;
+  double *d_role64 = nullptr, *d_hull64 = nullptr;   // tables of the f64 validation kernels (uploaded by nmf_set_precision)
+  int precision = 32;
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
   int resident_blocks = 0;                     // blocks of the step kernel (the model's variant) the device holds at once
@@ -167,7 +120,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
 
 extern "C" int nmf_destroy(nmf_handle* h) {
   if (!h) return NMF_OK;
-  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue);
+  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64);
   for (int k = 0; k < nmf_handle::MAX_PARTS; k++) { if (h->part_stream[k]) cudaStreamDestroy(h->part_stream[k]); if (h->part_done[k]) cudaEventDestroy(h->part_done[k]); }
   if (h->fork) cudaEventDestroy(h->fork);
   delete h;
@@ -222,18 +175,35 @@ extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table
 
 extern "C" int nmf_forward(nmf_handle* h, void* stream) { return launch_steps(h, 1, nullptr, 0, 0, 0, true, stream); }
 
-// flies [fly0, fly0 + count) only (count < 0: all): the buffers are addressed per fly, so a range is the same launch on offset pointers
-static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
-                        int fly0, int count) {
-  if (!h) return NMF_EINVAL;
-  if (!h->bound) { h->err = "nmf_step: not bound"; return NMF_ENOTBOUND; }
-  if (nsteps <= 0) return NMF_OK;
-  if (table && table_T <= 0) { h->err = "nmf_step: action table needs table_T > 0"; return NMF_EINVAL; }
-  if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
-    h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
+template <class real> struct KernelSet;
+template <> struct KernelSet<float> {
+  static const StepParamsT<float>& base(const nmf_handle* h) { return h->hm.par; }
+  static const float* role(const nmf_handle* h) { return h->d_role; }
+  static const float* hull(const nmf_handle* h) { return h->d_hull; }
+  static void launch(const StepParamsT<float>& p, int grid, cudaStream_t s) {
+    if (p.weld) nmf_step_tether_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.terrain) nmf_step_terrain_kernel<<<grid, CTA, 0, s>>>(p);
+    else nmf_step_kernel<<<grid, CTA, 0, s>>>(p);
   }
-  StepParams p = h->hm.par;
-  p.state = h->buf.state; p.role = h->d_role; p.hull = h->d_hull; p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
+};
+template <> struct KernelSet<double> {
+  static const StepParamsT<double>& base(const nmf_handle* h) { return h->hm.par64; }
+  static const double* role(const nmf_handle* h) { return h->d_role64; }
+  static const double* hull(const nmf_handle* h) { return h->d_hull64; }
+  static void launch(const StepParamsT<double>& p, int grid, cudaStream_t s) {
+    if (p.weld) nmf_step_tether_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.terrain) nmf_step_terrain_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else nmf_step_f64_kernel<<<grid, CTA, 0, s>>>(p);
+  }
+};
+
+// flies [fly0, fly0 + count) only (count < 0: all): the buffers are addressed per fly, so a range is the same launch on offset pointers
+template <class real>
+static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
+                          int fly0, int count) {
+  StepParamsT<real> p = KernelSet<real>::base(h);
+  p.max_newton = h->hm.par.max_newton; p.max_ls = h->hm.par.max_ls;       // nmf_set_solver edits the f32 copy
+  p.state = h->buf.state; p.role = KernelSet<real>::role(h); p.hull = KernelSet<real>::hull(h); p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
   p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
   p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps; p.forward_only = forward_only ? 1 : 0;
@@ -257,18 +227,45 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
     const int k = (nsteps + 12) / 25;
     sub = k >= 2 ? (nsteps + k - 1) / k : 0;
   }
-  if (!ranged && sub > 0 && h->n_flies > h->resident_blocks && nsteps >= 2 * sub) {   // more flies than resident blocks: work queue (one per handle)
+  // more flies than resident blocks: work queue (one per handle; sized for the f32 kernels' occupancy, so f32 only)
+  if (std::is_same<real, float>::value && !ranged && sub > 0 && h->n_flies > h->resident_blocks && nsteps >= 2 * sub) {
     if (sub * QUEUE_MAX_CHUNKS < nsteps) sub = (nsteps + QUEUE_MAX_CHUNKS - 1) / QUEUE_MAX_CHUNKS;
     const int nchunk = (nsteps + sub - 1) / sub;
     p.queue = h->d_queue; p.sub_steps = sub; p.n_items = nchunk * h->n_flies;
     grid = h->resident_blocks;
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)h->n_flies * nchunk + 2), (cudaStream_t)stream));
   }
-  if (p.weld) nmf_step_tether_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
-  else if (p.terrain) nmf_step_terrain_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
-  else nmf_step_kernel<<<grid, CTA, 0, (cudaStream_t)stream>>>(p);
+  KernelSet<real>::launch(p, grid, (cudaStream_t)stream);
   h->launches++;
   CK(cudaGetLastError());
+  return NMF_OK;
+}
+
+static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
+                        int fly0, int count) {
+  if (!h) return NMF_EINVAL;
+  if (!h->bound) { h->err = "nmf_step: not bound"; return NMF_ENOTBOUND; }
+  if (nsteps <= 0) return NMF_OK;
+  if (table && table_T <= 0) { h->err = "nmf_step: action table needs table_T > 0"; return NMF_EINVAL; }
+  if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
+    h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
+  }
+  return h->precision == 64 ? launch_steps_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count)
+                            : launch_steps_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count);
+}
+
+// Arithmetic of the step kernels: 32 (default, the product path) or 64 = the SAME kernel source instantiated in double precision
+// (validation: shadows the fp64 oracle over long horizons; the state records in HBM stay float32, so carry precision across
+// steps by fusing them into one launch).
+extern "C" int nmf_set_precision(nmf_handle* h, int bits) {
+  if (!h || (bits != 32 && bits != 64)) return NMF_EINVAL;
+  if (bits == 64 && !h->d_role64) {
+    CK(cudaMalloc(&h->d_role64, sizeof(double) * h->hm.role64.size()));
+    CK(cudaMemcpy(h->d_role64, h->hm.role64.data(), sizeof(double) * h->hm.role64.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_hull64, sizeof(double) * h->hm.hull64.size()));
+    CK(cudaMemcpy(h->d_hull64, h->hm.hull64.data(), sizeof(double) * h->hm.hull64.size(), cudaMemcpyHostToDevice));
+  }
+  h->precision = bits;
   return NMF_OK;
 }
 

@@ -41,14 +41,38 @@ inline void q2mat_d(const double* q, double* m) {
   m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = 1 - 2 * (x * x + y * y);
 }
 inline float i2f(int v) { float f; memcpy(&f, &v, 4); return f; }
+// integer fields of the role table: bit pattern in the float table, plain number in the double one (nmf_step_common.cuh role_int)
+template <class real> inline real int_field(int v);
+template <> inline float int_field<float>(int v) { return i2f(v); }
+template <> inline double int_field<double>(int v) { return (double)v; }
+
+// scalar parameters of the f32 kernels = the f64 ones narrowed (pointers stay null)
+inline StepParams narrow(const StepParamsT<double>& d) {
+  StepParams f{};
+  f.n_flies = d.n_flies; f.nsteps = d.nsteps; f.table_T = d.table_T; f.table_t0 = d.table_t0; f.table_cols = d.table_cols;
+  f.forward_only = d.forward_only; f.nu_pos = d.nu_pos; f.nu_adh = d.nu_adh; f.nseg = d.nseg; f.nhubgeom = d.nhubgeom;
+  f.dt = (float)d.dt; f.gx = (float)d.gx; f.gy = (float)d.gy; f.gz = (float)d.gz; f.inv_total_mass = (float)d.inv_total_mass;
+  f.mu = (float)d.mu; f.cK = (float)d.cK; f.cB = (float)d.cB; f.margin = (float)d.margin; f.impratio = (float)d.impratio;
+  for (int i = 0; i < 5; i++) { f.solimp[i] = (float)d.solimp[i]; f.weld_imp[i] = (float)d.weld_imp[i]; }
+  f.max_newton = d.max_newton; f.max_ls = d.max_ls; f.terrain = d.terrain; f.weld = d.weld;
+  for (int i = 0; i < 8; i++) f.terr[i] = (float)d.terr[i];
+  for (int i = 0; i < 3; i++) f.weld_a[i] = (float)d.weld_a[i];
+  for (int i = 0; i < 4; i++) f.weld_q[i] = (float)d.weld_q[i];
+  f.weld_K = (float)d.weld_K; f.weld_B = (float)d.weld_B; f.weld_ts = (float)d.weld_ts;
+  f.weld_invw[0] = (float)d.weld_invw[0]; f.weld_invw[1] = (float)d.weld_invw[1];
+  f.sub_steps = d.sub_steps; f.n_items = d.n_items;
+  return f;
+}
 
 struct HostModel {
-  std::vector<float> role;     // RF_COUNT * CTA
+  std::vector<float> role;     // RF_COUNT * CTA (f32 kernels); integer fields as bit patterns
   std::vector<float> hull;     // 3 * nhullvert
+  std::vector<double> role64, hull64;   // the same tables for the f64 validation kernels (integer fields as numbers)
   std::vector<int32_t> hull_nbr_adr, hull_nbr;   // CSR adjacency of the hull vertices
   std::vector<float> seg_tab;  // nseg * 8
   std::vector<float> key_state;  // S_STRIDE, the neutral keyframe as a state record
   StepParams par{};            // pointer members left null
+  StepParamsT<double> par64{};
   int nu = 0, nseg = 0;
   std::string err;
 
@@ -79,8 +103,10 @@ struct HostModel {
       int bb = 1 + l * NLINK + k;
       if (dofnum[bb] != want_dofs[k] || body_parent[bb] != (k == 0 ? 0 : bb - 1) || body_leg[bb] != l) { err = "unsupported leg chain layout"; return false; }
     }
-    role.assign((size_t)RF_COUNT * CTA, 0.f);
-    auto set = [&](int field, int tid, float v) { role[(size_t)field * CTA + tid] = v; };
+    role64.assign((size_t)RF_COUNT * CTA, 0.0);
+    std::vector<char> int_field_of(RF_COUNT, 0);
+    auto set = [&](int field, int tid, double v) { role64[(size_t)field * CTA + tid] = v; };
+    auto seti = [&](int field, int tid, int v) { role64[(size_t)field * CTA + tid] = (double)v; int_field_of[field] = 1; };
     auto lane_of_body = [&](int bb) { return bb == 0 ? NLEG * NLINK : bb - 1; };
     double mtot = 0;
     for (int bb = 0; bb < nbody; bb++) mtot += body_mass[bb];
@@ -88,54 +114,54 @@ struct HostModel {
     for (int tid = 0; tid < CTA; tid++) {
       int bb = tid < NLEG * NLINK ? tid + 1 : 0;
       const bool hublane = tid >= NLEG * NLINK;   // hub chains: identity offset from the hub frame (seeded with the hub pose)
-      for (int i = 0; i < 3; i++) set(RF_BPOS + i, tid, hublane ? 0.f : (float)body_pos[3 * bb + i]);
-      for (int i = 0; i < 4; i++) set(RF_BQUAT + i, tid, hublane ? (i == 0 ? 1.f : 0.f) : (float)body_quat[4 * bb + i]);
-      for (int i = 0; i < 3; i++) set(RF_IPOS + i, tid, (float)body_ipos[3 * bb + i]);
+      for (int i = 0; i < 3; i++) set(RF_BPOS + i, tid, hublane ? 0.f : body_pos[3 * bb + i]);
+      for (int i = 0; i < 4; i++) set(RF_BQUAT + i, tid, hublane ? (i == 0 ? 1.f : 0.f) : body_quat[4 * bb + i]);
+      for (int i = 0; i < 3; i++) set(RF_IPOS + i, tid, body_ipos[3 * bb + i]);
       double Rm[9]; q2mat_d(body_iquat + 4 * bb, Rm);
       double Ib[9];
       for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += Rm[3 * i + k] * body_inertia[3 * bb + k] * Rm[3 * j + k]; Ib[3 * i + j] = s; }
-      set(RF_IB + 0, tid, (float)Ib[0]); set(RF_IB + 1, tid, (float)Ib[4]); set(RF_IB + 2, tid, (float)Ib[8]);
-      set(RF_IB + 3, tid, (float)Ib[1]); set(RF_IB + 4, tid, (float)Ib[2]); set(RF_IB + 5, tid, (float)Ib[5]);
-      set(RF_MASS, tid, (float)body_mass[bb]); set(RF_INVW, tid, (float)invw[2 * bb]);
+      set(RF_IB + 0, tid, Ib[0]); set(RF_IB + 1, tid, Ib[4]); set(RF_IB + 2, tid, Ib[8]);
+      set(RF_IB + 3, tid, Ib[1]); set(RF_IB + 4, tid, Ib[2]); set(RF_IB + 5, tid, Ib[5]);
+      set(RF_MASS, tid, body_mass[bb]); set(RF_INVW, tid, invw[2 * bb]);
       if (hublane && tid != NLEG * NLINK) {       // only lane 48 carries the hub's mass / inertia
         set(RF_MASS, tid, 0.f);
         for (int i = 0; i < 6; i++) set(RF_IB + i, tid, 0.f);
       }
-      set(RF_GTYPE, tid, i2f(-1)); set(RF_ADH_CIDX, tid, i2f(-1));
-      for (int j = 0; j < 3; j++) set(RF_CIDX + j, tid, i2f(-1));
+      seti(RF_GTYPE, tid, -1); seti(RF_ADH_CIDX, tid, -1);
+      for (int j = 0; j < 3; j++) seti(RF_CIDX + j, tid, -1);
       if (bb > 0) {
-        set(RF_NDOF, tid, i2f(dofnum[bb])); set(RF_DOF0, tid, i2f(dofadr[bb]));
+        seti(RF_NDOF, tid, dofnum[bb]); seti(RF_DOF0, tid, dofadr[bb]);
         for (int j = 0; j < dofnum[bb]; j++) {
           int d = dofadr[bb] + j;
-          for (int i = 0; i < 3; i++) set(RF_AXIS + 3 * j + i, tid, (float)dof_axis[3 * d + i]);
-          set(RF_STIFF + j, tid, (float)stiff[d]); set(RF_DAMP + j, tid, (float)damp[d]); set(RF_ARM + j, tid, (float)arm[d]);
-          set(RF_SREF + j, tid, (float)sref[d]);
+          for (int i = 0; i < 3; i++) set(RF_AXIS + 3 * j + i, tid, dof_axis[3 * d + i]);
+          set(RF_STIFF + j, tid, stiff[d]); set(RF_DAMP + j, tid, damp[d]); set(RF_ARM + j, tid, arm[d]);
+          set(RF_SREF + j, tid, sref[d]);
         }
         bool sens = false;   // the leg sensor covers the subtree rooted at the most proximal contact segment
         int l = body_leg[bb]; if (l >= 0 && leg_root[l] >= 0 && bb >= leg_root[l]) sens = true;
-        set(RF_LEGSENSOR, tid, i2f(sens ? 1 : 0));
-      } else { set(RF_NDOF, tid, i2f(0)); set(RF_DOF0, tid, i2f(0)); }
+        seti(RF_LEGSENSOR, tid, sens ? 1 : 0);
+      } else { seti(RF_NDOF, tid, 0); seti(RF_DOF0, tid, 0); }
     }
     // armature / damping of the matrix columns each lane holds in the chain factorisation
     for (int tid = 0; tid < CTA; tid++) {
       const int g = tid / NLINK, t = tid % NLINK;
       if (g >= NLEG) { for (int s = 0; s < 3; s++) { set(RF_CARM + s, tid, 1.f); set(RF_CDMP + s, tid, 0.f); } continue; }
       const int lb = 6 + NLEGDOF * g; const int cols[3] = {t >= 6 ? lb + t - 6 : -1, lb + t + 2, lb + 10};
-      for (int s = 0; s < 3; s++) { set(RF_CARM + s, tid, cols[s] >= 0 ? (float)arm[cols[s]] : 0.f); set(RF_CDMP + s, tid, cols[s] >= 0 ? (float)damp[cols[s]] : 0.f); }
+      for (int s = 0; s < 3; s++) { set(RF_CARM + s, tid, cols[s] >= 0 ? arm[cols[s]] : 0.f); set(RF_CDMP + s, tid, cols[s] >= 0 ? damp[cols[s]] : 0.f); }
     }
     for (int a = 0; a < nu_pos; a++) {
       int d = act_dof[a], bb = -1, j = 0;
       for (int c = 1; c < nbody; c++) if (d >= dofadr[c] && d < dofadr[c] + dofnum[c]) { bb = c; j = d - dofadr[c]; }
       if (bb < 0) { err = "actuator on a free-joint dof is not supported"; return false; }
       int tid = lane_of_body(bb);
-      set(RF_KP + j, tid, (float)kp[a]); set(RF_KV + j, tid, (float)kv[a]); set(RF_FLO + j, tid, (float)frc[2 * a]);
-      set(RF_FHI + j, tid, (float)frc[2 * a + 1]); set(RF_CIDX + j, tid, i2f(a));
+      set(RF_KP + j, tid, kp[a]); set(RF_KV + j, tid, kv[a]); set(RF_FLO + j, tid, frc[2 * a]);
+      set(RF_FHI + j, tid, frc[2 * a + 1]); seti(RF_CIDX + j, tid, a);
     }
     for (int a = 0; a < nu_adh; a++) {
       int bb = adh_body[a]; if (bb <= 0) { err = "adhesion on the hub is not supported"; return false; }
       int tid = lane_of_body(bb);
-      set(RF_ADH_GAIN, tid, (float)again[a]); set(RF_ADH_LO, tid, (float)actrl[2 * a]); set(RF_ADH_HI, tid, (float)actrl[2 * a + 1]);
-      set(RF_ADH_CIDX, tid, i2f(nu_pos + a));
+      set(RF_ADH_GAIN, tid, again[a]); set(RF_ADH_LO, tid, actrl[2 * a]); set(RF_ADH_HI, tid, actrl[2 * a + 1]);
+      seti(RF_ADH_CIDX, tid, nu_pos + a);
     }
     int nhub = 0;
     std::vector<char> used(CTA, 0);
@@ -144,14 +170,20 @@ struct HostModel {
       if (bb == 0) { if (nhub >= NHUBLANE) { err = "more than 16 contact geoms on the hub"; return false; } tid = NLEG * NLINK + nhub++; }
       else { tid = lane_of_body(bb); if (used[tid]) { err = "more than one contact geom on a leg body"; return false; } }
       used[tid] = 1;
-      set(RF_GTYPE, tid, i2f(geom_type[g]));
+      seti(RF_GTYPE, tid, geom_type[g]);
       double Rm[9]; q2mat_d(gquat + 4 * g, Rm);
-      for (int i = 0; i < 3; i++) { set(RF_GPOS + i, tid, (float)gpos[3 * g + i]); set(RF_GAXIS + i, tid, (float)Rm[3 * i + 2]); }
-      set(RF_GRAD, tid, (float)gsize[2 * g]); set(RF_GHALF, tid, (float)gsize[2 * g + 1]);
-      set(RF_GVADR, tid, i2f(gvadr[g])); set(RF_GVNUM, tid, i2f(gvnum[g]));
+      for (int i = 0; i < 3; i++) { set(RF_GPOS + i, tid, gpos[3 * g + i]); set(RF_GAXIS + i, tid, Rm[3 * i + 2]); }
+      set(RF_GRAD, tid, gsize[2 * g]); set(RF_GHALF, tid, gsize[2 * g + 1]);
+      seti(RF_GVADR, tid, gvadr[g]); seti(RF_GVNUM, tid, gvnum[g]);
     }
-    hull.assign((size_t)3 * (nhv > 0 ? nhv : 1), 0.f);
-    for (int i = 0; i < 3 * nhv; i++) hull[i] = (float)hv[i];
+    hull64.assign((size_t)3 * (nhv > 0 ? nhv : 1), 0.0);
+    for (int i = 0; i < 3 * nhv; i++) hull64[i] = hv[i];
+    hull.assign(hull64.begin(), hull64.end());
+    role.resize(role64.size());
+    for (int f = 0; f < RF_COUNT; f++) for (int t = 0; t < CTA; t++) {
+      const double v = role64[(size_t)f * CTA + t];
+      role[(size_t)f * CTA + t] = int_field_of[f] ? i2f((int)v) : (float)v;
+    }
     {
       int na = 0, nn = 0; const int32_t* adr = b.get<int32_t>("hull_nbr_adr", &na); const int32_t* nb = b.get<int32_t>("hull_nbr", &nn);
       if (nhv > 0 && (!adr || !nb || na != nhv + 1)) { err = "blob has no hull adjacency (re-bake the model)"; return false; }
@@ -168,34 +200,35 @@ struct HostModel {
     key_state.assign(S_STRIDE, 0.f);
     for (int i = 0; i < nq; i++) key_state[S_QPOS + i] = (float)key_qpos[i];
     for (int i = 0; i < nu; i++) key_state[S_CTRL + i] = (float)key_ctrl[i];
-    par = StepParams{};
-    par.nu_pos = nu_pos; par.nu_adh = nu_adh; par.nseg = nseg; par.nhubgeom = nhub;
-    par.dt = (float)opt[0]; par.gx = (float)opt[1]; par.gy = (float)opt[2]; par.gz = (float)opt[3];
-    par.inv_total_mass = (float)(1.0 / mtot);
-    par.impratio = (float)opt[10];
-    par.mu = (float)contact[0];
+    StepParamsT<double>& P = par64;
+    P = StepParamsT<double>{};
+    P.nu_pos = nu_pos; P.nu_adh = nu_adh; P.nseg = nseg; P.nhubgeom = nhub;
+    P.dt = opt[0]; P.gx = opt[1]; P.gy = opt[2]; P.gz = opt[3];
+    P.inv_total_mass = (1.0 / mtot);
+    P.impratio = opt[10];
+    P.mu = contact[0];
     double tc = std::fmax(contact[1], 2 * opt[0]), dr = contact[2];
     auto clampimp = [](double v) { return std::fmin(0.9999, std::fmax(0.0001, v)); };
     double dmax = clampimp(contact[4]);
-    par.cK = (float)(1.0 / (dmax * dmax * tc * tc * dr * dr)); par.cB = (float)(2.0 / (dmax * tc));
-    par.solimp[0] = (float)clampimp(contact[3]); par.solimp[1] = (float)dmax; par.solimp[2] = (float)std::fmax(0.0, contact[5]);
-    par.solimp[3] = (float)clampimp(contact[6]); par.solimp[4] = (float)std::fmax(1.0, contact[7]);
-    par.margin = (float)(contact[8] - contact[9]);
-    par.max_newton = (int)opt[4]; par.max_ls = (int)opt[6]; par.nsteps = 1;   // reference: iterations=100 (mujoco_globals.yaml:14), ls_iterations=50 (MuJoCo default)
-    if (par.max_newton < 1) par.max_newton = 100;
-    if (par.max_ls < 1) par.max_ls = 50;
+    P.cK = (1.0 / (dmax * dmax * tc * tc * dr * dr)); P.cB = (2.0 / (dmax * tc));
+    P.solimp[0] = clampimp(contact[3]); P.solimp[1] = dmax; P.solimp[2] = std::fmax(0.0, contact[5]);
+    P.solimp[3] = clampimp(contact[6]); P.solimp[4] = std::fmax(1.0, contact[7]);
+    P.margin = (contact[8] - contact[9]);
+    P.max_newton = (int)opt[4]; P.max_ls = (int)opt[6]; P.nsteps = 1;   // reference: iterations=100 (mujoco_globals.yaml:14), ls_iterations=50 (MuJoCo default)
+    if (P.max_newton < 1) P.max_newton = 100;
+    if (P.max_ls < 1) P.max_ls = 50;
     {  // optional weld section (TetheredWorld): see flygym_b200/model.py WELD_FIELDS
       int nw = 0; const double* wd = b.get<double>("weld", &nw);
       if (wd && nw >= 18 && wd[0] != 0.0) {
         if (ngeom != 0) { err = "a tethered (welded) world cannot have ground-contact geoms"; return false; }
-        par.weld = 1;
-        for (int i = 0; i < 3; i++) par.weld_a[i] = (float)wd[1 + i];
-        for (int i = 0; i < 4; i++) par.weld_q[i] = (float)wd[4 + i];
+        P.weld = 1;
+        for (int i = 0; i < 3; i++) P.weld_a[i] = wd[1 + i];
+        for (int i = 0; i < 4; i++) P.weld_q[i] = wd[4 + i];
         const double wtc = std::fmax(wd[8], 2 * opt[0]), wdmax = clampimp(wd[11]);
-        par.weld_K = (float)(1.0 / (wdmax * wdmax * wtc * wtc * wd[9] * wd[9])); par.weld_B = (float)(2.0 / (wdmax * wtc));
-        par.weld_imp[0] = (float)clampimp(wd[10]); par.weld_imp[1] = (float)wdmax; par.weld_imp[2] = (float)std::fmax(0.0, wd[12]);
-        par.weld_imp[3] = (float)clampimp(wd[13]); par.weld_imp[4] = (float)std::fmax(1.0, wd[14]);
-        par.weld_ts = (float)wd[15]; par.weld_invw[0] = (float)wd[16]; par.weld_invw[1] = (float)wd[17];
+        P.weld_K = (1.0 / (wdmax * wdmax * wtc * wtc * wd[9] * wd[9])); P.weld_B = (2.0 / (wdmax * wtc));
+        P.weld_imp[0] = clampimp(wd[10]); P.weld_imp[1] = wdmax; P.weld_imp[2] = std::fmax(0.0, wd[12]);
+        P.weld_imp[3] = clampimp(wd[13]); P.weld_imp[4] = std::fmax(1.0, wd[14]);
+        P.weld_ts = wd[15]; P.weld_invw[0] = wd[16]; P.weld_invw[1] = wd[17];
       }
     }
     {  // optional terrain section: {type, Px, Py, hx, hy, top_even, top_odd, z_floor}
@@ -205,10 +238,11 @@ struct HostModel {
           err = "unsupported terrain description"; return false;
         }
         for (int g = 0; g < ngeom; g++) if (geom_type[g] != 0) { err = "terrain worlds need capsule collision geoms (simplify_geom=True)"; return false; }
-        par.terrain = 1;
-        for (int i = 0; i < 7; i++) par.terr[i] = (float)terr[1 + i];
+        P.terrain = 1;
+        for (int i = 0; i < 7; i++) P.terr[i] = terr[1 + i];
       }
     }
+    par = narrow(par64);
     (void)body_parent;
     return true;
   }

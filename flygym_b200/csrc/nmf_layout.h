@@ -76,10 +76,13 @@ constexpr int DBG_CDOF = DBG_XPOS + CTA * 3; // cdof[72][6]
 constexpr int DBG_HROWS = DBG_CDOF + NV * 6; // Euler matrix rows: 6 legs x 177, then 21 base
 constexpr int DBG_STRIDE = DBG_HROWS + NLEG * 177 + 21 + 3;
 
-struct StepParams {
+// `real` = the arithmetic of the kernel instantiation (float for the product path, double for the validation build); buffers
+// that live in HBM on behalf of the API (state records, observations, action table) are float32 in both.
+template <class real>
+struct StepParamsT {
   float* state;              // [n_flies][S_STRIDE]
-  const float* role;         // [RF_COUNT][CTA]
-  const float* hull;         // hull vertices (xyz) in body frames
+  const real* role;          // [RF_COUNT][CTA]
+  const real* hull;          // hull vertices (xyz) in body frames
   const float* act_table;    // optional [n_flies][table_T][table_cols] -> ctrl[0:table_cols]; nullptr = use ctrl in state
   const float* seg_tab;      // [nseg][8]: body lane (as float), pos xyz, quat wxyz  (static segments on the hub)
   float* out_xpos;           // optional [n_flies][nseg][3]
@@ -92,22 +95,23 @@ struct StepParams {
   int n_flies, nsteps, table_T, table_t0, table_cols;
   int forward_only;          // 1: evaluate the current state (outputs) without advancing it (mj_forward)
   int nu_pos, nu_adh, nseg, nhubgeom;
-  float dt, gx, gy, gz, inv_total_mass;
-  float mu, cK, cB, margin, impratio;
-  float solimp[5];           // sanitised: d0, dmax, width, midpoint, power
+  real dt, gx, gy, gz, inv_total_mass;
+  real mu, cK, cB, margin, impratio;
+  real solimp[5];           // sanitised: d0, dmax, width, midpoint, power
   int max_newton, max_ls;
   // terrain: 0 = ground plane z = 0 (FlatGroundWorld); 1 = floor plane + grid of box columns, terr = {Px, Py, hx, hy, top_even,
   // top_odd, z_floor, 0}: column (i, j) covers |x - i Px| <= hx, |y - j Py| <= hy, z <= top_{(i+j)&1}
   int terrain;
-  float terr[8];
+  real terr[8];
   // TetheredWorld weld (reference world.py:350-366): the hub-frame point weld_a is pulled onto the world origin and
   // q_hub * weld_q onto the identity by six always-active (equality) rows with their own solref / solimp
   int weld;
-  float weld_a[3], weld_q[4], weld_K, weld_B, weld_imp[5], weld_ts, weld_invw[2];
+  real weld_a[3], weld_q[4], weld_K, weld_B, weld_imp[5], weld_ts, weld_invw[2];
   // work-queue scheduling (nullptr = one block per fly for the whole launch): queue[0] = next work item,
   // queue[1 + fly] = number of sub-chunks of that fly already written back
   int* queue;
   int sub_steps, n_items;
 };
+using StepParams = StepParamsT<float>;
 
 }  // namespace nmf

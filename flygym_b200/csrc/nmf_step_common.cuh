@@ -1,0 +1,140 @@
+// nmf_step.cuh — one NeuroMechFly physics step per thread block (sm_100a).
+//
+// Replaces, for the reference benchmark model, the whole of
+//   GPUSimulation.step -> mujoco_warp.step   (reference src/flygym/warp/simulation.py:260-263)
+//   Simulation.step    -> mujoco.mj_step     (reference src/flygym/simulation.py:74-76)
+// with ONE fused kernel: forward kinematics, composite inertias, bias forces,
+// position + adhesion actuators, geom-plane collision, soft-contact Newton solve
+// and semi-implicit Euler, state staying in shared memory / registers for
+// `nsteps` consecutive steps.
+//
+// Mapping (B200-first, not a port): a block of 64 threads owns one fly.
+//   tid  0..47 : leg-body lanes, (leg = tid/8, link = tid%8); 8-lane shuffle
+//                segments = one kinematic chain, so every chain recursion of the
+//                classical algorithms becomes a 3-step warp-shuffle scan:
+//                  FK           = inclusive scan of rigid transforms
+//                  velocities   = prefix sums of spatial vectors (common c-frame)
+//                  CRBA / RNE   = suffix sums of spatial inertias / wrenches
+//   tid 48..63 : hub lanes (free body, its 6 DoFs, its contact geoms)
+// Newton Hessian: M + J'DJ is assembled as a CRBA over *contact-augmented*
+// spatial inertias (each contact adds X'WX to its body), so it keeps M's
+// arrowhead sparsity (hub 6x6 + six 11x11 chains); each chain block is factorised
+// L'DL in registers, one matrix column per lane, the hub block by Schur complement.
+//
+// The same source is compiled by g++ against tests/simt_emu/simt_emu.h
+// (NMF_SIMT_EMU) so it can be exercised without a GPU; that is test
+// infrastructure, not a fallback: the shipped library only contains the nvcc build.
+#pragma once
+#include <type_traits>
+
+#include "nmf_layout.h"
+
+// Precision-independent part of the step kernel source.  nmf_step.cuh (the kernel body) is written in terms of `real` and is
+// included twice by nmf_step_all.cuh: as namespace nmf::f32 (real = float, the product path) and nmf::f64 (real = double, a
+// validation instantiation of the SAME source that shadows the fp64 oracle over long horizons).
+namespace nmf {
+
+#define NMF_FULL 0xffffffffu
+
+// Block barrier that first reconverges each warp: __syncthreads() is the *aligned* barrier and is undefined when a warp
+// reaches it diverged (ptxas may leave lanes diverged after predicated stores; compute-sanitizer synccheck flags it).
+__device__ __forceinline__ void block_sync() { __syncwarp(NMF_FULL); __syncthreads(); }
+
+// ------------------------------------------------------------------ TMA (bulk async copy) of the float32 state record
+// One elected thread moves the whole 1216-byte record HBM <-> shared memory with cp.async.bulk (SASS: UBLKCP); the block
+// waits on an mbarrier.  Under the SIMT emulator the same copies are plain loops.
+#ifndef NMF_SIMT_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_f32(float* dst_smem, const float* src_gmem, unsigned long long* mbar, int tid) {
+  const unsigned bar = smem_u32(mbar), dst = smem_u32(dst_smem);
+  constexpr unsigned bytes = S_STRIDE * sizeof(float);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  block_sync();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+  block_sync();
+  if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");   // the slot is re-initialised by the next work item
+}
+// `published`: the caller hands the record to another block afterwards (work-queue scheduling), so wait until the
+// global writes have completed, not only until shared memory has been read.
+__device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_smem, int tid, bool published) {
+  block_sync();                                                      // all generic-proxy writes to the record are done
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // make them visible to the async (TMA) proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"((unsigned)(S_STRIDE * sizeof(float))) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (published) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until the copy has read it
+  }
+}
+#else
+__device__ __forceinline__ void tma_load_f32(float* dst_smem, const float* src_gmem, unsigned long long*, int tid) {
+  for (int i = tid; i < S_STRIDE; i += CTA) dst_smem[i] = src_gmem[i];
+  block_sync();
+}
+__device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_smem, int tid, bool) {
+  block_sync();
+  for (int i = tid; i < S_STRIDE; i += CTA) dst_gmem[i] = src_smem[i];
+}
+#endif
+
+// ------------------------------------------------------------------ float / double spellings of the math used by the body
+__device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float m_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double m_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float m_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double m_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float m_rsqrt(float a) { return rsqrtf(a); }
+__device__ __forceinline__ double m_rsqrt(double a) { return 1.0 / sqrt(a); }
+__device__ __forceinline__ float m_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double m_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float m_rint(float a) { return rintf(a); }
+__device__ __forceinline__ double m_rint(double a) { return rint(a); }
+__device__ __forceinline__ float m_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double m_pow(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ float m_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double m_fma(double a, double b, double c) { return fma(a, b, c); }
+// integer fields of the role table: bit patterns in the float table, plain numbers in the double one
+__device__ __forceinline__ int role_int(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int role_int(double v) { return (int)v; }
+// line-search stopping thresholds (relative derivative, relative bracket): at the resolution of the arithmetic
+template <class real> struct Prec;
+template <> struct Prec<float> { static constexpr float ls_rel = 2e-6f, ls_bracket = 1e-6f, ls_amin = 1e-3f; };
+template <> struct Prec<double> { static constexpr double ls_rel = 1e-14, ls_bracket = 1e-15, ls_amin = 1e-3; };
+
+// sin/cos with a 2-term Cody-Waite reduction and cephes-style minimax polynomials (|err| ~ 1 ulp for |x| < ~1e3):
+// replaces sincosf, whose inlined slow path bloated the instruction footprint of an I-cache-bound kernel.
+__device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
+  const float kf = rintf(x * 0.63661977236758134f);
+  float r = fmaf(-kf, 1.5707962512969971f, x);
+  r = fmaf(-kf, 7.5497894158615964e-8f, r);
+  const int q = (int)kf;
+  const float r2 = r * r;
+  const float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f) * r2, r, r);
+  const float pc = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f) * r2, r2, fmaf(-0.5f, r2, 1.0f));
+  const float s0 = (q & 1) ? pc : ps, c0 = (q & 1) ? ps : pc;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+__device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+
+// packed upper-triangular index of a symmetric 6x6, a <= b
+__device__ __forceinline__ constexpr int s6(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }
+#ifdef NMF_SIMT_EMU
+#define NMF_COLD
+#else
+#define NMF_COLD __noinline__
+#endif
+
+}  // namespace nmf

@@ -332,6 +332,11 @@ class B200Simulation:
     def set_solver(self, max_newton: int = 8, max_linesearch: int = 8) -> None:
         self._check(self._lib.nmf_set_solver(self._h, int(max_newton), int(max_linesearch)))
 
+    def set_precision(self, bits: int = 32) -> None:
+        """Arithmetic of the step kernel: 32 (default) or 64 (the same kernel source in double precision: a validation path that
+        shadows the fp64 oracle; the state stays float32 in HBM, so fuse the steps of interest into one ``step(n)`` call)."""
+        self._check(self._lib.nmf_set_precision(self._h, int(bits)))
+
     def set_schedule(self, sub_steps: int = -1) -> None:
         """Steps per work item of multi-step launches (0 = one block per fly for the whole launch, -1 = automatic)."""
         self._check(self._lib.nmf_set_schedule(self._h, int(sub_steps)))

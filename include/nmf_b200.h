@@ -91,6 +91,12 @@ int nmf_step_host(nmf_handle* h, const float* actions_host, int action_cols, int
 
 int nmf_set_solver(nmf_handle* h, int max_newton_iterations, int max_linesearch_iterations);
 
+/* Arithmetic of the step kernels: 32 (default; the product path, what GPUSimulation / MuJoCo-Warp compute in) or 64 = the same
+ * kernel source instantiated in double precision (what Simulation / MuJoCo's mjtNum computes in).  The 64-bit build is a
+ * validation path: it shadows the fp64 oracle over long horizons and so separates algorithmic differences from float32
+ * round-off.  State records and observations in HBM stay float32; fuse the steps into one launch to carry the precision. */
+int nmf_set_precision(nmf_handle* h, int bits);
+
 /* Number of kernels this library has launched on behalf of the handle (bench.py's gpu_launches). */
 int64_t nmf_launch_count(const nmf_handle* h);
 

@@ -42,7 +42,7 @@ def key_state(model):
     return out
 
 
-def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0, max_newton=0, max_ls=0):
+def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0, max_newton=0, max_ls=0, precision=32):
     """state: float32 [n, S_STRIDE], updated in place. Returns dict of optional outputs."""
     blob = model.to_blob()
     n = state.shape[0]
@@ -56,7 +56,7 @@ def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0,
     T = 0 if act_table is None else act_table.shape[1]
     cols = 0 if act_table is None else act_table.shape[2]
     rc = lib().emu_step(blob, ctypes.c_size_t(len(blob)), _p(state), n, nsteps, _p(d), _p(ox), _p(oq), _p(oa), _p(os_),
-                        _p(act_table), T, t0, cols, max_newton, max_ls)
+                        _p(act_table), T, t0, cols, max_newton, max_ls, precision)
     assert rc == 0
     res.update(dbg=d, xpos=ox, xquat=oq, actf=oa, sensor=os_)
     return res

@@ -161,6 +161,17 @@ inline float __shfl_xor_sync(unsigned mask, float v, int lanemask, int width = 3
   if (src / width != lane / width) src = lane;
   return simt::shfl_from(mask, v, src);
 }
+// 64-bit shuffles move the two halves one after the other, as the hardware does
+#define SIMT_SHFL_F64(NAME, ARGT)                                                         \
+  inline double NAME(unsigned mask, double v, ARGT a, int width = 32) {                   \
+    float h[2]; memcpy(h, &v, 8);                                                         \
+    h[0] = NAME(mask, h[0], a, width); h[1] = NAME(mask, h[1], a, width);                 \
+    memcpy(&v, h, 8); return v;                                                           \
+  }
+SIMT_SHFL_F64(__shfl_sync, int)
+SIMT_SHFL_F64(__shfl_up_sync, unsigned)
+SIMT_SHFL_F64(__shfl_down_sync, unsigned)
+SIMT_SHFL_F64(__shfl_xor_sync, int)
 inline int __shfl_sync(unsigned mask, int v, int src, int width = 32) {
   float f; memcpy(&f, &v, 4); f = __shfl_sync(mask, f, src, width); memcpy(&v, &f, 4); return v;
 }
@@ -175,6 +186,7 @@ inline int __any_sync(unsigned mask, int pred) {
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline void sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __frcp_rn(float a) { return 1.0f / a; }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }

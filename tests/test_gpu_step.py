@@ -382,3 +382,39 @@ def test_replay_table_built_on_device():
         assert np.abs(dev - host).max() <= 2.4e-7          # fp64 evaluation, one float32 rounding apart at most
     with pytest.raises(ValueError):
         replay_table_device(m, 2, 30000, "cuda")
+
+
+def test_fp64_kernel_meets_the_north_star_tolerance_for_every_walking_fly():
+    """BASELINE north_star: qpos within 1e-4 rel of the CPU reference after 1000 steps.  Walking contact dynamics amplify float32
+    round-off by ~1e5 over 1000 steps, so single flies of the fp32 kernel leave that band (test_cpg_and_perturbed_parity).  The
+    fp64 instantiation of the SAME kernel source stays within float32 rounding of the fp64 oracle for EVERY fly: the kernel's
+    algorithm is the oracle's; what separates the fp32 trajectories is arithmetic precision only."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    from oracle.oracle import Oracle
+    for terrain, n, T in ((None, 8, 1000), ("blocks", 4, 400)):
+        m = NMFModel.bench(True, terrain=terrain)
+        a = dict(m.arrays); opt = a["opt"].copy(); opt[5] = 1e-16; a["opt"] = opt
+        mt = NMFModel(a, m.names, m.meta)
+        tab = cpg_table(m, n, T)
+        q0 = np.tile(m.arrays["key_qpos"], (n, 1)); q0[:, 2] = -0.17; q0[:, 0] += np.linspace(0, 1.0, n)
+        q0 = q0.astype(np.float32)
+        out = {}
+        for bits in (64, 32):
+            sim = B200Simulation(m, n_worlds=n, outputs=False)
+            sim.set_precision(bits)
+            sim.qpos.copy_(torch.from_numpy(q0)); sim.ctrl[:, 42:] = 1.0
+            sim.step(T, torch.from_numpy(tab).cuda(), 0)            # one launch: the state stays in double for all T steps
+            out[bits] = sim.qpos.cpu().numpy().astype(np.float64)
+        errs = {64: [], 32: []}
+        for k in range(n):
+            o = Oracle(mt); o.reset(); o.qpos[:] = q0[k].astype(np.float64); o.ctrl[42:] = 1.0
+            o.step_table(tab[k].astype(np.float64))
+            for bits in (64, 32):
+                errs[bits].append(float(np.abs(out[bits][k] - o.qpos).max() / np.abs(o.qpos).max()))
+        print(terrain, "fp64:", ["%.1e" % e for e in errs[64]], "fp32:", ["%.1e" % e for e in errs[32]])
+        assert max(errs[64]) < 1e-6, errs          # north_star tolerance is 1e-4
+        assert np.median(errs[32]) < 1e-3
+    with pytest.raises(RuntimeError):
+        sim.set_precision(16)
