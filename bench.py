@@ -264,6 +264,7 @@ def run_ours(args, rank, world, local_rank):
     nu_pos = model.dim("nu_pos")
     per_step = wl in ("vision", "olfaction")          # sensors are evaluated after every physics step
     sim = B200Simulation(model, n_worlds=n, device=dev, outputs=per_step)
+    sim.set_precision(args.precision)
     if args.actions == "replay":
         from flygym_b200.actions import replay_table_device
         table = replay_table_device(model, n, 1000, dev, fly_offset=rank * n)                 # sim_steps = 1000 as run_gpu_benchmark.py
@@ -425,11 +426,11 @@ def run_ours(args, rank, world, local_rank):
         achieved = roof["alg_bytes"] / (roof["ms"] * 1e-3) / 1e9
         cpu = cpu_baseline_leg(model, n, stance_adhesion=(wl == "terrain")) if (world == 1 and not args.no_cpu) else None
         cfg = dict(workload_config(args, n, chunk), actions=args.actions)
-        traffic = NCU_TRAFFIC.get((wl, n, chunk), (None, None)) if args.actions == "cpg" and not args.mesh else (None, None)
+        traffic = NCU_TRAFFIC.get((wl, n, chunk), (None, None)) if args.actions == "cpg" and not args.mesh and args.precision == 32 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "dtype": f"f{args.precision}", "data": "synthetic", "config": cfg,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * act_cols * 4),
                     "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps},
@@ -440,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall, "state_finite": finite,
         }
-        if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh:
+        if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh and args.precision == 32:
             line["roofline"]["limiter"] = NCU_LIMITER[wl]
         if "retina_over_buffers" in roof:
             rb = dict(roof["retina_over_buffers"]); rb["frac"] = rb["achieved"] / peak
@@ -471,6 +472,8 @@ def main():
     ap.add_argument("--mesh", action="store_true", help="mesh-hull collision geoms (simplify_geom=False)")
     ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64], help="arithmetic of the step kernel: 32 = product path; 64 = the same "
+                    "kernel source in double precision (validation build that shadows the fp64 oracle)")
     args = ap.parse_args()
     if args.n_flies is None:
         args.n_flies = DEFAULT_FLIES[args.workload]
