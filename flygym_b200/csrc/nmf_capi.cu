@@ -29,9 +29,12 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_ste
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether_kernel(const StepParams p) { f32::step_entry<f32::W_TETHER>(p); }
 // fp64 instantiations of the same source: a validation build (nmf_set_precision(h, 64)), not a product path -- every
 // quantity takes two registers, so occupancy is whatever 255 registers leave
-extern "C" __global__ void __launch_bounds__(CTA, 4) nmf_step_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT>(p); }
-extern "C" __global__ void __launch_bounds__(CTA, 4) nmf_step_terrain_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN>(p); }
-extern "C" __global__ void __launch_bounds__(CTA, 4) nmf_step_tether_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER>(p); }
+#ifndef NMF_MINBLOCKS_F64
+#define NMF_MINBLOCKS_F64 4
+#endif
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER>(p); }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
   int fly = blockIdx.x;
