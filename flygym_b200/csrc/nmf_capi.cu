@@ -63,6 +63,7 @@ struct nmf_handle {
   float *d_role = nullptr, *d_hull = nullptr, *d_seg = nullptr, *d_key = nullptr;
   int *d_nbr_adr = nullptr, *d_nbr = nullptr;
   double *d_role64 = nullptr, *d_hull64 = nullptr;   // tables of the f64 validation kernels (uploaded by nmf_set_precision)
+  double* d_state64 = nullptr; float* d_shadow = nullptr;   // f64: full-precision records between launches + float image of the last launch
   int precision = 32;
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
@@ -123,7 +124,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
 
 extern "C" int nmf_destroy(nmf_handle* h) {
   if (!h) return NMF_OK;
-  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64);
+  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64); cudaFree(h->d_state64); cudaFree(h->d_shadow);
   for (int k = 0; k < nmf_handle::MAX_PARTS; k++) { if (h->part_stream[k]) cudaStreamDestroy(h->part_stream[k]); if (h->part_done[k]) cudaEventDestroy(h->part_done[k]); }
   if (h->fork) cudaEventDestroy(h->fork);
   delete h;
@@ -206,7 +207,9 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
                           int fly0, int count) {
   StepParamsT<real> p = KernelSet<real>::base(h);
   p.max_newton = h->hm.par.max_newton; p.max_ls = h->hm.par.max_ls;       // nmf_set_solver edits the f32 copy
-  p.state = h->buf.state; p.role = KernelSet<real>::role(h); p.hull = KernelSet<real>::hull(h); p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
+  p.state = h->buf.state; p.state64 = nullptr; p.shadow = nullptr;
+  if (std::is_same<real, double>::value) { p.state64 = h->d_state64; p.shadow = h->d_shadow; }
+  p.role = KernelSet<real>::role(h); p.hull = KernelSet<real>::hull(h); p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
   p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
   p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps; p.forward_only = forward_only ? 1 : 0;
@@ -214,6 +217,7 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   if (ranged) {
     const size_t f = (size_t)fly0, nu = (size_t)(p.nu_pos + p.nu_adh);
     p.state += f * S_STRIDE; p.n_flies = count;
+    if (p.state64) { p.state64 += f * S_STRIDE; p.shadow += f * S_STRIDE; }
     if (p.act_table) p.act_table += f * (size_t)table_T * table_cols;
     if (p.out_xpos) p.out_xpos += f * p.nseg * 3;
     if (p.out_xquat) p.out_xquat += f * p.nseg * 4;
@@ -267,6 +271,12 @@ extern "C" int nmf_set_precision(nmf_handle* h, int bits) {
     CK(cudaMemcpy(h->d_role64, h->hm.role64.data(), sizeof(double) * h->hm.role64.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->d_hull64, sizeof(double) * h->hm.hull64.size()));
     CK(cudaMemcpy(h->d_hull64, h->hm.hull64.data(), sizeof(double) * h->hm.hull64.size(), cudaMemcpyHostToDevice));
+    // full-precision records: start empty; a shadow of NaNs never equals a float record, so the first launch reads the float state
+    const size_t nrec = (size_t)h->n_flies * S_STRIDE;
+    CK(cudaMalloc(&h->d_state64, sizeof(double) * nrec));
+    CK(cudaMalloc(&h->d_shadow, sizeof(float) * nrec));
+    CK(cudaMemset(h->d_state64, 0, sizeof(double) * nrec));
+    CK(cudaMemset(h->d_shadow, 0xff, sizeof(float) * nrec));
   }
   h->precision = bits;
   return NMF_OK;

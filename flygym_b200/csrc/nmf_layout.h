@@ -81,6 +81,8 @@ constexpr int DBG_STRIDE = DBG_HROWS + NLEG * 177 + 21 + 3;
 template <class real>
 struct StepParamsT {
   float* state;              // [n_flies][S_STRIDE]
+  double* state64;           // f64 build only, optional [n_flies][S_STRIDE]: the records at full precision between launches
+  float* shadow;             //   and the float records as the last f64 launch left them (to detect edits made through the API)
   const real* role;          // [RF_COUNT][CTA]
   const real* hull;          // hull vertices (xyz) in body frames
   const float* act_table;    // optional [n_flies][table_T][table_cols] -> ctrl[0:table_cols]; nullptr = use ctrl in state

@@ -708,7 +708,8 @@ __device__ __forceinline__ void arrowhead_solve(real* sm, const real* s_cdof, co
 // ------------------------------------------------------------------ state record <-> shared memory
 // The record is float32 in HBM and moves with one TMA bulk copy (nmf_step_common.cuh).  The f32 instantiation copies straight
 // into / out of its working state; the f64 one stages the floats next to it and widens / narrows them.
-__device__ __forceinline__ void load_record(real* st, real* sm, const float* src_gmem, int tid) {
+__device__ __forceinline__ void load_record(const SP& p, real* st, real* sm, int fly, int tid) {
+  const float* src_gmem = p.state + (size_t)fly * S_STRIDE;
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sm + SM_MBAR);
   if (std::is_same<real, float>::value) {
     tma_load_f32(reinterpret_cast<float*>(st), src_gmem, mbar, tid);
@@ -716,16 +717,28 @@ __device__ __forceinline__ void load_record(real* st, real* sm, const float* src
     float* stage = reinterpret_cast<float*>(sm + SM_STAGE);
     tma_load_f32(stage, src_gmem, mbar, tid);
     block_sync();
-    for (int i = tid; i < S_STRIDE; i += CTA) st[i] = (real)stage[i];
+    if (p.state64) {
+      // full-precision records persist between launches.  An entry whose float32 image still equals what the last f64 launch
+      // wrote is taken from the double record; anything else was edited through the API (reset, setters, direct writes to the
+      // state tensor) and is taken from the float record.
+      const double* s64 = p.state64 + (size_t)fly * S_STRIDE; const float* sh = p.shadow + (size_t)fly * S_STRIDE;
+      for (int i = tid; i < S_STRIDE; i += CTA) st[i] = (stage[i] == sh[i]) ? (real)s64[i] : (real)stage[i];
+    } else {
+      for (int i = tid; i < S_STRIDE; i += CTA) st[i] = (real)stage[i];
+    }
   }
 }
-__device__ __forceinline__ void store_record(float* dst_gmem, const real* st, real* sm, int tid, bool published) {
+__device__ __forceinline__ void store_record(const SP& p, const real* st, real* sm, int fly, int tid, bool published) {
+  float* dst_gmem = p.state + (size_t)fly * S_STRIDE;
   if (std::is_same<real, float>::value) {
     tma_store_f32(dst_gmem, reinterpret_cast<const float*>(st), tid, published);
   } else {
     float* stage = reinterpret_cast<float*>(sm + SM_STAGE);
     block_sync();
-    for (int i = tid; i < S_STRIDE; i += CTA) stage[i] = (float)st[i];
+    for (int i = tid; i < S_STRIDE; i += CTA) {
+      stage[i] = (float)st[i];
+      if (p.state64) { p.state64[(size_t)fly * S_STRIDE + i] = (double)st[i]; p.shadow[(size_t)fly * S_STRIDE + i] = stage[i]; }
+    }
     tma_store_f32(dst_gmem, stage, tid, published);
   }
 }
@@ -758,7 +771,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
 
   // ---- load the state record (one TMA bulk copy of 1216 B), clear the u staging (hub chains keep u = 0)
   for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = real(0.);
-  load_record(st, sm, p.state + (size_t)fly * S_STRIDE, tid);
+  load_record(p, st, sm, fly, tid);
   block_sync();
 
   // per-lane constants that stay in registers for the whole launch
@@ -1302,7 +1315,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
   }
 
   // ---- write the record back (TMA bulk store)
-  if (!p.forward_only) store_record(p.state + (size_t)fly * S_STRIDE, st, sm, tid, published);
+  if (!p.forward_only) store_record(p, st, sm, fly, tid, published);
 }
 
 

@@ -333,8 +333,10 @@ class B200Simulation:
         self._check(self._lib.nmf_set_solver(self._h, int(max_newton), int(max_linesearch)))
 
     def set_precision(self, bits: int = 32) -> None:
-        """Arithmetic of the step kernel: 32 (default) or 64 (the same kernel source in double precision: a validation path that
-        shadows the fp64 oracle; the state stays float32 in HBM, so fuse the steps of interest into one ``step(n)`` call)."""
+        """Arithmetic of the step kernel: 32 (default, what the reference's ``GPUSimulation`` computes in) or 64 (the same kernel
+        source in double precision, what the reference's CPU ``Simulation`` computes in: a validation path that shadows the fp64
+        oracle).  The tensors of this class stay float32; the library keeps full-precision records between launches and picks
+        up anything written to ``state`` / ``qpos`` / ``ctrl`` in between."""
         self._check(self._lib.nmf_set_precision(self._h, int(bits)))
 
     def set_schedule(self, sub_steps: int = -1) -> None:

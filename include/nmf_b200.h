@@ -94,7 +94,8 @@ int nmf_set_solver(nmf_handle* h, int max_newton_iterations, int max_linesearch_
 /* Arithmetic of the step kernels: 32 (default; the product path, what GPUSimulation / MuJoCo-Warp compute in) or 64 = the same
  * kernel source instantiated in double precision (what Simulation / MuJoCo's mjtNum computes in).  The 64-bit build is a
  * validation path: it shadows the fp64 oracle over long horizons and so separates algorithmic differences from float32
- * round-off.  State records and observations in HBM stay float32; fuse the steps into one launch to carry the precision. */
+ * round-off.  The records the API sees stay float32; the library keeps full-precision copies between launches and takes an
+ * entry from the float record only where it was edited through the API since (reset, setters, direct writes). */
 int nmf_set_precision(nmf_handle* h, int bits);
 
 /* Number of kernels this library has launched on behalf of the handle (bench.py's gpu_launches). */
