@@ -1362,7 +1362,7 @@ __device__ __forceinline__ void step_entry(const SP& p) {
     }
     step_block<WORLD>(p, sm, fly, step0, nsub, p.queue != nullptr);
     if (!p.queue) return;
-    if (tid == 0) {   // the TMA store of the record has completed (tma_store_record waited for it): hand the fly on
+    if (tid == 0) {   // the TMA store of the record has completed (store_record waited for it): hand the fly on
       const int done = step0 / p.sub_steps + 1;
       p.queue[2 + fly] = done;
       if (done * p.sub_steps < p.nsteps) {

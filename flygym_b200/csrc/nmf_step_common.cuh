@@ -1,4 +1,4 @@
-// nmf_step.cuh — one NeuroMechFly physics step per thread block (sm_100a).
+// nmf_step_common.cuh — one NeuroMechFly physics step per thread block (sm_100a): overview + precision-independent helpers.
 //
 // Replaces, for the reference benchmark model, the whole of
 //   GPUSimulation.step -> mujoco_warp.step   (reference src/flygym/warp/simulation.py:260-263)
