@@ -48,6 +48,8 @@ NCU_TRAFFIC = {
     ("flat", 4096, 100): (0.1176e9 + 2.7727e9, "profiles/ncu_step_r01i_summary.txt: 0.118 GB read + 2.77 GB written (local-memory spill lines "
                                                "evicted from L2) vs 0.79 GB algorithmic"),
     ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt (80-register build): 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
+    ("olfaction", 32768, 10): (0.0774e9 + 0.6436e9, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs): 0.077 GB read + "
+                                                    "0.644 GB written (spill lines) vs 0.162 GB algorithmic"),
     ("vision", 1024, 10): (0.81e6, "profiles/ncu_vision_r01s2_summary.txt: the fused kernel reads 0.81 MB (run table, poses) and never materialises the 1.4 GB of eye buffers"),
 }
 RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.txt: 1.009 GB read + 8.3 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
@@ -57,6 +59,7 @@ NCU_LIMITER = {
              "issue_ceiling_env_steps_per_s": 148 * 4 * 1.965e9 / 21200,
              "source": "profiles/ncu_step_r01i_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
+    "olfaction": {"issue_slots_busy": 0.509, "top_stall": "no_inst (instruction fetch)", "source": "profiles/ncu_step_olfaction_r01_summary.txt"},
     "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
                "source": "profiles/ncu_vision_r01s2_summary.txt"},
 }
