@@ -24,7 +24,7 @@ constexpr int S_QPOS = 0;       // 73 (+3 pad)
 constexpr int S_QVEL = 76;      // 72
 constexpr int S_WARM = 148;     // 72  qacc_warmstart
 constexpr int S_CTRL = 220;     // nu <= MAXU
-constexpr int S_TIME = 300;     // time, status, 2 pad
+constexpr int S_TIME = 300;     // time, status, steps since reset, pad
 constexpr int S_STRIDE = 304;
 
 // thread-role constant table: role[field * CTA + tid]

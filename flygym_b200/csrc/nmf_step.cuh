@@ -1309,7 +1309,8 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       }
       qnormalize(q);
       st[S_QPOS + 3] = q[0]; st[S_QPOS + 4] = q[1]; st[S_QPOS + 5] = q[2]; st[S_QPOS + 6] = q[3];
-      st[S_TIME] += p.dt;
+      st[S_TIME + 2] += real(1.);                 // step count since reset (exact up to 2^24 in float32)
+      st[S_TIME] = st[S_TIME + 2] * p.dt;         // time = n dt, not an accumulated sum (5e4 float32 additions drift by 1e-4 relative)
     }
     block_sync();
   }
