@@ -45,7 +45,7 @@ RETINA_ALG_BYTES = 2 * 512 * 450 * 3 + 2 * 721 * 2 * 4   # 1 393 936 B per fly-f
 # DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture on
 # B200, profiles/ncu_*_summary.txt), keyed by (workload, flies, steps per launch); None for configurations not captured
 NCU_TRAFFIC = {
-    ("flat", 4096, 100): (0.1176e9 + 2.7727e9, "profiles/ncu_step_r01i_summary.txt: 0.118 GB read + 2.77 GB written (local-memory spill lines "
+    ("flat", 4096, 100): (0.1271e9 + 2.9768e9, "profiles/ncu_step_r01j_summary.txt: 0.127 GB read + 2.98 GB written (local-memory spill lines "
                                                "evicted from L2) vs 0.79 GB algorithmic"),
     ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt (80-register build): 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
     ("olfaction", 32768, 10): (0.0774e9 + 0.6436e9, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs): 0.077 GB read + "
@@ -57,7 +57,7 @@ RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.tx
 NCU_LIMITER = {
     "flat": {"issue_slots_busy": 0.402, "top_stall": "no_inst (instruction fetch) 46 % of samples", "warp_instructions_per_fly_step": 21200,
              "issue_ceiling_env_steps_per_s": 148 * 4 * 1.965e9 / 21200,
-             "source": "profiles/ncu_step_r01i_summary.txt"},
+             "source": "profiles/ncu_step_r01j_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
     "olfaction": {"issue_slots_busy": 0.509, "top_stall": "no_inst (instruction fetch)", "source": "profiles/ncu_step_olfaction_r01_summary.txt"},
     "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
