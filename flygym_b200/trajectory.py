@@ -38,14 +38,16 @@ class TrajectoryRecorder:
     def gather(self):
         k = self.count
         out = {"time": self.time[:k].cpu().numpy()}
+        root = True
         for name, buf in (("qpos", self.qpos), ("qvel", self.qvel)):
             if buf is None:
                 continue
             full = gather_to_rank0(buf[:k].transpose(0, 1).contiguous())       # (n_local, S, d) slabs, fly-major for the gather
             if full is None:
-                return None
+                root = False            # every rank takes part in every collective; only rank 0 keeps the result
+                continue
             out[name] = full.transpose(0, 1).cpu().numpy()
-        return out
+        return out if root else None
 
     def save(self, path) -> bool:
         data = self.gather()
