@@ -98,6 +98,20 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
+class StdoutToStderr:
+    """NCCL prints its version banner to stdout when the communicator is created; the contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -260,7 +274,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                  # creates the communicator (and prints NCCL's banner) now
     wl = args.workload
     n = args.n_flies
     model = bench_model(args)
