@@ -42,16 +42,16 @@ TABLE_T = 2500                 # 3 exact CPG periods at 12 Hz, dt = 1e-4
 
 ALG_BYTES_OBS = 4940           # the same + the full observation set written every step
 RETINA_ALG_BYTES = 2 * 512 * 450 * 3 + 2 * 721 * 2 * 4   # 1 393 936 B per fly-frame
-# DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture on
-# B200, profiles/ncu_*_summary.txt), keyed by (workload, flies, steps per launch); None for configurations not captured
-NCU_TRAFFIC = {
-    ("flat", 4096, 100): (0.1271e9 + 2.9768e9, "profiles/ncu_step_r01j_summary.txt: 0.127 GB read + 2.98 GB written (local-memory spill lines "
-                                               "evicted from L2) vs 0.79 GB algorithmic"),
-    ("terrain", 4096, 100): (0.0896e9 + 0.5587e9, "profiles/ncu_step_terrain_r01_summary.txt (80-register build): 0.090 GB read + 0.559 GB written vs 0.79 GB algorithmic"),
-    ("olfaction", 32768, 10): (0.0774e9 + 0.6436e9, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs): 0.077 GB read + "
-                                                    "0.644 GB written (spill lines) vs 0.162 GB algorithmic"),
-    ("vision", 1024, 10): (0.81e6, "profiles/ncu_vision_r01s2_summary.txt: the fused kernel reads 0.81 MB (run table, poses) and never materialises the 1.4 GB of eye buffers"),
+# DRAM bytes of the dominant kernel per fly-step (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture on
+# B200 divided by the fly-steps of the captured launch; profiles/ncu_*_summary.txt).  roofline.traffic = this x the fly-steps of one
+# launch of the run that prints it, and traffic_source names the capture it was scaled from.
+NCU_TRAFFIC_PER_FLY_STEP = {
+    "flat": ((0.1271e9 + 2.9768e9) / (4096 * 100), "profiles/ncu_step_r01j_summary.txt (4096 flies x 100 steps: 0.127 GB read + 2.98 GB written, the writes being "
+                                                   "local-memory spill lines evicted from L2, vs 0.79 GB algorithmic)"),
+    "terrain": ((0.0896e9 + 0.5587e9) / (4096 * 100), "profiles/ncu_step_terrain_r01_summary.txt (4096 flies x 100 steps, 80-register build)"),
+    "olfaction": ((0.0774e9 + 0.6436e9) / 32768, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs)"),
 }
+VISION_TRAFFIC = (0.81e6 / 1024, "profiles/ncu_vision_r01s2_summary.txt: the fused kernel reads 0.81 MB per 1024 flies (run table, poses) and never materialises the eye buffers")
 RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.txt: 1.009 GB read + 8.3 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
 # what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
 NCU_LIMITER = {
@@ -156,7 +156,7 @@ class CpuArm:
     def __init__(self, model, threads):
         from oracle.oracle import Oracle
         self.model, self.threads = model, threads
-        self.oracles = [Oracle(model) for _ in range(threads)]
+        self.oracles = [Oracle(model, native=True) for _ in range(threads)]    # -O3 -march=native build made on this host
         for o in self.oracles:
             o.ctrl[model.dim("nu_pos"):] = 1.0
             o.step(500)
@@ -186,21 +186,40 @@ def host_adhesion_table(model, n_flies, n_steps, n_total):
     return np.where(np.sin(2 * np.pi * 12.0 * t[None, :, None] + psi[:, None, None] + legph[None, None, :]) < 0, 100.0, 1.0)
 
 
-def cpu_baseline_leg(model, n_total, target_s=20.0, stance_adhesion=False):
-    """cpu_baseline: the oracle on every host core, sized to ~target_s seconds of CPU work from a short pilot run."""
+def mujoco_probe():
+    """use real MuJoCo for the CPU arm if it is ever importable.  (It has never been: not in the image, not in
+    /opt/wheelhouse; composing the reference's model additionally needs dm_control.)"""
+    try:
+        import mujoco  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+CPU_KIND_NOTE = ("oracle/nmf_oracle.c (fp64 restatement of mj_step: dense M, dense Cholesky per Newton iteration) built -O3 -march=native on "
+                 "this host; real MuJoCo (sparse L'DL) is not importable here")
+
+
+def cpu_baseline_leg(model, n_total, target_s=16.0, stance_adhesion=False):
+    """cpu_baseline: the oracle on every host core, sized to ~target_s seconds of CPU work from a short pilot run, plus a
+    single-thread figure (BASELINE.md 2.1 quotes the reference per core)."""
     from flygym_b200.actions import cpg_table
     cores = os.cpu_count() or 1
     pilot = 200
-    adh = (lambda k: host_adhesion_table(model, cores, k, n_total)) if stance_adhesion else (lambda k: None)
+    adh = (lambda k, c=cores: host_adhesion_table(model, c, k, n_total)) if stance_adhesion else (lambda k, c=cores: None)
     arm = CpuArm(model, cores)
     tb = cpg_table(model, cores, pilot, n_flies_total=n_total).astype(np.float64)
     v0, _ = arm.run(tb, pilot, adh(pilot))
     cs = int(min(100000, max(500, target_s * v0 / cores)))
     tb = cpg_table(model, cores, cs, n_flies_total=n_total).astype(np.float64)
     v, dt = arm.run(tb, cs, adh(cs))
+    one = CpuArm(model, 1)
+    c1 = int(min(100000, max(500, 4.0 * v0 / cores)))
+    v1, dt1 = one.run(tb[:1, :c1], c1, adh(c1, 1))
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} threads x 1 fly x {cs} CPG steps after a 500-step warm-up (oracle/nmf_oracle.c, fp64 restatement of "
-                      f"mj_step), {dt:.1f} s"}
+            "sample": f"{cores} threads x 1 fly x {cs} CPG steps after a 500-step warm-up, {dt:.1f} s; {CPU_KIND_NOTE}",
+            "single_thread": {"value": v1, "unit": UNIT, "sample": f"1 thread x 1 fly x {c1} CPG steps, {dt1:.1f} s"},
+            "mujoco_importable": mujoco_probe()}
 
 
 def bench_model(args):
@@ -234,7 +253,8 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + "; " + CPU_KIND_NOTE,
+                         "mujoco_importable": mujoco_probe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU fp64 restatement of the reference's mujoco.mj_step path (oracle/nmf_oracle.c); real MuJoCo 3.6.0 is not installable "
                 "here.  Physics only: the CPU arm has no vision / olfaction leg",
@@ -265,18 +285,31 @@ def device_cpg_table(torch, model, n, T, dev, fly_offset, n_total, adhesion_stan
     return out
 
 
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """what one measurement needs to know about the process: rank layout, device, torch / dist modules"""
+
+    def __init__(self, torch, dist, rank, world, dev):
+        self.torch, self.dist, self.rank, self.world, self.dev = torch, dist, rank, world, dev
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=True):
+    """One workload (args.workload / mesh / precision / n_flies / chunk ...) measured three ways: device-timed `value` over
+    exactly `steps` steps, the dominant kernel alone (roofline), and `e2e` through the host-buffer API.  Returns a dict."""
+    torch, dist, rank, world, dev = ctx.torch, ctx.dist, ctx.rank, ctx.world, ctx.dev
     from flygym_b200 import B200Simulation
     from flygym_b200.anatomy import ActuatorType
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        with StdoutToStderr():
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()                  # creates the communicator (and prints NCCL's banner) now
     wl = args.workload
     n = args.n_flies
     model = bench_model(args)
@@ -292,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
     table_T = table.shape[1]
     sim.set_leg_adhesion_states("nmf", np.ones((n, 6), np.float32))     # as the reference benchmark (time_gpu_simulation.py:130)
     sim.warmup()                                                        # 500 steps at the neutral pose
-    chunk = max(1, min(args.chunk, args.steps))
+    chunk = max(1, min(args.chunk, steps))
 
     # ---- the sensors of the workload
     eyes = odor = sens_out = None
@@ -321,53 +354,47 @@ def run_ours(args, rank, world, local_rank):
                 state["odor"] = odor()
             state["launches"] += 1
 
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         advance(chunk)
     torch.cuda.synchronize(dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- timed region: exactly K steps, CUDA events on the launching stream around every launch group
     state["launches"] = 0
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
+    sampler = ClockSampler(dev.index) if sample_clocks else None
+    ctx.barrier()
+    if sampler is not None and rank == 0:
         sampler.start()
     wall0 = time.perf_counter()
     ev = []
     done = 0
     gathered_slabs = 0
-    while done < args.steps:
-        c = min(chunk, args.steps - done)
-        flush.fill_(1)
+    gather_ms = 0.0
+    while done < steps:
+        c = min(chunk, steps - done)
+        ctx.flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); advance(c); b.record()
         ev.append((a, b, c)); done += c
         if wl == "olfaction" and world > 1 and done % 100 == 0:      # config 5: metrics slab over NCCL every 100 steps
             slab = torch.cat([sim.qpos[:, :3], sim.qvel[:, :1], state["odor"].reshape(n, -1)[:, :4]], dim=1).contiguous()
             outl = [torch.empty_like(slab) for _ in range(world)]
-            dist.all_gather(outl, slab); gathered_slabs += 1
-    barrier()
+            ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ga.record(); dist.all_gather(outl, slab); gb.record(); ev.append((ga, gb, 0)); gathered_slabs += 1
+    ctx.barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
+    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+    kernel_ms = sum(a.elapsed_time(b) for a, b, c in ev if c > 0)
+    gather_ms = sum(a.elapsed_time(b) for a, b, c in ev if c == 0)
     n_launch = state["launches"]
-    ms_total = max_ranks(kernel_ms)
-    value = world * n * args.steps / (ms_total * 1e-3)
+    # the all-gathers of config 5 are issued between the launch groups of the same stream: their device time is part of the step
+    ms_total = ctx.max_ranks(kernel_ms + gather_ms)
+    value = world * n * steps / (ms_total * 1e-3)
 
     # ---- dominant-kernel time for the roofline (per launch, CUDA events around that kernel alone)
     roof = {}
-    if wl == "vision":
+    if not dominant:
+        pass
+    elif wl == "vision":
         imgs = [eyes.render() for _ in range(2)]       # two 1.4 GB buffer sets alternated: no launch finds its input in L2
         for i in range(3):
             eyes.ret(imgs[i % 2], sens_out)
@@ -382,7 +409,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
         ret_ms = float(np.mean([a.elapsed_time(b) for a, b in tms])); fused_ms = float(np.mean([a.elapsed_time(b) for a, b in fms]))
         alg = n * RETINA_ALG_BYTES
-        roof = {"kernel": "nmf_eye_retina_kernel (fused eye-camera image formation + Retina)", "ms": fused_ms, "alg_bytes": alg,
+        roof = {"kernel": "nmf_eye_retina_kernel (fused eye-camera image formation + Retina)", "ms": fused_ms, "alg_bytes": alg, "fly_steps": n,
                 "retina_over_buffers": {"kernel": "nmf_retina_kernel", "ms_per_launch": ret_ms, "achieved": alg / (ret_ms * 1e-3) / 1e9,
                                         "note": "the HBM-bound form of the operator: eye buffers materialised in HBM (two 1.4 GB sets alternated); a pure "
                                                 "read stream that skips chunks outside the ommatidia hexagon, hence above the copy-measured peak"},
@@ -399,14 +426,16 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize(dev)
             step_ms = float(np.mean([a.elapsed_time(b) for a, b in tms]))
         else:
-            step_ms = kernel_ms / max(1, len(ev))
+            step_ms = kernel_ms / max(1, len([1 for _, _, c in ev if c > 0]))
         per_fly = ALG_BYTES_OBS if per_step else ALG_BYTES_CORE
-        roof = {"kernel": "nmf_step_terrain_kernel" if wl == "terrain" else "nmf_step_kernel", "ms": step_ms, "alg_bytes": per_fly * n * per_launch_steps,
-                "note": "the fused step is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); algorithmic bytes "
+        kname = "nmf_step_terrain" if wl == "terrain" else "nmf_step"
+        kname += "_f64_kernel" if args.precision == 64 else ("_x8_kernel" if n >= 8 * 148 else "_kernel")
+        roof = {"kernel": kname, "ms": step_ms, "alg_bytes": per_fly * n * per_launch_steps, "fly_steps": n * per_launch_steps,
+                "note": "the fused step is bound by instruction fetch / FP32 issue, not by HBM (SURVEY.md 8d, DESIGN.md 4.1); algorithmic bytes "
                         f"= {per_fly} B per fly-step"}
 
     # ---- end-to-end through the public API with HOST buffers, every step: H2D actions, step (+ sensors), D2H result
-    e2e_steps = min(args.steps, 200)
+    e2e_steps = min(steps, e2e_cap)
     act_cols = table.shape[2] if wl == "terrain" else nu_pos        # terrain: the six adhesion inputs travel with the position targets
     act_host = table[:, :e2e_steps, :act_cols].permute(1, 0, 2).contiguous().cpu().pin_memory()
     if not per_step:
@@ -424,12 +453,12 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.current_stream(dev).synchronize()
     for s in range(3):
         e2e_step(s)
-    barrier()
+    ctx.barrier()
     w0 = time.perf_counter()
     for s in range(e2e_steps):
         e2e_step(s)
-    barrier()
-    e2e_value = world * n * e2e_steps / max_ranks(time.perf_counter() - w0)
+    ctx.barrier()
+    e2e_value = world * n * e2e_steps / ctx.max_ranks(time.perf_counter() - w0)
 
     # ---- metrics slab gathered over NCCL (the only collective of the path)
     slab = torch.stack([sim.qpos[:, 0], sim.qpos[:, 1], sim.qpos[:, 2], sim.qvel[:, 0]], dim=1).contiguous()
@@ -439,26 +468,83 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             slab = torch.cat(gathered)
     finite = bool(torch.isfinite(slab).all().item())
+    out = {"value": value, "ms_total": ms_total, "ms_per_step": ms_total / steps, "steps": steps, "chunk": chunk, "n": n, "model": model,
+           "clocks": clocks, "launches": int(n_launch), "roof": roof, "wall": wall, "finite": finite, "gathered_slabs": gathered_slabs,
+           "gather_ms": gather_ms, "kernel_ms": kernel_ms,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * act_cols * 4),
+                   "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps}}
+    del sim, table
+    torch.cuda.empty_cache()
+    return out
+
+
+def sub_record(args, m, note):
+    """A secondary measurement printed inside the main JSON line (same metric and unit)."""
+    rec = {"value": m["value"], "unit": UNIT, "ms_per_step": m["ms_per_step"], "steps": m["steps"], "dtype": f"f{args.precision}",
+           "config": dict(workload_config(args, m["n"], m["chunk"]), actions=args.actions), "e2e": m["e2e"], "gpu_launches": m["launches"],
+           "state_finite": m["finite"], "note": note}
+    if m["gathered_slabs"]:
+        rec["nccl_all_gathers_in_timed_region"] = m["gathered_slabs"]
+        rec["nccl_all_gather_ms_total"] = m["gather_ms"]; rec["step_kernels_ms_total"] = m["kernel_ms"]
+    return rec
+
+
+def run_ours(args, rank, world, local_rank):
+    import copy
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        with StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                  # creates the communicator (and prints NCCL's banner) now
+    ctx = Ctx(torch, dist, rank, world, dev)
+    wl = args.workload
+    m = measure(ctx, args, steps=args.steps, warmup=args.warmup, sample_clocks=True)
+    n, chunk, model, roof = m["n"], m["chunk"], m["model"], m["roof"]
+
+    # ---- secondary records next to the headline (default flat workload only): the parity-qualified fp64 build and the
+    # reference's default mesh-hull geometry at N = 1; BASELINE config 5 (32768 flies per GPU + olfaction + NCCL all-gather of a
+    # metrics slab every 100 steps) when several GPUs take part
+    extras = {}
+    if wl == "flat" and args.extras and args.actions == "cpg" and args.precision == 32 and not args.mesh and args.n_flies == DEFAULT_FLIES["flat"]:
+        if world == 1:
+            a2 = copy.copy(args); a2.mesh = True
+            extras["mesh"] = sub_record(a2, measure(ctx, a2, steps=300, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
+                                        "simplify_geom=False: mesh convex hulls (tarsus5 capsules), up to 4 plane-hull contacts per geom")
+            a3 = copy.copy(args); a3.precision = 64
+            extras["f64"] = sub_record(a3, measure(ctx, a3, steps=200, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
+                                       "the same kernel source in double precision: the build that stays within 1e-4 of the fp64 oracle for every walking fly")
+        else:
+            a5 = copy.copy(args); a5.workload = "olfaction"; a5.n_flies = DEFAULT_FLIES["olfaction"]; a5.chunk = DEFAULT_CHUNK["olfaction"]
+            extras["config5"] = sub_record(a5, measure(ctx, a5, steps=200, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
+                                           "BASELINE config 5: 32768 flies per GPU, odor sensors after every step, all_gather of a (n, 8) metrics slab every "
+                                           "100 steps issued on the stepping stream (its device time is inside ms_per_step)")
 
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
         achieved = roof["alg_bytes"] / (roof["ms"] * 1e-3) / 1e9
         cpu = cpu_baseline_leg(model, n, stance_adhesion=(wl == "terrain")) if (world == 1 and not args.no_cpu) else None
         cfg = dict(workload_config(args, n, chunk), actions=args.actions)
-        traffic = NCU_TRAFFIC.get((wl, n, chunk), (None, None)) if args.actions == "cpg" and not args.mesh and args.precision == 32 else (None, None)
+        if wl == "vision":
+            tr = (VISION_TRAFFIC[0] * n, VISION_TRAFFIC[1])
+        else:
+            per, src = NCU_TRAFFIC_PER_FLY_STEP[wl]
+            tr = (per * roof["fly_steps"], f"{per:.0f} B per fly-step x {roof['fly_steps']} fly-steps of this launch shape; scaled from {src}")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"f{args.precision}", "data": "synthetic", "config": cfg,
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * act_cols * 4),
-                    "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps},
-            "gpu_launches": int(n_launch),
+            "clocks": m["clocks"],
+            "e2e": m["e2e"],
+            "gpu_launches": m["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic[0], "traffic_source": traffic[1], "peak_kind": peak_kind, "kernel": roof["kernel"], "kernel_ms_per_launch": roof["ms"],
+                         "traffic": tr[0], "traffic_source": tr[1], "peak_kind": peak_kind, "kernel": roof["kernel"], "kernel_ms_per_launch": roof["ms"],
                          "note": roof["note"]},
             "cpu_baseline": cpu,
-            "wall_s_timed_region": wall, "state_finite": finite,
+            "wall_s_timed_region": m["wall"], "state_finite": m["finite"],
         }
         if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh and args.precision == 32:
             line["roofline"]["limiter"] = NCU_LIMITER[wl]
@@ -467,8 +553,10 @@ def run_ours(args, rank, world, local_rank):
             if n == 1024:
                 rb["traffic"], rb["traffic_source"] = RETINA_BUFFERS_TRAFFIC
             line["roofline"]["retina_over_buffers"] = rb
-        if gathered_slabs:
-            line["nccl_all_gathers_in_timed_region"] = gathered_slabs
+        if m["gathered_slabs"]:
+            line["nccl_all_gathers_in_timed_region"] = m["gathered_slabs"]
+        if extras:
+            line["extras"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -491,6 +579,7 @@ def main():
     ap.add_argument("--mesh", action="store_true", help="mesh-hull collision geoms (simplify_geom=False)")
     ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary records (mesh / f64 at N = 1, config 5 at N > 1)")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64], help="arithmetic of the step kernel: 32 = product path; 64 = the same "
                     "kernel source in double precision (validation build that shadows the fp64 oracle)")
     args = ap.parse_args()

@@ -52,11 +52,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 class NmfInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "n_flies", "nq", "nv", "nu_pos", "nu_adh", "nseg", "nleg", "state_stride", "off_qpos", "off_qvel",
-        "off_qacc_warmstart", "off_ctrl", "off_time", "dbg_stride")] + [("timestep", ctypes.c_float)]
+        "off_qacc_warmstart", "off_ctrl", "off_time", "dbg_stride")] + [("timestep", ctypes.c_float), ("off_status", ctypes.c_int32)]
 
 
 class NmfBuffers(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ("state", "seg_xpos", "seg_xquat", "act_force", "sensordata", "debug")]
+    _fields_ = [(n, ctypes.c_void_p) for n in ("state", "seg_xpos", "seg_xquat", "act_force", "sensordata", "debug", "energy")]
 
 
 class NmfEyeParams(ctypes.Structure):
@@ -87,6 +87,7 @@ def load() -> ctypes.CDLL:
     lib.nmf_step.argtypes = [vp, ci, vp, ci, ci, ci, vp]
     lib.nmf_set_schedule.argtypes = [vp, ci]
     lib.nmf_set_precision.argtypes = [vp, ci]
+    lib.nmf_set_flies_per_block.argtypes = [vp, ci]
     lib.nmf_forward.argtypes = [vp, vp]
     lib.nmf_replay_table.argtypes = [vp, vp, ci, ci, ctypes.c_double, ctypes.c_double, ci, ci, ci, ci, vp, vp]
     lib.nmf_replay_table.restype = ci
@@ -97,7 +98,7 @@ def load() -> ctypes.CDLL:
     lib.nmf_launch_count.argtypes = [vp]
     lib.nmf_launch_count.restype = ctypes.c_int64
     for fn in ("nmf_create", "nmf_destroy", "nmf_model_info", "nmf_bind", "nmf_reset", "nmf_step", "nmf_scatter_ctrl",
-               "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_forward"):
+               "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_forward", "nmf_set_flies_per_block"):
         getattr(lib, fn).restype = ci
     lib.nmf_retina_create.argtypes = [vp, vp, ci, ci, ci, ci, ctypes.POINTER(vp)]
     lib.nmf_retina_destroy.argtypes = [vp]
@@ -121,7 +122,7 @@ def load() -> ctypes.CDLL:
 # symbols declared in include/nmf_b200.h (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
     "nmf_create", "nmf_destroy", "nmf_model_info", "nmf_last_error", "nmf_bind", "nmf_reset", "nmf_step",
-    "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_forward", "nmf_replay_table", "nmf_launch_count",
+    "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_set_flies_per_block", "nmf_forward", "nmf_replay_table", "nmf_launch_count",
     "nmf_retina_create", "nmf_retina_destroy", "nmf_retina_last_error", "nmf_retina_launch_count", "nmf_retina_forward",
     "nmf_retina_forward_host", "nmf_odor_intensity", "nmf_eye_render", "nmf_eye_retina",
 ]

@@ -19,12 +19,19 @@ using namespace nmf;
 #define NMF_MINBLOCKS 16   // <= 64 registers/thread: best measured trade-off between occupancy and spills (profiles/)
 #endif
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT>(p); }
+// FPB fly slots per block, realigned at every stage so that the block's warps share instruction fetches (nmf_step.cuh, step_block)
+extern "C" __global__ void __launch_bounds__(2 * CTA, NMF_MINBLOCKS / 2) nmf_step_x2_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 2>(p); }
+extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS / 4) nmf_step_x4_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 4>(p); }
+extern "C" __global__ void __launch_bounds__(8 * CTA, NMF_MINBLOCKS / 8) nmf_step_x8_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 8>(p); }
 // terrain worlds (box columns: BASELINE config 3): general contact frames need 8 more registers per lane; measured on B200 at
 // 12 / 14 / 16 blocks per SM (80 / 72 / 64 registers): 15.8 / 16.8 / 16.8 M env-steps/s -> occupancy wins over spills here too
 #ifndef NMF_MINBLOCKS_TERRAIN
 #define NMF_MINBLOCKS_TERRAIN 16
 #endif
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_step_terrain_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN>(p); }
+extern "C" __global__ void __launch_bounds__(2 * CTA, NMF_MINBLOCKS_TERRAIN / 2) nmf_step_terrain_x2_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 2>(p); }
+extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS_TERRAIN / 4) nmf_step_terrain_x4_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 4>(p); }
+extern "C" __global__ void __launch_bounds__(8 * CTA, NMF_MINBLOCKS_TERRAIN / 8) nmf_step_terrain_x8_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 8>(p); }
 // TetheredWorld (reference world.py:334-366): no ground contacts, six weld rows on the free body
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether_kernel(const StepParams p) { f32::step_entry<f32::W_TETHER>(p); }
 // fp64 instantiations of the same source: a validation build (nmf_set_precision(h, 64)), not a product path -- every
@@ -67,8 +74,10 @@ struct nmf_handle {
   int precision = 32;
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
-  int resident_blocks = 0;                     // blocks of the step kernel (the model's variant) the device holds at once
   int sub_steps = -1;                          // steps per work item: -1 = chosen per launch, 0 = never use the queue
+  int fpb = 0;                                 // fly slots per block of the f32 flat / terrain kernels: 1, 2, 4, 8 or 0 = chosen per launch (see step_block)
+  int resident[9] = {};                        // resident blocks of the model's f32 kernel per fpb (index = fpb)
+  int sms = 0;
   static constexpr int MAX_PARTS = 4;          // nmf_step_host: slices of the batch pipelined over private streams
   int host_parts = 4;                          // measured on B200, 4096 flies: 13.4 / 14.4 / 14.6 M env-steps/s end to end with 1 / 2 / 4 slices
   cudaStream_t part_stream[MAX_PARTS] = {};
@@ -81,6 +90,13 @@ struct nmf_handle {
 
 constexpr int QUEUE_MAX_CHUNKS = 16;   // sub-chunks per fly and launch the queue buffer is sized for
 
+// every entry point that touches the device runs on the handle's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess; }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return NMF_ECUDA; } } while (0)
 
 static int upload(nmf_handle* h, float** dst, const std::vector<float>& v) {
@@ -88,6 +104,8 @@ static int upload(nmf_handle* h, float** dst, const std::vector<float>& v) {
   CK(cudaMemcpy(*dst, v.data(), sizeof(float) * v.size(), cudaMemcpyHostToDevice));
   return NMF_OK;
 }
+
+static int set_resident_blocks(nmf_handle* h);
 
 extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int device, nmf_handle** out) {
   if (!out) return NMF_EINVAL;
@@ -98,7 +116,12 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   if (n_flies <= 0) { h->err = "n_flies must be positive"; return NMF_EINVAL; }
   if (!h->hm.build(blob, nbytes)) { h->err = h->hm.err; return NMF_EINVAL; }
   h->n_flies = n_flies; h->device = device;
-  CK(cudaSetDevice(device));
+  {
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return NMF_EINVAL; }
+  }
+  DeviceGuard guard(device);
   int rc;
   if ((rc = upload(h, &h->d_role, h->hm.role))) return rc;
   if ((rc = upload(h, &h->d_hull, h->hm.hull))) return rc;
@@ -109,13 +132,11 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   CK(cudaMalloc(&h->d_nbr, sizeof(int) * h->hm.hull_nbr.size()));
   CK(cudaMemcpy(h->d_nbr, h->hm.hull_nbr.data(), sizeof(int) * h->hm.hull_nbr.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_queue, sizeof(int) * ((size_t)n_flies * QUEUE_MAX_CHUNKS + 2)));
+  if (const char* e = getenv("NMF_FPB")) { int v = atoi(e); if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8) h->fpb = v; }
+  if (h->hm.par.weld) h->fpb = 1;
   {
-    int per_sm = 0, sms = 0;
-    if (h->hm.par.weld) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_tether_kernel, CTA, 0));
-    else if (h->hm.par.terrain) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_terrain_kernel, CTA, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmf_step_kernel, CTA, 0));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    h->resident_blocks = per_sm * sms;
+    int rc2 = set_resident_blocks(h);
+    if (rc2) return rc2;
   }
   if (const char* e = getenv("NMF_QUEUE_SUBSTEPS")) h->sub_steps = atoi(e);
   if (const char* e = getenv("NMF_HOST_PARTS")) { int v = atoi(e); if (v >= 1 && v <= nmf_handle::MAX_PARTS) h->host_parts = v; }
@@ -124,6 +145,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
 
 extern "C" int nmf_destroy(nmf_handle* h) {
   if (!h) return NMF_OK;
+  DeviceGuard guard(h->device);
   cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64); cudaFree(h->d_state64); cudaFree(h->d_shadow);
   for (int k = 0; k < nmf_handle::MAX_PARTS; k++) { if (h->part_stream[k]) cudaStreamDestroy(h->part_stream[k]); if (h->part_done[k]) cudaEventDestroy(h->part_done[k]); }
   if (h->fork) cudaEventDestroy(h->fork);
@@ -138,7 +160,7 @@ extern "C" int nmf_model_info(const nmf_handle* h, nmf_info* info) {
   if (!h || !info) return NMF_EINVAL;
   info->n_flies = h->n_flies; info->nq = NQ; info->nv = NV; info->nu_pos = h->hm.par.nu_pos; info->nu_adh = h->hm.par.nu_adh;
   info->nseg = h->hm.nseg; info->nleg = NLEG; info->state_stride = S_STRIDE; info->off_qpos = S_QPOS; info->off_qvel = S_QVEL;
-  info->off_qacc_warmstart = S_WARM; info->off_ctrl = S_CTRL; info->off_time = S_TIME; info->dbg_stride = DBG_STRIDE;
+  info->off_qacc_warmstart = S_WARM; info->off_ctrl = S_CTRL; info->off_time = S_TIME; info->dbg_stride = DBG_STRIDE; info->off_status = S_TIME + 1;
   info->timestep = h->hm.par.dt;
   return NMF_OK;
 }
@@ -158,6 +180,7 @@ extern "C" int nmf_set_solver(nmf_handle* h, int max_newton, int max_ls) {
 extern "C" int nmf_reset(nmf_handle* h, const uint8_t* mask, void* stream) {
   if (!h) return NMF_EINVAL;
   if (!h->bound) { h->err = "nmf_reset: not bound"; return NMF_ENOTBOUND; }
+  DeviceGuard guard(h->device);
   nmf_reset_kernel<<<h->n_flies, 64, 0, (cudaStream_t)stream>>>(h->buf.state, h->d_key, mask, h->n_flies);
   h->launches++;
   CK(cudaGetLastError());
@@ -167,6 +190,12 @@ extern "C" int nmf_reset(nmf_handle* h, const uint8_t* mask, void* stream) {
 extern "C" int nmf_set_schedule(nmf_handle* h, int sub_steps) {
   if (!h || sub_steps < -1) return NMF_EINVAL;
   h->sub_steps = sub_steps;
+  return NMF_OK;
+}
+
+extern "C" int nmf_set_flies_per_block(nmf_handle* h, int fpb) {
+  if (!h || (fpb != 0 && fpb != 1 && fpb != 2 && fpb != 4 && fpb != 8)) return NMF_EINVAL;
+  h->fpb = h->hm.par.weld ? 1 : fpb;
   return NMF_OK;
 }
 
@@ -180,21 +209,50 @@ extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table
 extern "C" int nmf_forward(nmf_handle* h, void* stream) { return launch_steps(h, 1, nullptr, 0, 0, 0, true, stream); }
 
 template <class real> struct KernelSet;
+typedef void (*step_kernel_f32)(const StepParams);
+static step_kernel_f32 kernel_f32(bool weld, bool terrain, int fpb) {
+  if (weld) return nmf_step_tether_kernel;
+  if (terrain) return fpb == 8 ? nmf_step_terrain_x8_kernel : fpb == 4 ? nmf_step_terrain_x4_kernel : fpb == 2 ? nmf_step_terrain_x2_kernel : nmf_step_terrain_kernel;
+  return fpb == 8 ? nmf_step_x8_kernel : fpb == 4 ? nmf_step_x4_kernel : fpb == 2 ? nmf_step_x2_kernel : nmf_step_kernel;
+}
+// blocks of 8 fly slots exceed the 48 KB of static shared memory: their per-fly regions live in (opt-in) dynamic shared memory
+static size_t dyn_smem_f32(int fpb) { return fpb >= 8 ? (size_t)fpb * f32::SM_WELD * sizeof(float) : 0; }
+static int set_resident_blocks(nmf_handle* h) {
+  DeviceGuard guard(h->device);
+  CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
+  for (int fpb = 1; fpb <= 8; fpb *= 2) {
+    if (h->hm.par.weld && fpb > 1) break;
+    int per_sm = 0;
+    const size_t dyn = dyn_smem_f32(fpb);
+    if (dyn) CK(cudaFuncSetAttribute(kernel_f32(h->hm.par.weld, h->hm.par.terrain, fpb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_f32(h->hm.par.weld, h->hm.par.terrain, fpb), CTA * fpb, dyn));
+    h->resident[fpb] = per_sm * h->sms;
+  }
+  return NMF_OK;
+}
+// fly slots per block for a launch over n flies: the handle's setting, or the largest block that still gives every SM one
+// (sharing instruction fetches among the slots of a block is worth more than spreading a small batch thinly)
+static int pick_fpb(const nmf_handle* h, int n) {
+  if (h->hm.par.weld) return 1;
+  if (h->fpb) return h->fpb;
+  for (int fpb = 8; fpb > 1; fpb /= 2) if (n >= fpb * h->sms) return fpb;
+  return 1;
+}
 template <> struct KernelSet<float> {
   static const StepParamsT<float>& base(const nmf_handle* h) { return h->hm.par; }
   static const float* role(const nmf_handle* h) { return h->d_role; }
   static const float* hull(const nmf_handle* h) { return h->d_hull; }
-  static void launch(const StepParamsT<float>& p, int grid, cudaStream_t s) {
-    if (p.weld) nmf_step_tether_kernel<<<grid, CTA, 0, s>>>(p);
-    else if (p.terrain) nmf_step_terrain_kernel<<<grid, CTA, 0, s>>>(p);
-    else nmf_step_kernel<<<grid, CTA, 0, s>>>(p);
+  static int fpb(const nmf_handle* h, int n) { return pick_fpb(h, n); }
+  static void launch(const StepParamsT<float>& p, int fpb, int grid, cudaStream_t s) {
+    kernel_f32(p.weld, p.terrain, fpb)<<<grid, CTA * fpb, dyn_smem_f32(fpb), s>>>(p);
   }
 };
 template <> struct KernelSet<double> {
   static const StepParamsT<double>& base(const nmf_handle* h) { return h->hm.par64; }
   static const double* role(const nmf_handle* h) { return h->d_role64; }
   static const double* hull(const nmf_handle* h) { return h->d_hull64; }
-  static void launch(const StepParamsT<double>& p, int grid, cudaStream_t s) {
+  static int fpb(const nmf_handle*, int) { return 1; }
+  static void launch(const StepParamsT<double>& p, int, int grid, cudaStream_t s) {
     if (p.weld) nmf_step_tether_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.terrain) nmf_step_terrain_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else nmf_step_f64_kernel<<<grid, CTA, 0, s>>>(p);
@@ -212,6 +270,7 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   p.role = KernelSet<real>::role(h); p.hull = KernelSet<real>::hull(h); p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
   p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
+  p.out_energy = h->buf.energy;
   p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps; p.forward_only = forward_only ? 1 : 0;
   const bool ranged = count >= 0 && (fly0 != 0 || count != h->n_flies);
   if (ranged) {
@@ -223,26 +282,31 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
     if (p.out_xquat) p.out_xquat += f * p.nseg * 4;
     if (p.out_actf) p.out_actf += f * nu;
     if (p.out_sensor) p.out_sensor += f * NLEG * 16;
+    if (p.out_energy) p.out_energy += f * 2;
     if (p.dbg) p.dbg += f * DBG_STRIDE;
   }
-  int grid = p.n_flies;
-  p.queue = nullptr; p.sub_steps = nsteps; p.n_items = p.n_flies;
+  const int fpb = KernelSet<real>::fpb(h, p.n_flies);
+  const int n_units = (p.n_flies + fpb - 1) / fpb;      // a block steps a unit of fpb consecutive flies
+  int grid = n_units;
+  p.queue = nullptr; p.sub_steps = nsteps; p.n_items = n_units;
   int sub = h->sub_steps;
   if (sub < 0) {
     // ~25 steps per item: measured on B200 (profiles/queue_sweep_r01.txt) an item costs ~0.6 step of fixed overhead (its
-    // set-up code and constants are cold in the instruction / L1 caches), while items of 50+ steps leave a visible tail
-    const int k = (nsteps + 12) / 25;
+    // set-up code and constants are cold in the instruction / L1 caches), while items of 50+ steps leave a visible tail.
+    // Short launches (14 .. 37 steps) are still cut in two: without items they are one partial wave.
+    int k = (nsteps + 12) / 25;
+    if (k < 2 && nsteps >= 14) k = 2;
     sub = k >= 2 ? (nsteps + k - 1) / k : 0;
   }
-  // more flies than resident blocks: work queue (one per handle; sized for the f32 kernels' occupancy, so f32 only)
-  if (std::is_same<real, float>::value && !ranged && sub > 0 && h->n_flies > h->resident_blocks && nsteps >= 2 * sub) {
+  // more units than resident blocks: work queue (one per handle; sized for the f32 kernels' occupancy, so f32 only)
+  if (std::is_same<real, float>::value && !ranged && sub > 0 && n_units > h->resident[fpb] && nsteps >= 2 * sub) {
     if (sub * QUEUE_MAX_CHUNKS < nsteps) sub = (nsteps + QUEUE_MAX_CHUNKS - 1) / QUEUE_MAX_CHUNKS;
     const int nchunk = (nsteps + sub - 1) / sub;
-    p.queue = h->d_queue; p.sub_steps = sub; p.n_items = nchunk * h->n_flies;
-    grid = h->resident_blocks;
-    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)h->n_flies * nchunk + 2), (cudaStream_t)stream));
+    p.queue = h->d_queue; p.sub_steps = sub; p.n_items = nchunk * n_units;
+    grid = h->resident[fpb];
+    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)n_units * nchunk + 2), (cudaStream_t)stream));
   }
-  KernelSet<real>::launch(p, grid, (cudaStream_t)stream);
+  KernelSet<real>::launch(p, fpb, grid, (cudaStream_t)stream);
   h->launches++;
   CK(cudaGetLastError());
   return NMF_OK;
@@ -254,6 +318,8 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
   if (!h->bound) { h->err = "nmf_step: not bound"; return NMF_ENOTBOUND; }
   if (nsteps <= 0) return NMF_OK;
   if (table && table_T <= 0) { h->err = "nmf_step: action table needs table_T > 0"; return NMF_EINVAL; }
+  if (table) table_t0 = ((table_t0 % table_T) + table_T) % table_T;    // any integer start row, negative ones included
+  DeviceGuard guard(h->device);
   if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
     h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
   }
@@ -266,6 +332,7 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
 // steps by fusing them into one launch).
 extern "C" int nmf_set_precision(nmf_handle* h, int bits) {
   if (!h || (bits != 32 && bits != 64)) return NMF_EINVAL;
+  DeviceGuard guard(h->device);
   if (bits == 64 && !h->d_role64) {
     CK(cudaMalloc(&h->d_role64, sizeof(double) * h->hm.role64.size()));
     CK(cudaMemcpy(h->d_role64, h->hm.role64.data(), sizeof(double) * h->hm.role64.size(), cudaMemcpyHostToDevice));
@@ -285,6 +352,7 @@ extern "C" int nmf_set_precision(nmf_handle* h, int bits) {
 extern "C" int nmf_scatter_ctrl(nmf_handle* h, const float* src, const int32_t* cols, int ncols, void* stream) {
   if (!h || !src || !cols || ncols <= 0) return NMF_EINVAL;
   if (!h->bound) return NMF_ENOTBOUND;
+  DeviceGuard guard(h->device);
   int total = h->n_flies * ncols;
   nmf_scatter_cols_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->buf.state, S_CTRL, src, cols, ncols, h->n_flies);
   h->launches++;
@@ -295,6 +363,7 @@ extern "C" int nmf_scatter_ctrl(nmf_handle* h, const float* src, const int32_t* 
 extern "C" int nmf_gather_state(nmf_handle* h, int off, const int32_t* cols, int ncols, float* dst, void* stream) {
   if (!h || !dst || ncols <= 0 || off < 0 || off >= S_STRIDE) return NMF_EINVAL;
   if (!h->bound) return NMF_ENOTBOUND;
+  DeviceGuard guard(h->device);
   int total = h->n_flies * ncols;
   nmf_gather_cols_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->buf.state, off, cols, ncols, dst, h->n_flies);
   h->launches++;
@@ -308,6 +377,7 @@ extern "C" int nmf_gather_state(nmf_handle* h, int off, const int32_t* cols, int
 extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, void* stream_) {
   if (!h || !actions_host || !qpos_host) return NMF_EINVAL;
   if (!h->bound) return NMF_ENOTBOUND;
+  DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nu = h->hm.par.nu_pos + h->hm.par.nu_adh, n = h->n_flies;
   if (action_cols != h->hm.par.nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
@@ -315,9 +385,6 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
   int parts = h->host_parts;
   while (parts > 1 && n < 1024 * parts) parts--;   // at least 1024 flies per slice
   if (parts > 1 && !h->part_stream[0]) {
-    int cur = -1;
-    CK(cudaGetDevice(&cur));
-    if (cur != h->device) { h->err = "nmf_step_host: the handle's device is not the current CUDA device"; return NMF_EINVAL; }
     for (int k = 0; k < nmf_handle::MAX_PARTS; k++) {
       CK(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));

@@ -17,13 +17,33 @@ namespace nmf {
 
 struct BlobView {
   const char* p = nullptr; size_t n = 0;
-  bool ok() const { return p && n >= 16 && memcmp(p, "NMFB200", 8) == 0; }
-  template <typename T> const T* get(const char* name, int* count = nullptr) const {
-    int32_t nsec; memcpy(&nsec, p + 12, 4);
-    for (int i = 0; i < nsec; i++) {
+  int32_t nsec() const { int32_t v; memcpy(&v, p + 12, 4); return v; }
+  // header + section table inside the buffer, every section's payload inside it too (a truncated or corrupt blob is rejected
+  // before anything is dereferenced)
+  bool ok() const {
+    if (!p || n < 16 || memcmp(p, "NMFB200", 8) != 0) return false;
+    const int32_t ns = nsec();
+    if (ns < 0 || ns > 4096 || 16 + (size_t)40 * ns > n) return false;
+    for (int i = 0; i < ns; i++) {
+      const char* e = p + 16 + 40 * i;
+      int32_t dt, cnt; int64_t off; memcpy(&dt, e + 24, 4); memcpy(&cnt, e + 28, 4); memcpy(&off, e + 32, 8);
+      if ((dt != 0 && dt != 1) || cnt < 0 || off < 0 || (off & 3)) return false;
+      const size_t esz = dt == 0 ? 8 : 4;
+      if ((size_t)off > n || (size_t)cnt > (n - (size_t)off) / esz) return false;
+    }
+    return true;
+  }
+  // section `name` with element size sizeof(T); nullptr when absent, of the wrong type, or shorter than `need` elements
+  template <typename T> const T* get(const char* name, int* count = nullptr, int need = 0) const {
+    const int32_t ns = nsec();
+    for (int i = 0; i < ns; i++) {
       const char* e = p + 16 + 40 * i; char nm[25] = {0}; memcpy(nm, e, 24);
-      int32_t cnt; int64_t off; memcpy(&cnt, e + 28, 4); memcpy(&off, e + 32, 8);
-      if (!strcmp(nm, name)) { if (count) *count = cnt; return reinterpret_cast<const T*>(p + off); }
+      int32_t dt, cnt; int64_t off; memcpy(&dt, e + 24, 4); memcpy(&cnt, e + 28, 4); memcpy(&off, e + 32, 8);
+      if (!strcmp(nm, name)) {
+        if ((dt == 0 ? 8 : 4) != (int)sizeof(T) || cnt < need) return nullptr;
+        if (count) *count = cnt;
+        return reinterpret_cast<const T*>(p + off);
+      }
     }
     return nullptr;
   }
@@ -79,25 +99,34 @@ struct HostModel {
   bool build(const void* blob, size_t nbytes) {
     BlobView b{(const char*)blob, nbytes};
     if (!b.ok()) { err = "bad model blob"; return false; }
-    const int32_t* dims = b.get<int32_t>("dims");
+    const int32_t* dims = b.get<int32_t>("dims", nullptr, 10);
     if (!dims) { err = "blob has no dims"; return false; }
     const int nbody = dims[0], nq = dims[1], nv = dims[2], nu_pos = dims[3], nu_adh = dims[4], ngeom = dims[5];
     nseg = dims[7]; const int nleg = dims[8], nhv = dims[9];
     nu = nu_pos + nu_adh;
     if (nbody != 1 + NLEG * NLINK || nv != NV || nq != NQ || nleg != NLEG) { err = "unsupported topology: need hub + 6 legs x 8 links, nv=72"; return false; }
-    if (nu > MAXU) { err = "too many actuators"; return false; }
-    auto D = [&](const char* n) { return b.get<double>(n); };
-    auto I = [&](const char* n) { return b.get<int32_t>(n); };
-    const double *body_pos = D("body_pos"), *body_quat = D("body_quat"), *body_mass = D("body_mass"), *body_ipos = D("body_ipos"),
-                 *body_iquat = D("body_iquat"), *body_inertia = D("body_inertia"), *invw = D("body_invweight0"), *dof_axis = D("dof_axis"),
-                 *stiff = D("dof_stiffness"), *damp = D("dof_damping"), *arm = D("dof_armature"), *sref = D("dof_springref"),
-                 *kp = D("act_kp"), *kv = D("act_kv"), *frc = D("act_frcrange"), *again = D("adh_gain"), *actrl = D("adh_ctrlrange"),
-                 *gpos = D("geom_pos"), *gquat = D("geom_quat"), *gsize = D("geom_size"), *hv = D("hull_vert"), *segpos = D("seg_pos"),
-                 *segquat = D("seg_quat"), *key_qpos = D("key_qpos"), *key_ctrl = D("key_ctrl"), *opt = D("opt"), *contact = D("contact");
-    const int32_t *body_parent = I("body_parent"), *dofadr = I("body_dofadr"), *dofnum = I("body_dofnum"), *body_leg = I("body_leg"),
-                  *act_dof = I("act_dof"), *adh_body = I("adh_body"), *geom_body = I("geom_body"), *geom_type = I("geom_type"),
-                  *gvadr = I("geom_vertadr"), *gvnum = I("geom_vertnum"), *seg_body = I("seg_body"), *leg_root = I("leg_rootbody");
-    if (!body_pos || !body_parent || !opt || !contact || !key_qpos) { err = "blob is missing sections"; return false; }
+    if (nu_pos < 0 || nu_adh < 0 || nu > MAXU) { err = "too many actuators"; return false; }
+    if (ngeom < 0 || nseg < 0 || nhv < 0 || nseg > 4096 || ngeom > CTA) { err = "bad dims"; return false; }
+    bool missing = false;
+    auto D = [&](const char* n, int need) { const double* q = b.get<double>(n, nullptr, need); if (!q) { missing = true; err = std::string("blob section missing or too short: ") + n; } return q; };
+    auto I = [&](const char* n, int need) { const int32_t* q = b.get<int32_t>(n, nullptr, need); if (!q) { missing = true; err = std::string("blob section missing or too short: ") + n; } return q; };
+    const double *body_pos = D("body_pos", 3 * nbody), *body_quat = D("body_quat", 4 * nbody), *body_mass = D("body_mass", nbody), *body_ipos = D("body_ipos", 3 * nbody),
+                 *body_iquat = D("body_iquat", 4 * nbody), *body_inertia = D("body_inertia", 3 * nbody), *invw = D("body_invweight0", 2 * nbody), *dof_axis = D("dof_axis", 3 * nv),
+                 *stiff = D("dof_stiffness", nv), *damp = D("dof_damping", nv), *arm = D("dof_armature", nv), *sref = D("dof_springref", nv),
+                 *kp = D("act_kp", nu_pos), *kv = D("act_kv", nu_pos), *frc = D("act_frcrange", 2 * nu_pos), *again = D("adh_gain", nu_adh), *actrl = D("adh_ctrlrange", 2 * nu_adh),
+                 *gpos = D("geom_pos", 3 * ngeom), *gquat = D("geom_quat", 4 * ngeom), *gsize = D("geom_size", 2 * ngeom), *hv = D("hull_vert", 3 * nhv), *segpos = D("seg_pos", 3 * nseg),
+                 *segquat = D("seg_quat", 4 * nseg), *key_qpos = D("key_qpos", nq), *key_ctrl = D("key_ctrl", nu), *opt = D("opt", 11), *contact = D("contact", 10);
+    const int32_t *body_parent = I("body_parent", nbody), *dofadr = I("body_dofadr", nbody), *dofnum = I("body_dofnum", nbody), *body_leg = I("body_leg", nbody),
+                  *act_dof = I("act_dof", nu_pos), *adh_body = I("adh_body", nu_adh), *geom_body = I("geom_body", ngeom), *geom_type = I("geom_type", ngeom),
+                  *gvadr = I("geom_vertadr", ngeom), *gvnum = I("geom_vertnum", ngeom), *seg_body = I("seg_body", nseg), *leg_root = I("leg_rootbody", nleg);
+    if (missing) return false;
+    for (int a = 0; a < nu_pos; a++) if (act_dof[a] < 6 || act_dof[a] >= nv) { err = "actuator on a free-joint dof is not supported"; return false; }
+    for (int a = 0; a < nu_adh; a++) if (adh_body[a] <= 0 || adh_body[a] >= nbody) { err = "adhesion on the hub is not supported"; return false; }
+    for (int g = 0; g < ngeom; g++) {
+      if (geom_body[g] < 0 || geom_body[g] >= nbody) { err = "geom_body out of range"; return false; }
+      if (gvadr[g] < 0 || gvnum[g] < 0 || gvadr[g] + gvnum[g] > nhv) { err = "hull vertex range out of bounds"; return false; }
+    }
+    for (int sg = 0; sg < nseg; sg++) if (seg_body[sg] < 0 || seg_body[sg] >= nbody) { err = "seg_body out of range"; return false; }
     static const int want_dofs[NLINK] = {3, 2, 1, 1, 1, 1, 1, 1};
     for (int l = 0; l < NLEG; l++) for (int k = 0; k < NLINK; k++) {
       int bb = 1 + l * NLINK + k;
@@ -187,6 +216,11 @@ struct HostModel {
     {
       int na = 0, nn = 0; const int32_t* adr = b.get<int32_t>("hull_nbr_adr", &na); const int32_t* nb = b.get<int32_t>("hull_nbr", &nn);
       if (nhv > 0 && (!adr || !nb || na != nhv + 1)) { err = "blob has no hull adjacency (re-bake the model)"; return false; }
+      if (nhv > 0) {
+        for (int v = 0; v < nhv; v++) if (adr[v] < 0 || adr[v] > adr[v + 1] || adr[v + 1] > nn) { err = "hull adjacency offsets out of bounds"; return false; }
+        for (int g = 0; g < ngeom; g++) for (int v = gvadr[g]; v < gvadr[g] + gvnum[g]; v++)
+          for (int e = adr[v]; e < adr[v + 1]; e++) if (nb[e] < 0 || nb[e] >= gvnum[g]) { err = "hull adjacency entry out of bounds"; return false; }
+      }
       hull_nbr_adr.assign(adr ? adr : nullptr, adr ? adr + na : nullptr); hull_nbr.assign(nb ? nb : nullptr, nb ? nb + nn : nullptr);
       if (hull_nbr_adr.empty()) hull_nbr_adr.push_back(0);
       if (hull_nbr.empty()) hull_nbr.push_back(0);

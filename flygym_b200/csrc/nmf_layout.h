@@ -24,7 +24,12 @@ constexpr int S_QPOS = 0;       // 73 (+3 pad)
 constexpr int S_QVEL = 76;      // 72
 constexpr int S_WARM = 148;     // 72  qacc_warmstart
 constexpr int S_CTRL = 220;     // nu <= MAXU
-constexpr int S_TIME = 300;     // time, status, steps since reset, pad
+constexpr int S_TIME = 300;     // time, status word, steps since reset, pad
+// status word (S_TIME + 1, a small integer kept as a float; sticky until the fly is reset): device-side faults are reported
+// per fly, never by trapping (SURVEY.md 8b error convention)
+constexpr int ST_NONFINITE = 1;   // a velocity became NaN / infinite
+constexpr int ST_NEWTON_CAP = 2;  // the Newton solver hit its iteration cap with the active set still changing
+constexpr int ST_LS_CAP = 4;      // a line search used up its evaluation cap
 constexpr int S_STRIDE = 304;
 
 // thread-role constant table: role[field * CTA + tid]
@@ -91,6 +96,7 @@ struct StepParamsT {
   float* out_xquat;          // optional [n_flies][nseg][4]
   float* out_actf;           // optional [n_flies][nu]
   float* out_sensor;         // optional [n_flies][NLEG*16]
+  float* out_energy;         // optional [n_flies][2]: potential, kinetic energy of the state the last step started from
   float* dbg;                // optional [n_flies][DBG_STRIDE]
   const int* hull_nbr_adr;   // CSR adjacency of the hull vertices: neighbours of vertex v are hull_nbr[hull_nbr_adr[v] .. hull_nbr_adr[v+1])
   const int* hull_nbr;       //   (indices local to the geom)

@@ -99,7 +99,7 @@ __device__ __forceinline__ void chain_suffix(real* v, unsigned mask, int k) {  /
 
 // block-wide sum of N values; call from converged code only (all 64 threads)
 template <int N>
-__device__ __forceinline__ void cta_reduce(real* v, real* s_red, int& parity, int tid) {
+__device__ __forceinline__ void cta_reduce(real* v, real* s_red, int& parity, int tid, int bar) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
@@ -110,7 +110,7 @@ __device__ __forceinline__ void cta_reduce(real* v, real* s_red, int& parity, in
 #pragma unroll
     for (int n = 0; n < N; n++) buf[(tid >> 5) * 8 + n] = v[n];
   }
-  block_sync();
+  block_sync(bar);
 #pragma unroll
   for (int n = 0; n < N; n++) v[n] = buf[n] + buf[8 + n];
   parity ^= 1;
@@ -535,7 +535,8 @@ constexpr int SM_HBB = SM_BASE + 168;               // 21 hub block + 6 xb + 6 S
 constexpr int SM_HUB = SM_HBB + 112;                // hub uniforms
 constexpr int SM_RED = SM_HUB + 64;                 // 32
 constexpr int SM_MBAR = SM_RED + 32;                // 8-byte mbarrier for the TMA record load (16-byte slot)
-constexpr int SM_STAGE = SM_MBAR + 4;               // f64 only: the float32 record as it travels (S_STRIDE floats)
+constexpr int SM_WORK = SM_MBAR + 4;                // 4 words of per-fly scratch flags (non-finite detector)
+constexpr int SM_STAGE = SM_WORK + 4;               // f64 only: the float32 record as it travels (S_STRIDE floats)
 constexpr int SM_WELD = SM_STAGE + (sizeof(real) == 8 ? S_STRIDE / 2 : 0);   // weld rows of the tethered world (WL_COUNT)
 constexpr int SM_TOTAL = SM_WELD + WL_COUNT;
 constexpr int HU_CVEL = 0, HU_CACC = 6;
@@ -663,7 +664,7 @@ __device__ __forceinline__ void hub_solve(real* sm, real* xb) {
 // factor + solve of the arrowhead system  H x = -rhs(SM_GRAD), H given by the staged u vectors (chains) and SM_HBB (hub);
 // the result is written to SM_X.  WITH_SH: lane 48 also publishes the hub part of the spatial acceleration of x.
 __device__ __forceinline__ void arrowhead_solve(real* sm, const real* s_cdof, const Cols& cl, int grp, int t, bool is_leg, int hl, int lbase,
-                                                const int* pb, const int* pc, float* dbg_rows) {
+                                                const int* pb, const int* pc, float* dbg_rows, int bar) {
   real hk0[NLEGDOF], hk1[NLEGDOF], d10, i0own = real(0.), i1own = real(0.), i10 = real(0.), contrib[3];
   load_columns(sm + SM_U + grp * U_STRIDE, cl, t, hk0, hk1, d10);
   if (dbg_rows) {
@@ -678,7 +679,7 @@ __device__ __forceinline__ void arrowhead_solve(real* sm, const real* s_cdof, co
         x10 = is_leg ? -sm[SM_GRAD + lbase + 10] : real(0.);
   chain_solve_up(hk0, hk1, t, x0, x1, x10);
   if (is_leg && t < 6) sm[SM_BASE + NLEG * 21 + grp * 6 + t] = x0;
-  block_sync();
+  block_sync(bar);
   if (!is_leg) {   // Schur block and hub right-hand side assembled by the 16 hub lanes, then solved by lane 48
     for (int i = hl; i < 27; i += NHUBLANE) {
       real v;
@@ -697,7 +698,7 @@ __device__ __forceinline__ void arrowhead_solve(real* sm, const real* s_cdof, co
     }
     for (int i = 0; i < 6; i++) sm[SM_HBB + HB_SH + i] = Sh[i];
   }
-  block_sync();
+  block_sync(bar);
   chain_solve_down(hk0, hk1, t, t < 6 ? sm[SM_HBB + HB_XB + t] : real(0.), i0own, i1own, i10, x0, x1, x10);
   real* sx = sm + SM_X + lbase;
   if (is_leg && t >= 6) sx[t - 6] = x0;
@@ -708,15 +709,15 @@ __device__ __forceinline__ void arrowhead_solve(real* sm, const real* s_cdof, co
 // ------------------------------------------------------------------ state record <-> shared memory
 // The record is float32 in HBM and moves with one TMA bulk copy (nmf_step_common.cuh).  The f32 instantiation copies straight
 // into / out of its working state; the f64 one stages the floats next to it and widens / narrows them.
-__device__ __forceinline__ void load_record(const SP& p, real* st, real* sm, int fly, int tid) {
+__device__ __forceinline__ void load_record(const SP& p, real* st, real* sm, int fly, int tid, int bar) {
   const float* src_gmem = p.state + (size_t)fly * S_STRIDE;
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sm + SM_MBAR);
   if (std::is_same<real, float>::value) {
-    tma_load_f32(reinterpret_cast<float*>(st), src_gmem, mbar, tid);
+    tma_load_f32(reinterpret_cast<float*>(st), src_gmem, mbar, tid, bar);
   } else {
     float* stage = reinterpret_cast<float*>(sm + SM_STAGE);
-    tma_load_f32(stage, src_gmem, mbar, tid);
-    block_sync();
+    tma_load_f32(stage, src_gmem, mbar, tid, bar);
+    block_sync(bar);
     if (p.state64) {
       // full-precision records persist between launches.  An entry whose float32 image still equals what the last f64 launch
       // wrote is taken from the double record; anything else was edited through the API (reset, setters, direct writes to the
@@ -728,18 +729,18 @@ __device__ __forceinline__ void load_record(const SP& p, real* st, real* sm, int
     }
   }
 }
-__device__ __forceinline__ void store_record(const SP& p, const real* st, real* sm, int fly, int tid, bool published) {
+__device__ __forceinline__ void store_record(const SP& p, const real* st, real* sm, int fly, int tid, bool published, int bar) {
   float* dst_gmem = p.state + (size_t)fly * S_STRIDE;
   if (std::is_same<real, float>::value) {
-    tma_store_f32(dst_gmem, reinterpret_cast<const float*>(st), tid, published);
+    tma_store_f32(dst_gmem, reinterpret_cast<const float*>(st), tid, published, bar);
   } else {
     float* stage = reinterpret_cast<float*>(sm + SM_STAGE);
-    block_sync();
+    block_sync(bar);
     for (int i = tid; i < S_STRIDE; i += CTA) {
       stage[i] = (float)st[i];
       if (p.state64) { p.state64[(size_t)fly * S_STRIDE + i] = (double)st[i]; p.shadow[(size_t)fly * S_STRIDE + i] = stage[i]; }
     }
-    tma_store_f32(dst_gmem, stage, tid, published);
+    tma_store_f32(dst_gmem, stage, tid, published, bar);
   }
 }
 
@@ -749,12 +750,25 @@ __device__ __forceinline__ void store_record(const SP& p, const real* st, real* 
 // WORLD selects the kernel instantiation: W_FLAT = the reference's FlatGroundWorld; W_TERRAIN = general-frame contact
 // slots + capsule-vs-box-column narrow phase; W_TETHER = TetheredWorld (no ground, weld equality on the hub).
 constexpr int W_FLAT = 0, W_TERRAIN = 1, W_TETHER = 2;
-template <int WORLD>
+// FPB > 1: the block steps FPB flies side by side (64 threads and a private shared-memory region each; `fly` < 0 = an empty
+// slot).  The kernel is bound by instruction fetch, not by issue slots: the flies of a block meet at a block-wide barrier at the
+// top of every solver pass, so that its warps stream the same stretch of code at the same time and share the fetches (L0 /
+// L1.5 instruction caches); a fly that needs fewer Newton iterations than its neighbours waits for them there.  Everything else
+// synchronises over the fly's own named barrier.  Results do not depend on FPB (bit-identical records).  Measured on B200
+// (profiles/fpb_sweep_r02.txt, 4096 flies): 21.5 / 24.4 / 25.3 M env-steps/s at FPB = 1 / 4 / 8; letting the flies of a block
+// drift apart by whole stages instead of waiting (no idle slots, but two code streams per block) was slower: 21.7 M;
+// one or two more alignment barriers inside a pass changed nothing (25.4 / 24.8 M at FPB = 4 / 8).
+template <int WORLD, int FPB = 1>
 __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly, const int step0, const int nsub, const bool published) {
   using Con = typename std::conditional<WORLD == W_TERRAIN, ContactG, Contact>::type;
   constexpr bool TETHER = WORLD == W_TETHER;
   real* sw = sm + SM_WELD;
-  const int tid = threadIdx.x;
+  const int tid = fly_tid<FPB>();
+  const int bar = FPB == 1 ? 0 : 1 + fly_slot<FPB>();
+  if (FPB > 1 && fly < 0) {   // empty slot: only keeps the block-wide pass barriers of the other flies company
+    for (int step = 0; step < nsub; step++) while (__syncthreads_or(0)) {}
+    return;
+  }
   const bool weld_lane = TETHER && tid == NLEG * NLINK;
   const int grp = tid >> 3, k = tid & 7, t = k;
   const bool is_leg = grp < NLEG;
@@ -771,8 +785,8 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
 
   // ---- load the state record (one TMA bulk copy of 1216 B), clear the u staging (hub chains keep u = 0)
   for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = real(0.);
-  load_record(p, st, sm, fly, tid);
-  block_sync();
+  load_record(p, st, sm, fly, tid, bar);
+  block_sync(bar);
 
   // per-lane constants that stay in registers for the whole launch
   const int ndof = role_int(role[RF_NDOF * CTA + tid]);                 // 0 on hub lanes
@@ -812,7 +826,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
     if (p.act_table) {
       const float* row = p.act_table + ((size_t)fly * p.table_T + (size_t)((p.table_t0 + step) % p.table_T)) * p.table_cols;
       for (int i = tid; i < p.table_cols; i += CTA) st[S_CTRL + i] = row[i];
-      block_sync();
+      block_sync(bar);
     }
 
     // =====================================================================
@@ -877,7 +891,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
     real com[3];
     {
       real v[3] = {mass * xipos[0], mass * xipos[1], mass * xipos[2]};
-      cta_reduce<3>(v, s_red, parity, tid);
+      cta_reduce<3>(v, s_red, parity, tid, bar);
       com[0] = v[0] * p.inv_total_mass; com[1] = v[1] * p.inv_total_mass; com[2] = v[2] * p.inv_total_mass;
     }
     real cinert[10];
@@ -940,7 +954,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         for (int i = 0; i < 6; i++) { s_hub[HU_CVEL + i] = cvel[i]; s_hub[HU_CACC + i] = cacc[i]; sm[SM_HBB + HB_SH + i] = Sh[i]; }
       }
     }
-    block_sync();   // cdof, hub cvel/cacc, S_h visible
+    block_sync(bar);   // cdof, hub cvel/cacc, S_h visible
 
     // =====================================================================
     // B. velocities, composite inertia, collision, bias + actuator forces (all lanes, convergent)
@@ -977,6 +991,18 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       // body wrench  W = -(I a + v x* I v)  (+ adhesion below)
       real t1[6], t2[6], t3[6], W[6];
       mul_inert(cinert, cacc, t1); mul_inert(cinert, cvel, t2); cross_force(cvel, t2, t3);
+      if (p.out_energy && step == p.nsteps - 1) {
+        // `energy` flag of the reference model (mujoco_globals.yaml:19): potential = -sum m g.x + joint springs, kinetic = 1/2 v'Mv
+        real e[2] = {-mass * (p.gx * xipos[0] + p.gy * xipos[1] + p.gz * xipos[2]), real(0.5) * dot6(cvel, t2)};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const real dq = msk[j] * (st[S_QPOS + 1 + dj[j]] - role[(RF_SREF + j) * CTA + tid]);
+          e[0] += real(0.5) * role[(RF_STIFF + j) * CTA + tid] * dq * dq;
+          e[1] += real(0.5) * armv[j] * qv[j] * qv[j];
+        }
+        cta_reduce<2>(e, s_red, parity, tid, bar);
+        if (tid == 0) { p.out_energy[2 * (size_t)fly] = (float)e[0]; p.out_energy[2 * (size_t)fly + 1] = (float)e[1]; }
+      }
 #pragma unroll
       for (int i = 0; i < 6; i++) W[i] = -(t1[i] + t3[i]);
       // composite inertia
@@ -1042,7 +1068,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       if (TETHER && weld_lane) weld_setup(p, sw, qh, xh, com, s_hub + HU_CVEL, Sa);
     }
     const bool any0 = __any_sync(NMF_FULL, con[0].D > real(0.)), any1 = __any_sync(NMF_FULL, con[1].D > real(0.));
-    block_sync();   // chain roots (wrench, crb) visible to the hub lanes
+    block_sync(bar);   // chain roots (wrench, crb) visible to the hub lanes
     real crbh[10];    // hub-dof lanes: composite inertia of the whole fly
     if (!is_leg) hub_root_totals(sm, hl, 0, 16);
     __syncwarp(NMF_FULL);
@@ -1054,7 +1080,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       for (int i = 0; i < 6; i++) W[i] = sm[SM_HBB + HB_TOT + i];
       fs_own[0] = dot6(s_cdof + CDS * hl, W); sm[SM_FS + hl] = fs_own[0];
     }
-    block_sync();   // roots consumed before the solver overwrites them
+    block_sync(bar);   // roots consumed before the solver overwrites them
 
     // =====================================================================
     // C. soft-contact solve: primal Newton on  1/2 (a-a0)'M(a-a0) + s(Ja - aref)
@@ -1063,11 +1089,19 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
     // =====================================================================
     real* qacc = st + S_WARM;      // qacc lives in the warm-start slot of the record
     int niter = 0, nls_total = 0, nchanged_last = 0;
+    int fault = 0;                 // bits of the per-fly status word raised by this step (nmf_layout.h ST_*)
     // One loop body serves every Newton iteration AND the final implicit-damping (Euler) solve, so the large unrolled
     // factorisation exists once in the instruction stream (the kernel is I-cache sensitive):
     //   pass `iter`:  forces(qacc) -> gradient/fc -> [converged? euler : newton] system -> arrowhead solve -> (line search, move)
+    bool running = true;
     for (int iter = 0;; iter++) {
+      if (FPB > 1) {   // pass boundary: the flies of the block realign; a fly that is through waits here for the others
+        __syncwarp(NMF_FULL);
+        if (!__syncthreads_or(running ? 1 : 0)) break;
+        if (!running) continue;
+      }
       const bool euler = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
+      if (euler && nchanged_last != 0) fault |= ST_NEWTON_CAP;      // iteration cap reached with the active set still changing
       // ---- forces, active set, contact augmentation
       real Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
 #pragma unroll
@@ -1100,7 +1134,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
 #pragma unroll
         for (int i = 0; i < 21; i++) rt[16 + i] = am * A[i];
       }
-      block_sync();
+      block_sync(bar);
       {
         real P[21];
         if (!is_leg) hub_root_totals(sm, hl, 0, 37);
@@ -1137,9 +1171,9 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         Cols c = cl;
         c.add0 = euler ? cle.add0 : cl.add0; c.add1 = euler ? cle.add1 : cl.add1; c.add10 = euler ? cle.add10 : cl.add10;
         float* dbg_rows = (euler && p.dbg && is_leg) ? p.dbg + (size_t)fly * DBG_STRIDE + DBG_HROWS + grp * 177 : nullptr;
-        arrowhead_solve(sm, s_cdof, c, grp, t, is_leg, hl, lbase, pb, pc, dbg_rows);
+        arrowhead_solve(sm, s_cdof, c, grp, t, is_leg, hl, lbase, pb, pc, dbg_rows, bar);
       }
-      if (euler) { niter = iter; break; }
+      if (euler) { niter = iter; if (FPB == 1) break; running = false; continue; }
       __syncwarp(NMF_FULL);
       real sown[3];
 #pragma unroll
@@ -1170,7 +1204,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         if (any1) { project_point(con[1], Ss, p.mu, sv1); ls_eval(con[1], sv1, real(0.), red[2], red[3], dummy); }
         if (TETHER && weld_lane) { point_and_rot(sw, Ss, sw + WL_SV); weld_ls(sw, real(0.), red[2], red[3]); }
       }
-      cta_reduce<5>(red, s_red, parity, tid);
+      cta_reduce<5>(red, s_red, parity, tid, bar);
       // ---- exact line search along the Newton direction (safeguarded Newton on the derivative)
       real alpha = real(0.);
       nchanged_last = 0;
@@ -1180,6 +1214,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         const int nls = (red[4] > real(1e-30) && d1 > real(0.)) ? p.max_ls : 0;   // zero direction: nothing to search
         for (int it = 0; it < nls; it++) {
           if (it > 0 && (m_abs(d0) <= Prec<real>::ls_rel * d1 * m_max(m_abs(alpha), Prec<real>::ls_amin) || (hi < real(1.0e38) && hi - lo <= Prec<real>::ls_bracket * hi))) break;
+          if (it == nls - 1) fault |= ST_LS_CAP;                     // the last allowed evaluation is about to be spent
           if (d0 < real(0.)) lo = alpha; else hi = alpha;
           real nx = alpha - d0 / d1;
           if (nx <= lo || nx >= hi) nx = (hi > real(1.0e38)) ? real(2.) * m_max(alpha, real(1.)) : real(0.5) * (lo + hi);
@@ -1188,7 +1223,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
           if (any0) ls_eval(con[0], sv0, alpha, e[0], e[1], e[2]);
           if (any1) ls_eval(con[1], sv1, alpha, e[0], e[1], e[2]);
           if (TETHER && weld_lane) weld_ls(sw, alpha, e[0], e[1]);
-          cta_reduce<3>(e, s_red, parity, tid);
+          cta_reduce<3>(e, s_red, parity, tid, bar);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
           nchanged_last = (int)e[2];
           nls_total++;
@@ -1204,7 +1239,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       if (TETHER && weld_lane) for (int i = 0; i < 6; i++) sw[WL_W + i] += alpha * sw[WL_SV + i];
     }
     // SM_X now holds the implicit-damping (Euler) acceleration  (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
-    block_sync();
+    block_sync(bar);
 
     // ---- optional outputs of this step (derived quantities belong to the pre-integration state, as in mj_step)
     const bool last_step = step == p.nsteps - 1;
@@ -1225,7 +1260,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         for (int i = 0; i < 3; i++) dg[DBG_XPOS + tid * 3 + i] = xpos[i];
         for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[CDS * (i / 6) + i % 6];
         real nc[1] = {con_on(con[0]) + con_on(con[1])};
-        cta_reduce<1>(nc, s_red, parity, tid);
+        cta_reduce<1>(nc, s_red, parity, tid, bar);
         if (tid == 0) dg[DBG_NCON] = nc[0];
       }
       if (p.out_actf) {
@@ -1276,10 +1311,10 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         }
       }
       if (p.out_xpos || p.out_xquat) {
-        block_sync();   // the u staging is free again: reuse it as the pose exchange buffer
+        block_sync(bar);   // the u staging is free again: reuse it as the pose exchange buffer
         real* ps = sm + SM_U + tid * 8;
         ps[0] = xpos[0]; ps[1] = xpos[1]; ps[2] = xpos[2]; ps[3] = xq[0]; ps[4] = xq[1]; ps[5] = xq[2]; ps[6] = xq[3];
-        block_sync();
+        block_sync(bar);
         for (int sgi = tid; sgi < p.nseg; sgi += CTA) {
           const float* tb = p.seg_tab + sgi * 8; const real* bp = sm + SM_U + __float_as_int(tb[0]) * 8;
           real lp[3] = {tb[1], tb[2], tb[3]}, lq[4] = {tb[4], tb[5], tb[6], tb[7]}, w[3], wq[4];
@@ -1287,17 +1322,26 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
           if (p.out_xpos) { float* o = p.out_xpos + ((size_t)fly * p.nseg + sgi) * 3; o[0] = bp[0] + w[0]; o[1] = bp[1] + w[1]; o[2] = bp[2] + w[2]; }
           if (p.out_xquat) { float* o = p.out_xquat + ((size_t)fly * p.nseg + sgi) * 4; o[0] = wq[0]; o[1] = wq[1]; o[2] = wq[2]; o[3] = wq[3]; }
         }
-        block_sync();
+        block_sync(bar);
         for (int i = tid; i < NGROUP * U_STRIDE; i += CTA) sm[SM_U + i] = real(0.);   // restore the staging invariant (hub chains: u = 0)
       }
     }
 
     // ---- advance: qvel += dt a' ; positions integrate with the NEW velocity ; qacc stays as next warm start
-    block_sync();
-    for (int i = tid; i < NV; i += CTA) st[S_QVEL + i] += p.dt * sm[SM_X + i];
-    block_sync();
+    block_sync(bar);
+    int* s_fault = reinterpret_cast<int*>(sm + SM_WORK);       // raised by any thread that sees a non-finite velocity (benign race: all write 1)
+    if (tid == 0) *s_fault = 0;
+    block_sync(bar);
+    for (int i = tid; i < NV; i += CTA) {
+      const real v = st[S_QVEL + i] + p.dt * sm[SM_X + i];
+      st[S_QVEL + i] = v;
+      if (!(m_abs(v) < real(3.0e38))) *s_fault = 1;            // NaN or infinity
+    }
+    block_sync(bar);
     for (int i = tid + 6; i < NV; i += CTA) st[S_QPOS + 1 + i] += p.dt * st[S_QVEL + i];
     if (tid == 0) {
+      if (*s_fault) fault |= ST_NONFINITE;
+      if (fault) st[S_TIME + 1] = (real)((int)st[S_TIME + 1] | fault);    // sticky until the fly is reset
       for (int i = 0; i < 3; i++) st[S_QPOS + i] += p.dt * st[S_QVEL + i];
       real w[3] = {st[S_QVEL + 3], st[S_QVEL + 4], st[S_QVEL + 5]};
       real n = m_sqrt(dot3(w, w));
@@ -1312,64 +1356,71 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       st[S_TIME + 2] += real(1.);                 // step count since reset (exact up to 2^24 in float32)
       st[S_TIME] = st[S_TIME + 2] * p.dt;         // time = n dt, not an accumulated sum (5e4 float32 additions drift by 1e-4 relative)
     }
-    block_sync();
+    block_sync(bar);
   }
 
   // ---- write the record back (TMA bulk store)
-  if (!p.forward_only) store_record(p, st, sm, fly, tid, published);
+  if (!p.forward_only) store_record(p, st, sm, fly, tid, published, bar);
 }
 
 
 #ifndef NMF_SIMT_EMU
-// Two schedules, one call site of the (large) step body:
-//  * p.queue == nullptr: block b advances fly b by all p.nsteps steps (grid = n_flies);
-//  * work queue: the launch is cut into items (fly, sub-chunk of p.sub_steps steps) served to a grid that just fills the
-//    GPU.  n_flies is rarely a multiple of the 148 x 16 resident blocks, and this latency-bound kernel slows down in
+// Two schedules, one call site of the (large) step body.  A work unit = FPB consecutive flies = what one block steps:
+//  * p.queue == nullptr: block b advances unit b by all p.nsteps steps (grid = number of units);
+//  * work queue: the launch is cut into items (unit, sub-chunk of p.sub_steps steps) served to a grid that just fills the
+//    GPU.  The number of units is rarely a multiple of the resident blocks, and this latency-bound kernel slows down in
 //    proportion to the empty slots of a partial last wave; with items a launch is many waves long instead of one or two.
-//    The queue is a FIFO of READY flies: entries 0..n-1 are implicit (every fly's first sub-chunk), and a block that has
-//    written a fly's record back appends the fly again (release) unless that was its last sub-chunk.  Entry i >= n is
-//    therefore filled by the (i-n)-th completion; when a block pops it at most `grid` items are still running, i.e. at
-//    least i - grid >= i - n have completed (the queue is only used when n_flies >= grid), so pops do not wait.
-//    queue[0] = pop counter, queue[1] = push counter, queue[2 + f] = sub-chunks of fly f done, queue[2 + n + j] = ring entry j.
-template <int WORLD>
+//    The queue is a FIFO of READY units: entries 0..n-1 are implicit (every unit's first sub-chunk), and a block that has
+//    written the records back appends the unit again (release) unless that was its last sub-chunk.
+//    queue[0] = pop counter, queue[1] = push counter, queue[2 + u] = sub-chunks of unit u done, queue[2 + n + j] = ring entry j.
+//    A block may have to wait for a ring entry, but only for items that are running on OTHER blocks (its own previous item
+//    has been pushed before it pops), so the wait always ends.
+template <int WORLD, int FPB = 1>
 __device__ __forceinline__ void step_entry(const SP& p) {
-  __shared__ __align__(16) real sm[WORLD == W_TETHER ? SM_TOTAL : SM_WELD];   // only the tethered world keeps weld rows
+  constexpr int SM_FLY = WORLD == W_TETHER ? SM_TOTAL : SM_WELD;       // only the tethered world keeps weld rows
+  constexpr bool DYN = (size_t)FPB * SM_FLY * sizeof(real) > 48 * 1024;   // beyond the static limit: dynamic shared memory (opt-in on the host side)
+  __shared__ __align__(16) real sm_static[DYN ? 1 : FPB * SM_FLY];
+  extern __shared__ __align__(16) unsigned char sm_dynamic[];
   __shared__ int s_fly, s_chunk;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, slot = fly_slot<FPB>();
+  real* sm = (DYN ? reinterpret_cast<real*>(sm_dynamic) : sm_static) + slot * SM_FLY;
+  const int n_units = (p.n_flies + FPB - 1) / FPB;
   for (;;) {
-    int fly = blockIdx.x, step0 = 0, nsub = p.nsteps;
+    int unit = blockIdx.x, step0 = 0, nsub = p.nsteps;
     if (p.queue) {
       if (tid == 0) {
-        const int i = atomicAdd(p.queue, 1);
+        const int i = NMF_ATOMIC_ADD(p.queue, 1);
         int f = -1;
-        if (i < p.n_flies) f = i;
+        if (i < n_units) f = i;
         else if (i < p.n_items) {
-          const int* slot = p.queue + 2 + p.n_flies + (i - p.n_flies);
+          const int* slot_p = p.queue + 2 + n_units + (i - n_units);
           int v = 0;
           for (unsigned spins = 0; spins < (1u << 24); spins++) {      // bounded: a scheduling bug must not hang the GPU
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+            v = NMF_LD_ACQUIRE(slot_p);
             if (v) break;
             __nanosleep(64);
           }
           f = v - 1;
-          asm volatile("fence.proxy.async;" ::: "memory");            // the record is read through the async proxy (TMA) next
+          NMF_FENCE_PROXY_ASYNC();            // the records are read through the async proxy (TMA) next
         }
         s_fly = f; s_chunk = f >= 0 ? p.queue[2 + f] : 0;
       }
-      block_sync();
-      fly = s_fly;
-      if (fly < 0) return;
+      block_sync(0);
+      unit = s_fly;
+      if (unit < 0) return;
       step0 = s_chunk * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
     }
-    step_block<WORLD>(p, sm, fly, step0, nsub, p.queue != nullptr);
+    const int fly = unit * FPB + slot;
+    step_block<WORLD, FPB>(p, sm, fly < p.n_flies ? fly : -1, step0, nsub, p.queue != nullptr);
     if (!p.queue) return;
-    if (tid == 0) {   // the TMA store of the record has completed (store_record waited for it): hand the fly on
+    block_sync(0);     // every slot's record store has completed (store_record waited for it); s_fly / s_chunk are free again
+    if (tid == 0) {    // hand the unit on
       const int done = step0 / p.sub_steps + 1;
-      p.queue[2 + fly] = done;
+      p.queue[2 + unit] = done;
       if (done * p.sub_steps < p.nsteps) {
-        __threadfence();
-        const int j = atomicAdd(p.queue + 1, 1);
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.queue + 2 + p.n_flies + j), "r"(fly + 1) : "memory");
+        NMF_THREADFENCE();
+        const int j = NMF_ATOMIC_ADD(p.queue + 1, 1);
+        NMF_ST_RELEASE(p.queue + 2 + n_units + j, unit + 1);
       }
     }
   }

@@ -38,37 +38,80 @@ namespace nmf {
 
 // Block barrier that first reconverges each warp: __syncthreads() is the *aligned* barrier and is undefined when a warp
 // reaches it diverged (ptxas may leave lanes diverged after predicated stores; compute-sanitizer synccheck flags it).
-__device__ __forceinline__ void block_sync() { __syncwarp(NMF_FULL); __syncthreads(); }
+// `bar` selects the barrier: 0 = the whole block (one fly per block); b > 0 = named barrier b over the CTA (= 64) threads of ONE
+// fly, used when a block steps several flies side by side (step_entry<WORLD, FPB > 1>).
+#ifndef NMF_SIMT_EMU
+__device__ __forceinline__ void block_sync(int bar) {
+  __syncwarp(NMF_FULL);
+  if (bar == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(CTA) : "memory");
+}
+#else
+inline void block_sync(int bar) { __syncwarp(NMF_FULL); if (bar == 0) __syncthreads(); else simt_named_barrier(bar, CTA); }
+#endif
+
+// work-queue primitives (device: gpu-scope acquire / release; emulator: one block at a time, plain accesses)
+#ifndef NMF_SIMT_EMU
+#define NMF_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
+__device__ __forceinline__ int nmf_ld_acquire(const int* ptr) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory"); return v; }
+__device__ __forceinline__ void nmf_st_release(int* ptr, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory"); }
+#define NMF_LD_ACQUIRE(ptr) nmf_ld_acquire(ptr)
+#define NMF_ST_RELEASE(ptr, v) nmf_st_release((ptr), (v))
+#define NMF_FENCE_PROXY_ASYNC() asm volatile("fence.proxy.async;" ::: "memory")
+#define NMF_THREADFENCE() __threadfence()
+#else
+inline int nmf_emu_atomic_add(int* ptr, int v) { const int old = *ptr; *ptr = old + v; return old; }
+#define NMF_ATOMIC_ADD(ptr, v) nmf_emu_atomic_add((ptr), (v))
+#define NMF_LD_ACQUIRE(ptr) (*(ptr))
+#define NMF_ST_RELEASE(ptr, v) (*(ptr) = (v))
+#define NMF_FENCE_PROXY_ASYNC() ((void)0)
+#define NMF_THREADFENCE() ((void)0)
+#endif
+
+// Several flies per block (step_slot<WORLD, FPB>): which fly slot a thread serves and its thread index inside that fly.
+// NMF_FPB_INTERLEAVE = 1 gives fly s the warps s and s + FPB of the block (warp w runs on SM sub-partition w % 4, so with
+// FPB = 4 the two warps of a fly share one sub-partition's L0 instruction cache); 0 = consecutive warps.
+#ifndef NMF_FPB_INTERLEAVE
+#define NMF_FPB_INTERLEAVE 0
+#endif
+template <int FPB> __device__ __forceinline__ int fly_slot() {
+  if (FPB == 1) return 0;
+  return NMF_FPB_INTERLEAVE ? (int)(threadIdx.x >> 5) % FPB : (int)(threadIdx.x / CTA);
+}
+template <int FPB> __device__ __forceinline__ int fly_tid() {
+  if (FPB == 1) return (int)threadIdx.x;
+  return NMF_FPB_INTERLEAVE ? (int)((threadIdx.x >> 5) / FPB) * 32 + (int)(threadIdx.x & 31) : (int)(threadIdx.x & (CTA - 1));
+}
 
 // ------------------------------------------------------------------ TMA (bulk async copy) of the float32 state record
 // One elected thread moves the whole 1216-byte record HBM <-> shared memory with cp.async.bulk (SASS: UBLKCP); the block
 // waits on an mbarrier.  Under the SIMT emulator the same copies are plain loops.
 #ifndef NMF_SIMT_EMU
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tma_load_f32(float* dst_smem, const float* src_gmem, unsigned long long* mbar, int tid) {
-  const unsigned bar = smem_u32(mbar), dst = smem_u32(dst_smem);
+__device__ __forceinline__ void tma_load_f32(float* dst_smem, const float* src_gmem, unsigned long long* mbar, int tid, int bar) {
+  const unsigned mb = smem_u32(mbar), dst = smem_u32(dst_smem);
   constexpr unsigned bytes = S_STRIDE * sizeof(float);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  block_sync();
+  block_sync(bar);
   if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+                 ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(mb) : "memory");
   }
   unsigned done = 0;
   while (!done) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
   }
-  block_sync();
-  if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");   // the slot is re-initialised by the next work item
+  block_sync(bar);
+  if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");   // the slot is re-initialised by the next work item
 }
 // `published`: the caller hands the record to another block afterwards (work-queue scheduling), so wait until the
 // global writes have completed, not only until shared memory has been read.
-__device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_smem, int tid, bool published) {
-  block_sync();                                                      // all generic-proxy writes to the record are done
+__device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_smem, int tid, bool published, int bar) {
+  block_sync(bar);                                                      // all generic-proxy writes to the record are done
   if (tid == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // make them visible to the async (TMA) proxy
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"((unsigned)(S_STRIDE * sizeof(float))) : "memory");
@@ -78,12 +121,12 @@ __device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_
   }
 }
 #else
-__device__ __forceinline__ void tma_load_f32(float* dst_smem, const float* src_gmem, unsigned long long*, int tid) {
+__device__ __forceinline__ void tma_load_f32(float* dst_smem, const float* src_gmem, unsigned long long*, int tid, int bar) {
   for (int i = tid; i < S_STRIDE; i += CTA) dst_smem[i] = src_gmem[i];
-  block_sync();
+  block_sync(bar);
 }
-__device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_smem, int tid, bool) {
-  block_sync();
+__device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_smem, int tid, bool, int bar) {
+  block_sync(bar);
   for (int i = tid; i < S_STRIDE; i += CTA) dst_gmem[i] = src_smem[i];
 }
 #endif

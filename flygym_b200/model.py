@@ -252,7 +252,8 @@ class NMFModel:
         actuator and a zero keyframe angle."""
         locked_names = set(locked_names)
         all_dofs = self.names["jointdofs"]
-        idx = np.array([6 + j for j, nm in enumerate(all_dofs) if nm in locked_names], dtype=np.int32)
+        ex = self.exposed_hinge_dofs()          # position j of names['jointdofs'] is hinge DoF ex[j] of the kernel layout
+        idx = np.array([6 + int(ex[j]) for j, nm in enumerate(all_dofs) if nm in locked_names], dtype=np.int32)
         if len(idx) != len(locked_names):
             raise ValueError("unknown DoF names: " + ", ".join(sorted(locked_names - set(all_dofs))))
         act = set(int(d) for d in self.arrays["act_dof"])

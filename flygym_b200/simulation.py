@@ -83,10 +83,14 @@ class B200Simulation:
         self.renderer = None
         self.n_worlds = int(n_worlds)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"B200Simulation needs a CUDA device, got {self.device}")
+        if self.device.index is None:       # plain "cuda": the current device, where the tensors below are allocated
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _lib.load()
         blob = self.model.to_blob()
         h = ctypes.c_void_p()
-        rc = self._lib.nmf_create(blob, len(blob), self.n_worlds, self.device.index or 0, ctypes.byref(h))
+        rc = self._lib.nmf_create(blob, len(blob), self.n_worlds, int(self.device.index), ctypes.byref(h))
         self._h = h
         if rc != 0:
             msg = self._lib.nmf_last_error(h).decode() if h else "allocation failed"
@@ -101,6 +105,7 @@ class B200Simulation:
         self.act_force = torch.zeros((n, i.nu_pos + i.nu_adh), dtype=torch.float32, device=dev) if outputs else None
         self.sensordata = torch.zeros((n, i.nleg * 16), dtype=torch.float32, device=dev) if outputs else None
         self.debug = torch.zeros((n, i.dbg_stride), dtype=torch.float32, device=dev) if debug else None
+        self.energy = torch.zeros((n, 2), dtype=torch.float32, device=dev) if outputs else None
         self._bind()
         self._build_index_maps()
         self._curr_step = 0
@@ -123,7 +128,7 @@ class B200Simulation:
 
     def _bind(self) -> None:
         b = _lib.NmfBuffers(self._ptr(self.state), self._ptr(self.seg_xpos), self._ptr(self.seg_xquat),
-                            self._ptr(self.act_force), self._ptr(self.sensordata), self._ptr(self.debug))
+                            self._ptr(self.act_force), self._ptr(self.sensordata), self._ptr(self.debug), self._ptr(self.energy))
         self._check(self._lib.nmf_bind(self._h, ctypes.byref(b)))
 
     def _build_index_maps(self) -> None:
@@ -304,6 +309,23 @@ class B200Simulation:
     def qacc_warmstart(self) -> torch.Tensor:
         return self.state[:, self.info.off_qacc_warmstart: self.info.off_qacc_warmstart + self.info.nv]
 
+    # bits of the per-fly status word (include/nmf_b200.h, enum nmf_fly_status)
+    ST_NONFINITE, ST_NEWTON_CAP, ST_LS_CAP = 1, 2, 4
+
+    @property
+    def status(self) -> torch.Tensor:
+        """Per-world status word ``(n_worlds,)`` int32: OR of ``ST_NONFINITE`` (a velocity became NaN / infinite),
+        ``ST_NEWTON_CAP`` (the solver hit the model's ``iterations`` with the active set still changing) and ``ST_LS_CAP`` (a
+        line search used up its evaluations).  Sticky until the world is reset.  Device-side faults are reported here, never by
+        trapping (the reference's MuJoCo emits ``mju_warning`` / resets the data instead)."""
+        return self.state[:, self.info.off_status].to(torch.int32)
+
+    def get_energy(self) -> torch.Tensor:
+        """``(n_worlds, 2)`` potential and kinetic energy of the state the last step started from (``mjData.energy`` with the
+        reference model's ``energy`` flag, ``mujoco_globals.yaml:19``)."""
+        self._need_outputs()
+        return self.energy.clone()
+
     @property
     def time(self) -> float:
         """Current simulation time in seconds (from world 0; forces a device sync like the reference)."""
@@ -342,6 +364,10 @@ class B200Simulation:
     def set_schedule(self, sub_steps: int = -1) -> None:
         """Steps per work item of multi-step launches (0 = one block per fly for the whole launch, -1 = automatic)."""
         self._check(self._lib.nmf_set_schedule(self._h, int(sub_steps)))
+
+    def set_flies_per_block(self, fpb: int = 0) -> None:
+        """Fly slots per thread block of the float32 kernels (1, 2, 4, 8; 0 = chosen per launch); results do not depend on it."""
+        self._check(self._lib.nmf_set_flies_per_block(self._h, int(fpb)))
 
     @property
     def launch_count(self) -> int:

@@ -34,7 +34,15 @@ typedef struct nmf_info {
   int32_t state_stride, off_qpos, off_qvel, off_qacc_warmstart, off_ctrl, off_time;
   int32_t dbg_stride;
   float timestep;
+  int32_t off_status;   /* per-fly status word (a small integer stored as a float), OR of NMF_ST_* bits; sticky until the fly is reset */
 } nmf_info;
+
+/* Device-side faults are reported per fly through the status word of the state record, never by trapping. */
+enum nmf_fly_status {
+  NMF_ST_NONFINITE = 1,    /* a generalised velocity became NaN / infinite */
+  NMF_ST_NEWTON_CAP = 2,   /* the Newton solver hit `iterations` (mujoco_globals.yaml:14) with the active set still changing */
+  NMF_ST_LS_CAP = 4        /* a line search used up its evaluation cap (MuJoCo's ls_iterations) */
+};
 
 /* Device buffers owned by the caller (PyTorch tensors in the Python host). `state`
  * is required; the observation buffers are optional (NULL = not produced). */
@@ -45,6 +53,7 @@ typedef struct nmf_buffers {
   float* act_force;    /* DEVICE [n_flies][nu]        -> Simulation.get_actuator_forces */
   float* sensordata;   /* DEVICE [n_flies][nleg*16]   -> Simulation.get_ground_contact_info */
   float* debug;        /* DEVICE [n_flies][dbg_stride] solver internals for the parity tests (optional) */
+  float* energy;       /* DEVICE [n_flies][2]         potential, kinetic energy (the model's `energy` flag, mujoco_globals.yaml:19) */
 } nmf_buffers;
 
 /* Simulation.__init__ / GPUSimulation.__init__ (simulation.py:32-57, warp/simulation.py:49-62):
@@ -71,11 +80,18 @@ int nmf_step(nmf_handle* h, int nsteps, const float* action_table_or_null, int t
  * following Simulation.reset (simulation.py:59-72 resets without forward). */
 int nmf_forward(nmf_handle* h, void* cuda_stream);
 
-/* Scheduling of multi-step launches: with more flies than the GPU holds resident blocks, a launch of nsteps >= 2*sub_steps
+/* Scheduling of multi-step launches: with more flies than the GPU holds resident fly slots, a launch of nsteps >= 2*sub_steps
  * is cut into (fly, sub_steps-step) work items served from a device-side queue (results are identical; only the order in
  * which flies advance changes).  sub_steps = 0 disables the queue (one block per fly for the whole launch); -1 (default)
  * lets the library pick the sub-chunk length that fills whole waves of resident blocks best. */
 int nmf_set_schedule(nmf_handle* h, int sub_steps);
+
+/* Fly slots per thread block of the float32 kernels: 1, 2, 4, 8, or 0 (default) = chosen per launch from the batch size.  The
+ * step is bound by instruction fetch, so the slots of a block advance in stages separated by a block-wide barrier (a stage =
+ * the kinematics .. smooth-force part of a step, or one solver pass): the block's warps then stream the same code at the same
+ * time and share its fetches, while every slot still takes its own work items and nobody waits for a neighbour's Newton
+ * iterations.  Results are bit-identical for every setting. */
+int nmf_set_flies_per_block(nmf_handle* h, int flies_per_block);
 
 /* set_actuator_inputs / set_leg_adhesion_states (warp/simulation.py:213-258; kernel warp/utils.py:84-104):
  * state.ctrl[:, cols[k]] = src[:, k]   (src DEVICE [n_flies][ncols], cols DEVICE int32[ncols]) */

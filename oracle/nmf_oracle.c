@@ -74,6 +74,7 @@ typedef struct {
   double *geom_xpos, *geom_xmat, *site_xpos, *seg_xpos, *seg_xquat, *sensordata;
   /* solver stats */
   int solver_niter; double solver_cost, solver_gradnorm;
+  double energy[2];   /* potential, kinetic (mjData.energy with the model's `energy` flag) */
   char err[256];
 } nmfo;
 
@@ -697,6 +698,16 @@ static void sensors(nmfo* o) {
   }
 }
 
+/* mj_energyPos / mj_energyVel (the reference model enables the `energy` flag, mujoco_globals.yaml:19):
+ * potential = -sum_b m_b g.xipos_b + sum_hinges 1/2 k (q - springref)^2 ;  kinetic = 1/2 qvel' M qvel */
+static void energy(nmfo* o) {
+  int nv = o->nv; double ep = 0, ek = 0;
+  for (int b = 0; b < o->nbody; b++) ep -= o->body_mass[b] * dot3(o->grav, o->xipos + 3 * b);
+  for (int d = 6; d < nv; d++) { double dq = o->qpos[d + 1] - o->dof_springref[d]; ep += 0.5 * o->dof_stiffness[d] * dq * dq; }
+  for (int i = 0; i < nv; i++) ek += 0.5 * o->qvel[i] * dotn(o->M + (size_t)i * nv, o->qvel, nv);
+  o->energy[0] = ep; o->energy[1] = ek;
+}
+
 /* ------------------------------------------------------------------ mj_forward / mj_step */
 void nmfo_forward(nmfo* o) {
   int nv = o->nv;
@@ -709,6 +720,7 @@ void nmfo_forward(nmfo* o) {
   free(L);
   solve_constraints(o);
   sensors(o);
+  energy(o);
 }
 
 /* mj_Euler with implicit joint damping (eulerdamp) + mj_advance */
@@ -766,7 +778,7 @@ double* nmfo_array(nmfo* o, const char* name, int* count) {
   A("efc_jar", o->efc_jar, o->nefc) A("efc_pos", o->efc_pos, o->nefc)
   A("site_xpos", o->site_xpos, 3 * o->nsite) A("seg_xpos", o->seg_xpos, 3 * o->nseg) A("seg_xquat", o->seg_xquat, 4 * o->nseg)
   A("sensordata", o->sensordata, 16 * o->nleg) A("geom_xpos", o->geom_xpos, 3 * o->ngeom) A("cvel", o->cvel, 6 * nb)
-  A("solver_gradnorm", &o->solver_gradnorm, 1) A("solver_cost", &o->solver_cost, 1)
+  A("solver_gradnorm", &o->solver_gradnorm, 1) A("solver_cost", &o->solver_cost, 1) A("energy", o->energy, 2)
 #undef A
   return NULL;
 }

@@ -25,36 +25,61 @@ def build(force: bool = False) -> Path:
     return so
 
 
-def _lib():
-    global _LIB
+def build_native() -> Path | None:
+    """The same source built ``-O3 -march=native`` ON THE MACHINE THAT RUNS IT (bench.py's CPU arm only: a build made for
+    this container's CPU must not travel to another host).  Returns None when no compiler is available."""
+    so = _HERE / "_native" / "libnmf_oracle_native.so"
+    src = _HERE / "nmf_oracle.c"
+    try:
+        so.parent.mkdir(exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=c11", "-shared", "-o", str(so), str(src), "-lm"],
+                              stderr=subprocess.DEVNULL)
+        return so
+    except Exception:
+        return None
+
+
+_LIB_NATIVE = None
+
+
+def _lib(native: bool = False):
+    global _LIB, _LIB_NATIVE
+    if native:
+        if _LIB_NATIVE is None:
+            so = build_native()
+            _LIB_NATIVE = _bind(ctypes.CDLL(str(so))) if so is not None else _lib()
+        return _LIB_NATIVE
     if _LIB is None:
-        lib = ctypes.CDLL(str(build()))
-        lib.nmfo_create.restype = ctypes.c_void_p
-        lib.nmfo_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
-        lib.nmfo_destroy.argtypes = [ctypes.c_void_p]
-        lib.nmfo_reset.argtypes = [ctypes.c_void_p]
-        lib.nmfo_forward.argtypes = [ctypes.c_void_p]
-        lib.nmfo_step.argtypes = [ctypes.c_void_p]
-        lib.nmfo_step_n.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        lib.nmfo_step_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-        lib.nmfo_step_table_cols.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-        lib.nmfo_dim.restype = ctypes.c_int
-        lib.nmfo_dim.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
-        lib.nmfo_array.restype = ctypes.POINTER(ctypes.c_double)
-        lib.nmfo_array.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
-        lib.nmfo_con_geom.restype = ctypes.c_int
-        lib.nmfo_con_geom.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
-        lib.nmfo_last_error.restype = ctypes.c_char_p
-        lib.nmfo_last_error.argtypes = [ctypes.c_void_p]
-        _LIB = lib
+        _LIB = _bind(ctypes.CDLL(str(build())))
     return _LIB
+
+
+def _bind(lib):
+    lib.nmfo_create.restype = ctypes.c_void_p
+    lib.nmfo_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    lib.nmfo_destroy.argtypes = [ctypes.c_void_p]
+    lib.nmfo_reset.argtypes = [ctypes.c_void_p]
+    lib.nmfo_forward.argtypes = [ctypes.c_void_p]
+    lib.nmfo_step.argtypes = [ctypes.c_void_p]
+    lib.nmfo_step_n.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.nmfo_step_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.nmfo_step_table_cols.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.nmfo_dim.restype = ctypes.c_int
+    lib.nmfo_dim.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.nmfo_array.restype = ctypes.POINTER(ctypes.c_double)
+    lib.nmfo_array.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+    lib.nmfo_con_geom.restype = ctypes.c_int
+    lib.nmfo_con_geom.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    lib.nmfo_last_error.restype = ctypes.c_char_p
+    lib.nmfo_last_error.argtypes = [ctypes.c_void_p]
+    return lib
 
 
 class Oracle:
     """One fly, fp64.  ``get(name)`` returns a *view* (numpy) into oracle memory."""
 
-    def __init__(self, model):
-        self._lib = _lib()
+    def __init__(self, model, native: bool = False):
+        self._lib = _lib(native)
         blob = model.to_blob()
         self._h = self._lib.nmfo_create(blob, len(blob))
         if not self._h:

@@ -42,7 +42,7 @@ def key_state(model):
     return out
 
 
-def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0, max_newton=0, max_ls=0, precision=32):
+def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0, max_newton=0, max_ls=0, precision=32, fpb=1, sub_steps=0):
     """state: float32 [n, S_STRIDE], updated in place. Returns dict of optional outputs."""
     blob = model.to_blob()
     n = state.shape[0]
@@ -53,10 +53,11 @@ def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0,
     oq = np.zeros((n, nseg, 4), np.float32) if outputs else None
     oa = np.zeros((n, nu), np.float32) if outputs else None
     os_ = np.zeros((n, 96), np.float32) if outputs else None
+    oe = np.zeros((n, 2), np.float32) if outputs else None
     T = 0 if act_table is None else act_table.shape[1]
     cols = 0 if act_table is None else act_table.shape[2]
     rc = lib().emu_step(blob, ctypes.c_size_t(len(blob)), _p(state), n, nsteps, _p(d), _p(ox), _p(oq), _p(oa), _p(os_),
-                        _p(act_table), T, t0, cols, max_newton, max_ls, precision)
+                        _p(act_table), T, t0, cols, max_newton, max_ls, precision, fpb, sub_steps, _p(oe))
     assert rc == 0
-    res.update(dbg=d, xpos=ox, xquat=oq, actf=oa, sensor=os_)
+    res.update(dbg=d, xpos=ox, xquat=oq, actf=oa, sensor=os_, energy=oe)
     return res

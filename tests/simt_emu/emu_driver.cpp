@@ -4,7 +4,7 @@
 #include "../../flygym_b200/csrc/nmf_host.h"
 #include "../../flygym_b200/csrc/nmf_step_all.cuh"
 
-static float g_sm[nmf::f32::SM_TOTAL];
+static float g_sm[8 * nmf::f32::SM_TOTAL];
 static double g_sm64[nmf::f64::SM_TOTAL];
 
 extern "C" int emu_key_state(const void* blob, size_t nbytes, float* out) {
@@ -16,33 +16,50 @@ extern "C" int emu_key_state(const void* blob, size_t nbytes, float* out) {
 
 extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_flies, int nsteps, float* dbg, float* out_xpos,
                         float* out_xquat, float* out_actf, float* out_sensor, const float* act_table, int table_T, int table_t0, int table_cols,
-                        int max_newton, int max_ls, int precision) {
+                        int max_newton, int max_ls, int precision, int fpb, int sub_steps, float* out_energy) {
   nmf::HostModel hm;
   if (!hm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", hm.err.c_str()); return -1; }
-  nmf::StepParams p = hm.par;
-  p.state = state; p.role = hm.role.data(); p.hull = hm.hull.data(); p.seg_tab = hm.seg_tab.data(); p.hull_nbr_adr = hm.hull_nbr_adr.data(); p.hull_nbr = hm.hull_nbr.data();
-  p.act_table = act_table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table_cols;
-  p.out_xpos = out_xpos; p.out_xquat = out_xquat; p.out_actf = out_actf; p.out_sensor = out_sensor; p.dbg = dbg;
-  p.n_flies = n_flies; p.nsteps = nsteps;
-  if (max_newton > 0) p.max_newton = max_newton;
-  if (max_ls > 0) p.max_ls = max_ls;
-  if (precision == 64) {   // the f64 instantiation of the same source
-    nmf::StepParamsT<double> q = hm.par64;
-    q.state = state; q.role = hm.role64.data(); q.hull = hm.hull64.data(); q.seg_tab = hm.seg_tab.data(); q.hull_nbr_adr = hm.hull_nbr_adr.data(); q.hull_nbr = hm.hull_nbr.data();
+  if (fpb != 1 && fpb != 2 && fpb != 4 && fpb != 8) return -2;
+  // sub_steps > 0: the launch is cut into (fly, sub_steps-step) items served from the work queue to ONE block of fpb slots
+  std::vector<int> queue;
+  int n_items = n_flies;
+  if (sub_steps > 0) {
+    const int nchunk = (nsteps + sub_steps - 1) / sub_steps;
+    n_items = nchunk * n_flies;
+    queue.assign(2 + (size_t)n_flies * (nchunk + 1), 0);
+  }
+  auto fill = [&](auto& q, const auto* role, const auto* hull) {
+    q.state = state; q.role = role; q.hull = hull; q.seg_tab = hm.seg_tab.data(); q.hull_nbr_adr = hm.hull_nbr_adr.data(); q.hull_nbr = hm.hull_nbr.data();
     q.act_table = act_table; q.table_T = table_T; q.table_t0 = table_t0; q.table_cols = table_cols;
-    q.out_xpos = out_xpos; q.out_xquat = out_xquat; q.out_actf = out_actf; q.out_sensor = out_sensor; q.dbg = dbg;
+    q.out_xpos = out_xpos; q.out_xquat = out_xquat; q.out_actf = out_actf; q.out_sensor = out_sensor; q.out_energy = out_energy; q.dbg = dbg;
     q.n_flies = n_flies; q.nsteps = nsteps;
     if (max_newton > 0) q.max_newton = max_newton;
     if (max_ls > 0) q.max_ls = max_ls;
-    for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() {
-      if (q.weld) nmf::f64::step_block<nmf::f64::W_TETHER>(q, g_sm64, f, 0, q.nsteps, false);
-      else if (q.terrain) nmf::f64::step_block<nmf::f64::W_TERRAIN>(q, g_sm64, f, 0, q.nsteps, false);
-      else nmf::f64::step_block<nmf::f64::W_FLAT>(q, g_sm64, f, 0, q.nsteps, false); });
+    q.queue = sub_steps > 0 ? queue.data() : nullptr; q.sub_steps = sub_steps > 0 ? sub_steps : nsteps; q.n_items = n_items;
+  };
+  if (sub_steps > 0) return -3;    // the work queue needs concurrently running blocks: exercised on the GPU only
+  const int n_blocks = (n_flies + fpb - 1) / fpb;
+  if (precision == 64) {   // the f64 instantiation of the same source (one fly per block)
+    if (fpb != 1) return -2;
+    nmf::StepParamsT<double> q = hm.par64;
+    fill(q, hm.role64.data(), hm.hull64.data());
+    for (int b = 0; b < n_blocks; b++) simt::run_block(nmf::CTA, b, n_blocks, [&]() {
+      if (q.weld) nmf::f64::step_block<nmf::f64::W_TETHER>(q, g_sm64, b, 0, q.nsteps, false);
+      else if (q.terrain) nmf::f64::step_block<nmf::f64::W_TERRAIN>(q, g_sm64, b, 0, q.nsteps, false);
+      else nmf::f64::step_block<nmf::f64::W_FLAT>(q, g_sm64, b, 0, q.nsteps, false); });
     return 0;
   }
-  for (int f = 0; f < n_flies; f++) simt::run_block(nmf::CTA, f, n_flies, [&]() {
-    if (p.weld) nmf::f32::step_block<nmf::f32::W_TETHER>(p, g_sm, f, 0, p.nsteps, false);
-    else if (p.terrain) nmf::f32::step_block<nmf::f32::W_TERRAIN>(p, g_sm, f, 0, p.nsteps, false);
-    else nmf::f32::step_block<nmf::f32::W_FLAT>(p, g_sm, f, 0, p.nsteps, false); });
+  nmf::StepParams p = hm.par;
+  fill(p, hm.role.data(), hm.hull.data());
+  for (int b = 0; b < n_blocks; b++) simt::run_block(nmf::CTA * fpb, b, n_blocks, [&]() {
+    const int slot = threadIdx.x / nmf::CTA; int f = b * fpb + slot; if (f >= n_flies) f = -1;
+    float* sm = g_sm + slot * nmf::f32::SM_TOTAL;
+#define EMU_RUN(W) switch (fpb) { case 1: nmf::f32::step_block<W, 1>(p, sm, f, 0, p.nsteps, false); break; case 2: nmf::f32::step_block<W, 2>(p, sm, f, 0, p.nsteps, false); break; \
+                                  case 4: nmf::f32::step_block<W, 4>(p, sm, f, 0, p.nsteps, false); break; default: nmf::f32::step_block<W, 8>(p, sm, f, 0, p.nsteps, false); }
+    if (p.weld) nmf::f32::step_block<nmf::f32::W_TETHER, 1>(p, sm, f, 0, p.nsteps, false);
+    else if (p.terrain) { EMU_RUN(nmf::f32::W_TERRAIN) }
+    else { EMU_RUN(nmf::f32::W_FLAT) }
+#undef EMU_RUN
+  });
   return 0;
 }

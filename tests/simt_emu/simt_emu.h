@@ -36,6 +36,7 @@ struct Block {
   int cur = 0, nthreads = 0, block_id = 0, grid = 1;
   std::map<uint64_t, Barrier> barriers;
   float slot_f[1024];
+  int or_acc = 0;
   std::function<void()> body;
 };
 
@@ -133,6 +134,18 @@ inline float shfl_from(unsigned mask, float v, int src_lane) {
 #define gridDim (simt::grid_dim())
 
 inline void __syncthreads() { simt::rendezvous(1, simt::blk()->nthreads); }
+// named barrier over `count` threads (PTX bar.sync id, count)
+inline void simt_named_barrier(int id, int count) { simt::rendezvous(0x100 + (uint64_t)id, count); }
+inline int __syncthreads_or(int pred) {
+  simt::Block* b = simt::blk();
+  if (pred) b->or_acc = 1;
+  simt::rendezvous(5, b->nthreads);
+  const int r = b->or_acc;
+  simt::rendezvous(6, b->nthreads);
+  b->or_acc = 0;                      // every thread clears it; nobody sets it again before passing rendezvous 5 of the next call
+  simt::rendezvous(7, b->nthreads);
+  return r;
+}
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
   simt::Block* b = simt::blk();
   int warp = b->cur / 32;

@@ -1,0 +1,217 @@
+"""GPU parity of EVERY quantity the north star names, not only qpos: after 1 and 100 steps from identical state and action
+sequence the CUDA path (through the C ABI) must agree with the fp64 oracle on
+
+  qvel, actuator forces (42 position + 6 adhesion), segment positions / orientations (what get_body_positions / rotations and
+  get_site_positions return), and the per-leg ground-contact sensor (found flag, net force, torque, position)
+
+for the flat world with capsule and with mesh-hull geoms, both terrain worlds and the tethered world.  Reference surface:
+src/flygym/simulation.py:142-256 (getters), compose/world.py:311-331 (sensor definition).  Tolerances (float32 kernel vs float64
+oracle) are written next to each assertion; they are ~5x the errors measured on B200 (profiles/parity_outputs_r02.json).
+PARITY UNPINNED against real MuJoCo (see oracle/nmf_oracle.c)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CHECK = (1, 100)
+
+
+def _worlds():
+    from flygym_b200 import NMFModel
+    return {
+        "flat_capsule": (lambda: NMFModel.bench(True), -0.17, False),
+        "flat_mesh": (lambda: NMFModel.bench(False), -0.17, False),
+        "blocks": (lambda: NMFModel.bench(True, terrain="blocks"), -0.15, True),
+        "gapped": (lambda: NMFModel.bench(True, terrain="gapped"), -0.17, True),
+        "tethered": (lambda: __import__("flygym_b200").NMFModel.tethered(), None, False),
+    }
+
+
+def _stance_adhesion(model, n, T):
+    from flygym_b200.actions import TRIPOD_PHASE
+    t = np.arange(T) * model.timestep
+    legph = np.array([TRIPOD_PHASE[l] for l in model.names["legs"]])
+    psi = 2 * np.pi * np.arange(n) / n
+    return np.where(np.sin(2 * np.pi * 12.0 * t[None, :, None] + psi[:, None, None] + legph[None, None, :]) < 0, 100.0, 1.0)
+
+
+def run_world(wname, precision=32, check=CHECK):
+    """-> {checkpoint: {quantity: [per-case error]}} for the standing fly + 4 CPG walkers of one world."""
+    import torch
+    from flygym_b200 import B200Simulation
+    from flygym_b200.actions import cpg_table
+    from oracle.oracle import Oracle
+    make, stand_z, stance = _worlds()[wname]
+    model = make()
+    T = max(check)
+    nu_pos, nu = model.dim("nu_pos"), model.nu
+    key = model.arrays["key_qpos"].copy()
+    stand = key.copy()
+    if stand_z is not None:
+        stand[2] = stand_z
+    cpg = cpg_table(model, 4, T).astype(np.float64)
+    hold = np.tile(model.arrays["key_ctrl"][:nu_pos], (T, 1))
+    adh_on = np.ones((T, 6))
+    adh_st = _stance_adhesion(model, 4, T)
+    cases = [(stand, hold, adh_on)]
+    for k in range(4):
+        q0 = stand + np.r_[0.35 * k, 0.22 * k, np.zeros(model.nq - 2)] * (stand_z is not None)
+        cases.append((q0, cpg[k], adh_st[k] if stance else adh_on))
+    n = len(cases)
+    sim = B200Simulation(model, n_worlds=n, outputs=True)
+    sim.set_precision(precision)
+    tab = np.zeros((n, T, nu), np.float32)
+    for i, (q0, pos, adh) in enumerate(cases):
+        sim.qpos[i].copy_(torch.as_tensor(q0, dtype=torch.float32))
+        tab[i, :, :nu_pos] = pos; tab[i, :, nu_pos:] = adh
+    tabd = torch.from_numpy(tab).cuda()
+    got, done = {}, 0
+    for cp in check:
+        sim.step(cp - done, tabd, done); done = cp
+        f64 = lambda t: t.cpu().numpy().astype(np.float64)
+        got[cp] = dict(qpos=f64(sim.qpos), qvel=f64(sim.qvel), actf=f64(sim.act_force), xpos=f64(sim.seg_xpos), xquat=f64(sim.seg_xquat),
+                       sens=f64(sim.sensordata).reshape(n, 6, 16))
+    errs = {cp: {} for cp in check}
+    for i, (q0, pos, adh) in enumerate(cases):
+        o = Oracle(model); o.reset(); o.qpos[:] = q0
+        done = 0
+        for cp in check:
+            o.step_table_full(tab[i, done:cp].astype(np.float64)); done = cp
+            g = got[cp]
+            e = errs[cp]
+            def add(k, v): e.setdefault(k, []).append(float(v))
+            qv = o.qvel.copy()
+            add("qpos_rel", np.abs(g["qpos"][i] - o.qpos).max() / np.abs(o.qpos).max())
+            add("qvel_rel", np.abs(g["qvel"][i] - qv).max() / max(1.0, np.abs(qv).max()))
+            af = o.get("actuator_force").copy()
+            add("actf_abs", np.abs(g["actf"][i] - af).max())
+            add("xpos_abs", np.abs(g["xpos"][i] - o.get("seg_xpos").reshape(-1, 3)).max())
+            oq = o.get("seg_xquat").reshape(-1, 4)
+            sgn = np.sign((g["xquat"][i] * oq).sum(1, keepdims=True))        # q and -q are the same rotation
+            add("xquat_abs", np.abs(g["xquat"][i] * sgn - oq).max())
+            so, sg = o.get("sensordata").reshape(6, 16).copy(), g["sens"][i]
+            add("found_mismatch", np.abs(sg[:, 0] - so[:, 0]).max())
+            both = (so[:, 0] > 0) & (sg[:, 0] > 0)
+            fmax = max(1.0, np.abs(so[:, 1:4]).max())
+            add("force_rel", np.abs(sg[:, 1:4] - so[:, 1:4]).max() / fmax)
+            add("torque_rel", np.abs(sg[:, 4:7] - so[:, 4:7]).max() / fmax)          # uN mm against uN: lever arms are O(0.1 mm)
+            add("pos_abs", np.abs(sg[both, 7:10] - so[both, 7:10]).max() if both.any() else 0.0)
+            add("frame_abs", np.abs(sg[:, 10:16] - so[:, 10:16]).max())
+            add("ncon", o.dim("ncon"))
+    return errs
+
+
+@pytest.mark.parametrize("wname", ["flat_capsule", "flat_mesh", "blocks", "gapped", "tethered"])
+def test_every_output_matches_the_oracle(wname):
+    errs = run_world(wname)
+    e1, e100 = errs[1], errs[100]
+    print(wname, {cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    has_ground = wname != "tethered"
+    if has_ground:
+        assert max(e1["ncon"]) >= 6                       # the scenario really exercises the contact solver
+    # ---- one step: pure arithmetic differences of one pass through the pipeline
+    assert max(e1["qpos_rel"]) < 1e-6
+    assert max(e1["qvel_rel"]) < 5e-4                      # measured <= 1e-4 (tethered: the weld snaps the thorax at ~1e4 mm/s)
+    assert max(e1["actf_abs"]) < 1e-4                      # uN, on forces up to 30 uN
+    assert max(e1["xpos_abs"]) < 2e-6 and max(e1["xquat_abs"]) < 2e-6          # mm / unit quaternion components
+    assert max(e1["found_mismatch"]) == 0 and max(e1["frame_abs"]) == 0
+    assert max(e1["force_rel"]) < 5e-5 and max(e1["torque_rel"]) < 5e-5         # measured ~5e-6 of the largest leg force (40-180 uN)
+    assert max(e1["pos_abs"]) < 1e-5
+    # ---- 100 steps: the standing fly (case 0) and the walkers stay together; a walker on the terrain worlds may resolve an
+    # edge contact one step apart in fp32 and fp64, hence the median there
+    worst = max if wname in ("flat_capsule", "flat_mesh", "tethered") else np.median
+    assert worst(e100["qpos_rel"]) < 1e-4
+    assert worst(e100["qvel_rel"]) < 1e-3
+    assert worst(e100["actf_abs"]) < 2e-3
+    assert worst(e100["xpos_abs"]) < 1e-4 and worst(e100["xquat_abs"]) < 1e-4
+    assert worst(e100["found_mismatch"]) == 0
+    assert worst(e100["force_rel"]) < 1e-3 and worst(e100["torque_rel"]) < 1e-3
+    assert worst(e100["pos_abs"]) < 1e-3
+    for k in ("qpos_rel", "qvel_rel", "force_rel"):        # the standing fly is not chaotic in any world
+        assert e100[k][0] < 1e-3, k
+
+
+def test_every_output_matches_the_oracle_in_double_precision():
+    """The f64 instantiation of the kernel source: the same comparison at the resolution of the float32 buffers the API exposes."""
+    errs = run_world("flat_capsule", precision=64)
+    print({cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    for cp in CHECK:
+        e = errs[cp]
+        assert max(e["qpos_rel"]) < 2e-7 and max(e["qvel_rel"]) < 2e-7
+        assert max(e["actf_abs"]) < 5e-6 and max(e["xpos_abs"]) < 5e-7 and max(e["xquat_abs"]) < 2e-7
+        assert max(e["found_mismatch"]) == 0 and max(e["force_rel"]) < 5e-7 and max(e["torque_rel"]) < 5e-7 and max(e["pos_abs"]) < 5e-7
+
+
+def test_getters_return_the_oracle_values_in_fly_order():
+    """get_body_positions / get_body_rotations / get_site_positions / get_actuator_forces / get_ground_contact_info through the
+    public class (reference simulation.py:168-256), values against the oracle after 20 standing steps."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel, ActuatorType
+    from oracle.oracle import Oracle
+    model = NMFModel.bench(True)
+    sim = B200Simulation(model, n_worlds=2)
+    start = model.arrays["key_qpos"].copy(); start[2] = -0.17
+    sim.qpos.copy_(torch.as_tensor(np.tile(start, (2, 1)), dtype=torch.float32))
+    sim.set_leg_adhesion_states("nmf", np.ones((2, 6), np.float32))
+    sim.step(20)
+    o = Oracle(model); o.reset(); o.qpos[:] = start; o.ctrl[42:] = 1.0; o.step(20)
+    pos = sim.get_body_positions("nmf")[0].cpu().numpy()
+    assert np.abs(pos - o.get("seg_xpos").reshape(-1, 3)).max() < 1e-5
+    rot = sim.get_body_rotations("nmf")[0].cpu().numpy(); oq = o.get("seg_xquat").reshape(-1, 4)
+    assert np.abs(rot * np.sign((rot * oq).sum(1, keepdims=True)) - oq).max() < 1e-5
+    sites = sim.get_site_positions("nmf")[0].cpu().numpy()
+    assert np.abs(sites - o.get("site_xpos").reshape(-1, 3)).max() < 1e-5
+    af = o.get("actuator_force")
+    assert np.abs(sim.get_actuator_forces("nmf", ActuatorType.POSITION)[0].cpu().numpy() - af[:42]).max() < 1e-3
+    assert np.abs(sim.get_actuator_forces("nmf", ActuatorType.ADHESION)[0].cpu().numpy() - af[42:]).max() < 1e-6
+    found, force, torque, cpos, normal, tangent = (t[0].cpu().numpy() for t in sim.get_ground_contact_info("nmf"))
+    so = o.get("sensordata").reshape(6, 16)
+    assert np.array_equal(found, so[:, 0]) and found.sum() == 6
+    assert np.abs(force - so[:, 1:4]).max() < 1e-3 * np.abs(so[:, 1:4]).max()
+    assert np.abs(torque - so[:, 4:7]).max() < 1e-3 * np.abs(so[:, 1:4]).max()
+    assert np.abs(cpos - so[:, 7:10]).max() < 1e-4
+    assert np.array_equal(normal, so[:, 10:13]) and np.array_equal(tangent, so[:, 13:16])
+
+
+def test_status_word_reports_device_faults_per_fly():
+    """SURVEY 8b error convention: NaN / solver-cap faults are reported through a per-fly status word, never by trapping; the
+    word is sticky until that fly is reset and faults of one fly do not leak into its neighbours."""
+    import torch
+    from flygym_b200 import B200Simulation
+    sim = B200Simulation(None, n_worlds=6, outputs=False)
+    start = sim.qpos.clone(); start[:, 2] = -0.17
+    sim.qpos.copy_(start)
+    sim.step(20)
+    assert int(sim.status.abs().max()) == 0
+    sim.qvel[3, 17] = float("nan")                         # inject a fault into world 3 only
+    sim.step(3)
+    st = sim.status.cpu().numpy()
+    assert st[3] & sim.ST_NONFINITE and not (np.delete(st, 3) & sim.ST_NONFINITE).any()
+    assert torch.isfinite(sim.qpos[[0, 1, 2, 4, 5]]).all()
+    sim.reset(mask=[False, False, False, True, False, False])
+    sim.step(2)
+    assert int(sim.status.abs().max()) == 0 and bool(torch.isfinite(sim.state).all())
+    sim.set_solver(1, 50)                                  # one Newton iteration is not enough once contacts switch
+    sim.qpos.copy_(start); sim.qvel.zero_()
+    sim.step(30)
+    assert (sim.status.cpu().numpy() & sim.ST_NEWTON_CAP).any()
+    sim.set_solver(100, 1)
+    sim.reset(); sim.qpos.copy_(start)
+    sim.step(30)
+    assert (sim.status.cpu().numpy() & sim.ST_LS_CAP).any()
+
+
+def test_energy_output_matches_the_oracle():
+    """`energy` flag of the reference model (mujoco_globals.yaml:19): potential and kinetic energy of every world."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from oracle.oracle import Oracle
+    model = NMFModel.bench(True)
+    sim = B200Simulation(model, n_worlds=3)
+    q0 = np.tile(model.arrays["key_qpos"], (3, 1)); q0[:, 2] = [-0.17, 0.3, 0.8]
+    sim.qpos.copy_(torch.as_tensor(q0, dtype=torch.float32))
+    sim.step(40)
+    e = sim.get_energy().cpu().numpy()
+    for i in range(3):
+        o = Oracle(model); o.reset(); o.qpos[:] = q0[i]; o.step(40)
+        assert np.abs(e[i] - o.get("energy")).max() < 1e-4 * np.abs(o.get("energy")).max(), (i, e[i], o.get("energy"))
