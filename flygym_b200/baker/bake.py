@@ -304,7 +304,8 @@ def bake(
     opt = dict(timestep=float(o["timestep"]), gx=float(o["gravity"][0]), gy=float(o["gravity"][1]),
                gz=float(o["gravity"][2]), iterations=float(o["iterations"]), tolerance=1e-8,
                ls_iterations=50.0, ls_tolerance=0.01, noslip_iterations=float(noslip_iterations),
-               meaninertia=0.0, impratio=1.0)
+               meaninertia=0.0, impratio=1.0,
+               multiccd=1.0 if str(glob.get("option", {}).get("flag", {}).get("multiccd", "disable")) == "enable" else 0.0)
     contact = dict(mu=sliding_friction, solref0=solref[0], solref1=solref[1], solimp0=solimp[0],
                    solimp1=solimp[1], solimp2=solimp[2], solimp3=solimp[3], solimp4=solimp[4],
                    margin=margin, gap=0.0)

@@ -32,6 +32,15 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_TERRAIN) nmf_ste
 extern "C" __global__ void __launch_bounds__(2 * CTA, NMF_MINBLOCKS_TERRAIN / 2) nmf_step_terrain_x2_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 2>(p); }
 extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS_TERRAIN / 4) nmf_step_terrain_x4_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 4>(p); }
 extern "C" __global__ void __launch_bounds__(8 * CTA, NMF_MINBLOCKS_TERRAIN / 8) nmf_step_terrain_x8_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 8>(p); }
+// flat world with convex-hull geoms and the `multiccd` flag: four contact slots per lane (up to 4 plane-hull contacts per geom).
+// 40 of the 64 registers would be contact slots, so these run at 80 registers / 3 blocks of 4 flies per SM
+#ifndef NMF_MINBLOCKS_MESH
+#define NMF_MINBLOCKS_MESH 12
+#endif
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_MESH) nmf_step_mesh_kernel(const StepParams p) { f32::step_entry<f32::W_MESH>(p); }
+extern "C" __global__ void __launch_bounds__(2 * CTA, NMF_MINBLOCKS_MESH / 2) nmf_step_mesh_x2_kernel(const StepParams p) { f32::step_entry<f32::W_MESH, 2>(p); }
+extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS_MESH / 4) nmf_step_mesh_x4_kernel(const StepParams p) { f32::step_entry<f32::W_MESH, 4>(p); }
+extern "C" __global__ void __launch_bounds__(8 * CTA, (NMF_MINBLOCKS_MESH + 7) / 8) nmf_step_mesh_x8_kernel(const StepParams p) { f32::step_entry<f32::W_MESH, 8>(p); }
 // TetheredWorld (reference world.py:334-366): no ground contacts, six weld rows on the free body
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether_kernel(const StepParams p) { f32::step_entry<f32::W_TETHER>(p); }
 // fp64 instantiations of the same source: a validation build (nmf_set_precision(h, 64)), not a product path -- every
@@ -42,6 +51,13 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_mesh_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_MESH>(p); }
+// with the noslip post-solver of the reference's CPU path (mujoco_globals.yaml:15; selected by the blob's noslip_iterations > 0):
+// the `Simulation` (MuJoCo, float64) semantics, where `GPUSimulation` strips noslip (warp/simulation.py:427-448)
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_mesh_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_MESH, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 1, true>(p); }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
   int fly = blockIdx.x;
@@ -88,7 +104,7 @@ struct nmf_handle {
   std::string err;
 };
 
-constexpr int QUEUE_MAX_CHUNKS = 16;   // sub-chunks per fly and launch the queue buffer is sized for
+constexpr int QUEUE_MAX_CHUNKS = 64;   // sub-chunks per fly and launch the queue buffer is sized for
 
 // every entry point that touches the device runs on the handle's device and leaves the caller's current device as it found it
 struct DeviceGuard {
@@ -195,7 +211,7 @@ extern "C" int nmf_set_schedule(nmf_handle* h, int sub_steps) {
 
 extern "C" int nmf_set_flies_per_block(nmf_handle* h, int fpb) {
   if (!h || (fpb != 0 && fpb != 1 && fpb != 2 && fpb != 4 && fpb != 8)) return NMF_EINVAL;
-  h->fpb = h->hm.par.weld ? 1 : fpb;
+  h->fpb = (h->hm.par.weld || h->hm.par.noslip_iterations > 0) ? 1 : fpb;
   return NMF_OK;
 }
 
@@ -210,8 +226,11 @@ extern "C" int nmf_forward(nmf_handle* h, void* stream) { return launch_steps(h,
 
 template <class real> struct KernelSet;
 typedef void (*step_kernel_f32)(const StepParams);
-static step_kernel_f32 kernel_f32(bool weld, bool terrain, int fpb) {
+static step_kernel_f32 kernel_f32(const StepParams& q, int fpb) {
+  const bool weld = q.weld, terrain = q.terrain;
   if (weld) return nmf_step_tether_kernel;
+  if (q.noslip_iterations > 0) return nmf_step_noslip_kernel;       // flat world with capsule geoms only (checked in launch_steps)
+  if (q.multiccd) return fpb == 8 ? nmf_step_mesh_x8_kernel : fpb == 4 ? nmf_step_mesh_x4_kernel : fpb == 2 ? nmf_step_mesh_x2_kernel : nmf_step_mesh_kernel;
   if (terrain) return fpb == 8 ? nmf_step_terrain_x8_kernel : fpb == 4 ? nmf_step_terrain_x4_kernel : fpb == 2 ? nmf_step_terrain_x2_kernel : nmf_step_terrain_kernel;
   return fpb == 8 ? nmf_step_x8_kernel : fpb == 4 ? nmf_step_x4_kernel : fpb == 2 ? nmf_step_x2_kernel : nmf_step_kernel;
 }
@@ -221,11 +240,11 @@ static int set_resident_blocks(nmf_handle* h) {
   DeviceGuard guard(h->device);
   CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
   for (int fpb = 1; fpb <= 8; fpb *= 2) {
-    if (h->hm.par.weld && fpb > 1) break;
+    if ((h->hm.par.weld || h->hm.par.noslip_iterations > 0) && fpb > 1) break;
     int per_sm = 0;
     const size_t dyn = dyn_smem_f32(fpb);
-    if (dyn) CK(cudaFuncSetAttribute(kernel_f32(h->hm.par.weld, h->hm.par.terrain, fpb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_f32(h->hm.par.weld, h->hm.par.terrain, fpb), CTA * fpb, dyn));
+    if (dyn) CK(cudaFuncSetAttribute(kernel_f32(h->hm.par, fpb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_f32(h->hm.par, fpb), CTA * fpb, dyn));
     h->resident[fpb] = per_sm * h->sms;
   }
   return NMF_OK;
@@ -233,7 +252,7 @@ static int set_resident_blocks(nmf_handle* h) {
 // fly slots per block for a launch over n flies: the handle's setting, or the largest block that still gives every SM one
 // (sharing instruction fetches among the slots of a block is worth more than spreading a small batch thinly)
 static int pick_fpb(const nmf_handle* h, int n) {
-  if (h->hm.par.weld) return 1;
+  if (h->hm.par.weld || h->hm.par.noslip_iterations > 0) return 1;
   if (h->fpb) return h->fpb;
   for (int fpb = 8; fpb > 1; fpb /= 2) if (n >= fpb * h->sms) return fpb;
   return 1;
@@ -244,7 +263,7 @@ template <> struct KernelSet<float> {
   static const float* hull(const nmf_handle* h) { return h->d_hull; }
   static int fpb(const nmf_handle* h, int n) { return pick_fpb(h, n); }
   static void launch(const StepParamsT<float>& p, int fpb, int grid, cudaStream_t s) {
-    kernel_f32(p.weld, p.terrain, fpb)<<<grid, CTA * fpb, dyn_smem_f32(fpb), s>>>(p);
+    kernel_f32(p, fpb)<<<grid, CTA * fpb, dyn_smem_f32(fpb), s>>>(p);
   }
 };
 template <> struct KernelSet<double> {
@@ -254,6 +273,10 @@ template <> struct KernelSet<double> {
   static int fpb(const nmf_handle*, int) { return 1; }
   static void launch(const StepParamsT<double>& p, int, int grid, cudaStream_t s) {
     if (p.weld) nmf_step_tether_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.noslip_iterations > 0 && p.multiccd) nmf_step_mesh_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.noslip_iterations > 0 && p.terrain) nmf_step_terrain_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.noslip_iterations > 0) nmf_step_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.multiccd) nmf_step_mesh_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.terrain) nmf_step_terrain_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else nmf_step_f64_kernel<<<grid, CTA, 0, s>>>(p);
   }
@@ -291,11 +314,11 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   p.queue = nullptr; p.sub_steps = nsteps; p.n_items = n_units;
   int sub = h->sub_steps;
   if (sub < 0) {
-    // ~25 steps per item: measured on B200 (profiles/queue_sweep_r01.txt) an item costs ~0.6 step of fixed overhead (its
-    // set-up code and constants are cold in the instruction / L1 caches), while items of 50+ steps leave a visible tail.
-    // Short launches (14 .. 37 steps) are still cut in two: without items they are one partial wave.
-    int k = (nsteps + 12) / 25;
-    if (k < 2 && nsteps >= 14) k = 2;
+    // ~8 steps per item.  Measured on B200 with 8 flies per block (profiles/queue_sweep_r02.txt, 4096 flies): a 20-step launch
+    // runs at 20.9 / 24.0 / 23.9 / 22.2 M env-steps/s with no queue / items of 3 / 7 / 10 steps, a 100-step launch at
+    // 21.7 / 25.1 / 24.6 / 22.7 M with no queue / 10 / 25 / 50: a block's fixed cost per item (record load, set-up code) is
+    // small next to the empty slots that long items leave in the last wave.
+    const int k = (nsteps + 7) / 8;
     sub = k >= 2 ? (nsteps + k - 1) / k : 0;
   }
   // more units than resident blocks: work queue (one per handle; sized for the f32 kernels' occupancy, so f32 only)
@@ -322,6 +345,12 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
   DeviceGuard guard(h->device);
   if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
     h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
+  }
+  if (h->hm.par.noslip_iterations > 0 && h->hm.par.weld) {
+    h->err = "nmf_step: noslip_iterations > 0 is not implemented for the tethered world (its weld rows would join the noslip sweeps)"; return NMF_EINVAL;
+  }
+  if (h->hm.par.noslip_iterations > 0 && h->precision != 64 && (h->hm.par.terrain || h->hm.par.multiccd)) {
+    h->err = "nmf_step: noslip on terrain / mesh-hull worlds needs nmf_set_precision(h, 64) (float32 noslip is built for the flat capsule world only)"; return NMF_EINVAL;
   }
   return h->precision == 64 ? launch_steps_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count)
                             : launch_steps_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count);

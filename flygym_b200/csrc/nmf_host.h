@@ -74,7 +74,8 @@ inline StepParams narrow(const StepParamsT<double>& d) {
   f.dt = (float)d.dt; f.gx = (float)d.gx; f.gy = (float)d.gy; f.gz = (float)d.gz; f.inv_total_mass = (float)d.inv_total_mass;
   f.mu = (float)d.mu; f.cK = (float)d.cK; f.cB = (float)d.cB; f.margin = (float)d.margin; f.impratio = (float)d.impratio;
   for (int i = 0; i < 5; i++) { f.solimp[i] = (float)d.solimp[i]; f.weld_imp[i] = (float)d.weld_imp[i]; }
-  f.max_newton = d.max_newton; f.max_ls = d.max_ls; f.terrain = d.terrain; f.weld = d.weld;
+  f.max_newton = d.max_newton; f.max_ls = d.max_ls; f.terrain = d.terrain; f.weld = d.weld; f.multiccd = d.multiccd;
+  f.noslip_iterations = d.noslip_iterations; f.noslip_tol = (float)d.noslip_tol; f.noslip_scale = (float)d.noslip_scale;
   for (int i = 0; i < 8; i++) f.terr[i] = (float)d.terr[i];
   for (int i = 0; i < 3; i++) f.weld_a[i] = (float)d.weld_a[i];
   for (int i = 0; i < 4; i++) f.weld_q[i] = (float)d.weld_q[i];
@@ -156,7 +157,7 @@ struct HostModel {
         set(RF_MASS, tid, 0.f);
         for (int i = 0; i < 6; i++) set(RF_IB + i, tid, 0.f);
       }
-      seti(RF_GTYPE, tid, -1); seti(RF_ADH_CIDX, tid, -1);
+      seti(RF_GTYPE, tid, -1); seti(RF_ADH_CIDX, tid, -1); seti(RF_GIDX, tid, 1 << 20);
       for (int j = 0; j < 3; j++) seti(RF_CIDX + j, tid, -1);
       if (bb > 0) {
         seti(RF_NDOF, tid, dofnum[bb]); seti(RF_DOF0, tid, dofadr[bb]);
@@ -203,7 +204,7 @@ struct HostModel {
       double Rm[9]; q2mat_d(gquat + 4 * g, Rm);
       for (int i = 0; i < 3; i++) { set(RF_GPOS + i, tid, gpos[3 * g + i]); set(RF_GAXIS + i, tid, Rm[3 * i + 2]); }
       set(RF_GRAD, tid, gsize[2 * g]); set(RF_GHALF, tid, gsize[2 * g + 1]);
-      seti(RF_GVADR, tid, gvadr[g]); seti(RF_GVNUM, tid, gvnum[g]);
+      seti(RF_GVADR, tid, gvadr[g]); seti(RF_GVNUM, tid, gvnum[g]); seti(RF_GIDX, tid, g);
     }
     hull64.assign((size_t)3 * (nhv > 0 ? nhv : 1), 0.0);
     for (int i = 0; i < 3 * nhv; i++) hull64[i] = hv[i];
@@ -248,6 +249,15 @@ struct HostModel {
     P.solimp[0] = clampimp(contact[3]); P.solimp[1] = dmax; P.solimp[2] = std::fmax(0.0, contact[5]);
     P.solimp[3] = clampimp(contact[6]); P.solimp[4] = std::fmax(1.0, contact[7]);
     P.margin = (contact[8] - contact[9]);
+    {   // `multiccd` flag of the reference model (mujoco_globals.yaml:18): opt[11] when the blob carries it; it only matters for hull geoms
+      int nopt = 0; b.get<double>("opt", &nopt);
+      bool hulls = false;
+      for (int g = 0; g < ngeom; g++) hulls = hulls || geom_type[g] == 1;
+      P.multiccd = (hulls && nopt > 11 && opt[11] != 0.0) ? 1 : 0;
+    }
+    P.noslip_iterations = (int)opt[8] > 0 ? (int)opt[8] : 0;
+    P.noslip_tol = 1e-6;                                  // MuJoCo default; the reference does not set it
+    P.noslip_scale = 1.0 / ((opt[9] > 0 ? opt[9] : 1.0) * NV);
     P.max_newton = (int)opt[4]; P.max_ls = (int)opt[6]; P.nsteps = 1;   // reference: iterations=100 (mujoco_globals.yaml:14), ls_iterations=50 (MuJoCo default)
     if (P.max_newton < 1) P.max_newton = 100;
     if (P.max_ls < 1) P.max_ls = 50;

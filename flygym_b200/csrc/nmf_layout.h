@@ -30,6 +30,7 @@ constexpr int S_TIME = 300;     // time, status word, steps since reset, pad
 constexpr int ST_NONFINITE = 1;   // a velocity became NaN / infinite
 constexpr int ST_NEWTON_CAP = 2;  // the Newton solver hit its iteration cap with the active set still changing
 constexpr int ST_LS_CAP = 4;      // a line search used up its evaluation cap
+constexpr int ST_NOSLIP_SKIP = 8; // more simultaneous contacts than the noslip pass handles: the step ran without it
 constexpr int S_STRIDE = 304;
 
 // thread-role constant table: role[field * CTA + tid]
@@ -66,7 +67,8 @@ enum RoleField {
   RF_LEGSENSOR = 71,      // int: 1 if this body's contacts count for the leg contact sensor
   RF_CARM = 72,           // 3: armature of the lane's matrix-column DoFs (leg dof t-6 | t+2 | 10); 1 on hub chains
   RF_CDMP = 75,           // 3: damping of the same DoFs
-  RF_COUNT = 78
+  RF_GIDX = 78,           // int: index of the lane's contact geom in the model's geom order (contact order of the noslip sweeps)
+  RF_COUNT = 79
 };
 
 // debug dump (floats per fly), only written when a dump buffer is passed
@@ -75,8 +77,9 @@ constexpr int DBG_FS = 4;                    // qfrc_smooth[72]
 constexpr int DBG_QACC = DBG_FS + NV;        // qacc[72]
 constexpr int DBG_FC = DBG_QACC + NV;        // qfrc_constraint[72]
 constexpr int DBG_QACCE = DBG_FC + NV;       // Euler (implicit-damping) acceleration[72]
-constexpr int DBG_CON = DBG_QACCE + NV;      // per thread, 2 slots x (active, dist, x, y, z, fn) = 12
-constexpr int DBG_XPOS = DBG_CON + CTA * 12; // per thread xpos (3)
+constexpr int DBG_NSLOT = 4;                 // contact slots per thread in the dump (the capsule kernels fill the first two)
+constexpr int DBG_CON = DBG_QACCE + NV;      // per thread, DBG_NSLOT slots x (active, dist, x, y, z, fn)
+constexpr int DBG_XPOS = DBG_CON + CTA * DBG_NSLOT * 6; // per thread xpos (3)
 constexpr int DBG_CDOF = DBG_XPOS + CTA * 3; // cdof[72][6]
 constexpr int DBG_HROWS = DBG_CDOF + NV * 6; // Euler matrix rows: 6 legs x 177, then 21 base
 constexpr int DBG_STRIDE = DBG_HROWS + NLEG * 177 + 21 + 3;
@@ -107,6 +110,9 @@ struct StepParamsT {
   real mu, cK, cB, margin, impratio;
   real solimp[5];           // sanitised: d0, dmax, width, midpoint, power
   int max_newton, max_ls;
+  int noslip_iterations;     // sweeps of the noslip post-solver (NOSLIP kernel instantiations; mujoco_globals.yaml:15), 0 = off
+  real noslip_tol, noslip_scale;   // MuJoCo's noslip_tolerance (1e-6) and the cost scale 1 / (meaninertia * nv)
+  int multiccd;              // 1: plane-hull contacts also at the support vertex's neighbours within the margin (W_MESH kernels)
   // terrain: 0 = ground plane z = 0 (FlatGroundWorld); 1 = floor plane + grid of box columns, terr = {Px, Py, hx, hy, top_even,
   // top_odd, z_floor, 0}: column (i, j) covers |x - i Px| <= hx, |y - j Py| <= hy, z <= top_{(i+j)&1}
   int terrain;

@@ -162,11 +162,17 @@ __device__ __forceinline__ void finish_contact(const SP& p, Contact& c, real act
 }
 
 // geom-vs-ground-plane narrow phase for the geom carried by this lane's body
-// (plane z = 0, normal +z: reference world.py:251-260).  Fills two slots.
+// (plane z = 0, normal +z: reference world.py:251-260).  Fills NSLOT slots: a capsule uses two (its end spheres); a convex
+// hull uses one (the support vertex) when NSLOT = 2 and up to four when NSLOT = 4 -- [PRIOR] mjc_PlaneConvex on a mesh with the
+// `multiccd` flag (mujoco_globals.yaml:18): the neighbours of the support vertex in the hull's vertex graph that are also
+// within the margin become contacts too, in graph order, up to 4 per geom.
+template <int NSLOT>
 __device__ __forceinline__ real collide(const SP& p, const real* role, int tid, const real* xpos, const real* R,
                                          const real* com, const real* cvel, real invw, Contact* con, int& hullv) {
   const int gtype = role_int(role[RF_GTYPE * CTA + tid]);
-  real pos0[3] = {real(0.), real(0.), real(0.)}, pos1[3] = {real(0.), real(0.), real(0.)}, d0 = real(1.), d1 = real(1.), a0 = real(0.), a1 = real(0.), hx = real(0.), hy = real(1.);
+  real pos[NSLOT][3], dist[NSLOT], act[NSLOT], hx = real(0.), hy = real(1.);
+#pragma unroll
+  for (int s = 0; s < NSLOT; s++) { pos[s][0] = pos[s][1] = pos[s][2] = real(0.); dist[s] = real(1.); act[s] = real(0.); }
   {  // capsule: two sphere-plane tests, frame aligned with the capsule axis (evaluated on every lane, masked by type)
     real gp[3] = {role[(RF_GPOS + 0) * CTA + tid], role[(RF_GPOS + 1) * CTA + tid], role[(RF_GPOS + 2) * CTA + tid]};
     real ga[3] = {role[(RF_GAXIS + 0) * CTA + tid], role[(RF_GAXIS + 1) * CTA + tid], role[(RF_GAXIS + 2) * CTA + tid]};
@@ -183,22 +189,25 @@ __device__ __forceinline__ real collide(const SP& p, const real* role, int tid, 
     if (cap) { hx = hn2 < real(1e-24) ? real(1.) : a[0] * inv; hy = hn2 < real(1e-24) ? real(0.) : a[1] * inv; }
     real e0 = c[2] + half * a[2], e1 = c[2] - half * a[2];
     if (cap) {
-      d0 = e0 - rad; d1 = e1 - rad;
-      pos0[0] = c[0] + half * a[0]; pos0[1] = c[1] + half * a[1]; pos0[2] = real(0.5) * d0;
-      pos1[0] = c[0] - half * a[0]; pos1[1] = c[1] - half * a[1]; pos1[2] = real(0.5) * d1;
-      a0 = (e0 <= p.margin + rad) ? real(1.) : real(0.); a1 = (e1 <= p.margin + rad) ? real(1.) : real(0.);
+      dist[0] = e0 - rad; dist[1] = e1 - rad;
+      pos[0][0] = c[0] + half * a[0]; pos[0][1] = c[1] + half * a[1]; pos[0][2] = real(0.5) * dist[0];
+      pos[1][0] = c[0] - half * a[0]; pos[1][1] = c[1] - half * a[1]; pos[1][2] = real(0.5) * dist[1];
+      act[0] = (e0 <= p.margin + rad) ? real(1.) : real(0.); act[1] = (e1 <= p.margin + rad) ? real(1.) : real(0.);
     }
   }
   if (gtype == 1) {
     // convex hull: deepest vertex = support point along -z.  Steepest-descent walk on the hull's vertex graph, warm-started
     // from the previous step's support vertex (exact: on a convex polytope a vertex with no lower neighbour is the global
-    // minimum of a linear function).  Lane-dependent trip count: the warp reconverges below.
+    // minimum of a linear function).  Lane-dependent trip count: the warp reconverges below.  The last sweep of the walk has
+    // looked at every neighbour of the support vertex, which is where the extra (multiccd) contacts are picked up.
     const int adr = role_int(role[RF_GVADR * CTA + tid]), num = role_int(role[RF_GVNUM * CTA + tid]);
     int bi = hullv < num ? hullv : 0;
     real best = real(3.0e38);
     if (num > 0) { const real* hv = p.hull + 3 * (adr + bi); best = R[6] * __ldg(hv) + R[7] * __ldg(hv + 1) + R[8] * __ldg(hv + 2); }
+    int extra[NSLOT > 2 ? NSLOT - 1 : 1], nextra = 0;
+    const real zlim = p.margin - xpos[2];       // a vertex with R[2,:] . v <= zlim lies within the margin of the plane
     for (int moved = num > 0; moved;) {
-      moved = 0;
+      moved = 0; nextra = 0;
       const int n0 = __ldg(p.hull_nbr_adr + adr + bi), n1 = __ldg(p.hull_nbr_adr + adr + bi + 1);
       int cand = bi;
       for (int e = n0; e < n1; e++) {
@@ -206,22 +215,35 @@ __device__ __forceinline__ real collide(const SP& p, const real* role, int tid, 
         const real* hv = p.hull + 3 * (adr + v);
         real z = R[6] * __ldg(hv) + R[7] * __ldg(hv + 1) + R[8] * __ldg(hv + 2);
         if (z < best) { best = z; cand = v; moved = 1; }
+        if (NSLOT > 2 && z <= zlim && nextra < NSLOT - 1) {
+#pragma unroll
+          for (int q = 0; q < NSLOT - 1; q++) if (q == nextra) extra[q] = v;
+          nextra++;
+        }
       }
       bi = cand;
     }
     hullv = bi;
-    const real* hv = p.hull + 3 * (adr + bi);
-    real h0 = __ldg(hv), h1 = __ldg(hv + 1), h2 = __ldg(hv + 2);
-    d0 = best + xpos[2];
-    pos0[0] = xpos[0] + R[0] * h0 + R[1] * h1 + R[2] * h2;
-    pos0[1] = xpos[1] + R[3] * h0 + R[4] * h1 + R[5] * h2;
-    pos0[2] = real(0.5) * d0;
-    a0 = (num > 0 && d0 <= p.margin) ? real(1.) : real(0.);
+    if (!(NSLOT > 2 && p.multiccd)) nextra = 0;
+#pragma unroll
+    for (int s = 0; s < (NSLOT > 2 ? NSLOT : 1); s++) {
+      const int v = s == 0 ? bi : extra[s - 1];
+      const bool on = num > 0 && (s == 0 || s - 1 < nextra);
+      const real* hv = p.hull + 3 * (adr + (on ? v : 0));
+      real h0 = __ldg(hv), h1 = __ldg(hv + 1), h2 = __ldg(hv + 2);
+      const real d = xpos[2] + R[6] * h0 + R[7] * h1 + R[8] * h2;
+      dist[s] = on ? d : real(1.);
+      pos[s][0] = xpos[0] + R[0] * h0 + R[1] * h1 + R[2] * h2;
+      pos[s][1] = xpos[1] + R[3] * h0 + R[4] * h1 + R[5] * h2;
+      pos[s][2] = real(0.5) * dist[s];
+      act[s] = (on && dist[s] <= p.margin) ? real(1.) : real(0.);
+    }
   }
   __syncwarp(NMF_FULL);
-  finish_contact(p, con[0], a0, d0, pos0, hx, hy, com, cvel, invw);
-  finish_contact(p, con[1], a1, d1, pos1, hx, hy, com, cvel, invw);
-  return a0 + a1;   // number of contacts of this geom (adhesion transmission divides by it)
+  real total = real(0.);
+#pragma unroll
+  for (int s = 0; s < NSLOT; s++) { finish_contact(p, con[s], act[s], dist[s], pos[s], hx, hy, com, cvel, invw); total += act[s]; }
+  return total;   // number of contacts of this geom (adhesion transmission divides by it)
 }
 
 // point "acceleration" of a contact for a body spatial vector S (ang, lin), projected on (n, mu t1, mu t2)
@@ -355,6 +377,7 @@ __device__ __forceinline__ void sphere_terrain(const SP& p, const real* c, real 
 }
 
 // capsule-vs-terrain narrow phase for the geom carried by this lane's body: the two end spheres, one contact each
+template <int NSLOT>
 __device__ __forceinline__ real collide(const SP& p, const real* role, int tid, const real* xpos, const real* R,
                                          const real* com, const real* cvel, real invw, ContactG* con, int&) {
   const int gtype = role_int(role[RF_GTYPE * CTA + tid]);
@@ -440,6 +463,43 @@ __device__ __forceinline__ void adhesion_wrench(const ContactG& c, real f, real*
 // signed distance of an active slot (debug dump only)
 __device__ __forceinline__ real con_dist(const Contact& c, const real* com) { return real(2.) * (c.r[2] + com[2]); }
 __device__ __forceinline__ real con_dist(const ContactG&, const real*) { return real(0.); }
+
+// ------------------------------------------------------------------ contact basis and explicit contact forces (noslip)
+// Basis of a contact's force space: e0 = n, e1 = mu t1, e2 = mu t2 (what project_point projects on).  The four pyramid rows are
+// e0 +- e1, e0 +- e2, so row forces f map to basis forces G = (f0+f1+f2+f3, f0-f1, f2-f3) and the contact force is sum G_k e_k.
+__device__ __forceinline__ void contact_normal(const Contact&, real* n) { n[0] = real(0.); n[1] = real(0.); n[2] = real(1.); }
+__device__ __forceinline__ void contact_normal(const ContactG& c, real* n) { n[0] = c.n[0]; n[1] = c.n[1]; n[2] = c.n[2]; }
+__device__ __forceinline__ void contact_tangent(const Contact& c, int k, real mu, real* d) {
+  d[0] = mu * (k == 0 ? c.cx : -c.cy); d[1] = mu * (k == 0 ? c.cy : c.cx); d[2] = real(0.);
+}
+__device__ __forceinline__ void contact_tangent(const ContactG& c, int k, real mu, real* d) {
+  real t2[3]; cross3(c.n, c.t, t2);
+#pragma unroll
+  for (int i = 0; i < 3; i++) d[i] = mu * (k == 0 ? c.t[i] : t2[i]);
+}
+// Newton-form row forces of a slot in basis coordinates, the two pair sums (the normal force each pair of opposing edges
+// carries; noslip keeps them) and 1/2 sum f_r^2 R_r
+template <class Con>
+__device__ __forceinline__ void basis_forces(const Con& c, real* G, real* lim, real& cost_r) {
+  real jar[4]; rows4(c.w, c.c0, jar);
+  real f[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) f[r] = -c.D * m_min(jar[r], real(0.));
+  G[0] = f[0] + f[1] + f[2] + f[3]; G[1] = f[0] - f[1]; G[2] = f[2] - f[3];
+  lim[0] = f[0] + f[1]; lim[1] = f[2] + f[3];
+  cost_r = c.D > real(0.) ? real(0.5) * (f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]) / c.D : real(0.);
+}
+// wrench about the COM (ang, lin) of the basis force G at the contact point, accumulated into W
+template <class Con>
+__device__ __forceinline__ void basis_wrench(const Con& c, const real* G, real mu, real* W, real* Fout) {
+  real n[3], d1[3], d2[3]; contact_normal(c, n); contact_tangent(c, 0, mu, d1); contact_tangent(c, 1, mu, d2);
+  real F[3] = {G[0] * n[0] + G[1] * d1[0] + G[2] * d2[0], G[0] * n[1] + G[1] * d1[1] + G[2] * d2[1], G[0] * n[2] + G[1] * d1[2] + G[2] * d2[2]};
+  real T[3]; cross3(c.r, F, T);
+  W[0] += T[0]; W[1] += T[1]; W[2] += T[2]; W[3] += F[0]; W[4] += F[1]; W[5] += F[2];
+  if (Fout) { Fout[0] = F[0]; Fout[1] = F[1]; Fout[2] = F[2]; }
+}
+constexpr int NS_MAXC = 24;             // contacts the noslip pass handles (more: the pass is skipped and ST_NOSLIP_SKIP is raised)
+constexpr int NS_LD = 2 * NS_MAXC;      // two friction dimensions per contact
 
 // ------------------------------------------------------------------ weld equality of the TetheredWorld (hub lane only)
 // Six always-active rows on the free body: rows 0-2 = world position of the hub-frame point weld_a, rows 3-5 =
@@ -539,6 +599,9 @@ constexpr int SM_WORK = SM_MBAR + 4;                // 4 words of per-fly scratc
 constexpr int SM_STAGE = SM_WORK + 4;               // f64 only: the float32 record as it travels (S_STRIDE floats)
 constexpr int SM_WELD = SM_STAGE + (sizeof(real) == 8 ? S_STRIDE / 2 : 0);   // weld rows of the tethered world (WL_COUNT)
 constexpr int SM_TOTAL = SM_WELD + WL_COUNT;
+// noslip instantiations only (appended after the slot's regular region): B (NS_LD x NS_LD), current / Newton friction forces,
+// pair sums, tangential residuals; the ranking keys of the contacts alias B before it is filled
+constexpr int NS_B = 0, NS_G = NS_B + NS_LD * NS_LD, NS_G0 = NS_G + NS_LD, NS_LIM = NS_G0 + NS_LD, NS_JT = NS_LIM + NS_LD, NS_COUNT = NS_JT + NS_LD + 8;
 constexpr int HU_CVEL = 0, HU_CACC = 6;
 constexpr int HB_S = 0, HB_XB = 21, HB_SH = 27, HB_TOT = 33, HB_SR = 72;   // TOT: 37 root totals; SR: assembled Schur block (21) + rhs (6)
 
@@ -749,7 +812,8 @@ __device__ __forceinline__ void store_record(const SP& p, const real* st, real* 
 // launch when flies map 1:1 to blocks, a sub-chunk under work-queue scheduling).
 // WORLD selects the kernel instantiation: W_FLAT = the reference's FlatGroundWorld; W_TERRAIN = general-frame contact
 // slots + capsule-vs-box-column narrow phase; W_TETHER = TetheredWorld (no ground, weld equality on the hub).
-constexpr int W_FLAT = 0, W_TERRAIN = 1, W_TETHER = 2;
+// W_MESH = W_FLAT with four contact slots per lane: convex-hull geoms with the `multiccd` flag (up to 4 plane-hull contacts).
+constexpr int W_FLAT = 0, W_TERRAIN = 1, W_TETHER = 2, W_MESH = 3;
 // FPB > 1: the block steps FPB flies side by side (64 threads and a private shared-memory region each; `fly` < 0 = an empty
 // slot).  The kernel is bound by instruction fetch, not by issue slots: the flies of a block meet at a block-wide barrier at the
 // top of every solver pass, so that its warps stream the same stretch of code at the same time and share the fetches (L0 /
@@ -758,10 +822,11 @@ constexpr int W_FLAT = 0, W_TERRAIN = 1, W_TETHER = 2;
 // (profiles/fpb_sweep_r02.txt, 4096 flies): 21.5 / 24.4 / 25.3 M env-steps/s at FPB = 1 / 4 / 8; letting the flies of a block
 // drift apart by whole stages instead of waiting (no idle slots, but two code streams per block) was slower: 21.7 M;
 // one or two more alignment barriers inside a pass changed nothing (25.4 / 24.8 M at FPB = 4 / 8).
-template <int WORLD, int FPB = 1>
+template <int WORLD, int FPB = 1, bool NOSLIP = false>
 __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly, const int step0, const int nsub, const bool published) {
   using Con = typename std::conditional<WORLD == W_TERRAIN, ContactG, Contact>::type;
   constexpr bool TETHER = WORLD == W_TETHER;
+  constexpr int NSLOT = WORLD == W_MESH ? 4 : 2;      // contact slots per lane
   real* sw = sm + SM_WELD;
   const int tid = fly_tid<FPB>();
   const int bar = FPB == 1 ? 0 : 1 + fly_slot<FPB>();
@@ -960,7 +1025,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
     // B. velocities, composite inertia, collision, bias + actuator forces (all lanes, convergent)
     // =====================================================================
     real crb[10], cvel[6], Sa[6];
-    Con con[2];
+    Con con[NSLOT];
     real fs_own[3] = {real(0.), real(0.), real(0.)};
     real actf[3] = {real(0.), real(0.), real(0.)}, adhf = real(0.);
     {
@@ -1010,7 +1075,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       for (int i = 0; i < 10; i++) crb[i] = cinert[i];
       chain_suffix<10>(crb, NMF_FULL, k);
       // collision for this body's geom
-      const real ncon_lane = collide(p, role, tid, xpos, R, com, cvel, invw, con, hullv);
+      const real ncon_lane = collide<NSLOT>(p, role, tid, xpos, R, com, cvel, invw, con, hullv);
       // adhesion (body transmission): force pulls the body onto the plane along each contact normal
       {
         const int acidx = role_int(role[RF_ADH_CIDX * CTA + tid]);
@@ -1019,11 +1084,11 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         if constexpr (WORLD == W_TERRAIN) {
           const real pull = ncon_lane > real(0.) ? adhf / ncon_lane : real(0.);
 #pragma unroll
-          for (int s = 0; s < 2; s++) adhesion_wrench(con[s], pull, W);
+          for (int s = 0; s < NSLOT; s++) adhesion_wrench(con[s], pull, W);
         } else {   // z-normal slots: written out in place (routing this through a helper cost 3 % on B200: register allocation)
           real fz = ncon_lane > real(0.) ? -adhf / ncon_lane : real(0.);
 #pragma unroll
-          for (int s = 0; s < 2; s++) { real f = con_on(con[s]) * fz; W[0] += con[s].r[1] * f; W[1] -= con[s].r[0] * f; W[5] += f; }
+          for (int s = 0; s < NSLOT; s++) { real f = con_on(con[s]) * fz; W[0] += con[s].r[1] * f; W[1] -= con[s].r[0] * f; W[5] += f; }
         }
       }
       chain_suffix<6>(W, NMF_FULL, k);
@@ -1061,13 +1126,15 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       for (int i = 0; i < 6; i++) Sa[i] = sl[i] + sm[SM_HBB + HB_SH + i];
       // contact rows at the warm-start acceleration
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
+      for (int s = 0; s < NSLOT; s++) {
         real ap[3]; project_point(con[s], Sa, p.mu, ap);
         con[s].w[0] += ap[0]; con[s].w[1] += ap[1]; con[s].w[2] += ap[2];
       }
       if (TETHER && weld_lane) weld_setup(p, sw, qh, xh, com, s_hub + HU_CVEL, Sa);
     }
-    const bool any0 = __any_sync(NMF_FULL, con[0].D > real(0.)), any1 = __any_sync(NMF_FULL, con[1].D > real(0.));
+    bool any[NSLOT];     // warp-uniform: some lane of the warp uses slot s (most lanes have no contact)
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) any[s] = __any_sync(NMF_FULL, con[s].D > real(0.));
     block_sync(bar);   // chain roots (wrench, crb) visible to the hub lanes
     real crbh[10];    // hub-dof lanes: composite inertia of the whole fly
     if (!is_leg) hub_root_totals(sm, hl, 0, 16);
@@ -1090,6 +1157,8 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
     real* qacc = st + S_WARM;      // qacc lives in the warm-start slot of the record
     int niter = 0, nls_total = 0, nchanged_last = 0;
     int fault = 0;                 // bits of the per-fly status word raised by this step (nmf_layout.h ST_*)
+    real G[NSLOT][3];              // noslip: explicit contact forces in basis coordinates (normal, mu t1, mu t2), valid when explicit_f
+    bool explicit_f = false;
     // One loop body serves every Newton iteration AND the final implicit-damping (Euler) solve, so the large unrolled
     // factorisation exists once in the instruction stream (the kernel is I-cache sensitive):
     //   pass `iter`:  forces(qacc) -> gradient/fc -> [converged? euler : newton] system -> arrowhead solve -> (line search, move)
@@ -1102,12 +1171,171 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
       }
       const bool euler = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
       if (euler && nchanged_last != 0) fault |= ST_NEWTON_CAP;      // iteration cap reached with the active set still changing
+      if (NOSLIP && euler && p.noslip_iterations > 0) {
+        // =================================================================
+        // noslip post-solver of the reference's CPU path (mujoco_globals.yaml:15; [PRIOR] mj_solNoSlip): projected Gauss-Seidel
+        // on the friction dimensions of the DUAL problem without the regulariser.  In the basis (n, mu t1, mu t2) of every
+        // contact the update of a pair of opposing pyramid edges is a plain Gauss-Seidel step on one tangential component,
+        //     g <- clamp(g - h / B_gg, -lim, lim),   h = jar_t(qacc) + B_tt (g - g_newton),   B_tt = E_t M^-1 E_t',
+        // with lim = the normal force the pair carries (kept).  B_tt is built column by column with the arrowhead solver on
+        // the plain inertia matrix (the matrix-free J / J' of the rest of the kernel), the sweeps run on it in shared memory
+        // in the oracle's contact order (geom order, then slot), and qacc moves by M^-1 E_t' (g - g_newton) at the end.
+        // =================================================================
+        real* ns = sm + SM_TOTAL;
+        int* keys = reinterpret_cast<int*>(ns + NS_B);
+        const int gidx = role_int(role[RF_GIDX * CTA + tid]);
+        real lim[NSLOT][2], costr = real(0.);
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+          real c1; basis_forces(con[s], G[s], lim[s], c1); costr += c1;
+          keys[tid * NSLOT + s] = con[s].D > real(0.) ? gidx * NSLOT + s : 0x7fffffff;
+        }
+        real c0r[1] = {costr};
+        cta_reduce<1>(c0r, s_red, parity, tid, bar);            // (also makes the keys visible)
+        int rank[NSLOT], C = 0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) rank[s] = 0;
+        for (int i = 0; i < CTA * NSLOT; i++) {
+          const int ki = keys[i];
+          C += ki != 0x7fffffff ? 1 : 0;
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++) rank[s] += ki < keys[tid * NSLOT + s] ? 1 : 0;
+        }
+        block_sync(bar);                                        // keys alias B: everybody has ranked before B is written
+        if (C > NS_MAXC) fault |= ST_NOSLIP_SKIP;
+        else if (C > 0) {
+          // ---- stage the plain inertia matrix (the same staging the Euler pass repeats with its damping diagonal)
+          {
+            real P[21];
+            if (hubdof) {
+              expand_inert(crbh, P);
+              real u[6]; sym6_mul(P, s_cdof + CDS * hl, u);
+              for (int c = 0; c <= hl; c++) sm[SM_HBB + HB_S + hl * (hl + 1) / 2 + c] = dot6(s_cdof + CDS * c, u);
+            }
+            expand_inert(crb, P);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              real u[6]; sym6_mul(P, CDO(j), u);
+              if (j < ndof) {
+                real* up = su + 8 * (ldof0 + j);
+#pragma unroll
+                for (int i = 0; i < 6; i++) up[i] = u[i];
+              }
+            }
+          }
+          block_sync(bar);
+          // x = M^-1 J'(lane wrenches W): on return W holds the spatial acceleration of x at this lane's body, xo its own DoFs
+          auto m_solve = [&](real* W, real* xo) {
+            chain_suffix<6>(W, NMF_FULL, k);
+#pragma unroll
+            for (int j = 0; j < 3; j++) if (j < ndof) sm[SM_GRAD + dj[j]] = -dot6(CDO(j), W);
+            if (k == 0) {
+#pragma unroll
+              for (int i = 0; i < 6; i++) rt[i] = W[i];
+            }
+            block_sync(bar);
+            if (!is_leg) hub_root_totals(sm, hl, 0, 6);
+            __syncwarp(NMF_FULL);
+            if (hubdof) sm[SM_GRAD + hl] = -dot6(s_cdof + CDS * hl, sm + SM_HBB + HB_TOT);
+            block_sync(bar);
+            arrowhead_solve(sm, s_cdof, cl, grp, t, is_leg, hl, lbase, pb, pc, nullptr, bar);
+            __syncwarp(NMF_FULL);
+#pragma unroll
+            for (int j = 0; j < 3; j++) xo[j] = msk[j] * sm[SM_X + dj[j]];
+            if (hubdof) xo[0] = sm[SM_X + hl];
+            real sl[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+              for (int i = 0; i < 6; i++) sl[i] += (is_leg ? CDO(j)[i] : real(0.)) * xo[j];
+            chain_prefix<6>(sl, NMF_FULL, k);
+#pragma unroll
+            for (int i = 0; i < 6; i++) W[i] = sl[i] + sm[SM_HBB + HB_SH + i];
+            block_sync(bar);                                    // SM_GRAD / SM_X / the root records are free again
+          };
+          // ---- columns of B_tt
+          for (int j = 0; j < 2 * C; j++) {
+            real W[6] = {0, 0, 0, 0, 0, 0}, xo[3];
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++)
+              if (con[s].D > real(0.) && rank[s] == (j >> 1)) {
+                real d[3], T[3]; contact_tangent(con[s], j & 1, p.mu, d); cross3(con[s].r, d, T);
+                W[0] = T[0]; W[1] = T[1]; W[2] = T[2]; W[3] = d[0]; W[4] = d[1]; W[5] = d[2];
+              }
+            m_solve(W, xo);
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++)
+              if (con[s].D > real(0.)) {
+                real o3[3]; project_point(con[s], W, p.mu, o3);
+                ns[NS_B + (2 * rank[s]) * NS_LD + j] = o3[1]; ns[NS_B + (2 * rank[s] + 1) * NS_LD + j] = o3[2];
+              }
+          }
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++)
+            if (con[s].D > real(0.)) {
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const int i = 2 * rank[s] + q;
+                ns[NS_G + i] = G[s][1 + q]; ns[NS_G0 + i] = G[s][1 + q]; ns[NS_LIM + i] = lim[s][q]; ns[NS_JT + i] = con[s].w[1 + q];
+              }
+            }
+          block_sync(bar);
+          // ---- the sweeps (serial Gauss-Seidel, one thread; the problem is 2C <= 48 unknowns)
+          if (tid == 0) {
+            const int n2 = 2 * C;
+            for (int it = 0; it < p.noslip_iterations; it++) {
+              real improvement = it == 0 ? c0r[0] : real(0.);
+              for (int i = 0; i < n2; i++) {
+                real h = ns[NS_JT + i];
+                for (int q = 0; q < n2; q++) h += ns[NS_B + i * NS_LD + q] * (ns[NS_G + q] - ns[NS_G0 + q]);
+                const real Bii = ns[NS_B + i * NS_LD + i], gold = ns[NS_G + i], l = ns[NS_LIM + i];
+                real gnew = real(0.);                           // K1 = 4 B_ii below MuJoCo's mjMINVAL: both edges get the mean
+                if (real(4.) * Bii >= real(1e-15)) gnew = m_min(l, m_max(-l, gold - h / Bii));
+                const real dy = real(0.5) * (gnew - gold);      // y = (f_j - f_j+1) / 2
+                real change = real(2.) * Bii * dy * dy + real(2.) * h * dy;
+                if (change > real(1e-10)) { gnew = gold; change = real(0.); }
+                ns[NS_G + i] = gnew; improvement -= change;
+              }
+              if (improvement * p.noslip_scale < p.noslip_tol) break;
+            }
+          }
+          block_sync(bar);
+          // ---- move: qacc += M^-1 E_t' (g - g_newton); rows and explicit forces follow
+          {
+            real W[6] = {0, 0, 0, 0, 0, 0}, xo[3];
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++)
+              if (con[s].D > real(0.)) {
+                real dG[3] = {real(0.), ns[NS_G + 2 * rank[s]] - G[s][1], ns[NS_G + 2 * rank[s] + 1] - G[s][2]};
+                basis_wrench(con[s], dG, p.mu, W, nullptr);
+                G[s][1] += dG[1]; G[s][2] += dG[2];
+              }
+            m_solve(W, xo);
+#pragma unroll
+            for (int j = 0; j < 3; j++) if (j < ndof || (j == 0 && hubdof)) qacc[dj[j]] += xo[j];
+#pragma unroll
+            for (int i = 0; i < 6; i++) Sa[i] += W[i];
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) {
+              real o3[3]; project_point(con[s], W, p.mu, o3);
+              con[s].w[0] += o3[0]; con[s].w[1] += o3[1]; con[s].w[2] += o3[2];
+            }
+            block_sync(bar);
+          }
+          explicit_f = true;
+        }
+      }
       // ---- forces, active set, contact augmentation
       real Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
 #pragma unroll
       for (int i = 0; i < 21; i++) A[i] = real(0.);
-      if (any0) contact_forces<true>(con[0], p.mu, Wc, A, nullptr);    // warp-uniform skips: most lanes have no contact
-      if (any1) contact_forces<true>(con[1], p.mu, Wc, A, nullptr);
+      if (NOSLIP && explicit_f) {      // (Euler pass after noslip: the forces are no longer a function of the rows)
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) if (any[s] && con[s].D > real(0.)) basis_wrench(con[s], G[s], p.mu, Wc, nullptr);
+      } else {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) if (any[s]) contact_forces<true>(con[s], p.mu, Wc, A, nullptr);    // warp-uniform skips
+      }
       if (TETHER && weld_lane) weld_forces(sw, Wc, A);
       // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
       real y[12];
@@ -1193,15 +1421,17 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         for (int i = 0; i < 6; i++) Ss[i] = sl[i] + sm[SM_HBB + HB_SH + i];
       }
       real red[5] = {real(0.), real(0.), real(0.), real(0.), real(0.)};   // s.g , s'Ms , d0 rows(0), d1 rows(0), |s|^2
-      real sv0[3] = {real(0.), real(0.), real(0.)}, sv1[3] = {real(0.), real(0.), real(0.)};   // row directions of the two contact slots along the search vector
+      real sv[NSLOT][3];   // row directions of the contact slots along the search vector
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) sv[s][0] = sv[s][1] = sv[s][2] = real(0.);
       {
         real t6[6]; mul_inert(cinert, Ss, t6);
         red[1] += dot6(Ss, t6);
 #pragma unroll
         for (int j = 0; j < 3; j++) { red[0] += sown[j] * gown[j]; red[1] += (is_leg ? armv[j] : real(0.)) * sown[j] * sown[j]; red[4] += sown[j] * sown[j]; }
         real dummy = real(0.);
-        if (any0) { project_point(con[0], Ss, p.mu, sv0); ls_eval(con[0], sv0, real(0.), red[2], red[3], dummy); }
-        if (any1) { project_point(con[1], Ss, p.mu, sv1); ls_eval(con[1], sv1, real(0.), red[2], red[3], dummy); }
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) if (any[s]) { project_point(con[s], Ss, p.mu, sv[s]); ls_eval(con[s], sv[s], real(0.), red[2], red[3], dummy); }
         if (TETHER && weld_lane) { point_and_rot(sw, Ss, sw + WL_SV); weld_ls(sw, real(0.), red[2], red[3]); }
       }
       cta_reduce<5>(red, s_red, parity, tid, bar);
@@ -1220,8 +1450,8 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
           if (nx <= lo || nx >= hi) nx = (hi > real(1.0e38)) ? real(2.) * m_max(alpha, real(1.)) : real(0.5) * (lo + hi);
           alpha = nx;
           real e[3] = {real(0.), real(0.), real(0.)};
-          if (any0) ls_eval(con[0], sv0, alpha, e[0], e[1], e[2]);
-          if (any1) ls_eval(con[1], sv1, alpha, e[0], e[1], e[2]);
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++) if (any[s]) ls_eval(con[s], sv[s], alpha, e[0], e[1], e[2]);
           if (TETHER && weld_lane) weld_ls(sw, alpha, e[0], e[1]);
           cta_reduce<3>(e, s_red, parity, tid, bar);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
@@ -1235,7 +1465,9 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
 #pragma unroll
       for (int i = 0; i < 6; i++) Sa[i] += alpha * Ss[i];
 #pragma unroll
-      for (int i = 0; i < 3; i++) { con[0].w[i] += alpha * sv0[i]; con[1].w[i] += alpha * sv1[i]; }
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) con[s].w[i] += alpha * sv[s][i];
       if (TETHER && weld_lane) for (int i = 0; i < 6; i++) sw[WL_W + i] += alpha * sw[WL_SV + i];
     }
     // SM_X now holds the implicit-damping (Euler) acceleration  (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
@@ -1249,9 +1481,10 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         if (tid == 0) { dg[DBG_NITER] = (real)niter; dg[DBG_NLS] = (real)nls_total; dg[DBG_NCHG] = (real)nchanged_last; }
         for (int i = tid; i < NV; i += CTA) { dg[DBG_FS + i] = sm[SM_FS + i]; dg[DBG_QACC + i] = qacc[i]; dg[DBG_FC + i] = -sm[SM_GRAD + i] - sm[SM_FS + i]; dg[DBG_QACCE + i] = sm[SM_X + i]; }
         if (tid < 21) dg[DBG_HROWS + NLEG * 177 + tid] = sm[SM_HBB + HB_S + tid];
-        for (int s = 0; s < 2; s++) {
-          float* c = dg + DBG_CON + (tid * 2 + s) * 6; real fn = real(0.), Wt[6] = {0, 0, 0, 0, 0, 0};
-          contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
+        for (int s = 0; s < NSLOT; s++) {
+          float* c = dg + DBG_CON + (tid * DBG_NSLOT + s) * 6; real fn = real(0.), Wt[6] = {0, 0, 0, 0, 0, 0};
+          if (NOSLIP && explicit_f) { if (con[s].D > real(0.)) basis_wrench(con[s], G[s], p.mu, Wt, nullptr); fn = con[s].D > real(0.) ? G[s][0] : real(0.); }
+          else contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
           const real on = con_on(con[s]);
           c[0] = on; c[1] = on * con_dist(con[s], com);
           c[2] = on * (con[s].r[0] + com[0]); c[3] = on * (con[s].r[1] + com[1]);
@@ -1259,7 +1492,9 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         }
         for (int i = 0; i < 3; i++) dg[DBG_XPOS + tid * 3 + i] = xpos[i];
         for (int i = tid; i < NV * 6; i += CTA) dg[DBG_CDOF + i] = s_cdof[CDS * (i / 6) + i % 6];
-        real nc[1] = {con_on(con[0]) + con_on(con[1])};
+        real nc[1] = {real(0.)};
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) nc[0] += con_on(con[s]);
         cta_reduce<1>(nc, s_red, parity, tid, bar);
         if (tid == 0) dg[DBG_NCON] = nc[0];
       }
@@ -1273,10 +1508,12 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         // per-leg contact sensor (world.py:311-331), reduce="netforce": found, force, torque, pos, normal, tangent
         const real sens = (is_leg && role_int(role[RF_LEGSENSOR * CTA + tid]) != 0) ? real(1.) : real(0.);
         real acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // F(3), fn-weighted pos(3), fn sum, count
-        real Fc[2][3], plain[3] = {0, 0, 0};
+        real Fc[NSLOT][3], plain[3] = {0, 0, 0};
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-          real Wt[6] = {0, 0, 0, 0, 0, 0}, fn = real(0.); contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
+        for (int s = 0; s < NSLOT; s++) {
+          real Wt[6] = {0, 0, 0, 0, 0, 0}, fn = real(0.);
+          if (NOSLIP && explicit_f) { if (con[s].D > real(0.)) basis_wrench(con[s], G[s], p.mu, Wt, nullptr); fn = con[s].D > real(0.) ? G[s][0] : real(0.); }
+          else contact_forces<false>(con[s], p.mu, Wt, nullptr, &fn);
           const real on = sens * con_on(con[s]);
           Fc[s][0] = on * Wt[3]; Fc[s][1] = on * Wt[4]; Fc[s][2] = on * Wt[5];
 #pragma unroll
@@ -1294,7 +1531,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         if (acc[7] > real(0.)) for (int i = 0; i < 3; i++) P3[i] = acc[6] > real(1e-15) ? acc[3 + i] / acc[6] : plain[i] / acc[7];
         real T[3] = {0, 0, 0};
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < NSLOT; s++) {
           const real on = sens * con_on(con[s]);
           real rr[3] = {on * (con[s].r[0] + com[0] - P3[0]), on * (con[s].r[1] + com[1] - P3[1]), on * (con[s].r[2] + com[2] - P3[2])}, tt[3];
           cross3(rr, Fc[s], tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
@@ -1375,9 +1612,9 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
 //    queue[0] = pop counter, queue[1] = push counter, queue[2 + u] = sub-chunks of unit u done, queue[2 + n + j] = ring entry j.
 //    A block may have to wait for a ring entry, but only for items that are running on OTHER blocks (its own previous item
 //    has been pushed before it pops), so the wait always ends.
-template <int WORLD, int FPB = 1>
+template <int WORLD, int FPB = 1, bool NOSLIP = false>
 __device__ __forceinline__ void step_entry(const SP& p) {
-  constexpr int SM_FLY = WORLD == W_TETHER ? SM_TOTAL : SM_WELD;       // only the tethered world keeps weld rows
+  constexpr int SM_FLY = NOSLIP ? SM_TOTAL + NS_COUNT : (WORLD == W_TETHER ? SM_TOTAL : SM_WELD);   // weld rows: tethered world only; noslip region: noslip kernels only
   constexpr bool DYN = (size_t)FPB * SM_FLY * sizeof(real) > 48 * 1024;   // beyond the static limit: dynamic shared memory (opt-in on the host side)
   __shared__ __align__(16) real sm_static[DYN ? 1 : FPB * SM_FLY];
   extern __shared__ __align__(16) unsigned char sm_dynamic[];
@@ -1406,12 +1643,12 @@ __device__ __forceinline__ void step_entry(const SP& p) {
         s_fly = f; s_chunk = f >= 0 ? p.queue[2 + f] : 0;
       }
       block_sync(0);
-      unit = s_fly;
+      unit = warp_uniform(s_fly);
       if (unit < 0) return;
-      step0 = s_chunk * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
+      step0 = warp_uniform(s_chunk) * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
     }
     const int fly = unit * FPB + slot;
-    step_block<WORLD, FPB>(p, sm, fly < p.n_flies ? fly : -1, step0, nsub, p.queue != nullptr);
+    step_block<WORLD, FPB, NOSLIP>(p, sm, fly < p.n_flies ? fly : -1, step0, nsub, p.queue != nullptr);
     if (!p.queue) return;
     block_sync(0);     // every slot's record store has completed (store_record waited for it); s_fly / s_chunk are free again
     if (tid == 0) {    // hand the unit on

@@ -74,9 +74,12 @@ inline int nmf_emu_atomic_add(int* ptr, int v) { const int old = *ptr; *ptr = ol
 #ifndef NMF_FPB_INTERLEAVE
 #define NMF_FPB_INTERLEAVE 0
 #endif
+// value of lane 0, which tells the compiler that v is the same in every lane of the warp: warp-uniform values (fly slot,
+// work item, shared-memory base of the slot) can then live in uniform registers instead of the 64 scarce vector registers
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(NMF_FULL, v, 0); }
 template <int FPB> __device__ __forceinline__ int fly_slot() {
   if (FPB == 1) return 0;
-  return NMF_FPB_INTERLEAVE ? (int)(threadIdx.x >> 5) % FPB : (int)(threadIdx.x / CTA);
+  return warp_uniform(NMF_FPB_INTERLEAVE ? (int)(threadIdx.x >> 5) % FPB : (int)(threadIdx.x / CTA));
 }
 template <int FPB> __device__ __forceinline__ int fly_tid() {
   if (FPB == 1) return (int)threadIdx.x;

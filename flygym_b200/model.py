@@ -52,9 +52,10 @@ _I32 = [
 ]
 DIM_FIELDS = ["nbody", "nq", "nv", "nu_pos", "nu_adh", "ngeom", "nsite", "nseg", "nleg", "nhullvert"]
 OPT_FIELDS = ["timestep", "gx", "gy", "gz", "iterations", "tolerance", "ls_iterations",
-              "ls_tolerance", "noslip_iterations", "meaninertia", "impratio"]
+              "ls_tolerance", "noslip_iterations", "meaninertia", "impratio", "multiccd"]
 CONTACT_FIELDS = ["mu", "solref0", "solref1", "solimp0", "solimp1", "solimp2", "solimp3",
                   "solimp4", "margin", "gap"]
+OPT_DEFAULTS = {"multiccd": 1.0}
 TERRAIN_FIELDS = ["type", "period_x", "period_y", "half_x", "half_y", "top_even", "top_odd", "z_floor"]
 # Terrain worlds.  FlyGym 2.0.1 ships only FlatGroundWorld / TetheredWorld (reference src/flygym/compose/world.py:229-366);
 # BASELINE.json config 3 asks for the v1-style "blocks" and "gapped" arenas, defined here as a floor plane plus a grid of
@@ -96,7 +97,23 @@ class NMFModel:
         return int(self.arrays["dims"][DIM_FIELDS.index(key)])
 
     def opt(self, key: str) -> float:
-        return float(self.arrays["opt"][OPT_FIELDS.index(key)])
+        return float(self._opt_full()[OPT_FIELDS.index(key)])
+
+    def _opt_full(self) -> np.ndarray:
+        """``opt`` padded to the current OPT_FIELDS (models baked before a field existed get the reference's setting:
+        ``multiccd`` is enabled in ``mujoco_globals.yaml:18``)."""
+        o = np.asarray(self.arrays["opt"], dtype=np.float64)
+        if len(o) < len(OPT_FIELDS):
+            o = np.r_[o, [OPT_DEFAULTS[k] for k in OPT_FIELDS[len(o):]]]
+        return o
+
+    def with_options(self, **kw) -> "NMFModel":
+        """Copy with solver / collision options changed: ``noslip_iterations`` (5 = the reference's CPU ``Simulation``,
+        0 = its ``GPUSimulation``, which strips noslip: ``warp/simulation.py:427-448``), ``multiccd`` (0 / 1), ``iterations`` ..."""
+        o = self._opt_full().copy()
+        for k, v in kw.items():
+            o[OPT_FIELDS.index(k)] = float(v)
+        return NMFModel(dict(self.arrays, opt=o), self.names, dict(self.meta))
 
     @property
     def nq(self): return self.dim("nq")
@@ -290,6 +307,7 @@ class NMFModel:
 
     def to_blob(self) -> bytes:
         arrays = dict(self.arrays)
+        arrays["opt"] = self._opt_full()
         arrays.setdefault("terrain", np.zeros(len(TERRAIN_FIELDS)))
         arrays.setdefault("weld", np.zeros(len(WELD_FIELDS)))
         secs = [(n, 0, np.ascontiguousarray(arrays[n], dtype=np.float64).ravel()) for n in _F64]

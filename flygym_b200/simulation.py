@@ -59,8 +59,9 @@ class B200Simulation:
     """GPU-resident parallel simulation of ``n_worlds`` independent flies.
 
     Args:
-        world: a baked :class:`NMFModel`, a :class:`WorldView`, or ``None`` for the
-            reference benchmark model (capsule geoms).
+        world: a baked :class:`NMFModel`, a :class:`WorldView`, a MuJoCo-compiled ``MjModel`` (anything exposing its public
+            fields) or a flygym world with ``compile()`` / ``fly_lookup`` -- both converted by
+            :func:`flygym_b200.convert.from_mjmodel` -- or ``None`` for the reference benchmark model (capsule geoms).
         n_worlds: number of parallel flies on this GPU.
         device: CUDA device (default: current).
         outputs: allocate the observation buffers (body poses, actuator forces,
@@ -72,6 +73,18 @@ class B200Simulation:
                  fly_name: str = "nmf") -> None:
         if world is None:
             world = NMFModel.bench(simplify_geom=True)
+        if hasattr(world, "compile") and hasattr(world, "fly_lookup") and not hasattr(world, "model"):
+            # a flygym world (reference compose/base.py:21-27): ingest its MuJoCo-compiled model like Simulation.__init__ does
+            if len(world.fly_lookup) == 0:
+                raise ValueError("The world must contain at least one fly.")
+            from .convert import from_mjmodel
+            fly_name = next(iter(world.fly_lookup))
+            mj_model = world.compile()
+            mj_model = mj_model[0] if isinstance(mj_model, tuple) else mj_model
+            world = WorldView(from_mjmodel(mj_model), fly_name)
+        elif hasattr(world, "nbody") and hasattr(world, "jnt_type"):          # a (duck-typed) MjModel
+            from .convert import from_mjmodel
+            world = from_mjmodel(world)
         if isinstance(world, NMFModel):
             world = WorldView(world, fly_name)
         if len(world.fly_lookup) == 0:
@@ -310,7 +323,7 @@ class B200Simulation:
         return self.state[:, self.info.off_qacc_warmstart: self.info.off_qacc_warmstart + self.info.nv]
 
     # bits of the per-fly status word (include/nmf_b200.h, enum nmf_fly_status)
-    ST_NONFINITE, ST_NEWTON_CAP, ST_LS_CAP = 1, 2, 4
+    ST_NONFINITE, ST_NEWTON_CAP, ST_LS_CAP, ST_NOSLIP_SKIP = 1, 2, 4, 8
 
     @property
     def status(self) -> torch.Tensor:
@@ -375,7 +388,8 @@ class B200Simulation:
 
     # ---- rendering hooks kept for API compatibility ---------------------------
     def set_renderer(self, *args, **kwargs):
-        raise NotImplementedError("rendering is outside the step path (SURVEY.md section 2, rows 13-14)")
+        raise NotImplementedError("rendering is outside the step path (SURVEY.md section 2, rows 13-14); export_state(world_id) returns the "
+                                  "qpos / qvel / time a MuJoCo renderer needs (what WarpCPURenderer pulls with mjw.get_data_into)")
 
     def render_as_needed(self) -> bool:
         return False if self.renderer is None else self.renderer.render_as_needed(self)

@@ -49,6 +49,8 @@ typedef struct {
   const int32_t *body_parent, *body_dofadr, *body_dofnum, *body_leg, *dof_body, *dof_parent;
   const int32_t *act_dof, *adh_body, *geom_body, *geom_type, *geom_vertadr, *geom_vertnum;
   const int32_t *site_body, *seg_body, *leg_rootbody;
+  const int32_t *hull_nbr_adr, *hull_nbr;   /* CSR adjacency of the hull vertices (optional; indices local to the geom) */
+  int multiccd;                             /* plane-hull: extra contacts at the support vertex's neighbours (mujoco_globals.yaml:18) */
   /* options */
   double dt, grav[3], tolerance, ls_tolerance, meaninertia, impratio;
   int iterations, ls_iterations, noslip_iterations;
@@ -73,7 +75,7 @@ typedef struct {
   /* outputs */
   double *geom_xpos, *geom_xmat, *site_xpos, *seg_xpos, *seg_xquat, *sensordata;
   /* solver stats */
-  int solver_niter; double solver_cost, solver_gradnorm;
+  int solver_niter, noslip_niter; double solver_cost, solver_gradnorm, noslip_tolerance;
   double energy[2];   /* potential, kinetic (mjData.energy with the model's `energy` flag) */
   char err[256];
 } nmfo;
@@ -193,10 +195,13 @@ nmfo* nmfo_create(const void* blob, size_t nbytes) {
   SEC(adh_body, "adh_body"); SEC(geom_body, "geom_body"); SEC(geom_type, "geom_type");
   SEC(geom_vertadr, "geom_vertadr"); SEC(geom_vertnum, "geom_vertnum"); SEC(site_body, "site_body");
   SEC(seg_body, "seg_body"); SEC(leg_rootbody, "leg_rootbody");
+  o->hull_nbr_adr = find_section(o->blob, "hull_nbr_adr", NULL); o->hull_nbr = find_section(o->blob, "hull_nbr", NULL);
   o->dt = o->opt[0]; o->grav[0] = o->opt[1]; o->grav[1] = o->opt[2]; o->grav[2] = o->opt[3];
   o->iterations = (int)o->opt[4]; o->tolerance = o->opt[5]; o->ls_iterations = (int)o->opt[6];
   o->ls_tolerance = o->opt[7]; o->noslip_iterations = (int)o->opt[8]; o->meaninertia = o->opt[9];
   o->impratio = o->opt[10];
+  o->noslip_tolerance = 1e-6;   /* MuJoCo default (the reference does not set it) */
+  { int nopt = 0; find_section(o->blob, "opt", &nopt); o->multiccd = nopt > 11 ? (int)o->opt[11] : 0; }
   o->mu = o->contact[0]; o->solref[0] = o->contact[1]; o->solref[1] = o->contact[2];
   for (int i = 0; i < 5; i++) o->solimp[i] = o->contact[3 + i];
   o->margin = o->contact[8]; o->gap = o->contact[9];
@@ -419,15 +424,27 @@ static void collision(nmfo* o) {
       }
     } else {  /* plane - convex hull: deepest hull vertex (support point along -normal) */
       int b = o->geom_body[g]; const double* R = o->xmat + 9 * b; const double* xp = o->xpos + 3 * b;
-      double best = 1e300, bp[3] = {0, 0, 0};
+      double best = 1e300, bp[3] = {0, 0, 0}; int bi = 0;
       for (int v = 0; v < o->geom_vertnum[g]; v++) {
         const double* lv = o->hull_vert + 3 * (o->geom_vertadr[g] + v); double w[3]; mat_vec(w, R, lv);
         for (int k = 0; k < 3; k++) w[k] += xp[k];
-        if (w[2] < best) { best = w[2]; memcpy(bp, w, 24); }
+        if (w[2] < best) { best = w[2]; memcpy(bp, w, 24); bi = v; }
       }
       if (best > o->margin) continue;
       double pos[3] = {bp[0], bp[1], bp[2] - best / 2}, zero[3] = {0, 0, 0};
       add_contact(o, g, best, pos, zero);
+      /* [PRIOR] mjc_PlaneConvex on a mesh with the `multiccd` flag (mujoco_globals.yaml:18): the neighbours of the support vertex
+       * in the hull's vertex graph that are also within the margin become contacts too, up to 4 per geom (graph order). */
+      if (o->multiccd && o->hull_nbr_adr && o->hull_nbr) {
+        int adr = o->geom_vertadr[g], cnt = 1;
+        for (int e = o->hull_nbr_adr[adr + bi]; e < o->hull_nbr_adr[adr + bi + 1] && cnt < 4; e++) {
+          const double* lv = o->hull_vert + 3 * (adr + o->hull_nbr[e]); double w[3]; mat_vec(w, R, lv);
+          for (int k = 0; k < 3; k++) w[k] += xp[k];
+          if (w[2] > o->margin) continue;
+          double p2[3] = {w[0], w[1], w[2] - w[2] / 2};
+          add_contact(o, g, w[2], p2, zero); cnt++;
+        }
+      }
     }
   }
 }
@@ -666,6 +683,71 @@ static void solve_constraints(nmfo* o) {
   free(Ma); free(jar); free(grad); free(search); free(Mv); free(jv); free(H); free(tmpf);
 }
 
+/* ------------------------------------------------------------------ noslip post-solver (CPU reference only)
+ * [PRIOR] mj_solNoSlip, run by mj_fwdConstraint after the main solver when opt.noslip_iterations > 0 (the reference sets 5 in
+ * mujoco_globals.yaml:15 and strips it on the GPU path, warp/simulation.py:427-448).  A projected Gauss-Seidel on the DUAL
+ * problem WITHOUT the regulariser R:  A = J M^-1 J',  b = J qacc_smooth - aref,  residual_i = A_i. f + b_i.
+ *   - equality rows: f_i -= residual_i / A_ii                      (unclamped)
+ *   - pyramidal contacts, per pair of opposing edges (j, j+1) = (n + mu t_k, n - mu t_k): the sum f_j + f_j+1 = 2 mid (the
+ *     normal force carried by the pair) is kept; y = (f_j - f_j+1)/2 minimises the unregularised cost over [-mid, mid]:
+ *     K1 = A00 + A11 - 2 A01,  K0 = mid (A00 - A11) + bc0 - bc1  with  bc = residual - Ac f_old,  y = -K0 / K1, clamped.
+ *   - an update that would raise the cost (> 1e-10) is undone; sweeps stop when the scaled improvement < noslip_tolerance (1e-6).
+ * Afterwards  qfrc_constraint = J' f,  qacc = qacc_smooth + M^-1 qfrc_constraint. */
+static double cost_change2(const double* Ac, double* f, const double* old, const double* res) {
+  double d0 = f[0] - old[0], d1 = f[1] - old[1];
+  double change = 0.5 * (d0 * (Ac[0] * d0 + Ac[1] * d1) + d1 * (Ac[2] * d0 + Ac[3] * d1)) + d0 * res[0] + d1 * res[1];
+  if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; change = 0; }
+  return change;
+}
+static void noslip(nmfo* o) {
+  int nv = o->nv, ne = o->nefc, neq = o->neq;
+  o->noslip_niter = 0;
+  if (!ne || o->noslip_iterations <= 0) return;
+  double *L = dalloc((size_t)nv * nv), *Y = dalloc((size_t)ne * nv), *A = dalloc((size_t)ne * ne), *b = dalloc(ne), *f = o->efc_force;
+  memcpy(L, o->M, sizeof(double) * nv * nv);
+  if (chol_factor(L, nv)) { snprintf(o->err, sizeof o->err, "noslip: M not PD"); free(L); free(Y); free(A); free(b); return; }
+  for (int e = 0; e < ne; e++) { memcpy(Y + (size_t)e * nv, o->efc_J + (size_t)e * nv, sizeof(double) * nv); chol_solve(L, nv, Y + (size_t)e * nv); }
+  for (int i = 0; i < ne; i++) {
+    for (int j = 0; j < ne; j++) A[(size_t)i * ne + j] = dotn(o->efc_J + (size_t)i * nv, Y + (size_t)j * nv, nv);
+    b[i] = dotn(o->efc_J + (size_t)i * nv, o->qacc_smooth, nv) - o->efc_aref[i];
+  }
+  double scale = 1.0 / (o->meaninertia * (nv > 1 ? nv : 1));
+  for (int iter = 0; iter < o->noslip_iterations; iter++) {
+    double improvement = 0;
+    if (iter == 0) for (int i = 0; i < ne; i++) improvement += 0.5 * f[i] * f[i] * o->efc_R[i];
+    for (int i = 0; i < neq; i++) {              /* equality rows */
+      double res = b[i] + dotn(A + (size_t)i * ne, f, ne), old = f[i], Aii = A[(size_t)i * ne + i];
+      f[i] -= res / fmax(MINVAL, Aii);
+      double d = f[i] - old, change = 0.5 * d * d * Aii + d * res;
+      if (change > 1e-10) { f[i] = old; change = 0; }
+      improvement -= change;
+    }
+    for (int j = neq; j + 1 < ne; j += 2) {      /* pairs of opposing pyramid edges */
+      double res[2] = {b[j] + dotn(A + (size_t)j * ne, f, ne), b[j + 1] + dotn(A + (size_t)(j + 1) * ne, f, ne)};
+      double old[2] = {f[j], f[j + 1]};
+      double Ac[4] = {A[(size_t)j * ne + j], A[(size_t)j * ne + j + 1], A[(size_t)(j + 1) * ne + j], A[(size_t)(j + 1) * ne + j + 1]};
+      double bc[2] = {res[0] - (Ac[0] * old[0] + Ac[1] * old[1]), res[1] - (Ac[2] * old[0] + Ac[3] * old[1])};
+      double mid = 0.5 * (f[j] + f[j + 1]);
+      double K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2], K0 = mid * (Ac[0] - Ac[3]) + bc[0] - bc[1];
+      if (K1 < MINVAL) { f[j] = f[j + 1] = mid; }
+      else {
+        double y = -K0 / K1;
+        if (y < -mid) { f[j] = 0; f[j + 1] = 2 * mid; }
+        else if (y > mid) { f[j] = 2 * mid; f[j + 1] = 0; }
+        else { f[j] = mid + y; f[j + 1] = mid - y; }
+      }
+      improvement -= cost_change2(Ac, f + j, old, res);
+    }
+    o->noslip_niter = iter + 1;
+    if (improvement * scale < o->noslip_tolerance) break;
+  }
+  for (int i = 0; i < nv; i++) { double sum = 0; for (int e = 0; e < ne; e++) sum += o->efc_J[(size_t)e * nv + i] * f[e]; o->qfrc_constraint[i] = sum; }
+  memcpy(o->qacc, o->qfrc_constraint, sizeof(double) * nv); chol_solve(L, nv, o->qacc);
+  for (int i = 0; i < nv; i++) o->qacc[i] += o->qacc_smooth[i];
+  for (int e = 0; e < ne; e++) o->efc_jar[e] = dotn(o->efc_J + (size_t)e * nv, o->qacc, nv) - o->efc_aref[e];
+  free(L); free(Y); free(A); free(b);
+}
+
 /* contact sensors (world.py:311-331): per leg, reduce=netforce over contacts of the leg subtree vs ground.
  * [PRIOR, unverified] layout: found, force(3), torque(3), pos(3), normal(3), tangent(3); net wrench expressed in
  * the world frame (contact frame of the synthetic net contact = identity), force = leg-on-ground. */
@@ -719,6 +801,7 @@ void nmfo_forward(nmfo* o) {
   memcpy(o->qacc_smooth, o->qfrc_smooth, sizeof(double) * nv); chol_solve(L, nv, o->qacc_smooth);
   free(L);
   solve_constraints(o);
+  noslip(o);
   sensors(o);
   energy(o);
 }
@@ -761,6 +844,7 @@ int nmfo_dim(const nmfo* o, const char* name) {
   if (!strcmp(name, "nbody")) return o->nbody; if (!strcmp(name, "ncon")) return o->ncon; if (!strcmp(name, "nefc")) return o->nefc;
   if (!strcmp(name, "ngeom")) return o->ngeom; if (!strcmp(name, "nsite")) return o->nsite; if (!strcmp(name, "nseg")) return o->nseg;
   if (!strcmp(name, "nleg")) return o->nleg; if (!strcmp(name, "solver_niter")) return o->solver_niter;
+  if (!strcmp(name, "noslip_niter")) return o->noslip_niter;
   return -1;
 }
 /* returns pointer + element count of a named double array (NULL if unknown) */

@@ -12,7 +12,7 @@ NV = 72
 DBG_FS = 4
 DBG_QACC, DBG_FC, DBG_QACCE = DBG_FS + NV, DBG_FS + 2 * NV, DBG_FS + 3 * NV
 DBG_CON = DBG_FS + 4 * NV
-DBG_XPOS = DBG_CON + 64 * 12
+DBG_XPOS = DBG_CON + 64 * 24
 DBG_CDOF = DBG_XPOS + 64 * 3
 DBG_HROWS = DBG_CDOF + NV * 6
 DBG_STRIDE = DBG_HROWS + 6 * 177 + 21 + 3

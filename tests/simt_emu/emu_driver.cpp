@@ -4,8 +4,8 @@
 #include "../../flygym_b200/csrc/nmf_host.h"
 #include "../../flygym_b200/csrc/nmf_step_all.cuh"
 
-static float g_sm[8 * nmf::f32::SM_TOTAL];
-static double g_sm64[nmf::f64::SM_TOTAL];
+static float g_sm[8 * (nmf::f32::SM_TOTAL + nmf::f32::NS_COUNT)];
+static double g_sm64[nmf::f64::SM_TOTAL + nmf::f64::NS_COUNT];
 
 extern "C" int emu_key_state(const void* blob, size_t nbytes, float* out) {
   nmf::HostModel hm;
@@ -44,7 +44,13 @@ extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_fli
     nmf::StepParamsT<double> q = hm.par64;
     fill(q, hm.role64.data(), hm.hull64.data());
     for (int b = 0; b < n_blocks; b++) simt::run_block(nmf::CTA, b, n_blocks, [&]() {
-      if (q.weld) nmf::f64::step_block<nmf::f64::W_TETHER>(q, g_sm64, b, 0, q.nsteps, false);
+      if (q.noslip_iterations > 0 && !q.weld) {    // the reference's CPU semantics: noslip post-solver
+        if (q.multiccd) nmf::f64::step_block<nmf::f64::W_MESH, 1, true>(q, g_sm64, b, 0, q.nsteps, false);
+        else if (q.terrain) nmf::f64::step_block<nmf::f64::W_TERRAIN, 1, true>(q, g_sm64, b, 0, q.nsteps, false);
+        else nmf::f64::step_block<nmf::f64::W_FLAT, 1, true>(q, g_sm64, b, 0, q.nsteps, false);
+      }
+      else if (q.weld) nmf::f64::step_block<nmf::f64::W_TETHER>(q, g_sm64, b, 0, q.nsteps, false);
+      else if (q.multiccd) nmf::f64::step_block<nmf::f64::W_MESH>(q, g_sm64, b, 0, q.nsteps, false);
       else if (q.terrain) nmf::f64::step_block<nmf::f64::W_TERRAIN>(q, g_sm64, b, 0, q.nsteps, false);
       else nmf::f64::step_block<nmf::f64::W_FLAT>(q, g_sm64, b, 0, q.nsteps, false); });
     return 0;
@@ -56,7 +62,9 @@ extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_fli
     float* sm = g_sm + slot * nmf::f32::SM_TOTAL;
 #define EMU_RUN(W) switch (fpb) { case 1: nmf::f32::step_block<W, 1>(p, sm, f, 0, p.nsteps, false); break; case 2: nmf::f32::step_block<W, 2>(p, sm, f, 0, p.nsteps, false); break; \
                                   case 4: nmf::f32::step_block<W, 4>(p, sm, f, 0, p.nsteps, false); break; default: nmf::f32::step_block<W, 8>(p, sm, f, 0, p.nsteps, false); }
-    if (p.weld) nmf::f32::step_block<nmf::f32::W_TETHER, 1>(p, sm, f, 0, p.nsteps, false);
+    if (p.noslip_iterations > 0 && !p.weld && !p.multiccd && !p.terrain) nmf::f32::step_block<nmf::f32::W_FLAT, 1, true>(p, sm, f, 0, p.nsteps, false);
+    else if (p.weld) nmf::f32::step_block<nmf::f32::W_TETHER, 1>(p, sm, f, 0, p.nsteps, false);
+    else if (p.multiccd) { EMU_RUN(nmf::f32::W_MESH) }
     else if (p.terrain) { EMU_RUN(nmf::f32::W_TERRAIN) }
     else { EMU_RUN(nmf::f32::W_FLAT) }
 #undef EMU_RUN

@@ -463,3 +463,65 @@ def test_fp64_state_persists_between_launches_and_follows_api_edits():
     # fly 1's kick was applied to the float32 image of its state (that is what an API edit is), hence ~1e-7 there
     assert errs[0] < 2e-7 and errs[1] < 5e-6 and errs[2] < 2e-7, errs
     assert abs(sim.time - (T * 1e-4)) < 1e-6
+
+
+@pytest.mark.parametrize("variant", ["flat", "mesh", "blocks"])
+def test_noslip_kernels_match_the_oracle(variant):
+    """`noslip_iterations: 5` (mujoco_globals.yaml:15): the reference's CPU `Simulation` runs MuJoCo's noslip post-solver after
+    Newton, its `GPUSimulation` strips it (warp/simulation.py:427-448).  A model baked with noslip_iterations = 5 selects the
+    NOSLIP kernel instantiations; they must follow the oracle's noslip ([PRIOR] mj_solNoSlip) on a settled fly pushed sideways
+    and then walking: f64 within float32 resolution over 300 steps, f32 (flat) within 1e-4; BASELINE config 1 (1000 steps,
+    hold-neutral) is reported for both settings."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    from oracle.oracle import Oracle
+    base = {"flat": NMFModel.bench(True), "mesh": NMFModel.bench(False), "blocks": NMFModel.bench(True, terrain="blocks")}[variant]
+    m = base.with_options(noslip_iterations=5)
+    o0 = Oracle(base); o0.reset(); o0.qpos[2] = -0.17 if variant != "blocks" else -0.15; o0.ctrl[42:] = 1.0; o0.step(1200)
+    q, v, w = o0.qpos.copy(), o0.qvel.copy(), o0.get("qacc_warmstart").copy()
+    v[0:2] += [3.0, -2.0]
+    T = 300
+    tab = cpg_table(m, 2, T)
+    o = [Oracle(m) for _ in range(2)]
+    for i, oi in enumerate(o):
+        oi.reset(); oi.qpos[:] = q; oi.qvel[:] = v; oi.get("qacc_warmstart")[:] = w; oi.ctrl[42:] = 1.0
+        oi.step_table(tab[i].astype(np.float64))
+    plain = Oracle(base); plain.reset(); plain.qpos[:] = q; plain.qvel[:] = v; plain.get("qacc_warmstart")[:] = w; plain.ctrl[42:] = 1.0
+    plain.step_table(tab[0].astype(np.float64))
+    for prec in ((64, 32) if variant == "flat" else (64,)):
+        sim = B200Simulation(m, n_worlds=2)
+        sim.set_precision(prec)
+        f32 = lambda a: torch.as_tensor(np.tile(a, (2, 1)), dtype=torch.float32)
+        sim.qpos.copy_(f32(q)); sim.qvel.copy_(f32(v)); sim.qacc_warmstart.copy_(f32(w)); sim.ctrl[:, 42:] = 1.0
+        sim.step(T, torch.from_numpy(tab).cuda(), 0)
+        got = sim.qpos.cpu().numpy().astype(np.float64)
+        err = max(np.abs(got[i] - o[i].qpos).max() / np.abs(o[i].qpos).max() for i in range(2))
+        gap = np.abs(plain.qpos - o[0].qpos).max() / np.abs(o[0].qpos).max()
+        print(f"noslip {variant} f{prec}: qpos rel Linf vs oracle {err:.1e}; noslip-vs-plain oracle {gap:.1e}")
+        assert err < (5e-7 if prec == 64 else 1e-4) and gap > 1e-4
+        so = np.stack([oi.get("sensordata") for oi in o])
+        assert np.abs(sim.sensordata.cpu().numpy() - so).max() < (1e-5 if prec == 64 else 1e-2) * max(1.0, np.abs(so).max())
+        assert int(sim.status.abs().max()) == 0
+    if variant == "flat":       # BASELINE config 1 under both solver settings (the north star's 1e-4 after 1000 steps)
+        key = base.arrays["key_qpos"]
+        for mm, tag in ((base, "noslip 0 (GPUSimulation semantics)"), (m, "noslip 5 (Simulation semantics)")):
+            oc = Oracle(mm); oc.reset(); oc.step(1000)
+            for prec in (32, 64):
+                sim = B200Simulation(mm, n_worlds=1, outputs=False); sim.set_precision(prec)
+                sim.step(1000)
+                e = np.abs(sim.qpos[0].cpu().numpy() - oc.qpos).max() / np.abs(oc.qpos).max()
+                print(f"config 1, {tag}, f{prec}: qpos rel Linf after 1000 steps = {e:.1e}")
+                assert e < 1e-4
+
+
+def test_noslip_is_refused_where_it_is_not_built():
+    """float32 noslip exists for the flat capsule world only; the tethered world's weld rows are not part of the pass."""
+    from flygym_b200 import B200Simulation, NMFModel
+    sim = B200Simulation(NMFModel.bench(False).with_options(noslip_iterations=5), n_worlds=1)
+    with pytest.raises(RuntimeError, match="precision"):
+        sim.step(1)
+    sim.set_precision(64); sim.step(1)
+    sim = B200Simulation(NMFModel.tethered().with_options(noslip_iterations=5), n_worlds=1)
+    with pytest.raises(RuntimeError, match="tethered"):
+        sim.step(1)
