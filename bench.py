@@ -46,8 +46,8 @@ RETINA_ALG_BYTES = 2 * 512 * 450 * 3 + 2 * 721 * 2 * 4   # 1 393 936 B per fly-f
 # B200 divided by the fly-steps of the captured launch; profiles/ncu_*_summary.txt).  roofline.traffic = this x the fly-steps of one
 # launch of the run that prints it, and traffic_source names the capture it was scaled from.
 NCU_TRAFFIC_PER_FLY_STEP = {
-    "flat": ((0.1271e9 + 2.9768e9) / (4096 * 100), "profiles/ncu_step_r01j_summary.txt (4096 flies x 100 steps: 0.127 GB read + 2.98 GB written, the writes being "
-                                                   "local-memory spill lines evicted from L2, vs 0.79 GB algorithmic)"),
+    "flat": ((0.1738e9 + 3.2041e9) / (4096 * 100), "profiles/ncu_step_r02f_summary.txt (nmf_step_x8_kernel, 4096 flies x 100 steps: 0.174 GB read + 3.20 GB written, "
+                                                   "the writes being local-memory spill lines evicted from L2, vs 0.79 GB algorithmic)"),
     "terrain": ((0.0896e9 + 0.5587e9) / (4096 * 100), "profiles/ncu_step_terrain_r01_summary.txt (4096 flies x 100 steps, 80-register build)"),
     "olfaction": ((0.0774e9 + 0.6436e9) / 32768, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs)"),
 }
@@ -55,9 +55,10 @@ VISION_TRAFFIC = (0.81e6 / 1024, "profiles/ncu_vision_r01s2_summary.txt: the fus
 RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.txt: 1.009 GB read + 8.3 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
 # what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
 NCU_LIMITER = {
-    "flat": {"issue_slots_busy": 0.402, "top_stall": "no_inst (instruction fetch) 46 % of samples", "warp_instructions_per_fly_step": 21200,
-             "issue_ceiling_env_steps_per_s": 148 * 4 * 1.965e9 / 21200,
-             "source": "profiles/ncu_step_r01j_summary.txt"},
+    "flat": {"issue_slots_busy": 0.542, "top_stall": "barrier 24.5 % (lockstep passes of the 8 flies of a block + the fly's own barriers), short scoreboard 24.5 % "
+             "(shuffles / shared memory), long scoreboard 16.3 % (register spills); no_inst 0.8 % (46 % before the flies of a block shared their fetches)",
+             "warp_instructions_per_fly_step": 23330, "issue_ceiling_env_steps_per_s": 148 * 4 * 1.965e9 / 23330,
+             "source": "profiles/ncu_step_r02f_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
     "olfaction": {"issue_slots_busy": 0.509, "top_stall": "no_inst (instruction fetch)", "source": "profiles/ncu_step_olfaction_r01_summary.txt"},
     "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",

@@ -216,7 +216,7 @@ extern "C" int nmf_set_flies_per_block(nmf_handle* h, int fpb) {
 }
 
 static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
-                        int fly0 = 0, int count = -1);
+                        int fly0 = 0, int count = -1, float* out_qpos = nullptr);
 
 extern "C" int nmf_step(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, void* stream) {
   return launch_steps(h, nsteps, table, table_T, table_t0, table_cols, false, stream);
@@ -285,7 +285,7 @@ template <> struct KernelSet<double> {
 // flies [fly0, fly0 + count) only (count < 0: all): the buffers are addressed per fly, so a range is the same launch on offset pointers
 template <class real>
 static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
-                          int fly0, int count) {
+                          int fly0, int count, float* out_qpos) {
   StepParamsT<real> p = KernelSet<real>::base(h);
   p.max_newton = h->hm.par.max_newton; p.max_ls = h->hm.par.max_ls;       // nmf_set_solver edits the f32 copy
   p.state = h->buf.state; p.state64 = nullptr; p.shadow = nullptr;
@@ -293,7 +293,7 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   p.role = KernelSet<real>::role(h); p.hull = KernelSet<real>::hull(h); p.seg_tab = h->d_seg; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr;
   p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
   p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
-  p.out_energy = h->buf.energy;
+  p.out_energy = h->buf.energy; p.out_qpos = out_qpos;      // (out_qpos already points at the first fly of a ranged launch)
   p.dbg = h->buf.debug; p.n_flies = h->n_flies; p.nsteps = nsteps; p.forward_only = forward_only ? 1 : 0;
   const bool ranged = count >= 0 && (fly0 != 0 || count != h->n_flies);
   if (ranged) {
@@ -336,7 +336,7 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
 }
 
 static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
-                        int fly0, int count) {
+                        int fly0, int count, float* out_qpos) {
   if (!h) return NMF_EINVAL;
   if (!h->bound) { h->err = "nmf_step: not bound"; return NMF_ENOTBOUND; }
   if (nsteps <= 0) return NMF_OK;
@@ -352,8 +352,8 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
   if (h->hm.par.noslip_iterations > 0 && h->precision != 64 && (h->hm.par.terrain || h->hm.par.multiccd)) {
     h->err = "nmf_step: noslip on terrain / mesh-hull worlds needs nmf_set_precision(h, 64) (float32 noslip is built for the flat capsule world only)"; return NMF_EINVAL;
   }
-  return h->precision == 64 ? launch_steps_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count)
-                            : launch_steps_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count);
+  return h->precision == 64 ? launch_steps_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos)
+                            : launch_steps_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos);
 }
 
 // Arithmetic of the step kernels: 32 (default, the product path) or 64 = the SAME kernel source instantiated in double precision
@@ -428,12 +428,9 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
     float* d_act = h->d_act + (size_t)f0 * action_cols;
     CK(cudaMemcpyAsync(d_act, actions_host + (size_t)f0 * action_cols, sizeof(float) * (size_t)cnt * action_cols, cudaMemcpyHostToDevice, s));
     // the action block doubles as a 1-row action table: ctrl[0:action_cols] <- actions (position actuators first, then adhesion)
-    int rc = launch_steps(h, nsteps, h->d_act, 1, 0, action_cols, false, s, f0, cnt);
+    // the step kernel packs qpos of its flies into d_qpos when it writes the records back (no separate gather launch)
+    int rc = launch_steps(h, nsteps, h->d_act, 1, 0, action_cols, false, s, f0, cnt, h->d_qpos + (size_t)f0 * NQ);
     if (rc) return rc;
-    const int total = cnt * NQ;
-    nmf_gather_cols_kernel<<<(total + 255) / 256, 256, 0, s>>>(h->buf.state + (size_t)f0 * S_STRIDE, S_QPOS, nullptr, NQ, h->d_qpos + (size_t)f0 * NQ, cnt);
-    h->launches++;
-    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(qpos_host + (size_t)f0 * NQ, h->d_qpos + (size_t)f0 * NQ, sizeof(float) * (size_t)cnt * NQ, cudaMemcpyDeviceToHost, s));
     if (parts > 1) { CK(cudaEventRecord(h->part_done[k], s)); CK(cudaStreamWaitEvent(stream, h->part_done[k], 0)); }
   }

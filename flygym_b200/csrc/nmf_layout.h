@@ -99,6 +99,7 @@ struct StepParamsT {
   float* out_xquat;          // optional [n_flies][nseg][4]
   float* out_actf;           // optional [n_flies][nu]
   float* out_sensor;         // optional [n_flies][NLEG*16]
+  float* out_qpos;           // optional [n_flies][NQ]: qpos after the launch's last step, packed (nmf_step_host reads it back)
   float* out_energy;         // optional [n_flies][2]: potential, kinetic energy of the state the last step started from
   float* dbg;                // optional [n_flies][DBG_STRIDE]
   const int* hull_nbr_adr;   // CSR adjacency of the hull vertices: neighbours of vertex v are hull_nbr[hull_nbr_adr[v] .. hull_nbr_adr[v+1])

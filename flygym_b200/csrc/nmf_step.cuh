@@ -1597,6 +1597,10 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
   }
 
   // ---- write the record back (TMA bulk store)
+  if (p.out_qpos && step0 + nsub == p.nsteps) {
+    float* o = p.out_qpos + (size_t)fly * NQ;
+    for (int i = tid; i < NQ; i += CTA) o[i] = (float)st[S_QPOS + i];
+  }
   if (!p.forward_only) store_record(p, st, sm, fly, tid, published, bar);
 }
 
