@@ -525,3 +525,48 @@ def test_noslip_is_refused_where_it_is_not_built():
     sim = B200Simulation(NMFModel.tethered().with_options(noslip_iterations=5), n_worlds=1)
     with pytest.raises(RuntimeError, match="tethered"):
         sim.step(1)
+
+
+def test_mujoco_golden_on_the_gpu_if_present():
+    """Twin of tests/test_cpu_suite.py::test_mujoco_golden_if_present for the CUDA path: where tests/golden/mujoco_golden.npz exists
+    (tools/dump_mujoco_golden.py, needs real MuJoCo + the reference package), the kernels -- f64 against the north star's 1e-4,
+    f32 against the bands of this file -- replay every recorded scenario for noslip 0 and 5 and are compared with MuJoCo's own
+    qpos / qvel / contact sensors.  Absent here (MuJoCo is not installable): parity vs MuJoCo is unpinned."""
+    import sys
+    from pathlib import Path
+    import torch
+    root = Path(__file__).resolve().parent.parent
+    path = root / "tests" / "golden" / "mujoco_golden.npz"
+    if not path.exists():
+        pytest.skip("parity vs MuJoCo: not run (golden file absent; see tools/dump_mujoco_golden.py)")
+    from flygym_b200 import B200Simulation, NMFModel
+    from test_cpu_suite import golden_scenarios
+    z = np.load(path, allow_pickle=False)
+    for tag, simplify in (("capsule", True), ("mesh", False)):
+        base = NMFModel.bench(simplify)
+        cps, scen = golden_scenarios(base, z, tag)
+        for noslip in sorted({int(k.split("/")[1][6:]) for k in z.files if k.startswith(f"{tag}/noslip")}):
+            model = base.with_options(noslip_iterations=noslip)
+            for prec in (64, 32):
+                if prec == 32 and noslip > 0 and not simplify:
+                    continue                                   # float32 noslip is built for the flat capsule world only
+                n = len(scen)
+                sim = B200Simulation(model, n_worlds=n); sim.set_precision(prec)
+                tab = np.zeros((n, cps[-1], 48), np.float32)
+                for i, (sname, z0, table, adh) in enumerate(scen):
+                    if z0 is not None:
+                        sim.qpos[i, 2] = z0
+                    tab[i, :, :42] = table; tab[i, :, 42:] = max(adh, 0.0)
+                tabd = torch.from_numpy(tab).cuda(); done = 0
+                for k, cp in enumerate(cps):
+                    sim.step(cp - done, tabd, done); done = cp
+                    q = sim.qpos.cpu().numpy().astype(np.float64); v = sim.qvel.cpu().numpy().astype(np.float64)
+                    errs = []
+                    for i, (sname, *_rest) in enumerate(scen):
+                        rq, rv = z[f"{tag}/noslip{noslip}/{sname}/qpos"][k], z[f"{tag}/noslip{noslip}/{sname}/qvel"][k]
+                        errs.append(np.abs(q[i] - rq).max() / np.abs(rq).max())
+                        if prec == 64:
+                            assert errs[-1] < 1e-4, (tag, noslip, sname, cp, errs[-1])             # the north star's tolerance
+                            assert np.abs(v[i] - rv).max() / max(1.0, np.abs(rv).max()) < 1e-3, (tag, noslip, sname, cp, "qvel")
+                    if prec == 32:                             # float32: every fly to 100 steps, median beyond (contact chaos, see the tests above)
+                        assert (max(errs) < 1e-4) if cp <= 100 else (np.median(errs) < 1e-3), (tag, noslip, cp, errs)

@@ -9,8 +9,11 @@ which composes the reference benchmark model exactly as src/flygym_demo/benchmar
 with MuJoCo and stores (i) the compiled constants the baker restates (body masses / inertias / inverse weights, geom sizes, the
 keyframe, solver options) and (ii) mj_step trajectories of BASELINE configs 1 and 2 (hold-neutral from the keyframe, zero actions,
 standing, CPG walking) for `noslip_iterations = 0` (what GPUSimulation runs, warp/simulation.py:427-448) and for the CPU default.
-tests/test_cpu_suite.py::test_mujoco_golden_if_present then compares the baked model and the oracle with it; without the file that
-test reports "parity vs MuJoCo: not run (golden file absent)".
+It also stores every public MjModel field that flygym_b200.convert.from_mjmodel reads.  With the file present, ONE command pins baker,
+converter, oracle and kernels:  tests/test_cpu_suite.py::test_mujoco_golden_if_present  replays the converter on the stored MjModel
+(vs the baked model), and the oracle on every scenario (qpos, qvel, contact sensors; noslip 0 and 5);
+tests/test_gpu_step.py::test_mujoco_golden_on_the_gpu_if_present  does the same with the CUDA kernels (f32 and f64).  Without the file
+both report "parity vs MuJoCo: not run (golden file absent)".
 """
 import argparse
 import sys
@@ -19,6 +22,31 @@ from pathlib import Path
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+MJMODEL_FIELDS = ["body_parentid", "body_pos", "body_quat", "body_mass", "body_ipos", "body_iquat", "body_inertia", "body_invweight0", "body_jntadr",
+                  "body_jntnum", "body_dofadr", "body_dofnum", "jnt_type", "jnt_bodyid", "jnt_axis", "jnt_pos", "jnt_qposadr", "jnt_dofadr", "jnt_stiffness",
+                  "qpos_spring", "qpos0", "dof_damping", "dof_armature", "actuator_trntype", "actuator_trnid", "actuator_gainprm", "actuator_biasprm",
+                  "actuator_forcerange", "actuator_forcelimited", "actuator_ctrlrange", "geom_type", "geom_bodyid", "geom_pos", "geom_quat", "geom_size",
+                  "geom_dataid", "mesh_vert", "mesh_vertadr", "mesh_vertnum", "mesh_graphadr", "mesh_graph", "pair_geom1", "pair_geom2", "pair_friction",
+                  "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "site_bodyid", "site_pos", "key_qpos", "key_ctrl", "eq_type", "eq_obj1id",
+                  "eq_obj2id", "eq_data", "eq_solref", "eq_solimp"]
+
+
+def mjmodel_from_golden(z, tag):
+    """Rebuild the duck-typed MjModel that flygym_b200.convert.from_mjmodel ingests from a golden file written by this tool."""
+    from types import SimpleNamespace
+    m = SimpleNamespace()
+    for key in MJMODEL_FIELDS:
+        if f"{tag}/mjmodel/{key}" in z:
+            setattr(m, key, z[f"{tag}/mjmodel/{key}"])
+    m.nbody, m.njnt, m.nq, m.nv, m.nu, m.ngeom, m.npair, m.nsite, m.nkey, m.neq, flags = (int(x) for x in z[f"{tag}/mjmodel/sizes"])
+    o = z[f"{tag}/opt"]
+    m.opt = SimpleNamespace(timestep=float(o[0]), gravity=o[1:4], iterations=int(o[4]), tolerance=float(o[5]), ls_iterations=int(o[6]), ls_tolerance=float(o[7]),
+                            noslip_iterations=int(o[8]), impratio=float(o[10]), enableflags=flags)
+    m.stat = SimpleNamespace(meaninertia=float(o[9]))
+    m.names = {k: [str(x) for x in z[f"{tag}/mjmodel/names_{k}"]] for k in ("body", "joint", "actuator", "geom", "site")}
+    return m
 
 
 def main():
@@ -63,6 +91,15 @@ def main():
         out[f"{tag}/opt"] = np.array([m.opt.timestep, *m.opt.gravity, m.opt.iterations, m.opt.tolerance, m.opt.ls_iterations, m.opt.ls_tolerance,
                                       m.opt.noslip_iterations, m.stat.meaninertia, m.opt.impratio, m.opt.cone, m.opt.integrator, m.opt.solver])
         out[f"{tag}/jointdofs_order"] = np.array([str(x.name) for x in fly.get_jointdofs_order()])
+        # ---- every public MjModel field flygym_b200.convert.from_mjmodel reads, so that the converter (and through it the baker)
+        # can be replayed against the real compiler's output wherever the golden file is available
+        for key in MJMODEL_FIELDS:
+            if hasattr(m, key):
+                out[f"{tag}/mjmodel/{key}"] = np.array(getattr(m, key))
+        out[f"{tag}/mjmodel/sizes"] = np.array([m.nbody, m.njnt, m.nq, m.nv, m.nu, m.ngeom, m.npair, m.nsite, m.nkey, m.neq, m.opt.enableflags])
+        for kind, obj, cnt in (("body", mj.mjtObj.mjOBJ_BODY, m.nbody), ("joint", mj.mjtObj.mjOBJ_JOINT, m.njnt), ("actuator", mj.mjtObj.mjOBJ_ACTUATOR, m.nu),
+                               ("geom", mj.mjtObj.mjOBJ_GEOM, m.ngeom), ("site", mj.mjtObj.mjOBJ_SITE, m.nsite)):
+            out[f"{tag}/mjmodel/names_{kind}"] = np.array([mj.mj_id2name(m, obj, i) or "" for i in range(cnt)])
         # ---- (ii) trajectories
         ours = NMFModel.bench(simplify_geom=simplify)
         cpg = cpg_table(ours, 4, args.steps).astype(np.float64)
