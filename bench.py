@@ -73,7 +73,7 @@ def workload_config(args, n_flies, chunk):
     what = {
         "flat": "flat terrain, CPG tripod gait (12 Hz sinusoids), adhesion on, no vision",
         "terrain": f"{args.terrain} terrain (box columns), CPG tripod gait, adhesion 100 in stance / 1 in swing, no vision",
-        "vision": "flat terrain, CPG tripod gait, adhesion on, two 512x450 eye-camera renders -> 721-ommatidia Retina after EVERY step",
+        "vision": "flat terrain, CPG tripod gait, adhesion on, two 512x450 eye-camera renders (checker ground, sky" + (", the fly's own body" if args.eye_body == "on" else "") + ") -> 721-ommatidia Retina after EVERY step",
         "olfaction": "flat terrain, CPG tripod gait, adhesion on, 4 odor sensors x 2 sources x 2 odor dims after every step",
     }[args.workload]
     cfg = {
@@ -332,7 +332,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
     eyes = odor = sens_out = None
     if wl == "vision":
         from flygym_b200.retina import EyeCameras
-        eyes = EyeCameras(sim)
+        eyes = EyeCameras(sim, body=args.eye_body == "on")
         sens_out = torch.empty((n, 2, eyes.ret.n_ommatidia, 2), dtype=torch.float32, device=dev)
     elif wl == "olfaction":
         from flygym_b200.retina import OdorSensor
@@ -518,6 +518,12 @@ def run_ours(args, rank, world, local_rank):
             a3 = copy.copy(args); a3.precision = 64
             extras["f64"] = sub_record(a3, measure(ctx, a3, steps=200, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
                                        "the same kernel source in double precision: the build that stays within 1e-4 of the fp64 oracle for every walking fly")
+            a4 = copy.copy(args); a4.workload = "terrain"; a4.chunk = DEFAULT_CHUNK["terrain"]
+            extras["config3_terrain"] = sub_record(a4, measure(ctx, a4, steps=300, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
+                                                   "BASELINE config 3: 4096 flies on the blocks terrain, stance-phase adhesion")
+            a6 = copy.copy(args); a6.workload = "vision"; a6.n_flies = DEFAULT_FLIES["vision"]; a6.chunk = DEFAULT_CHUNK["vision"]
+            extras["config4_vision"] = sub_record(a6, measure(ctx, a6, steps=100, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
+                                                  "BASELINE config 4: 1024 flies, two eye-camera renders (ground, sky, the fly's own body) -> Retina after every step")
         else:
             a5 = copy.copy(args); a5.workload = "olfaction"; a5.n_flies = DEFAULT_FLIES["olfaction"]; a5.chunk = DEFAULT_CHUNK["olfaction"]
             extras["config5"] = sub_record(a5, measure(ctx, a5, steps=200, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
@@ -579,6 +585,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=None, help="physics steps per timed launch group (fused into one launch when no sensors run)")
     ap.add_argument("--mesh", action="store_true", help="mesh-hull collision geoms (simplify_geom=False)")
     ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
+    ap.add_argument("--eye-body", default="on", choices=["on", "off"], help="vision workload: the eye cameras also see the fly's own body (capsule proxies)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary records (mesh / f64 at N = 1, config 5 at N > 1)")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64], help="arithmetic of the step kernel: 32 = product path; 64 = the same "

@@ -62,7 +62,8 @@ class NmfBuffers(ctypes.Structure):
 class NmfEyeParams(ctypes.Structure):
     _fields_ = [("eye_seg", ctypes.c_int32 * 2), ("rel_pos", ctypes.c_float * 6), ("R_local", ctypes.c_float * 18),
                 ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("inv_f", ctypes.c_float), ("inv_check", ctypes.c_float),
-                ("ground_lo", ctypes.c_uint32), ("ground_hi", ctypes.c_uint32), ("sky_g", ctypes.c_uint32), ("sky_b", ctypes.c_uint32)]
+                ("ground_lo", ctypes.c_uint32), ("ground_hi", ctypes.c_uint32), ("sky_g", ctypes.c_uint32), ("sky_b", ctypes.c_uint32),
+                ("body_g", ctypes.c_uint32), ("body_b", ctypes.c_uint32)]
 
 
 _LIB = None
@@ -111,6 +112,8 @@ def load() -> ctypes.CDLL:
     lib.nmf_odor_intensity.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, ci, ci, vp, vp]
     lib.nmf_eye_render.argtypes = [vp, ctypes.POINTER(NmfEyeParams), vp, vp, ci, ci, vp, vp]
     lib.nmf_eye_retina.argtypes = [vp, ctypes.POINTER(NmfEyeParams), vp, vp, ci, ci, vp, vp]
+    lib.nmf_eye_set_body.argtypes = [vp, vp, vp, vp, vp, ci]
+    lib.nmf_eye_set_body.restype = ci
     lib.nmf_eye_render.restype = ci
     lib.nmf_eye_retina.restype = ci
     for fn in ("nmf_retina_create", "nmf_retina_destroy", "nmf_retina_forward", "nmf_retina_forward_host", "nmf_odor_intensity"):
@@ -124,5 +127,5 @@ DECLARED_SYMBOLS = [
     "nmf_create", "nmf_destroy", "nmf_model_info", "nmf_last_error", "nmf_bind", "nmf_reset", "nmf_step",
     "nmf_scatter_ctrl", "nmf_gather_state", "nmf_step_host", "nmf_set_solver", "nmf_set_schedule", "nmf_set_precision", "nmf_set_flies_per_block", "nmf_forward", "nmf_replay_table", "nmf_launch_count",
     "nmf_retina_create", "nmf_retina_destroy", "nmf_retina_last_error", "nmf_retina_launch_count", "nmf_retina_forward",
-    "nmf_retina_forward_host", "nmf_odor_intensity", "nmf_eye_render", "nmf_eye_retina",
+    "nmf_retina_forward_host", "nmf_odor_intensity", "nmf_eye_render", "nmf_eye_retina", "nmf_eye_set_body",
 ]

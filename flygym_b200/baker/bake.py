@@ -165,15 +165,17 @@ def bake(
     contact_segs = A.contact_bodies(contact_preset)
     seg_mass, seg_com, seg_inertia = {}, {}, {}
     seg_geom = {}
+    viscap = {}
     for s in segs:
         tris = _segment_mesh(assets, s)
         mass = float(rigging[s]["mass"])
         V, com, I_unit = G.mesh_mass_properties(tris)
         w, ax = G.principal_axes(I_unit)
         is_capsule = simplify_geom or (A.is_leg(s) and A.seg_link(s) == "tarsus5")  # fly.py:585-589
+        box = G.inertia_box_halfsizes(V, w)
+        radius, half = G.fit_capsule(box)
+        viscap[s] = (com, ax[:, 2].copy(), radius, half)      # capsule proxy of EVERY segment: what the eye cameras see of the body
         if is_capsule:
-            box = G.inertia_box_halfsizes(V, w)
-            radius, half = G.fit_capsule(box)
             I_seg = ax @ np.diag(G.capsule_inertia(mass, radius, half)) @ ax.T
             seg_geom[s] = dict(type=GEOM_CAPSULE, pos=com, quat=G.mat_to_quat(ax), size=(radius, half),
                                verts=np.zeros((0, 3)), nbrs=[])
@@ -330,6 +332,10 @@ def bake(
         hull_vert=hull_vert, hull_nbr_adr=np.array(nbr_adr, np.int32), hull_nbr=np.array(nbr if nbr else [0], np.int32),
         site_body=site_body, site_pos=site_pos, seg_body=seg_body, seg_pos=seg_pos, seg_quat=seg_quat,
         leg_rootbody=leg_rootbody, key_qpos=key_qpos, key_ctrl=key_ctrl,
+        # not part of the blob: capsule proxy of every segment in its own frame (centre, axis, radius, half length), used by the
+        # eye cameras to draw the fly's own body (flygym_b200/retina.py)
+        viscap_pos=np.array([viscap[s][0] for s in segs]), viscap_axis=np.array([viscap[s][1] for s in segs]),
+        viscap_size=np.array([[viscap[s][2], viscap[s][3]] for s in segs]),
     )
     names = dict(
         bodies=body_names, segments=segs, jointdofs=[d.name for d in dofs],

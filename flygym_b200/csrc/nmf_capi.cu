@@ -148,6 +148,15 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   CK(cudaMalloc(&h->d_nbr, sizeof(int) * h->hm.hull_nbr.size()));
   CK(cudaMemcpy(h->d_nbr, h->hm.hull_nbr.data(), sizeof(int) * h->hm.hull_nbr.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_queue, sizeof(int) * ((size_t)n_flies * QUEUE_MAX_CHUNKS + 2)));
+  // staging of nmf_step_host (actions in, packed qpos out) and its pipeline streams: created here, so that no call on the
+  // stepping path allocates
+  CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n_flies * MAXU));
+  CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n_flies * NQ));
+  for (int k = 0; k < nmf_handle::MAX_PARTS; k++) {
+    CK(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
   if (const char* e = getenv("NMF_FPB")) { int v = atoi(e); if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8) h->fpb = v; }
   if (h->hm.par.weld) h->fpb = 1;
   {
@@ -410,16 +419,9 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nu = h->hm.par.nu_pos + h->hm.par.nu_adh, n = h->n_flies;
   if (action_cols != h->hm.par.nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
-  if (!h->d_act) { CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n * nu)); CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n * NQ)); }
+  if (!h->d_act) { h->err = "nmf_step_host: staging buffers missing"; return NMF_EINVAL; }     // allocated by nmf_create
   int parts = h->host_parts;
   while (parts > 1 && n < 1024 * parts) parts--;   // at least 1024 flies per slice
-  if (parts > 1 && !h->part_stream[0]) {
-    for (int k = 0; k < nmf_handle::MAX_PARTS; k++) {
-      CK(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));
-    }
-    CK(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
-  }
   if (parts > 1) CK(cudaEventRecord(h->fork, stream));
   for (int k = 0; k < parts; k++) {
     const int f0 = (int)((long long)n * k / parts), cnt = (int)((long long)n * (k + 1) / parts) - f0;

@@ -190,6 +190,28 @@ CHECKER_MM = 4.0                                   # world.py:233-250: 2000 mm p
 GROUND_U8, SKY_GB_U8 = (77, 102), (178, 229)       # rgb1 = 0.3, rgb2 = 0.4 (world.py:240-241); uniform light-blue sky
 
 
+BODY_GB_U8 = (64, 38)                              # the fly's own body in its eyes' view: one dark brown tone (green, blue)
+# segments the eye cameras do not see (flygym1_config.yaml:148-162, v1 names -> v2 via utils/api1to2.py:6-45)
+HIDDEN_SEGMENTS = ("lf_coxa", "l_eye", "l_arista", "l_funiculus", "l_pedicel", "rf_coxa", "r_eye", "r_arista", "r_funiculus", "r_pedicel",
+                   "c_head", "c_rostrum", "c_haustellum", "c_thorax")
+
+
+def body_capsules(model) -> dict | None:
+    """Capsule proxies (float32) of the segments the eye cameras see, from the baked model's ``viscap_*`` arrays (the capsule the
+    baker fits to every segment's mesh): segment index, the two end points in the segment frame, radius.  ``None`` for models
+    without them (e.g. converted from an ``MjModel``)."""
+    a = model.arrays
+    if "viscap_pos" not in a:
+        return None
+    segs = model.names["segments"]
+    keep = [i for i, s in enumerate(segs) if s not in HIDDEN_SEGMENTS]
+    pos, axis, size = (np.asarray(a[k], dtype=np.float64) for k in ("viscap_pos", "viscap_axis", "viscap_size"))
+    seg = np.array(keep, dtype=np.int32)
+    A = (pos[keep] + axis[keep] * size[keep, 1:2]).astype(np.float32)
+    B = (pos[keep] - axis[keep] * size[keep, 1:2]).astype(np.float32)
+    return dict(seg=seg, a=np.ascontiguousarray(A), b=np.ascontiguousarray(B), rad=size[keep, 0].astype(np.float32), colour=BODY_GB_U8)
+
+
 def euler_xyz_to_mat(e) -> np.ndarray:
     """Intrinsic x-y-z Euler angles -> rotation matrix (own convention, documented in DESIGN.md)."""
     a, b, c = e
@@ -214,9 +236,10 @@ class EyeCameras:
     """Image formation for the two compound-eye cameras on top of a :class:`B200Simulation` (segment poses of the last
     step): ``render()`` gives the raw buffers ``(n, 2, 512, 450, 3) uint8``; ``retina()`` is the fused
     render + Retina path that never materialises them.  The two are bit-identical by construction
-    (``retina() == Retina()(render())``)."""
+    (``retina() == Retina()(render())``).  The cameras see the checker ground, the sky and -- with ``body`` -- the fly's own
+    body: every segment outside the v1 hidden list as the capsule the baker fits to its mesh."""
 
-    def __init__(self, sim, retina: Retina | None = None):
+    def __init__(self, sim, retina: Retina | None = None, body: bool = True):
         self.sim = sim
         self.ret = retina if retina is not None else Retina(device=sim.device)
         self.params = eye_params(sim.model.names["segments"], self.ret.H, self.ret.W)
@@ -228,8 +251,16 @@ class EyeCameras:
         c.cx, c.cy, c.inv_f, c.inv_check = float(p["cx"]), float(p["cy"]), float(p["inv_f"]), float(p["inv_check"])
         c.ground_lo, c.ground_hi = p["ground"]
         c.sky_g, c.sky_b = p["sky"]
+        c.body_g, c.body_b = BODY_GB_U8
         self._c = c
         self._lib = _lib.load()
+        self.body = body_capsules(sim.model) if body else None
+        if self.body is not None:
+            b = self.body
+            ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+            self.ret._check(self._lib.nmf_eye_set_body(self.ret._h, ptr(b["seg"]), ptr(b["a"]), ptr(b["b"]), ptr(b["rad"]), len(b["seg"])))
+        else:
+            self.ret._check(self._lib.nmf_eye_set_body(self.ret._h, None, None, None, None, 0))
 
     def _args(self):
         sim = self.sim

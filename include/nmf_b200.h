@@ -154,7 +154,12 @@ typedef struct nmf_eye_params {
   float cx, cy, inv_f;     /* principal point (pixels) and 1/focal length (1/pixels): f = (H/2)/tan(fovy/2) */
   float inv_check;         /* 1 / checker square size (1/mm) */
   uint32_t ground_lo, ground_hi, sky_g, sky_b;   /* 8-bit colours: the two checker greys, sky green / blue */
+  uint32_t body_g, body_b;                       /* 8-bit colour of the fly's own body (nmf_eye_set_body) */
 } nmf_eye_params;
+/* The fly's own body as the eye cameras see it: ncap <= 64 capsules, capsule k rigidly attached to segment seg[k] with end points
+ * cap_a[k], cap_b[k] (segment frame) and radius[k]; HOST arrays, copied.  The visible segments are all but the v1 hidden list
+ * (flygym1_config.yaml:148-162).  ncap = 0 (default): ground and sky only. */
+int nmf_eye_set_body(nmf_retina* r, const int32_t* seg, const float* cap_a, const float* cap_b, const float* radius, int ncap);
 /* raw eye images DEVICE uint8 [n_flies][2][H][W][3] from the segment poses of the last step */
 int nmf_eye_render(nmf_retina* r, const nmf_eye_params* prm, const float* seg_xpos, const float* seg_xquat, int n_flies, int nseg,
                    uint8_t* images, void* cuda_stream);

@@ -48,7 +48,50 @@ def odor_oracle(seg_xpos, seg_xquat, sensor_seg, sensor_rel, src_pos, src_peak):
     return out
 
 
-def eye_render_oracle(seg_xpos, seg_xquat, prm, H, W):
+def _seg_matrix(q, f32=np.float32):
+    w, x, y, z = (f32(v) for v in q)
+    two, one = f32(2), f32(1)
+    return np.array([[one - two * (y * y + z * z), two * (x * y - w * z), two * (x * z + w * y)],
+                     [two * (x * y + w * z), one - two * (x * x + z * z), two * (y * z - w * x)],
+                     [two * (x * z - w * y), two * (y * z + w * x), one - two * (x * x + y * y)]], dtype=f32)
+
+
+def body_mask_oracle(seg_xpos_i, seg_xquat_i, body, pos, wx, wy, wz):
+    """float32 restatement of csrc/nmf_retina.cu::eye_body_hit for every pixel and every visible capsule (no culling here: the
+    kernel's culling is conservative): True where the ray from the camera at `pos` with direction (wx, wy, wz) passes within the
+    radius of a capsule's axis segment."""
+    f32 = np.float32
+    dot = lambda a0, a1, a2, b0, b1, b2: (a0 * b0 + a1 * b1) + a2 * b2
+    mask = np.zeros(wx.shape, dtype=bool)
+    cc = dot(wx, wy, wz, wx, wy, wz)
+    for k in range(len(body["seg"])):
+        seg = int(body["seg"][k])
+        xp = seg_xpos_i[seg].astype(f32); S = _seg_matrix(seg_xquat_i[seg])
+        a_, b_ = body["a"][k].astype(f32), body["b"][k].astype(f32)
+        A = np.array([xp[i] + dot(S[i, 0], S[i, 1], S[i, 2], a_[0], a_[1], a_[2]) for i in range(3)], dtype=f32)
+        B = np.array([xp[i] + dot(S[i, 0], S[i, 1], S[i, 2], b_[0], b_[1], b_[2]) for i in range(3)], dtype=f32)
+        W0 = (A - pos).astype(f32); U = (B - A).astype(f32)
+        a = dot(U[0], U[1], U[2], U[0], U[1], U[2]); d = dot(U[0], U[1], U[2], W0[0], W0[1], W0[2])
+        r2 = f32(body["rad"][k]) * f32(body["rad"][k])
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            b = dot(U[0], U[1], U[2], wx, wy, wz)
+            e = dot(wx, wy, wz, W0[0], W0[1], W0[2])
+            D = a * cc - b * b
+            ok = D > f32(1e-12)
+            s = np.where(ok, np.minimum(np.maximum((b * e - cc * d) * (f32(1) / np.where(ok, D, f32(1))), f32(0)), f32(1)), f32(0)).astype(f32)
+            t = ((b * s + e) * (f32(1) / cc)).astype(f32)
+            neg = t < 0
+            s_alt = np.minimum(np.maximum(-d / a, f32(0)), f32(1)) if a > 0 else f32(0)
+            s = np.where(neg, s_alt, s).astype(f32); t = np.where(neg, f32(0), t).astype(f32)
+            px = (W0[0] + s * U[0]) - t * wx; py = (W0[1] + s * U[1]) - t * wy; pz = (W0[2] + s * U[2]) - t * wz
+            n0, n1, n2 = wy * U[2] - wz * U[1], wz * U[0] - wx * U[2], wx * U[1] - wy * U[0]      # quick reject: the infinite cylinder about the axis
+            h = dot(W0[0], W0[1], W0[2], n0, n1, n2)
+            keep = ~((h * h) > (r2 * f32(1.01)) * dot(n0, n1, n2, n0, n1, n2))
+            mask |= keep & (dot(px, py, pz, px, py, pz) <= r2)
+    return mask
+
+
+def eye_render_oracle(seg_xpos, seg_xquat, prm, H, W, body=None):
     """float32 restatement of csrc/nmf_retina.cu::eye_pixel (same operation order, every op individually rounded):
     raw eye images (n, 2, H, W, 3) uint8 from float32 segment poses."""
     f32 = np.float32
@@ -82,6 +125,9 @@ def eye_render_oracle(seg_xpos, seg_xquat, prm, H, W):
             v = np.where(((ix.astype(np.int64) + iy) & 1) == 1, prm["ground"][1], prm["ground"][0])
             g = np.where(hit, v, prm["sky"][0]).astype(np.uint8)
             b = np.where(hit, v, prm["sky"][1]).astype(np.uint8)
+            if body is not None:
+                m = body_mask_oracle(seg_xpos[i], seg_xquat[i], body, pos, wx.astype(f32), wy.astype(f32), wz.astype(f32))
+                g = np.where(m, np.uint8(body["colour"][0]), g); b = np.where(m, np.uint8(body["colour"][1]), b)
             img[i, e, :, :, 0] = g
             img[i, e, :, :, 1] = g
             img[i, e, :, :, 2] = b

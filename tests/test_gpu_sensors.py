@@ -80,13 +80,21 @@ def test_eye_cameras_bit_exact_and_fused_path():
     sim.qpos[1, 3:7] = q.cuda()                       # tilt one fly so that the horizon is not axis-aligned
     sim.qpos[2, 0:3] = torch.tensor([3.3, -1.7, 2.0]).cuda()
     sim.step(2)
-    cams = EyeCameras(sim)
+    xp, xq = sim.seg_xpos.cpu().numpy(), sim.seg_xquat.cpu().numpy()
+    plain = EyeCameras(sim, body=False)                  # ground and sky only (round-1 behaviour)
+    ref0 = eye_render_oracle(xp, xq, plain.params, plain.ret.H, plain.ret.W)
+    assert np.array_equal(plain.render().cpu().numpy(), ref0)
+    cams = EyeCameras(sim)                               # + the fly's own body: the 55 segments outside the v1 hidden list, as capsules
+    assert cams.body is not None and len(cams.body["seg"]) == 55
     img = cams.render()
-    ref = eye_render_oracle(sim.seg_xpos.cpu().numpy(), sim.seg_xquat.cpu().numpy(), cams.params, cams.ret.H, cams.ret.W)
+    ref = eye_render_oracle(xp, xq, cams.params, cams.ret.H, cams.ret.W, body=cams.body)
     got = img.cpu().numpy()
     assert got.shape == (n, 2, 512, 450, 3)
     assert np.array_equal(got, ref), int((got != ref).sum())
-    assert len(np.unique(got[..., 1])) >= 3              # both checker greys and the sky are visible
+    assert len(np.unique(got[..., 1])) >= 4              # both checker greys, the sky and the body are visible
+    body_px = (got[..., 1] == cams.body["colour"][0]) & (got[..., 2] == cams.body["colour"][1])
+    assert 0.03 < body_px.mean() < 0.5                   # legs / abdomen / wings cover part of the view, not all of it
+    assert (got != ref0).any()
     fused = cams.retina()
     two_stage = cams.ret(img)
     assert torch.equal(fused, two_stage)

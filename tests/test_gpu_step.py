@@ -570,3 +570,33 @@ def test_mujoco_golden_on_the_gpu_if_present():
                             assert np.abs(v[i] - rv).max() / max(1.0, np.abs(rv).max()) < 1e-3, (tag, noslip, sname, cp, "qvel")
                     if prec == 32:                             # float32: every fly to 100 steps, median beyond (contact chaos, see the tests above)
                         assert (max(errs) < 1e-4) if cp <= 100 else (np.median(errs) < 1e-3), (tag, noslip, cp, errs)
+
+
+@pytest.mark.parametrize("world", ["flat", "mesh", "blocks"])
+def test_flies_per_block_is_bit_identical(world):
+    """A block steps 1, 2, 4 or 8 flies side by side (lockstep solver passes, step_block<WORLD, FPB>): ragged batch sizes (empty
+    slots in the last block), the work queue on and off, and every FPB must give the same bits -- state records, segment poses,
+    sensors -- as one fly per block.  Also the edge sizes n = 1 and n = 13."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    m = {"flat": lambda: NMFModel.bench(True), "mesh": lambda: NMFModel.bench(False), "blocks": lambda: NMFModel.bench(True, terrain="blocks")}[world]()
+    for n, steps in ((2500, 30), (13, 30), (1, 30)):                  # 2500 = 312 blocks of 8 + a block with 4 empty slots; > resident slots
+        table = torch.from_numpy(cpg_table(m, n, 64)).cuda()
+        ref = None
+        for fpb, sub in ((1, 0), (8, -1), (8, 0), (4, 7), (2, -1), (0, -1)):
+            sim = B200Simulation(m, n_worlds=n, outputs=True)
+            sim.set_flies_per_block(fpb); sim.set_schedule(sub)
+            sim.qpos[:, 2] = -0.15
+            sim.qpos[:, 0] += torch.linspace(0, 1, n, device="cuda")
+            sim.ctrl[:, 42:] = 1.0
+            sim.step(steps, table, 5)
+            sim.step(1, table, 5 + steps)
+            torch.cuda.synchronize()
+            got = (sim.state.clone(), sim.seg_xpos.clone(), sim.sensordata.clone(), sim.act_force.clone())
+            if ref is None:
+                ref = got
+                assert torch.isfinite(ref[0]).all()
+            else:
+                for a, b in zip(ref, got):
+                    assert torch.equal(a, b), (world, n, fpb, sub)
