@@ -49,6 +49,9 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether
 #define NMF_MINBLOCKS_F64 4
 #endif
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT>(p); }
+// the f64 flat kernel with 2 / 4 flies per block in lockstep passes (same register budget per SM: 255 x 64 x 4 threads)
+extern "C" __global__ void __launch_bounds__(2 * CTA, NMF_MINBLOCKS_F64 / 2) nmf_step_f64_x2_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 2>(p); }
+extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS_F64 / 4) nmf_step_f64_x4_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 4>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_mesh_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_MESH>(p); }
@@ -57,6 +60,7 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_me
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 1, true>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_mesh_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_MESH, 1, true>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER, 1, true>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 1, true>(p); }
 
 __global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
@@ -91,6 +95,7 @@ struct nmf_handle {
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
   int sub_steps = -1;                          // steps per work item: -1 = chosen per launch, 0 = never use the queue
+  int fpb64 = 4;                               // f64 flat kernel: flies per block (1, 2, 4; env NMF_FPB64).  B200, 4096 flies: 6.8 / 8.3 / 9.2 M env-steps/s
   int fpb = 0;                                 // fly slots per block of the f32 flat / terrain kernels: 1, 2, 4, 8 or 0 = chosen per launch (see step_block)
   int resident[9] = {};                        // resident blocks of the model's f32 kernel per fpb (index = fpb)
   int sms = 0;
@@ -157,6 +162,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
     CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
+  if (const char* e = getenv("NMF_FPB64")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->fpb64 = v; }
   if (const char* e = getenv("NMF_FPB")) { int v = atoi(e); if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8) h->fpb = v; }
   if (h->hm.par.weld) h->fpb = 1;
   {
@@ -279,9 +285,21 @@ template <> struct KernelSet<double> {
   static const StepParamsT<double>& base(const nmf_handle* h) { return h->hm.par64; }
   static const double* role(const nmf_handle* h) { return h->d_role64; }
   static const double* hull(const nmf_handle* h) { return h->d_hull64; }
-  static int fpb(const nmf_handle*, int) { return 1; }
-  static void launch(const StepParamsT<double>& p, int, int grid, cudaStream_t s) {
-    if (p.weld) nmf_step_tether_f64_kernel<<<grid, CTA, 0, s>>>(p);
+  static int fpb(const nmf_handle* h, int n) {
+    const int want = h->fpb64;
+    const bool plain_flat = !h->hm.par.weld && !h->hm.par.terrain && !h->hm.par.multiccd && h->hm.par.noslip_iterations == 0;
+    return (plain_flat && (want == 2 || want == 4) && n >= want) ? want : 1;
+  }
+  static void launch(const StepParamsT<double>& p, int fpb, int grid, cudaStream_t s) {
+    if (fpb == 4) {
+      static bool attr = false;
+      const size_t dyn = (size_t)4 * f64::SM_WELD * sizeof(double);
+      if (!attr) { cudaFuncSetAttribute(nmf_step_f64_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); attr = true; }
+      nmf_step_f64_x4_kernel<<<grid, 4 * CTA, dyn, s>>>(p); return;
+    }
+    if (fpb == 2) { nmf_step_f64_x2_kernel<<<grid, 2 * CTA, 0, s>>>(p); return; }
+    if (p.weld && p.noslip_iterations > 0) nmf_step_tether_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    else if (p.weld) nmf_step_tether_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.noslip_iterations > 0 && p.multiccd) nmf_step_mesh_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.noslip_iterations > 0 && p.terrain) nmf_step_terrain_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.noslip_iterations > 0) nmf_step_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
@@ -355,11 +373,8 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
   if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
     h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
   }
-  if (h->hm.par.noslip_iterations > 0 && h->hm.par.weld) {
-    h->err = "nmf_step: noslip_iterations > 0 is not implemented for the tethered world (its weld rows would join the noslip sweeps)"; return NMF_EINVAL;
-  }
-  if (h->hm.par.noslip_iterations > 0 && h->precision != 64 && (h->hm.par.terrain || h->hm.par.multiccd)) {
-    h->err = "nmf_step: noslip on terrain / mesh-hull worlds needs nmf_set_precision(h, 64) (float32 noslip is built for the flat capsule world only)"; return NMF_EINVAL;
+  if (h->hm.par.noslip_iterations > 0 && h->precision != 64 && (h->hm.par.terrain || h->hm.par.multiccd || h->hm.par.weld)) {
+    h->err = "nmf_step: noslip on terrain / mesh-hull / tethered worlds needs nmf_set_precision(h, 64) (float32 noslip is built for the flat capsule world only)"; return NMF_EINVAL;
   }
   return h->precision == 64 ? launch_steps_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos)
                             : launch_steps_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos);

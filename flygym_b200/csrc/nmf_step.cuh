@@ -506,7 +506,7 @@ constexpr int NS_LD = 2 * NS_MAXC;      // two friction dimensions per contact
 // torquescale * vec(q_hub * weld_q) with Jacobian G w = 0.5 ts vec((0, w) * q) (w = world angular velocity).  They only touch
 // the hub's 6x6 block, so they enter exactly like a contact on the hub: a wrench in the gradient and an X'WX augmentation
 // of the hub's spatial inertia.  State lives in shared memory (one lane uses it): r[3] G[9] D[6] c0[6] w[6] sv[6].
-constexpr int WL_R = 0, WL_G = 3, WL_D = 12, WL_C0 = 18, WL_W = 24, WL_SV = 30, WL_COUNT = 36;
+constexpr int WL_R = 0, WL_G = 3, WL_D = 12, WL_C0 = 18, WL_W = 24, WL_SV = 30, WL_F = 36, WL_COUNT = 42;   // WL_F: explicit row forces after noslip
 
 __device__ __forceinline__ void point_and_rot(const real* sw, const real* S, real* out) {   // J * (spatial vector of the hub)
   const real* r = sw + WL_R; const real* G = sw + WL_G;
@@ -537,11 +537,11 @@ __device__ __forceinline__ void weld_setup(const SP& p, real* sw, const real* qh
   }
 }
 // forces of the six rows for the current acceleration: wrench about the COM into Wc, Hessian augmentation into A
-__device__ __forceinline__ void weld_forces(const real* sw, real* Wc, real* A) {
+__device__ __forceinline__ void weld_forces(const real* sw, real* Wc, real* A, bool explicit_f = false) {
   const real* r = sw + WL_R; const real* G = sw + WL_G; const real* D = sw + WL_D;
   real f[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) f[i] = -D[i] * (sw[WL_W + i] + sw[WL_C0 + i]);
+  for (int i = 0; i < 6; i++) f[i] = explicit_f ? sw[WL_F + i] : -D[i] * (sw[WL_W + i] + sw[WL_C0 + i]);
   real T[3]; cross3(r, f, T);
 #pragma unroll
   for (int i = 0; i < 3; i++) { Wc[i] += T[i] + G[i] * f[3] + G[3 + i] * f[4] + G[6 + i] * f[5]; Wc[3 + i] += f[i]; }
@@ -1203,7 +1203,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
         }
         block_sync(bar);                                        // keys alias B: everybody has ranked before B is written
         if (C > NS_MAXC) fault |= ST_NOSLIP_SKIP;
-        else if (C > 0) {
+        if (TETHER || (C > 0 && C <= NS_MAXC)) {
           // ---- stage the plain inertia matrix (the same staging the Euler pass repeats with its damping diagonal)
           {
             real P[21];
@@ -1253,6 +1253,60 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
             for (int i = 0; i < 6; i++) W[i] = sl[i] + sm[SM_HBB + HB_SH + i];
             block_sync(bar);                                    // SM_GRAD / SM_X / the root records are free again
           };
+          if (TETHER) {
+            // TetheredWorld: the six weld rows are equality rows, which noslip sweeps unclamped ( f_i -= residual_i / A_ii ).
+            // A = J_w M^-1 J_w' (6 x 6) column by column; everything lives on the weld lane.
+            for (int j = 0; j < 6; j++) {
+              real W[6] = {0, 0, 0, 0, 0, 0}, xo[3];
+              if (weld_lane) {
+                const real* r = sw + WL_R; const real* Gm = sw + WL_G;
+                if (j < 3) { real e3[3] = {j == 0 ? real(1.) : real(0.), j == 1 ? real(1.) : real(0.), j == 2 ? real(1.) : real(0.)}, T[3]; cross3(r, e3, T);
+                             W[0] = T[0]; W[1] = T[1]; W[2] = T[2]; W[3] = e3[0]; W[4] = e3[1]; W[5] = e3[2]; }
+                else { W[0] = Gm[3 * (j - 3)]; W[1] = Gm[3 * (j - 3) + 1]; W[2] = Gm[3 * (j - 3) + 2]; }
+              }
+              m_solve(W, xo);
+              if (weld_lane) { real o6[6]; point_and_rot(sw, W, o6); for (int i = 0; i < 6; i++) ns[NS_B + i * NS_LD + j] = o6[i]; }
+            }
+            block_sync(bar);
+            if (weld_lane) {
+              real f[6], f0[6], jar[6], improvement0 = real(0.);
+              for (int i = 0; i < 6; i++) {
+                jar[i] = sw[WL_W + i] + sw[WL_C0 + i]; f0[i] = f[i] = -sw[WL_D + i] * jar[i];
+                improvement0 += real(0.5) * f0[i] * f0[i] / sw[WL_D + i];
+              }
+              for (int it = 0; it < p.noslip_iterations; it++) {
+                real improvement = it == 0 ? improvement0 : real(0.);
+                for (int i = 0; i < 6; i++) {
+                  real res = jar[i];
+                  for (int q = 0; q < 6; q++) res += ns[NS_B + i * NS_LD + q] * (f[q] - f0[q]);
+                  const real Aii = ns[NS_B + i * NS_LD + i], old = f[i];
+                  f[i] = old - res / m_max(real(1e-15), Aii);
+                  const real dd = f[i] - old;
+                  real change = real(0.5) * dd * dd * Aii + dd * res;
+                  if (change > real(1e-10)) { f[i] = old; change = real(0.); }
+                  improvement -= change;
+                }
+                if (improvement * p.noslip_scale < p.noslip_tol) break;
+              }
+              for (int i = 0; i < 6; i++) { sw[WL_F + i] = f[i]; ns[NS_G + i] = f[i] - f0[i]; }
+            }
+            block_sync(bar);
+            {
+              real W[6] = {0, 0, 0, 0, 0, 0}, xo[3];
+              if (weld_lane) {
+                const real* r = sw + WL_R; const real* Gm = sw + WL_G; const real* df = ns + NS_G;
+                real T[3]; cross3(r, df, T);
+                for (int i = 0; i < 3; i++) { W[i] = T[i] + Gm[i] * df[3] + Gm[3 + i] * df[4] + Gm[6 + i] * df[5]; W[3 + i] = df[i]; }
+              }
+              m_solve(W, xo);
+#pragma unroll
+              for (int j = 0; j < 3; j++) if (j < ndof || (j == 0 && hubdof)) qacc[dj[j]] += xo[j];
+#pragma unroll
+              for (int i = 0; i < 6; i++) Sa[i] += W[i];
+              if (weld_lane) { real o6[6]; point_and_rot(sw, W, o6); for (int i = 0; i < 6; i++) sw[WL_W + i] += o6[i]; }
+              block_sync(bar);
+            }
+          } else {
           // ---- columns of B_tt
           for (int j = 0; j < 2 * C; j++) {
             real W[6] = {0, 0, 0, 0, 0, 0}, xo[3];
@@ -1322,6 +1376,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
             }
             block_sync(bar);
           }
+          }
           explicit_f = true;
         }
       }
@@ -1336,7 +1391,7 @@ __device__ __forceinline__ void step_block(const SP& p, real* sm, const int fly,
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) if (any[s]) contact_forces<true>(con[s], p.mu, Wc, A, nullptr);    // warp-uniform skips
       }
-      if (TETHER && weld_lane) weld_forces(sw, Wc, A);
+      if (TETHER && weld_lane) weld_forces(sw, Wc, A, NOSLIP && explicit_f);
       // ---- gradient  g = C' suffix(I S - Wc) + armature a - fs ;  fc = C' suffix(Wc)
       real y[12];
       {

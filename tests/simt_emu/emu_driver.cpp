@@ -44,7 +44,8 @@ extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_fli
     nmf::StepParamsT<double> q = hm.par64;
     fill(q, hm.role64.data(), hm.hull64.data());
     for (int b = 0; b < n_blocks; b++) simt::run_block(nmf::CTA, b, n_blocks, [&]() {
-      if (q.noslip_iterations > 0 && !q.weld) {    // the reference's CPU semantics: noslip post-solver
+      if (q.noslip_iterations > 0 && q.weld) nmf::f64::step_block<nmf::f64::W_TETHER, 1, true>(q, g_sm64, b, 0, q.nsteps, false);
+      else if (q.noslip_iterations > 0) {    // the reference's CPU semantics: noslip post-solver
         if (q.multiccd) nmf::f64::step_block<nmf::f64::W_MESH, 1, true>(q, g_sm64, b, 0, q.nsteps, false);
         else if (q.terrain) nmf::f64::step_block<nmf::f64::W_TERRAIN, 1, true>(q, g_sm64, b, 0, q.nsteps, false);
         else nmf::f64::step_block<nmf::f64::W_FLAT, 1, true>(q, g_sm64, b, 0, q.nsteps, false);

@@ -516,15 +516,34 @@ def test_noslip_kernels_match_the_oracle(variant):
 
 
 def test_noslip_is_refused_where_it_is_not_built():
-    """float32 noslip exists for the flat capsule world only; the tethered world's weld rows are not part of the pass."""
+    """float32 noslip exists for the flat capsule world only; the other worlds need the f64 build."""
     from flygym_b200 import B200Simulation, NMFModel
-    sim = B200Simulation(NMFModel.bench(False).with_options(noslip_iterations=5), n_worlds=1)
-    with pytest.raises(RuntimeError, match="precision"):
-        sim.step(1)
-    sim.set_precision(64); sim.step(1)
-    sim = B200Simulation(NMFModel.tethered().with_options(noslip_iterations=5), n_worlds=1)
-    with pytest.raises(RuntimeError, match="tethered"):
-        sim.step(1)
+    for m in (NMFModel.bench(False), NMFModel.tethered()):
+        sim = B200Simulation(m.with_options(noslip_iterations=5), n_worlds=1)
+        with pytest.raises(RuntimeError, match="precision"):
+            sim.step(1)
+        sim.set_precision(64); sim.step(1)
+
+
+def test_tethered_world_with_noslip_matches_the_oracle():
+    """The world of the reference's own `tests/core/test_simulation.py` fixtures (TetheredWorld) under the CPU `Simulation`
+    semantics (noslip_iterations = 5): the six weld rows are equality rows, which MuJoCo's noslip sweeps unclamped -- the soft
+    weld becomes nearly hard.  f64 kernel vs the oracle over 300 CPG steps, and far from the plain (noslip 0) trajectory."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    from oracle.oracle import Oracle
+    base = NMFModel.tethered(); m = base.with_options(noslip_iterations=5)
+    tab = cpg_table(m, 2, 300)
+    sim = B200Simulation(m, n_worlds=2); sim.set_precision(64)
+    sim.step(300, torch.from_numpy(tab).cuda(), 0)
+    got = sim.qpos.cpu().numpy().astype(np.float64)
+    for i in range(2):
+        o = Oracle(m); o.reset(); o.step_table(tab[i].astype(np.float64))
+        assert np.abs(got[i] - o.qpos).max() / np.abs(o.qpos).max() < 5e-7
+    plain = Oracle(base); plain.reset(); plain.step_table(tab[0].astype(np.float64))
+    o = Oracle(m); o.reset(); o.step_table(tab[0].astype(np.float64))
+    assert np.abs(plain.qpos - o.qpos).max() > 1e-4 and int(sim.status.abs().max()) == 0
 
 
 def test_mujoco_golden_on_the_gpu_if_present():
