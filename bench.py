@@ -357,6 +357,9 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
 
     for _ in range(max(3, warmup)):
         advance(chunk)
+    if wl == "olfaction" and world > 1:      # NCCL sets its all-gather channels up on first use (tens of ms): part of the warm-up
+        slab = torch.cat([sim.qpos[:, :3], sim.qvel[:, :1], state["odor"].reshape(n, -1)[:, :4]], dim=1).contiguous()
+        dist.all_gather([torch.empty_like(slab) for _ in range(world)], slab)
     torch.cuda.synchronize(dev)
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream around every launch group

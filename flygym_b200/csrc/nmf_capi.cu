@@ -269,7 +269,8 @@ static int set_resident_blocks(nmf_handle* h) {
 static int pick_fpb(const nmf_handle* h, int n) {
   if (h->hm.par.weld || h->hm.par.noslip_iterations > 0) return 1;
   if (h->fpb) return h->fpb;
-  for (int fpb = 8; fpb > 1; fpb /= 2) if (n >= fpb * h->sms) return fpb;
+  if (n >= 8 * h->sms) return 8;
+  if (n >= 4 * h->sms) return 4;       // (2 flies per block share nothing in the L0 instruction caches and still wait: slower than 1)
   return 1;
 }
 template <> struct KernelSet<float> {
