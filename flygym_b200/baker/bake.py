@@ -489,6 +489,13 @@ def main():
     m = bake_kernel_layout(args.reference, "legs_active_only", simplify_geom=True)
     m.save(out / "nmf_bench_capsule_legs_active_only.npz")
     print("nmf_bench_capsule_legs_active_only.npz", {k: m.dim(k) for k in DIM_FIELDS}, "free hinge DoFs", len(m.names["jointdofs"]))
+    # general-topology models (stepped by the tree kernels): every joint preset with every segment as a contact body
+    # (ContactBodiesPreset.ALL; NMFModel.with_contact_bodies narrows it), capsule geoms; ALL_BIOLOGICAL also with mesh hulls
+    for preset, simplify, name in (("legs_only", True, "nmf_legs_only_allcontacts_capsule.npz"), ("all_biological", True, "nmf_all_biological_capsule.npz"),
+                                   ("all_possible", True, "nmf_all_possible_capsule.npz"), ("all_biological", False, "nmf_all_biological_mesh.npz")):
+        m = bake(args.reference, joint_preset=preset, simplify_geom=simplify, contact_preset="all")
+        m.save(out / name)
+        print(name, {k: m.dim(k) for k in DIM_FIELDS})
 
 
 if __name__ == "__main__":

@@ -10,8 +10,10 @@ environment; the tests drive it with a duck-typed model synthesised by :func:`mj
 
 What it does: finds the free body, fuses joint-less bodies into the nearest ancestor that has joints (mass, centre of
 mass and inertia combined exactly; geoms, sites and segment frames re-expressed in the owner's frame), checks that
-the result is the topology the kernels are written for (a hub + 6 chains of 8 links with 3, 2, 1, 1, 1, 1, 1, 1 hinges),
-and lays DoFs, actuators and contact geoms out in the kernels' order.  Index maps from MuJoCo addresses to the
+the result is something the kernels step -- a free hub carrying a tree of bodies with up to three hinges each: the hub + 6
+chains of 8 links with 3, 2, 1, 1, 1, 1, 1, 1 hinges of ``JointPreset.LEGS_ONLY`` runs on the star kernels, anything else
+(``ALL_BIOLOGICAL``, ``ALL_POSSIBLE``) on the general-topology kernels -- and lays DoFs, actuators and contact geoms out in
+the kernels' order.  Index maps from MuJoCo addresses to the
 kernel layout are returned in ``model.meta['mj_maps']`` -- a ``Simulation`` subclass indexes the state record through
 them, since MuJoCo's ``jnt_qposadr`` / actuator ids need not coincide with the record layout.
 """
@@ -109,26 +111,19 @@ def from_mjmodel(m, *, fly_root: str | None = None, segments: list[str] | None =
             rel[b] = rel[parent[b]] @ _T(m.body_pos[b], m.body_quat[b])
     movable = [b for b in range(nbody) if in_fly[b] and has_jnt[b] and b != hub_b]
 
-    # ---- chains: kernel body order = hub, then the chains in MuJoCo body order, root -> tip
+    # ---- kernel body order = hub, then the jointed bodies in MuJoCo order (parents before children; a chain stays contiguous).
+    # A hub + 6 chains of 8 links with (3, 2, 1, 1, 1, 1, 1, 1) hinges (JointPreset.LEGS_ONLY) is what the star kernels step;
+    # any other tree of hinge-jointed bodies (ALL_BIOLOGICAL, ALL_POSSIBLE ...) goes to the general-topology kernels.  The
+    # native library decides (nmf_create); here only what neither handles is rejected.
     mov_parent = {b: int(owner[parent[b]]) for b in movable}
-    roots = [b for b in movable if mov_parent[b] == hub_b]
-    chains = []
-    for r in roots:
-        ch = [r]
-        while True:
-            kids = [b for b in movable if mov_parent[b] == ch[-1]]
-            if len(kids) > 1:
-                raise ConversionError(f"body {body_names[ch[-1]]} has several jointed children: not a chain")
-            if not kids:
-                break
-            ch.append(kids[0])
-        chains.append(ch)
     dofnum_mj = np.asarray(m.body_dofnum)
-    if len(chains) != 6 or any(len(c) != 8 or tuple(int(dofnum_mj[b]) for b in c) != LEG_DOFS for c in chains) \
-            or sum(len(c) for c in chains) != len(movable):
-        raise ConversionError("unsupported topology: the sm_100a kernels need a free hub + 6 chains of 8 links with "
-                              f"{LEG_DOFS} hinge DoFs (JointPreset.LEGS_ONLY); found chains {[len(c) for c in chains]}")
-    kbodies = [hub_b] + [b for c in chains for b in c]    # kernel body index -> MuJoCo body id
+    if any(int(dofnum_mj[b]) > 3 for b in movable):
+        raise ConversionError("a body carries at most three hinge joints (one anatomical joint, anatomy.py:411-416)")
+    leg_names = list(A.LEGS)
+    def leg_of(b):               # leg index of a jointed body by its segment name ('lf_coxa' -> 0), -1 off the legs
+        nm = body_names[b]
+        return leg_names.index(nm.split("_")[0]) if A.is_leg(nm) and nm.split("_")[0] in leg_names else -1
+    kbodies = [hub_b] + movable                           # kernel body index -> MuJoCo body id
     kidx = {b: i for i, b in enumerate(kbodies)}
     nb = len(kbodies)
 
@@ -157,15 +152,14 @@ def from_mjmodel(m, *, fly_root: str | None = None, segments: list[str] | None =
     # ---- body frames relative to the owner of the parent
     body_parent = np.full(nb, -1, np.int32); body_pos = np.zeros((nb, 3)); body_quat = np.zeros((nb, 4))
     body_leg = np.full(nb, -1, np.int32)
-    for li, ch in enumerate(chains):
-        for b in ch:
-            fr = rel[parent[b]] @ _T(m.body_pos[b], m.body_quat[b])
-            body_parent[kidx[b]] = kidx[mov_parent[b]]; body_pos[kidx[b]] = fr.pos; body_quat[kidx[b]] = fr.quat
-            body_leg[kidx[b]] = li
+    for b in movable:
+        fr = rel[parent[b]] @ _T(m.body_pos[b], m.body_quat[b])
+        body_parent[kidx[b]] = kidx[mov_parent[b]]; body_pos[kidx[b]] = fr.pos; body_quat[kidx[b]] = fr.quat
+        body_leg[kidx[b]] = leg_of(b)
 
     # ---- DoFs in kernel order (6 free + chain hinges) and the MuJoCo <-> kernel address maps
     jnt_qposadr, jnt_dofadr, body_jntadr, body_jntnum = (np.asarray(getattr(m, k)) for k in ("jnt_qposadr", "jnt_dofadr", "body_jntadr", "body_jntnum"))
-    nv, nq = 6 + 66, 7 + 66
+    nv = 6 + int(sum(int(body_jntnum[b]) for b in movable)); nq = nv + 1
     dof_body = np.zeros(nv, np.int32); dof_parent = np.full(nv, -1, np.int32); dof_parent[1:6] = np.arange(5)
     dof_axis = np.zeros((nv, 3)); stiff = np.zeros(nv); damp = np.zeros(nv); arm = np.zeros(nv); sref = np.zeros(nv)
     body_dofadr = np.zeros(nb, np.int32); body_dofnum = np.zeros(nb, np.int32); body_dofnum[0] = 6
@@ -173,16 +167,15 @@ def from_mjmodel(m, *, fly_root: str | None = None, segments: list[str] | None =
     mjdof_of_k[:6] = jnt_dofadr[jfree] + np.arange(6); mjqpos_of_k[:7] = jnt_qposadr[jfree] + np.arange(7)
     kdof_names = []
     last = {0: 5}; k = 6
-    for ch in chains:
-        for b in ch:
-            kb = kidx[b]; body_dofadr[kb] = k; prev = last[int(body_parent[kb])]
-            for j in range(body_jntadr[b], body_jntadr[b] + body_jntnum[b]):
-                dof_axis[k] = m.jnt_axis[j]; dof_body[k] = kb; dof_parent[k] = prev
-                stiff[k] = m.jnt_stiffness[j]; sref[k] = m.qpos_spring[jnt_qposadr[j]]
-                damp[k] = m.dof_damping[jnt_dofadr[j]]; arm[k] = m.dof_armature[jnt_dofadr[j]]
-                mjdof_of_k[k] = jnt_dofadr[j]; mjqpos_of_k[k + 1] = jnt_qposadr[j]
-                kdof_names.append(jnt_names[j]); prev = k; k += 1
-            body_dofnum[kb] = k - body_dofadr[kb]; last[kb] = k - 1
+    for b in movable:
+        kb = kidx[b]; body_dofadr[kb] = k; prev = last[int(body_parent[kb])]
+        for j in range(body_jntadr[b], body_jntadr[b] + body_jntnum[b]):
+            dof_axis[k] = m.jnt_axis[j]; dof_body[k] = kb; dof_parent[k] = prev
+            stiff[k] = m.jnt_stiffness[j]; sref[k] = m.qpos_spring[jnt_qposadr[j]]
+            damp[k] = m.dof_damping[jnt_dofadr[j]]; arm[k] = m.dof_armature[jnt_dofadr[j]]
+            mjdof_of_k[k] = jnt_dofadr[j]; mjqpos_of_k[k + 1] = jnt_qposadr[j]
+            kdof_names.append(jnt_names[j]); prev = k; k += 1
+        body_dofnum[kb] = k - body_dofadr[kb]; last[kb] = k - 1
     k_of_mjdof = np.full(nv_mj, -1, np.int64); k_of_mjdof[mjdof_of_k] = np.arange(nv)
     k_of_mjqpos = np.full(nq_mj, -1, np.int64); k_of_mjqpos[mjqpos_of_k] = np.arange(nq)
 
@@ -211,7 +204,7 @@ def from_mjmodel(m, *, fly_root: str | None = None, segments: list[str] | None =
     for a in adh_ids:
         b = int(trnid[a, 0])
         if not in_fly[b] or owner[b] == hub_b:
-            raise ConversionError("adhesion actuators must sit on a leg body")
+            raise ConversionError("adhesion actuators must sit on a jointed body, not on the free hub")
         adh_body.append(kidx[int(owner[b])]); adh_gain.append(float(gainprm[a, 0]))
         adh_ctrl.append(np.asarray(m.actuator_ctrlrange).reshape(nu_mj, 2)[a])
     k_of_mjact = np.full(nu_mj, -1, np.int64)
@@ -311,10 +304,10 @@ def from_mjmodel(m, *, fly_root: str | None = None, segments: list[str] | None =
         anchor = rel[b1].apply(relpos); quat = G.quat_mul(rel[b1].quat, G.quat_normalize(relquat))
         arrays["weld"] = np.array([1.0, *anchor, *quat, *map(float, m.eq_solref[0][:2]), *map(float, m.eq_solimp[0][:5]), ts, invw[0, 0], invw[0, 1]])
         assert len(arrays["weld"]) == len(WELD_FIELDS)
-    legs = []
-    for ch in chains:
-        nm = body_names[ch[0]]; legs.append(nm.split("_")[0])
-    names = dict(bodies=["hub"] + [body_names[b] for c in chains for b in c], segments=[s for s, _ in seg_rows], jointdofs=kdof_names,
+    legs = [l for l in leg_names if any(leg_of(b) == leg_names.index(l) for b in movable)]
+    if legs != leg_names[:len(legs)] or len(legs) != 6:
+        raise ConversionError(f"expected the six legs {leg_names}; found {legs}")
+    names = dict(bodies=["hub"] + [body_names[b] for b in movable], segments=[s for s, _ in seg_rows], jointdofs=kdof_names,
                  actuated_position=[jnt_names[int(trnid[a, 0])] for a in pos_ids], legs=legs, contact_geoms=cnames,
                  sites=[site_names[s] for s in site_rows])
     meta = dict(source="MjModel", units="as the MuJoCo model", simplify_geom=bool(nvert == 0),

@@ -10,6 +10,7 @@
 
 #include "../../include/nmf_b200.h"
 #include "nmf_host.h"
+#include "nmf_tree_host.h"
 #include "nmf_step_all.cuh"
 
 using namespace nmf;
@@ -63,29 +64,47 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_te
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER, 1, true>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 1, true>(p); }
 
-__global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n) {
+// general-topology models (JointPreset.ALL_BIOLOGICAL / ALL_POSSIBLE, ContactBodiesPreset.ALL, ...): nmf_tree.cuh, one block of
+// 128 threads per fly, the whole fly in (dynamic) shared memory
+extern "C" __global__ void __launch_bounds__(TREE_CTA) nmf_tree_step_kernel(const TreeParamsT<float> p) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  f32::tree_step_block(p, reinterpret_cast<float*>(tree_smem), (int)blockIdx.x);
+}
+extern "C" __global__ void __launch_bounds__(TREE_CTA) nmf_tree_step_f64_kernel(const TreeParamsT<double> p) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  f64::tree_step_block(p, reinterpret_cast<double*>(tree_smem), (int)blockIdx.x);
+}
+
+__global__ void nmf_reset_kernel(float* state, const float* key, const uint8_t* mask, int n, int stride) {
   int fly = blockIdx.x;
   if (fly >= n || (mask && !mask[fly])) return;
-  for (int i = threadIdx.x; i < S_STRIDE; i += blockDim.x) state[(size_t)fly * S_STRIDE + i] = key[i];
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) state[(size_t)fly * stride + i] = key[i];
 }
 
-__global__ void nmf_scatter_cols_kernel(float* state, int off, const float* src, const int32_t* cols, int ncols, int n) {
+__global__ void nmf_scatter_cols_kernel(float* state, int stride, int off, const float* src, const int32_t* cols, int ncols, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * ncols) return;
   int fly = i / ncols, k = i - fly * ncols;
-  state[(size_t)fly * S_STRIDE + off + cols[k]] = src[i];
+  state[(size_t)fly * stride + off + cols[k]] = src[i];
 }
 
-__global__ void nmf_gather_cols_kernel(const float* state, int off, const int32_t* cols, int ncols, float* dst, int n) {
+__global__ void nmf_gather_cols_kernel(const float* state, int stride, int off, const int32_t* cols, int ncols, float* dst, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * ncols) return;
   int fly = i / ncols, k = i - fly * ncols;
-  dst[i] = state[(size_t)fly * S_STRIDE + off + (cols ? cols[k] : k)];
+  dst[i] = state[(size_t)fly * stride + off + (cols ? cols[k] : k)];
 }
 
 // ------------------------------------------------------------------ handle
 struct nmf_handle {
   HostModel hm;
+  // general-topology models: tables of the tree kernels instead of the role table (tree == true)
+  bool tree = false;
+  TreeModel tm;
+  int *d_it = nullptr; float* d_rt = nullptr; double* d_rt64 = nullptr;
+  // record layout of the model (star models: the constants of nmf_layout.h)
+  int stride = S_STRIDE, off_qpos = S_QPOS, off_qvel = S_QVEL, off_warm = S_WARM, off_ctrl = S_CTRL, off_time = S_TIME;
+  int nq = NQ, nv = NV, nu_pos = 0, nu_adh = 0, nseg = 0, nleg = NLEG;
   int n_flies = 0, device = 0;
   float *d_role = nullptr, *d_hull = nullptr, *d_seg = nullptr, *d_key = nullptr;
   int *d_nbr_adr = nullptr, *d_nbr = nullptr;
@@ -135,7 +154,17 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   if (!h) return NMF_EINVAL;
   *out = h;   // returned even on failure so that nmf_last_error() can be read
   if (n_flies <= 0) { h->err = "n_flies must be positive"; return NMF_EINVAL; }
-  if (!h->hm.build(blob, nbytes)) { h->err = h->hm.err; return NMF_EINVAL; }
+  const char* force_tree = getenv("NMF_FORCE_TREE");      // A/B runs: step a star-topology model with the general kernels
+  if ((force_tree && atoi(force_tree) != 0) || !h->hm.build(blob, nbytes)) {
+    // not the hub + 6 x 8 star the fast kernels are specialised to: any free root + hinge tree goes to the tree kernels
+    if (!h->tm.build(blob, nbytes)) { h->err = "star kernels: " + (h->hm.err.empty() ? std::string("not tried") : h->hm.err) + "; tree kernels: " + h->tm.err; return NMF_EINVAL; }
+    h->tree = true;
+    const TreeDims& d = h->tm.par.d;
+    h->stride = d.s_stride; h->off_qpos = d.s_qpos; h->off_qvel = d.s_qvel; h->off_warm = d.s_warm; h->off_ctrl = d.s_ctrl; h->off_time = d.s_time;
+    h->nq = d.nq; h->nv = d.nv; h->nu_pos = d.nu_pos; h->nu_adh = d.nu_adh; h->nseg = d.nseg; h->nleg = d.nleg;
+  } else {
+    h->nu_pos = h->hm.par.nu_pos; h->nu_adh = h->hm.par.nu_adh; h->nseg = h->hm.nseg;
+  }
   h->n_flies = n_flies; h->device = device;
   {
     int ndev = 0;
@@ -144,19 +173,32 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   }
   DeviceGuard guard(device);
   int rc;
-  if ((rc = upload(h, &h->d_role, h->hm.role))) return rc;
-  if ((rc = upload(h, &h->d_hull, h->hm.hull))) return rc;
-  if ((rc = upload(h, &h->d_seg, h->hm.seg_tab))) return rc;
-  if ((rc = upload(h, &h->d_key, h->hm.key_state))) return rc;
-  CK(cudaMalloc(&h->d_nbr_adr, sizeof(int) * h->hm.hull_nbr_adr.size()));
-  CK(cudaMemcpy(h->d_nbr_adr, h->hm.hull_nbr_adr.data(), sizeof(int) * h->hm.hull_nbr_adr.size(), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&h->d_nbr, sizeof(int) * h->hm.hull_nbr.size()));
-  CK(cudaMemcpy(h->d_nbr, h->hm.hull_nbr.data(), sizeof(int) * h->hm.hull_nbr.size(), cudaMemcpyHostToDevice));
+  const std::vector<int32_t>& nbr_adr = h->tree ? h->tm.hull_nbr_adr : h->hm.hull_nbr_adr;
+  const std::vector<int32_t>& nbr = h->tree ? h->tm.hull_nbr : h->hm.hull_nbr;
+  if (h->tree) {
+    if ((rc = upload(h, &h->d_rt, h->tm.rtab))) return rc;
+    CK(cudaMalloc(&h->d_it, sizeof(int) * h->tm.itab.size()));
+    CK(cudaMemcpy(h->d_it, h->tm.itab.data(), sizeof(int) * h->tm.itab.size(), cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)h->tm.par.d.m_total * sizeof(float);
+    int smem_max = 0;
+    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (smem > (size_t)smem_max) { h->err = "model too large for the tree kernels' shared-memory plan"; return NMF_EINVAL; }
+    CK(cudaFuncSetAttribute(nmf_tree_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    if ((rc = upload(h, &h->d_role, h->hm.role))) return rc;
+  }
+  if ((rc = upload(h, &h->d_hull, h->tree ? h->tm.hull : h->hm.hull))) return rc;
+  if ((rc = upload(h, &h->d_seg, h->tree ? h->tm.seg_tab : h->hm.seg_tab))) return rc;
+  if ((rc = upload(h, &h->d_key, h->tree ? h->tm.key_state : h->hm.key_state))) return rc;
+  CK(cudaMalloc(&h->d_nbr_adr, sizeof(int) * nbr_adr.size()));
+  CK(cudaMemcpy(h->d_nbr_adr, nbr_adr.data(), sizeof(int) * nbr_adr.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_nbr, sizeof(int) * nbr.size()));
+  CK(cudaMemcpy(h->d_nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_queue, sizeof(int) * ((size_t)n_flies * QUEUE_MAX_CHUNKS + 2)));
   // staging of nmf_step_host (actions in, packed qpos out) and its pipeline streams: created here, so that no call on the
   // stepping path allocates
-  CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n_flies * MAXU));
-  CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n_flies * NQ));
+  CK(cudaMalloc(&h->d_act, sizeof(float) * (size_t)n_flies * (h->nu_pos + h->nu_adh > MAXU ? h->nu_pos + h->nu_adh : MAXU)));
+  CK(cudaMalloc(&h->d_qpos, sizeof(float) * (size_t)n_flies * h->nq));
   for (int k = 0; k < nmf_handle::MAX_PARTS; k++) {
     CK(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));
@@ -165,7 +207,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
   if (const char* e = getenv("NMF_FPB64")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->fpb64 = v; }
   if (const char* e = getenv("NMF_FPB")) { int v = atoi(e); if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8) h->fpb = v; }
   if (h->hm.par.weld) h->fpb = 1;
-  {
+  if (!h->tree) {
     int rc2 = set_resident_blocks(h);
     if (rc2) return rc2;
   }
@@ -177,7 +219,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
 extern "C" int nmf_destroy(nmf_handle* h) {
   if (!h) return NMF_OK;
   DeviceGuard guard(h->device);
-  cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64); cudaFree(h->d_state64); cudaFree(h->d_shadow);
+  cudaFree(h->d_it); cudaFree(h->d_rt); cudaFree(h->d_rt64); cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64); cudaFree(h->d_state64); cudaFree(h->d_shadow);
   for (int k = 0; k < nmf_handle::MAX_PARTS; k++) { if (h->part_stream[k]) cudaStreamDestroy(h->part_stream[k]); if (h->part_done[k]) cudaEventDestroy(h->part_done[k]); }
   if (h->fork) cudaEventDestroy(h->fork);
   delete h;
@@ -189,10 +231,11 @@ extern "C" int64_t nmf_launch_count(const nmf_handle* h) { return h ? h->launche
 
 extern "C" int nmf_model_info(const nmf_handle* h, nmf_info* info) {
   if (!h || !info) return NMF_EINVAL;
-  info->n_flies = h->n_flies; info->nq = NQ; info->nv = NV; info->nu_pos = h->hm.par.nu_pos; info->nu_adh = h->hm.par.nu_adh;
-  info->nseg = h->hm.nseg; info->nleg = NLEG; info->state_stride = S_STRIDE; info->off_qpos = S_QPOS; info->off_qvel = S_QVEL;
-  info->off_qacc_warmstart = S_WARM; info->off_ctrl = S_CTRL; info->off_time = S_TIME; info->dbg_stride = DBG_STRIDE; info->off_status = S_TIME + 1;
-  info->timestep = h->hm.par.dt;
+  info->n_flies = h->n_flies; info->nq = h->nq; info->nv = h->nv; info->nu_pos = h->nu_pos; info->nu_adh = h->nu_adh;
+  info->nseg = h->nseg; info->nleg = h->nleg; info->state_stride = h->stride; info->off_qpos = h->off_qpos; info->off_qvel = h->off_qvel;
+  info->off_qacc_warmstart = h->off_warm; info->off_ctrl = h->off_ctrl; info->off_time = h->off_time; info->dbg_stride = h->tree ? TDBG_STRIDE : DBG_STRIDE;
+  info->off_status = h->off_time + 1;
+  info->timestep = h->tree ? h->tm.par.dt : h->hm.par.dt;
   return NMF_OK;
 }
 
@@ -205,6 +248,7 @@ extern "C" int nmf_bind(nmf_handle* h, const nmf_buffers* b) {
 extern "C" int nmf_set_solver(nmf_handle* h, int max_newton, int max_ls) {
   if (!h || max_newton < 1 || max_ls < 1) return NMF_EINVAL;
   h->hm.par.max_newton = max_newton; h->hm.par.max_ls = max_ls;
+  h->tm.par.max_newton = max_newton; h->tm.par.max_ls = max_ls;
   return NMF_OK;
 }
 
@@ -212,7 +256,7 @@ extern "C" int nmf_reset(nmf_handle* h, const uint8_t* mask, void* stream) {
   if (!h) return NMF_EINVAL;
   if (!h->bound) { h->err = "nmf_reset: not bound"; return NMF_ENOTBOUND; }
   DeviceGuard guard(h->device);
-  nmf_reset_kernel<<<h->n_flies, 64, 0, (cudaStream_t)stream>>>(h->buf.state, h->d_key, mask, h->n_flies);
+  nmf_reset_kernel<<<h->n_flies, 64, 0, (cudaStream_t)stream>>>(h->buf.state, h->d_key, mask, h->n_flies, h->stride);
   h->launches++;
   CK(cudaGetLastError());
   return NMF_OK;
@@ -226,6 +270,7 @@ extern "C" int nmf_set_schedule(nmf_handle* h, int sub_steps) {
 
 extern "C" int nmf_set_flies_per_block(nmf_handle* h, int fpb) {
   if (!h || (fpb != 0 && fpb != 1 && fpb != 2 && fpb != 4 && fpb != 8)) return NMF_EINVAL;
+  if (h->tree) return NMF_OK;                       // one fly per block in the tree kernels
   h->fpb = (h->hm.par.weld || h->hm.par.noslip_iterations > 0) ? 1 : fpb;
   return NMF_OK;
 }
@@ -363,6 +408,39 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   return NMF_OK;
 }
 
+// general-topology models: one block per fly, grid = flies of the (ranged) launch
+template <class real>
+static int launch_tree_t(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
+                         int fly0, int count, float* out_qpos) {
+  TreeParamsT<real> p;
+  if constexpr (std::is_same<real, double>::value) { p = h->tm.par64; p.rt = h->d_rt64; p.hull = h->d_hull64; p.state64 = h->d_state64; p.shadow = h->d_shadow; }
+  else { p = h->tm.par; p.rt = h->d_rt; p.hull = h->d_hull; p.state64 = nullptr; p.shadow = nullptr; }
+  p.max_newton = h->tm.par.max_newton; p.max_ls = h->tm.par.max_ls;
+  p.state = h->buf.state; p.it = h->d_it; p.hull_nbr_adr = h->d_nbr_adr; p.hull_nbr = h->d_nbr; p.seg_tab = h->d_seg;
+  p.act_table = table; p.table_T = table_T; p.table_t0 = table_t0; p.table_cols = table ? table_cols : 0;
+  p.out_xpos = h->buf.seg_xpos; p.out_xquat = h->buf.seg_xquat; p.out_actf = h->buf.act_force; p.out_sensor = h->buf.sensordata;
+  p.out_energy = h->buf.energy; p.out_qpos = out_qpos; p.dbg = h->buf.debug;
+  p.n_flies = h->n_flies; p.nsteps = nsteps; p.forward_only = forward_only ? 1 : 0;
+  if (count >= 0 && (fly0 != 0 || count != h->n_flies)) {
+    const size_t f = (size_t)fly0, nu = (size_t)(h->nu_pos + h->nu_adh);
+    p.state += f * h->stride; p.n_flies = count;
+    if (p.state64) { p.state64 += f * h->stride; p.shadow += f * h->stride; }
+    if (p.act_table) p.act_table += f * (size_t)table_T * table_cols;
+    if (p.out_xpos) p.out_xpos += f * h->nseg * 3;
+    if (p.out_xquat) p.out_xquat += f * h->nseg * 4;
+    if (p.out_actf) p.out_actf += f * nu;
+    if (p.out_sensor) p.out_sensor += f * h->nleg * 16;
+    if (p.out_energy) p.out_energy += f * 2;
+    if (p.dbg) p.dbg += f * TDBG_STRIDE;
+  }
+  const size_t smem = (size_t)p.d.m_total * sizeof(real);
+  if constexpr (std::is_same<real, double>::value) nmf_tree_step_f64_kernel<<<p.n_flies, TREE_CTA, smem, (cudaStream_t)stream>>>(p);
+  else nmf_tree_step_kernel<<<p.n_flies, TREE_CTA, smem, (cudaStream_t)stream>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return NMF_OK;
+}
+
 static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table_T, int table_t0, int table_cols, bool forward_only, void* stream,
                         int fly0, int count, float* out_qpos) {
   if (!h) return NMF_EINVAL;
@@ -371,9 +449,12 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
   if (table && table_T <= 0) { h->err = "nmf_step: action table needs table_T > 0"; return NMF_EINVAL; }
   if (table) table_t0 = ((table_t0 % table_T) + table_T) % table_T;    // any integer start row, negative ones included
   DeviceGuard guard(h->device);
-  if (table && table_cols != h->hm.par.nu_pos && table_cols != h->hm.par.nu_pos + h->hm.par.nu_adh) {
+  if (table && table_cols != h->nu_pos && table_cols != h->nu_pos + h->nu_adh) {
     h->err = "nmf_step: action table rows must hold nu_pos (position targets) or nu_pos + nu_adh (+ adhesion) controls"; return NMF_EINVAL;
   }
+  if (h->tree)
+    return h->precision == 64 ? launch_tree_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos)
+                              : launch_tree_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos);
   if (h->hm.par.noslip_iterations > 0 && h->precision != 64 && (h->hm.par.terrain || h->hm.par.multiccd || h->hm.par.weld)) {
     h->err = "nmf_step: noslip on terrain / mesh-hull / tethered worlds needs nmf_set_precision(h, 64) (float32 noslip is built for the flat capsule world only)"; return NMF_EINVAL;
   }
@@ -387,13 +468,24 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
 extern "C" int nmf_set_precision(nmf_handle* h, int bits) {
   if (!h || (bits != 32 && bits != 64)) return NMF_EINVAL;
   DeviceGuard guard(h->device);
-  if (bits == 64 && !h->d_role64) {
-    CK(cudaMalloc(&h->d_role64, sizeof(double) * h->hm.role64.size()));
-    CK(cudaMemcpy(h->d_role64, h->hm.role64.data(), sizeof(double) * h->hm.role64.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&h->d_hull64, sizeof(double) * h->hm.hull64.size()));
-    CK(cudaMemcpy(h->d_hull64, h->hm.hull64.data(), sizeof(double) * h->hm.hull64.size(), cudaMemcpyHostToDevice));
+  if (bits == 64 && !h->d_state64) {
+    if (h->tree) {
+      const size_t smem = (size_t)h->tm.par64.d.m_total * sizeof(double);
+      int smem_max = 0;
+      CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+      if (smem > (size_t)smem_max) { h->err = "model too large for the f64 tree kernel's shared-memory plan"; return NMF_EINVAL; }
+      CK(cudaFuncSetAttribute(nmf_tree_step_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaMalloc(&h->d_rt64, sizeof(double) * h->tm.rtab64.size()));
+      CK(cudaMemcpy(h->d_rt64, h->tm.rtab64.data(), sizeof(double) * h->tm.rtab64.size(), cudaMemcpyHostToDevice));
+    } else {
+      CK(cudaMalloc(&h->d_role64, sizeof(double) * h->hm.role64.size()));
+      CK(cudaMemcpy(h->d_role64, h->hm.role64.data(), sizeof(double) * h->hm.role64.size(), cudaMemcpyHostToDevice));
+    }
+    const std::vector<double>& hull64 = h->tree ? h->tm.hull64 : h->hm.hull64;
+    CK(cudaMalloc(&h->d_hull64, sizeof(double) * hull64.size()));
+    CK(cudaMemcpy(h->d_hull64, hull64.data(), sizeof(double) * hull64.size(), cudaMemcpyHostToDevice));
     // full-precision records: start empty; a shadow of NaNs never equals a float record, so the first launch reads the float state
-    const size_t nrec = (size_t)h->n_flies * S_STRIDE;
+    const size_t nrec = (size_t)h->n_flies * h->stride;
     CK(cudaMalloc(&h->d_state64, sizeof(double) * nrec));
     CK(cudaMalloc(&h->d_shadow, sizeof(float) * nrec));
     CK(cudaMemset(h->d_state64, 0, sizeof(double) * nrec));
@@ -408,18 +500,18 @@ extern "C" int nmf_scatter_ctrl(nmf_handle* h, const float* src, const int32_t* 
   if (!h->bound) return NMF_ENOTBOUND;
   DeviceGuard guard(h->device);
   int total = h->n_flies * ncols;
-  nmf_scatter_cols_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->buf.state, S_CTRL, src, cols, ncols, h->n_flies);
+  nmf_scatter_cols_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->buf.state, h->stride, h->off_ctrl, src, cols, ncols, h->n_flies);
   h->launches++;
   CK(cudaGetLastError());
   return NMF_OK;
 }
 
 extern "C" int nmf_gather_state(nmf_handle* h, int off, const int32_t* cols, int ncols, float* dst, void* stream) {
-  if (!h || !dst || ncols <= 0 || off < 0 || off >= S_STRIDE) return NMF_EINVAL;
+  if (!h || !dst || ncols <= 0 || off < 0 || off >= h->stride) return NMF_EINVAL;
   if (!h->bound) return NMF_ENOTBOUND;
   DeviceGuard guard(h->device);
   int total = h->n_flies * ncols;
-  nmf_gather_cols_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->buf.state, off, cols, ncols, dst, h->n_flies);
+  nmf_gather_cols_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->buf.state, h->stride, off, cols, ncols, dst, h->n_flies);
   h->launches++;
   CK(cudaGetLastError());
   return NMF_OK;
@@ -433,8 +525,8 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
   if (!h->bound) return NMF_ENOTBOUND;
   DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int nu = h->hm.par.nu_pos + h->hm.par.nu_adh, n = h->n_flies;
-  if (action_cols != h->hm.par.nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
+  const int nu = h->nu_pos + h->nu_adh, n = h->n_flies, NQ = h->nq;
+  if (action_cols != h->nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
   if (!h->d_act) { h->err = "nmf_step_host: staging buffers missing"; return NMF_EINVAL; }     // allocated by nmf_create
   int parts = h->host_parts;
   while (parts > 1 && n < 1024 * parts) parts--;   // at least 1024 flies per slice

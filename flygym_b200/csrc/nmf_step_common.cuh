@@ -134,6 +134,48 @@ __device__ __forceinline__ void tma_store_f32(float* dst_gmem, const float* src_
 }
 #endif
 
+// The same movers for a record of `nfloats` floats (a multiple of 4) and a block of any size synchronised with __syncthreads
+// (the general-topology kernels of nmf_tree.cuh: the record length depends on the model).
+#ifndef NMF_SIMT_EMU
+__device__ __forceinline__ void tma_load_n(float* dst_smem, const float* src_gmem, int nfloats, unsigned long long* mbar, int tid) {
+  const unsigned mb = smem_u32(mbar), dst = smem_u32(dst_smem), bytes = (unsigned)nfloats * 4u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  block_sync(0);
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(mb) : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+  }
+  block_sync(0);
+  if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
+}
+__device__ __forceinline__ void tma_store_n(float* dst_gmem, const float* src_smem, int nfloats, int tid) {
+  block_sync(0);
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"((unsigned)nfloats * 4u) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+#else
+__device__ __forceinline__ void tma_load_n(float* dst_smem, const float* src_gmem, int nfloats, unsigned long long*, int tid) {
+  for (int i = tid; i < nfloats; i += (int)blockDim.x) dst_smem[i] = src_gmem[i];
+  block_sync(0);
+}
+__device__ __forceinline__ void tma_store_n(float* dst_gmem, const float* src_smem, int nfloats, int tid) {
+  block_sync(0);
+  for (int i = tid; i < nfloats; i += (int)blockDim.x) dst_gmem[i] = src_smem[i];
+}
+#endif
+
 // ------------------------------------------------------------------ float / double spellings of the math used by the body
 __device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }

@@ -145,19 +145,38 @@ class NMFModel:
         return cls(arrays, names, meta)
 
     @classmethod
-    def bench(cls, simplify_geom: bool = True, terrain: str | None = None, joint_preset: str = "legs_only") -> "NMFModel":
+    def bench(cls, simplify_geom: bool = True, terrain: str | None = None, joint_preset: str = "legs_only",
+              contact_preset: str | None = None) -> "NMFModel":
         """The reference benchmark model (``time_gpu_simulation.py:21-64``); ``terrain`` = ``"blocks"`` / ``"gapped"``
         replaces the flat ground plane by a box-column terrain (capsule geoms only); ``joint_preset="legs_active_only"``
         (reference ``anatomy.py:402-409``: no passive tarsal joints, 42 hinge DoFs) is baked in the kernels' chain layout with
-        the tarsus2-5 links massless and their DoFs locked (``baker.bake.bake_kernel_layout``)."""
+        the tarsus2-5 links massless and their DoFs locked (``baker.bake.bake_kernel_layout``).
+
+        ``joint_preset="all_biological"`` (126 hinge DoFs: head, proboscis, antennae, eyes, abdomen, wings and halteres
+        articulated as well, reference ``anatomy.py:418-436``) and ``"all_possible"`` (204: three DoFs at every anatomical joint,
+        ``anatomy.py:411-416``) are general trees, stepped by the general-topology kernels (``csrc/nmf_tree.cuh``); so is
+        ``contact_preset="all"`` (``ContactBodiesPreset.ALL``, ``anatomy.py:519-526``: all 69 segments collide with the
+        ground) on any skeleton.  ``contact_preset`` defaults to the reference's ``legs_thorax_abdomen_head``."""
         if joint_preset == "legs_active_only":
             if not simplify_geom:
                 raise ValueError("the LEGS_ACTIVE_ONLY preset is baked with capsule geoms only")
+            if contact_preset == "all":
+                raise ValueError("ContactBodiesPreset.ALL is baked for the LEGS_ONLY / ALL_BIOLOGICAL / ALL_POSSIBLE skeletons")
             m = cls.load(ASSETS_DIR / "nmf_bench_capsule_legs_active_only.npz")    # flygym_b200.baker.bake.bake_kernel_layout
-            return m if terrain in (None, "flat") else m.with_terrain(terrain)
-        m = cls.load(ASSETS_DIR / ("nmf_bench_capsule.npz" if simplify_geom else "nmf_bench_mesh.npz"))
-        if joint_preset != "legs_only":
-            raise ValueError("the sm_100a kernels handle the LEGS_ONLY chain layout (and LEGS_ACTIVE_ONLY by DoF locking)")
+        elif joint_preset == "legs_only" and contact_preset != "all":
+            m = cls.load(ASSETS_DIR / ("nmf_bench_capsule.npz" if simplify_geom else "nmf_bench_mesh.npz"))
+        else:
+            files = {("legs_only", True): "nmf_legs_only_allcontacts_capsule.npz", ("all_biological", True): "nmf_all_biological_capsule.npz",
+                     ("all_possible", True): "nmf_all_possible_capsule.npz", ("all_biological", False): "nmf_all_biological_mesh.npz"}
+            if (joint_preset, bool(simplify_geom)) not in files:
+                raise ValueError(f"no baked model for joint_preset={joint_preset!r}, simplify_geom={simplify_geom} "
+                                 "(bake it with flygym_b200.baker.bake.bake where the reference's assets are available)")
+            m = cls.load(ASSETS_DIR / files[(joint_preset, bool(simplify_geom))])      # baked with every segment as a contact body
+            if contact_preset != "all":
+                m = m.with_contact_bodies(contact_preset or "legs_thorax_abdomen_head")
+            contact_preset = None
+        if contact_preset not in (None, "legs_thorax_abdomen_head"):
+            m = m.with_contact_bodies(contact_preset)
         return m if terrain in (None, "flat") else m.with_terrain(terrain)
 
     @classmethod

@@ -6,7 +6,9 @@ Presents the method set of the reference's ``flygym.Simulation`` as batched by
 error behaviour.  Differences, all forced by the environment:
 
 * the model comes from a baked :class:`~flygym_b200.model.NMFModel` instead of a
-  ``dm_control``/MuJoCo-compiled ``world`` (neither is installable here);
+  ``dm_control``/MuJoCo-compiled ``world`` (neither is installable here); the benchmark skeleton (hub + 6 x 8 leg links)
+  runs on the star-topology kernels, every other skeleton (``JointPreset.ALL_BIOLOGICAL`` / ``ALL_POSSIBLE``,
+  ``ContactBodiesPreset.ALL``) on the general-topology kernels -- the native library picks, the API is the same;
 * batched arrays are ``torch.Tensor`` (float32, ``(n_worlds, ...)``) where the
   reference returns ``wp.array``; numpy or torch inputs are accepted where the
   reference accepts numpy or warp;
@@ -301,7 +303,7 @@ class B200Simulation:
 
     def get_ground_contact_info(self, fly_name: str):
         self._fly(fly_name); self._need_outputs()
-        s = self.sensordata.view(self.n_worlds, 6, 16)
+        s = self.sensordata.view(self.n_worlds, self.info.nleg, 16)
         return (s[:, :, 0].clone(), s[:, :, 1:4].clone(), s[:, :, 4:7].clone(), s[:, :, 7:10].clone(),
                 s[:, :, 10:13].clone(), s[:, :, 13:16].clone())
 

@@ -61,3 +61,43 @@ def step(model, state, nsteps=1, dbg=False, outputs=False, act_table=None, t0=0,
     assert rc == 0
     res.update(dbg=d, xpos=ox, xquat=oq, actf=oa, sensor=os_, energy=oe)
     return res
+
+
+# ------------------------------------------------------------------ general-topology (tree) kernels
+TREE_INFO_FIELDS = ["s_stride", "s_qpos", "s_qvel", "s_warm", "s_ctrl", "s_time", "nq", "nv", "nu", "nseg", "nleg", "smem_f32", "smem_f64", "nH"]
+
+
+def tree_info(model):
+    blob = model.to_blob()
+    out = np.zeros(len(TREE_INFO_FIELDS), np.int32)
+    assert lib().emu_tree_info(blob, ctypes.c_size_t(len(blob)), _p(out)) == 0
+    return dict(zip(TREE_INFO_FIELDS, (int(v) for v in out)))
+
+
+def tree_key_state(model):
+    info = tree_info(model)
+    blob = model.to_blob()
+    out = np.zeros(info["s_stride"], np.float32)
+    assert lib().emu_tree_key_state(blob, ctypes.c_size_t(len(blob)), _p(out)) == 0
+    return out
+
+
+def tree_step(model, state, nsteps=1, outputs=False, act_table=None, t0=0, max_newton=0, max_ls=0, precision=32, forward_only=False, dbg=False):
+    """state: float32 [n, s_stride] of the tree layout, updated in place."""
+    blob = model.to_blob()
+    info = tree_info(model)
+    n = state.shape[0]
+    assert state.dtype == np.float32 and state.shape[1] == info["s_stride"] and state.flags.c_contiguous
+    nseg, nu, nleg = info["nseg"], info["nu"], info["nleg"]
+    ox = np.zeros((n, nseg, 3), np.float32) if outputs else None
+    oq = np.zeros((n, nseg, 4), np.float32) if outputs else None
+    oa = np.zeros((n, nu), np.float32) if outputs else None
+    os_ = np.zeros((n, nleg * 16), np.float32) if outputs else None
+    oe = np.zeros((n, 2), np.float32) if outputs else None
+    d = np.zeros((n, 4), np.float32) if dbg else None
+    T = 0 if act_table is None else act_table.shape[1]
+    cols = 0 if act_table is None else act_table.shape[2]
+    rc = lib().emu_tree_step(blob, ctypes.c_size_t(len(blob)), _p(state), n, nsteps, _p(d), _p(ox), _p(oq), _p(oa), _p(os_),
+                             _p(act_table), T, t0, cols, max_newton, max_ls, precision, _p(oe), int(forward_only))
+    assert rc == 0
+    return dict(xpos=ox, xquat=oq, actf=oa, sensor=os_, energy=oe, dbg=d, info=info)

@@ -2,6 +2,7 @@
 // through the SIMT emulator.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
 #include "simt_emu.h"
 #include "../../flygym_b200/csrc/nmf_host.h"
+#include "../../flygym_b200/csrc/nmf_tree_host.h"
 #include "../../flygym_b200/csrc/nmf_step_all.cuh"
 
 static float g_sm[8 * (nmf::f32::SM_TOTAL + nmf::f32::NS_COUNT)];
@@ -70,5 +71,48 @@ extern "C" int emu_step(const void* blob, size_t nbytes, float* state, int n_fli
     else { EMU_RUN(nmf::f32::W_FLAT) }
 #undef EMU_RUN
   });
+  return 0;
+}
+
+// ------------------------------------------------------------------ general-topology (tree) kernels, nmf_tree.cuh
+extern "C" int emu_tree_info(const void* blob, size_t nbytes, int* out /* s_stride, s_qpos, s_qvel, s_warm, s_ctrl, s_time, nq, nv, nu, nseg, nleg, smem_f32_bytes, smem_f64_bytes, nH */) {
+  nmf::TreeModel tm;
+  if (!tm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", tm.err.c_str()); return -1; }
+  const nmf::TreeDims& d = tm.par.d;
+  const int v[14] = {d.s_stride, d.s_qpos, d.s_qvel, d.s_warm, d.s_ctrl, d.s_time, d.nq, d.nv, d.nu_pos + d.nu_adh, d.nseg, d.nleg,
+                     d.m_total * 4, tm.par64.d.m_total * 8, d.nH};
+  memcpy(out, v, sizeof v);
+  return 0;
+}
+extern "C" int emu_tree_key_state(const void* blob, size_t nbytes, float* out) {
+  nmf::TreeModel tm;
+  if (!tm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", tm.err.c_str()); return -1; }
+  memcpy(out, tm.key_state.data(), sizeof(float) * tm.key_state.size());
+  return 0;
+}
+extern "C" int emu_tree_step(const void* blob, size_t nbytes, float* state, int n_flies, int nsteps, float* dbg, float* out_xpos, float* out_xquat,
+                             float* out_actf, float* out_sensor, const float* act_table, int table_T, int table_t0, int table_cols,
+                             int max_newton, int max_ls, int precision, float* out_energy, int forward_only) {
+  nmf::TreeModel tm;
+  if (!tm.build(blob, nbytes)) { fprintf(stderr, "emu: %s\n", tm.err.c_str()); return -1; }
+  auto fill = [&](auto& q, const auto* rt, const auto* hull) {
+    q.state = state; q.it = tm.itab.data(); q.rt = rt; q.hull = hull; q.hull_nbr_adr = tm.hull_nbr_adr.data(); q.hull_nbr = tm.hull_nbr.data();
+    q.seg_tab = tm.seg_tab.data(); q.act_table = act_table; q.table_T = table_T; q.table_t0 = table_t0; q.table_cols = table_cols;
+    q.out_xpos = out_xpos; q.out_xquat = out_xquat; q.out_actf = out_actf; q.out_sensor = out_sensor; q.out_energy = out_energy; q.dbg = dbg;
+    q.n_flies = n_flies; q.nsteps = nsteps; q.forward_only = forward_only;
+    if (max_newton > 0) q.max_newton = max_newton;
+    if (max_ls > 0) q.max_ls = max_ls;
+  };
+  if (precision == 64) {
+    nmf::TreeParamsT<double> q = tm.par64;
+    fill(q, tm.rtab64.data(), tm.hull64.data());
+    std::vector<double> sm(q.d.m_total, 0.0);
+    for (int b = 0; b < n_flies; b++) simt::run_block(nmf::TREE_CTA, b, n_flies, [&]() { nmf::f64::tree_step_block(q, sm.data(), b); });
+    return 0;
+  }
+  nmf::TreeParamsT<float> q = tm.par;
+  fill(q, tm.rtab.data(), tm.hull.data());
+  std::vector<float> sm(q.d.m_total, 0.f);
+  for (int b = 0; b < n_flies; b++) simt::run_block(nmf::TREE_CTA, b, n_flies, [&]() { nmf::f32::tree_step_block(q, sm.data(), b); });
   return 0;
 }

@@ -1,0 +1,128 @@
+"""General-topology step kernels (flygym_b200/csrc/nmf_tree.cuh) on the CPU: the REAL kernel source runs through the SIMT
+emulator (tests/simt_emu, test infrastructure) against the fp64 oracle, for the skeletons the star kernels reject:
+JointPreset.ALL_BIOLOGICAL / ALL_POSSIBLE (reference src/flygym/anatomy.py:388-460) and ContactBodiesPreset.ALL
+(anatomy.py:519-526).  PARITY UNPINNED against real MuJoCo (see oracle/nmf_oracle.c)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu
+from flygym_b200 import NMFModel
+from oracle.oracle import Oracle
+
+
+def _settled(model, settle=1200):
+    """(oracle, float32 tree-layout record): the fly after `settle` oracle steps from the keyframe (standing on its tarsi), the
+    oracle restarted from the float32-rounded state so that both sides start from identical numbers."""
+    info = emu.tree_info(model)
+    o = Oracle(model); o.reset(); o.step(settle)
+    st = np.zeros((1, info["s_stride"]), np.float32)
+    st[0, :info["nq"]] = o.qpos
+    st[0, info["s_qvel"]:info["s_qvel"] + info["nv"]] = o.qvel
+    st[0, info["s_warm"]:info["s_warm"] + info["nv"]] = o.get("qacc_warmstart")
+    st[0, info["s_ctrl"]:info["s_ctrl"] + info["nu"]] = o.ctrl
+    o.qpos[:] = st[0, :info["nq"]]; o.qvel[:] = st[0, info["s_qvel"]:info["s_qvel"] + info["nv"]]
+    o.get("qacc_warmstart")[:] = st[0, info["s_warm"]:info["s_warm"] + info["nv"]]
+    return o, st, info
+
+
+def _compare(model, nsteps, precision, settle=1200):
+    o, st, info = _settled(model, settle)
+    r = emu.tree_step(model, st, nsteps, precision=precision, outputs=True, dbg=True)
+    o.step(nsteps)
+    qpos = st[0, :info["nq"]].astype(np.float64); qvel = st[0, info["s_qvel"]:info["s_qvel"] + info["nv"]].astype(np.float64)
+    so = o.get("sensordata").reshape(-1, 16); sg = r["sensor"][0].reshape(-1, 16)
+    oq = o.get("seg_xquat").reshape(-1, 4); gq = r["xquat"][0]
+    return dict(ncon=o.dim("ncon"), qpos=np.abs(qpos - o.qpos).max(), qvel=np.abs(qvel - o.qvel).max() / max(1.0, np.abs(o.qvel).max()),
+                actf=np.abs(r["actf"][0] - o.get("actuator_force")).max(), xpos=np.abs(r["xpos"][0].ravel() - o.get("seg_xpos")).max(),
+                xquat=np.abs(gq * np.sign((gq * oq).sum(1, keepdims=True)) - oq).max(),
+                found=np.abs(sg[:, 0] - so[:, 0]).max(), force=np.abs(sg[:, 1:10] - so[:, 1:10]).max() / max(1.0, np.abs(so[:, 1:4]).max()),
+                energy=np.abs(r["energy"][0] - o.get("energy")).max() / np.abs(o.get("energy")).max(), ncon_kernel=int(r["dbg"][0, 1]))
+
+
+def test_all_biological_f64_kernel_source_matches_the_oracle():
+    """126 hinge DoFs (head, proboscis, antennae, eyes, abdomen, wings, halteres articulated): every output after 12 steps of a
+    standing fly, double-precision instantiation -> what is left is the float32 rounding of the buffers."""
+    m = NMFModel.bench(joint_preset="all_biological")
+    assert m.nv == 132 and m.dim("ngeom") == 55
+    e = _compare(m, 12, 64)
+    print(e)
+    assert e["ncon"] >= 6 and e["ncon_kernel"] == e["ncon"]
+    assert e["qpos"] < 3e-7 and e["qvel"] < 2e-5 and e["actf"] < 2e-5 and e["xpos"] < 5e-7 and e["xquat"] < 2e-7
+    assert e["found"] == 0 and e["force"] < 1e-5 and e["energy"] < 1e-6
+
+
+def test_all_biological_f32_kernel_source_matches_the_oracle():
+    m = NMFModel.bench(joint_preset="all_biological")
+    e = _compare(m, 12, 32)
+    print(e)
+    assert e["qpos"] < 2e-6 and e["qvel"] < 5e-4 and e["actf"] < 2e-4 and e["xpos"] < 3e-6 and e["found"] == 0 and e["force"] < 5e-4
+
+
+@pytest.mark.parametrize("kw", [dict(joint_preset="all_possible", contact_preset="all"), dict(joint_preset="all_biological", simplify_geom=False),
+                                dict(joint_preset="all_biological", terrain="blocks"), dict(contact_preset="all")],
+                         ids=["all_possible+all_contacts", "all_biological_mesh_multiccd", "all_biological_blocks", "legs_only+all_contacts"])
+def test_other_general_models_f64(kw):
+    """ALL_POSSIBLE (204 hinge DoFs) with ContactBodiesPreset.ALL, mesh hulls with multiccd, box-column terrain, and the LEGS_ONLY
+    skeleton with 21 contact geoms on the hub (more than the star kernels' 16 hub lanes)."""
+    m = NMFModel.bench(**kw)
+    e = _compare(m, 5, 64, settle=1000)
+    print(kw, e)
+    assert e["ncon"] >= 6 and e["ncon_kernel"] == e["ncon"]
+    assert e["qpos"] < 3e-7 and e["qvel"] < 2e-5 and e["xpos"] < 5e-7 and e["found"] == 0 and e["force"] < 1e-5
+
+
+def test_tree_kernel_equals_star_kernel_on_the_benchmark_model():
+    """The benchmark skeleton stepped by both kernel families (float32, 4 CPG walkers, 15 steps): same physics, different
+    factorisation order -> agreement at float32 rounding."""
+    from flygym_b200.actions import cpg_table
+    m = NMFModel.bench(True)
+    n, T = 3, 15
+    tab = np.zeros((n, T, m.nu), np.float32); tab[:, :, :42] = cpg_table(m, n, T); tab[:, :, 42:] = 1.0
+    key = emu.key_state(m); key[2] = -0.17
+    star = np.tile(key, (n, 1)); star[:, 0] = 0.3 * np.arange(n)
+    info = emu.tree_info(m)
+    tree = np.zeros((n, info["s_stride"]), np.float32)
+    tree[:, :73] = star[:, :73]; tree[:, info["s_ctrl"]:info["s_ctrl"] + 48] = star[:, emu.S_CTRL:emu.S_CTRL + 48]
+    emu.step(m, star, T, act_table=tab)
+    emu.tree_step(m, tree, T, act_table=tab)
+    dq = np.abs(star[:, :73] - tree[:, :73]).max(); dv = np.abs(star[:, emu.S_QVEL:emu.S_QVEL + 72] - tree[:, info["s_qvel"]:info["s_qvel"] + 72]).max()
+    print(dq, dv)
+    assert dq < 5e-6 and dv < 5e-3
+    assert tree[0, info["s_time"]] == np.float32(T * m.timestep) and tree[0, info["s_time"] + 1] == 0
+
+
+def test_tree_host_tables_and_limits():
+    """Shared-memory plans fit one SM (227 KB opt-in) in both precisions; what the tree kernels do not handle is refused with a
+    message instead of being stepped wrongly."""
+    for kw in (dict(joint_preset="all_biological"), dict(joint_preset="all_biological", simplify_geom=False), dict(joint_preset="all_possible", contact_preset="all")):
+        info = emu.tree_info(NMFModel.bench(**kw))
+        assert info["smem_f32"] < 100 * 1024 and info["smem_f64"] < 227 * 1024, info
+        assert info["s_stride"] % 4 == 0 and info["s_qvel"] >= info["nq"] and info["s_time"] >= info["s_ctrl"] + info["nu"]
+    m = NMFModel.bench(joint_preset="all_biological")
+    assert emu.tree_info(m)["nH"] == sum(len(_anc(m, k)) for k in range(m.nv))
+    out = np.zeros(14, np.int32)
+    for bad in (m.with_options(noslip_iterations=5),):
+        blob = bad.to_blob()
+        assert emu.lib().emu_tree_info(blob, ctypes.c_size_t(len(blob)), out.ctypes.data_as(ctypes.c_void_p)) == -1
+
+
+def _anc(m, k):
+    p = m.arrays["dof_parent"]; out = []
+    while k >= 0:
+        out.append(k); k = int(p[k])
+    return out
+
+
+def test_from_mjmodel_ingests_general_skeletons():
+    """The converter no longer insists on the star topology: an MjModel-shaped ALL_BIOLOGICAL world (71 bodies, joint-less ones as
+    static children, actuators adhesion-first) comes back as the baked arrays, and the oracle walks identically on both."""
+    from flygym_b200.convert import from_mjmodel, mjmodel_like
+    m = NMFModel.bench(joint_preset="all_biological")
+    m2 = from_mjmodel(mjmodel_like(m))
+    assert m2.nv == 132 and m2.names["jointdofs"] == m.names["jointdofs"] and m2.names["legs"] == m.names["legs"]
+    for k in ("body_pos", "body_mass", "body_inertia", "dof_axis", "geom_pos", "geom_size", "act_dof", "adh_body", "body_parent", "body_leg", "key_qpos"):
+        assert np.abs(np.asarray(m.arrays[k], float).ravel() - np.asarray(m2.arrays[k], float).ravel()).max() < 1e-9, k
+    o1, o2 = Oracle(m), Oracle(m2); o1.step(200); o2.step(200)
+    assert np.abs(o1.qpos - o2.qpos).max() < 1e-12

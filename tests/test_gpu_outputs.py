@@ -24,6 +24,12 @@ def _worlds():
         "blocks": (lambda: NMFModel.bench(True, terrain="blocks"), -0.15, True),
         "gapped": (lambda: NMFModel.bench(True, terrain="gapped"), -0.17, True),
         "tethered": (lambda: __import__("flygym_b200").NMFModel.tethered(), None, False),
+        # general-topology kernels (csrc/nmf_tree.cuh)
+        "allbio_capsule": (lambda: NMFModel.bench(True, joint_preset="all_biological"), -0.17, False),
+        "allbio_mesh": (lambda: NMFModel.bench(False, joint_preset="all_biological"), -0.17, False),
+        "allbio_blocks": (lambda: NMFModel.bench(True, terrain="blocks", joint_preset="all_biological"), -0.15, True),
+        "allpossible_allcontacts": (lambda: NMFModel.bench(True, joint_preset="all_possible", contact_preset="all"), -0.17, False),
+        "legsonly_allcontacts": (lambda: NMFModel.bench(True, contact_preset="all"), -0.17, False),
     }
 
 
