@@ -64,8 +64,13 @@ NCU_LIMITER = {
     "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
                "source": "profiles/ncu_vision_r01s2_summary.txt"},
 }
+TREE_TRAFFIC_PER_FLY_STEP = (274.0, "profiles/ncu_tree_r02_summary.txt (nmf_tree_step_kernel, ALL_BIOLOGICAL, 1480 flies x 20 steps: 8.1 MB read + 0.03 MB written = "
+                                    "the records and the model tables once; nothing spills)")
 ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
 ODOR_PEAKS = [[1.0, 0.0], [0.0, 1.0]]
+
+
+SKELETON_DIMS = {"legs_only": (72, 48), "all_biological": (132, 48), "all_possible": (210, 78)}      # nv, nu of the baked models
 
 
 def workload_config(args, n_flies, chunk):
@@ -79,9 +84,12 @@ def workload_config(args, n_flies, chunk):
     cfg = {
         "workload": f"{n_flies} NeuroMechFly per GPU, {what}, {geoms} collision geoms",
         "baseline_config": {"flat": 1, "terrain": 2, "vision": 3, "olfaction": 4}[args.workload],
-        "n_flies_per_gpu": n_flies, "nv": 72, "nu": 48, "timestep": 1e-4,
+        "n_flies_per_gpu": n_flies, "nv": SKELETON_DIMS[args.skeleton][0], "nu": SKELETON_DIMS[args.skeleton][1], "timestep": 1e-4,
         "l2": "flushed (256 MiB write) before every timed launch group; action table > L2",
     }
+    if args.skeleton != "legs_only":
+        cfg["workload"] += f", JointPreset.{args.skeleton.upper()} skeleton ({SKELETON_DIMS[args.skeleton][0] - 6} hinge DoFs; general-topology kernels)"
+        cfg["skeleton"] = args.skeleton
     if args.workload in ("flat", "terrain"):
         cfg["steps_per_launch"] = chunk
     else:
@@ -226,8 +234,8 @@ def cpu_baseline_leg(model, n_total, target_s=16.0, stance_adhesion=False):
 def bench_model(args):
     from flygym_b200.model import NMFModel
     if args.workload == "terrain":
-        return NMFModel.bench(simplify_geom=True, terrain=args.terrain)
-    return NMFModel.bench(simplify_geom=not args.mesh)
+        return NMFModel.bench(simplify_geom=True, terrain=args.terrain, joint_preset=args.skeleton)
+    return NMFModel.bench(simplify_geom=not args.mesh, joint_preset=args.skeleton)
 
 
 def run_reference(args, rank, world):
@@ -434,6 +442,9 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
         per_fly = ALG_BYTES_OBS if per_step else ALG_BYTES_CORE
         kname = "nmf_step_terrain" if wl == "terrain" else "nmf_step"
         kname += "_f64_kernel" if args.precision == 64 else ("_x8_kernel" if n >= 8 * 148 else "_kernel")
+        if args.skeleton != "legs_only":       # general formula of SURVEY.md 8d: 4 (2 nq + 4 nv + nu) bytes per fly-step
+            per_fly = 4 * (2 * model.nq + 4 * model.nv + model.nu) + (ALG_BYTES_OBS - ALG_BYTES_CORE if per_step else 0)
+            kname = "nmf_tree_step_f64_kernel" if args.precision == 64 else "nmf_tree_step_kernel"
         roof = {"kernel": kname, "ms": step_ms, "alg_bytes": per_fly * n * per_launch_steps, "fly_steps": n * per_launch_steps,
                 "note": "the fused step is bound by instruction fetch / FP32 issue, not by HBM (SURVEY.md 8d, DESIGN.md 4.1); algorithmic bytes "
                         f"= {per_fly} B per fly-step"}
@@ -513,7 +524,8 @@ def run_ours(args, rank, world, local_rank):
     # reference's default mesh-hull geometry at N = 1; BASELINE config 5 (32768 flies per GPU + olfaction + NCCL all-gather of a
     # metrics slab every 100 steps) when several GPUs take part
     extras = {}
-    if wl == "flat" and args.extras and args.actions == "cpg" and args.precision == 32 and not args.mesh and args.n_flies == DEFAULT_FLIES["flat"]:
+    if wl == "flat" and args.extras and args.actions == "cpg" and args.precision == 32 and not args.mesh and args.n_flies == DEFAULT_FLIES["flat"] \
+            and args.skeleton == "legs_only":
         if world == 1:
             a2 = copy.copy(args); a2.mesh = True
             extras["mesh"] = sub_record(a2, measure(ctx, a2, steps=300, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
@@ -524,6 +536,10 @@ def run_ours(args, rank, world, local_rank):
             a4 = copy.copy(args); a4.workload = "terrain"; a4.chunk = DEFAULT_CHUNK["terrain"]
             extras["config3_terrain"] = sub_record(a4, measure(ctx, a4, steps=300, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
                                                    "BASELINE config 3: 4096 flies on the blocks terrain, stance-phase adhesion")
+            a7 = copy.copy(args); a7.skeleton = "all_biological"
+            extras["all_biological"] = sub_record(a7, measure(ctx, a7, steps=200, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
+                                                  "JointPreset.ALL_BIOLOGICAL (anatomy.py:418-436): head, proboscis, antennae, eyes, abdomen, wings and halteres "
+                                                  "articulated too, 126 hinge DoFs; stepped by the general-topology kernels (csrc/nmf_tree.cuh)")
             a6 = copy.copy(args); a6.workload = "vision"; a6.n_flies = DEFAULT_FLIES["vision"]; a6.chunk = DEFAULT_CHUNK["vision"]
             extras["config4_vision"] = sub_record(a6, measure(ctx, a6, steps=100, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
                                                   "BASELINE config 4: 1024 flies, two eye-camera renders (ground, sky, the fly's own body) -> Retina after every step")
@@ -556,7 +572,11 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "wall_s_timed_region": m["wall"], "state_finite": m["finite"],
         }
-        if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh and args.precision == 32:
+        if args.skeleton != "legs_only":
+            line["roofline"]["traffic"] = TREE_TRAFFIC_PER_FLY_STEP[0] * roof["fly_steps"]
+            line["roofline"]["traffic_source"] = TREE_TRAFFIC_PER_FLY_STEP[1]
+            line["roofline"]["note"] = "general-topology kernel: the fly lives in shared memory, bound by instruction issue (DESIGN.md 4.5); algorithmic bytes = 4 (2 nq + 4 nv + nu) per fly-step"
+        if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh and args.precision == 32 and args.skeleton == "legs_only":
             line["roofline"]["limiter"] = NCU_LIMITER[wl]
         if "retina_over_buffers" in roof:
             rb = dict(roof["retina_over_buffers"]); rb["frac"] = rb["achieved"] / peak
@@ -587,6 +607,8 @@ def main():
     ap.add_argument("--n-flies", type=int, default=None, help="flies per GPU (default: the BASELINE config's)")
     ap.add_argument("--chunk", type=int, default=None, help="physics steps per timed launch group (fused into one launch when no sensors run)")
     ap.add_argument("--mesh", action="store_true", help="mesh-hull collision geoms (simplify_geom=False)")
+    ap.add_argument("--skeleton", default="legs_only", choices=list(SKELETON_DIMS), help="JointPreset of the fly: legs_only = the reference benchmark "
+                    "model (star kernels); all_biological / all_possible = the full skeletons (general-topology kernels)")
     ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
     ap.add_argument("--eye-body", default="on", choices=["on", "off"], help="vision workload: the eye cameras also see the fly's own body (capsule proxies)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -66,7 +66,10 @@ extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_noslip_kernel(cons
 
 // general-topology models (JointPreset.ALL_BIOLOGICAL / ALL_POSSIBLE, ContactBodiesPreset.ALL, ...): nmf_tree.cuh, one block of
 // 128 threads per fly, the whole fly in (dynamic) shared memory
-extern "C" __global__ void __launch_bounds__(TREE_CTA) nmf_tree_step_kernel(const TreeParamsT<float> p) {
+#ifndef NMF_TREE_MINBLOCKS
+#define NMF_TREE_MINBLOCKS 5     // <= 96 registers: the 45 KB of shared memory of the ALL_BIOLOGICAL fly allow 5 blocks per SM, the registers must too
+#endif
+extern "C" __global__ void __launch_bounds__(TREE_CTA, NMF_TREE_MINBLOCKS) nmf_tree_step_kernel(const TreeParamsT<float> p) {
   extern __shared__ __align__(16) unsigned char tree_smem[];
   f32::tree_step_block(p, reinterpret_cast<float*>(tree_smem), (int)blockIdx.x);
 }

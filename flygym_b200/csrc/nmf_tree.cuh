@@ -202,17 +202,34 @@ __device__ __forceinline__ void tree_factor_solve(const TP& p, real* sm, int tid
   real* H = sm + d.m_H; real* x = sm + d.m_x; real* dinv = sm + d.m_dinv;
   real* accS = sm + d.m_accS + w * 24; real* rb = sm + d.m_rb + w * 8;
   const int* rowadr = it + d.i_rowadr; const int* col = it + d.i_col;
+  const int* pairs = it + d.i_pair;
+  const int nHa = d.nHa, wofs = w * 24;
   if (lane < 24) accS[lane] = real(0.);
   if (lane < 8) rb[lane] = real(0.);
   __syncwarp(NMF_FULL);
+  // The tables live in global memory and the 5 resident flies of an SM leave ~28 KB of L1: every table access on the serial path
+  // of this loop costs an L2 round trip.  Hence one 4-int descriptor per DoF {k, row start, m, pair-list start}, fetched one DoF
+  // ahead, and the pair list streamed past L1 (__ldcs) four loads at a time.
   const int k0 = it[d.i_wk_adr + w], k1 = it[d.i_wk_adr + w + 1];
+  const int* kd = it + d.i_wk;
+  int nk = 0, nr0 = 0, nm = 0, ne0 = 0;
+  if (k0 < k1) { nk = kd[4 * k0]; nr0 = kd[4 * k0 + 1]; nm = kd[4 * k0 + 2]; ne0 = kd[4 * k0 + 3]; }
   for (int idx = k0; idx < k1; idx++) {
-    const int k = it[d.i_wk + idx], r0 = rowadr[k], m = rowadr[k + 1] - r0 - 1;     // m proper ancestors
+    const int k = nk, r0 = nr0, m = nm, e0 = ne0, e1 = e0 + m * (m + 1) / 2;     // m proper ancestors
+    if (idx + 1 < k1) { nk = kd[4 * idx + 4]; nr0 = kd[4 * idx + 5]; nm = kd[4 * idx + 6]; ne0 = kd[4 * idx + 7]; }
     const real ik = real(1.) / H[r0], xk = x[k];
-    for (int pp = lane + 1; pp <= m; pp += 32) {
-      const int a = col[r0 + pp]; const real tmp = H[r0 + pp] * ik;
-      if (a >= TREE_NROOT) { real* Ha = H + rowadr[a]; for (int q = pp; q <= m; q++) Ha[q - pp] -= tmp * H[r0 + q]; }
-      else { real* Sa = accS + a * (a + 1) / 2; for (int q = pp; q <= m; q++) Sa[a - (q - pp)] += tmp * H[r0 + q]; }
+    // H[a_p][a_q] -= (H[k][a_p] / H[k][k]) H[k][a_q] over all pairs p <= q, one pair per lane (distinct targets; the root block's
+    // pairs land in this warp's accumulator behind H)
+    for (int e = e0 + lane; e < e1; e += 128) {
+      int pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) pk[j] = e + 32 * j < e1 ? __ldcs(pairs + e + 32 * j) : -1;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (pk[j] >= 0) {
+          const int tgt = pk[j] & 0xffff;
+          H[tgt + (tgt >= nHa ? wofs : 0)] -= (H[r0 + ((pk[j] >> 16) & 0xff)] * ik) * H[r0 + (pk[j] >> 24)];
+        }
     }
     __syncwarp(NMF_FULL);
     for (int pp = lane + 1; pp <= m; pp += 32) {
@@ -231,7 +248,7 @@ __device__ __forceinline__ void tree_factor_solve(const TP& p, real* sm, int tid
 #pragma unroll
       for (int j = 0; j <= i; j++) {
         real v = H[rowadr[i] + (i - j)];
-        for (int ww = 0; ww < TREE_NW; ww++) v -= sm[d.m_accS + ww * 24 + i * (i + 1) / 2 + j];
+        for (int ww = 0; ww < TREE_NW; ww++) v += sm[d.m_accS + ww * 24 + i * (i + 1) / 2 + j];
         S[i * (i + 1) / 2 + j] = v;
       }
       real r = x[i];
@@ -243,16 +260,20 @@ __device__ __forceinline__ void tree_factor_solve(const TP& p, real* sm, int tid
     for (int i = 0; i < 6; i++) x[i] = xb[i];
   }
   tree_sync();
-  for (int idx = k0 + lane; idx < k1; idx += 32) { const int k = it[d.i_wk + idx]; x[k] *= dinv[k]; }
+  for (int idx = k0 + lane; idx < k1; idx += 32) { const int k = kd[4 * idx]; x[k] *= dinv[k]; }
   __syncwarp(NMF_FULL);
-  for (int dd = 0; dd <= d.maxdd; dd++) {
-    const int a0 = it[d.i_wd_adr + w * (d.maxdd + 1) + dd], a1 = it[d.i_wd_adr + w * (d.maxdd + 1) + dd + 1];
-    for (int idx = a0 + lane; idx < a1; idx += 32) {
-      const int k = it[d.i_wd + idx], r0 = rowadr[k], m = rowadr[k + 1] - r0 - 1;
-      real s = real(0.);
-      for (int pp = 1; pp <= m; pp++) s += H[r0 + pp] * x[col[r0 + pp]];
-      x[k] -= s;
-    }
+  // x[k] -= sum_p L[k][a_p] x[a_p], the warp's DoFs in ascending order (ancestors first): the products spread over the lanes; the
+  // descriptor and the column indices of the next DoF are fetched while this one is reduced
+  int na = 0;
+  if (k0 < k1) { nk = kd[4 * k1 - 4]; nr0 = kd[4 * k1 - 3]; nm = kd[4 * k1 - 2]; na = lane < nm ? col[nr0 + lane + 1] : 0; }
+  for (int idx = k1 - 1; idx >= k0; idx--) {
+    const int k = nk, r0 = nr0, m = nm, a0 = na;
+    if (idx > k0) { nk = kd[4 * idx - 4]; nr0 = kd[4 * idx - 3]; nm = kd[4 * idx - 2]; na = lane < nm ? col[nr0 + lane + 1] : 0; }
+    real s = lane < m ? H[r0 + lane + 1] * x[a0] : real(0.);
+    for (int pp = lane + 33; pp <= m; pp += 32) s += H[r0 + pp] * x[col[r0 + pp]];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(NMF_FULL, s, off);
+    if (lane == 0) x[k] -= s;
     __syncwarp(NMF_FULL);
   }
 }
@@ -285,7 +306,8 @@ __device__ __forceinline__ void tree_dof_to_body(const TP& p, real* sm, int tid,
 }
 
 // subtree sums, leaves -> root, of two per-body arrays (n1 / n2 reals per body; n2 may be 0)
-__device__ __forceinline__ void tree_backward(const TP& p, int tid, real* a1, int n1, real* a2, int n2) {
+template <int n1, int n2>
+__device__ __forceinline__ void tree_backward(const TP& p, int tid, real* a1, real* a2) {
   const TreeDims& d = p.d; const int* it = p.it;
   const int lane = tid & 31, w = tid >> 5;
   for (int dp = d.maxd - 1; dp >= 1; dp--) {
@@ -294,7 +316,9 @@ __device__ __forceinline__ void tree_backward(const TP& p, int tid, real* a1, in
       const int b = it[d.i_wb + idx], c0 = it[d.i_child_adr + b], c1 = it[d.i_child_adr + b + 1];
       for (int ci = c0; ci < c1; ci++) {
         const int c = it[d.i_child + ci];
+#pragma unroll
         for (int n = 0; n < n1; n++) a1[n1 * b + n] += a1[n1 * c + n];
+#pragma unroll
         for (int n = 0; n < n2; n++) a2[n2 * b + n] += a2[n2 * c + n];
       }
     }
@@ -512,7 +536,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
       if (tid == 0) { p.out_energy[2 * (size_t)fly] = (float)e[0]; p.out_energy[2 * (size_t)fly + 1] = (float)e[1]; }
     }
     tree_sync();
-    tree_backward(p, tid, yb, 12, crb, 10);       // (the upper six of y are not used yet; summing them costs less than a second pass shape)
+    tree_backward<12, 10>(p, tid, yb, crb);       // (the upper six of y are not used yet; summing them costs less than a second pass shape)
     for (int k = tid; k < nv; k += TREE_CTA) {
       const int b = it[d.i_dof_body + k];
       const real* dr = rt + d.r_dof + TR_DOF * k;
@@ -563,7 +587,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
         for (int i = 0; i < 21; i++) Pb[21 * b + i] = A[i];
       }
       tree_sync();
-      tree_backward(p, tid, yb, 12, Pb, euler ? 0 : 21);
+      if (euler) tree_backward<12, 0>(p, tid, yb, Pb); else tree_backward<12, 21>(p, tid, yb, Pb);
       // ---- gradient / right-hand side, u = (crb + A-hat) cdof of every DoF
       for (int k = tid; k < nv; k += TREE_CTA) {
         const int b = it[d.i_dof_body + k];
@@ -583,7 +607,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
       }
       tree_sync();
       for (int e = tid; e < d.nH; e += TREE_CTA) {
-        const int row = it[d.i_erow + e], cl = it[d.i_col + e];
+        const int rc = __ldcs(it + d.i_erow + e), row = rc & 0xffff, cl = rc >> 16;
         real v = dot6(cdof + 6 * cl, u + 6 * row);
         if (row == cl) { const real* dr = rt + d.r_dof + TR_DOF * row; v += dr[5] + (euler ? p.dt * dr[4] : real(0.)); }
         H[e] = v;

@@ -33,9 +33,11 @@ struct TreeModel {
     d.m_stage = take(sizeof(real) == 8 ? (d.s_stride + 1) / 2 : 0);
     d.m_xpos = take(3 * d.nb); d.m_xquat = take(4 * d.nb); d.m_cinert = take(10 * d.nb); d.m_crb = take(10 * d.nb);
     d.m_cdof = take(6 * d.nv); d.m_cvel = take(6 * d.nb); d.m_acc = take(6 * d.nb); d.m_y = take(12 * d.nb); d.m_P = take(21 * d.nb);
-    d.m_fs = take(d.nv); d.m_grad = take(d.nv); d.m_x = take(d.nv); d.m_u = take(6 * d.nv); d.m_H = take(d.nH); d.m_dinv = take(d.nv);
+    d.m_fs = take(d.nv); d.m_grad = take(d.nv); d.m_x = take(d.nv); d.m_u = take(6 * d.nv);
+    d.m_H = take(d.nH); d.m_accS = take(TREE_NW * 24);      // the per-warp root-block accumulators sit right behind H (one index space)
+    d.m_dinv = take(d.nv);
     d.m_con = take(d.ng * d.nslot * TCON_STRIDE);
-    d.m_accS = take(TREE_NW * 24); d.m_rb = take(TREE_NW * 8); d.m_red = take(2 * TREE_NW * 8);
+    d.m_rb = take(TREE_NW * 8); d.m_red = take(2 * TREE_NW * 8);
     d.m_hullv = take(d.ng); d.m_misc = take(16 + d.nu_pos + d.nu_adh);
     d.m_total = o;
   }
@@ -64,7 +66,7 @@ struct TreeModel {
     if (missing) return false;
     // ---- topology checks: body 0 = free root (6 DoFs), parents before children, hinge DoFs contiguous and ordered like the bodies
     if (body_parent[0] >= 0 || dofnum[0] != TREE_NROOT || dofadr[0] != 0) { err = "tree kernels need a free root body (6 DoFs) as body 0"; return false; }
-    std::vector<int> depth(nb, 0), ddepth(nv, 0);
+    std::vector<int> depth(nb, 0);
     int maxd = 0, next = TREE_NROOT;
     for (int bb = 1; bb < nb; bb++) {
       if (body_parent[bb] < 0 || body_parent[bb] >= bb) { err = "bodies must be ordered parents first"; return false; }
@@ -80,7 +82,6 @@ struct TreeModel {
       if (d > dofadr[bb]) want = d - 1;
       else { int a = body_parent[bb]; while (a >= 0 && dofnum[a] == 0) a = body_parent[a]; want = a < 0 ? -1 : dofadr[a] + dofnum[a] - 1; }
       if (dof_parent[d] != want) { err = "dof_parent inconsistent with the body tree"; return false; }
-      ddepth[d] = want < 0 ? 1 : ddepth[want] + 1;
     }
     for (int a = 0; a < nu_pos; a++) if (act_dof[a] < TREE_NROOT || act_dof[a] >= nv) { err = "actuator on a free-joint dof is not supported"; return false; }
     for (int a = 0; a < nu_adh; a++) if (adh_body[a] <= 0 || adh_body[a] >= nb) { err = "adhesion on the root body is not supported"; return false; }
@@ -114,9 +115,6 @@ struct TreeModel {
       for (int tb : tops) { int w = 0; for (int q = 1; q < TREE_NW; q++) if (load[q] < load[w]) w = q; load[w] += cost[tb]; warp_of[tb] = w; }
       for (int bb = 1; bb < nb; bb++) warp_of[bb] = warp_of[top[bb]];
     }
-    int maxdd = 0;
-    for (int k = TREE_NROOT; k < nv; k++) maxdd = std::max(maxdd, ddepth[k] - TREE_NROOT - 1);
-    d.maxdd = maxdd;
 
     // ---- int table
     itab.clear();
@@ -139,7 +137,9 @@ struct TreeModel {
       std::vector<int> rowadr(nv + 1, 0), col, erow;
       for (int k = 0; k < nv; k++) { rowadr[k] = (int)col.size(); for (int a = k; a >= 0; a = dof_parent[a]) { col.push_back(a); erow.push_back(k); } }
       rowadr[nv] = (int)col.size(); d.nH = (int)col.size();
-      d.i_rowadr = put(rowadr); d.i_col = put(col); d.i_erow = put(erow);
+      d.i_rowadr = put(rowadr); d.i_col = put(col);
+      for (size_t e = 0; e < col.size(); e++) erow[e] |= col[e] << 16;      // (row | column << 16) of every entry, streamed when H is formed
+      d.i_erow = put(erow);
     }
     d.i_gbody = putp(geom_body, ng); d.i_gtype = putp(geom_type, ng); d.i_gvadr = putp(gvadr, ng); d.i_gvnum = putp(gvnum, ng);
     d.i_adh_body = putp(adh_body, nu_adh);
@@ -150,15 +150,32 @@ struct TreeModel {
         if (dp >= 1) for (int bb = 1; bb < nb; bb++) if (warp_of[bb] == w && depth[bb] == dp) lst.push_back(bb);
       }
       adr.push_back((int)lst.size()); d.i_wb_adr = put(adr); d.i_wb = put(lst);
-      std::vector<int> kadr, kl;
-      for (int w = 0; w < TREE_NW; w++) { kadr.push_back((int)kl.size()); for (int k = nv - 1; k >= TREE_NROOT; k--) if (warp_of[dof_body[k]] == w) kl.push_back(k); }
-      kadr.push_back((int)kl.size()); d.i_wk_adr = put(kadr); d.i_wk = put(kl);
-      std::vector<int> dadr, dl;
-      for (int w = 0; w < TREE_NW; w++) for (int dd = 0; dd <= maxdd; dd++) {
-        dadr.push_back((int)dl.size());
-        for (int k = TREE_NROOT; k < nv; k++) if (warp_of[dof_body[k]] == w && ddepth[k] - TREE_NROOT - 1 == dd) dl.push_back(k);
+    }
+    {
+      // eliminating DoF k updates H[a_p][a_q] -= (H[k][a_p] / H[k][k]) H[k][a_q] for every pair p <= q of its proper ancestors a_1..a_m
+      // (row position = distance up the ancestor chain); pairs inside the root block go to the warp's accumulator instead
+      d.nHa = align4(d.nH);
+      const int* rowadr = itab.data() + d.i_rowadr; const int* col = itab.data() + d.i_col;
+      if (d.nHa + 24 > 0xffff) { err = "model too large for the packed elimination table"; return false; }
+      std::vector<int> padr(nv + 1, 0), pl;
+      for (int k = 0; k < nv; k++) {
+        padr[k] = (int)pl.size();
+        if (k < TREE_NROOT) continue;
+        const int r0 = rowadr[k], m = rowadr[k + 1] - r0 - 1;
+        if (m > 127) { err = "kinematic chain too deep"; return false; }
+        for (int pp = 1; pp <= m; pp++) for (int q = pp; q <= m; q++) {
+          const int a = col[r0 + pp];
+          const int tgt = a >= TREE_NROOT ? rowadr[a] + (q - pp) : d.nHa + a * (a + 1) / 2 + (a - (q - pp));
+          pl.push_back(tgt | (pp << 16) | (q << 24));
+        }
       }
-      dadr.push_back((int)dl.size()); d.i_wd_adr = put(dadr); d.i_wd = put(dl);
+      std::vector<int> kadr, kl;
+      for (int w = 0; w < TREE_NW; w++) {
+        kadr.push_back((int)kl.size() / 4);
+        for (int k = nv - 1; k >= TREE_NROOT; k--) if (warp_of[dof_body[k]] == w) { kl.push_back(k); kl.push_back(rowadr[k]); kl.push_back(rowadr[k + 1] - rowadr[k] - 1); kl.push_back(padr[k]); }
+      }
+      kadr.push_back((int)kl.size() / 4); d.i_wk_adr = put(kadr); d.i_wk = put(kl);
+      d.i_pair = put(pl);
     }
     d.i_total = (int)itab.size();
 

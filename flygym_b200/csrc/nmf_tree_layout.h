@@ -16,7 +16,7 @@ constexpr int TREE_MAXBODY = 96, TREE_MAXNV = 256, TREE_MAXGEOM = 96, TREE_MAXNU
 constexpr int TCON_STRIDE = 18;                // reals per contact slot in shared memory: ContactG (14) + sv (3) + adhesion pull (1)
 
 struct TreeDims {
-  int nb, nq, nv, nu_pos, nu_adh, ng, nseg, nleg, nslot, nH, maxd, maxdd;
+  int nb, nq, nv, nu_pos, nu_adh, ng, nseg, nleg, nslot, nH, maxd;
   // state record (floats): qpos | qvel | qacc_warmstart | ctrl | time, status, step count, pad ; every section 16-byte aligned
   int s_qpos, s_qvel, s_warm, s_ctrl, s_time, s_stride;
   // int table
@@ -24,12 +24,14 @@ struct TreeDims {
   int i_child_adr, i_child;                    // CSR children of a body: [nb + 1], [nb - 1]
   int i_bg_adr, i_bg;                          // CSR contact geoms of a body: [nb + 1], [ng]
   int i_dof_body, i_cidx;                      // [nv]: body of a DoF, ctrl index of its position actuator (-1 = none)
-  int i_rowadr, i_col, i_erow;                 // ancestor-sparse matrix rows: [nv + 1]; [nH] column (ancestor DoF) and row of every entry
+  int i_rowadr, i_col, i_erow;                 // ancestor-sparse matrix rows: [nv + 1]; [nH] column (ancestor DoF) of every entry; [nH] row | column << 16
   int i_gbody, i_gtype, i_gvadr, i_gvnum;      // [ng]
   int i_adh_body;                              // [nu_adh]
   int i_wb_adr, i_wb;                          // bodies of warp w at tree depth d (d >= 1): adr[w * (maxd + 1) + d .. + 1], list
-  int i_wk_adr, i_wk;                          // non-root DoFs of warp w, descending: adr[w .. w + 1], list
-  int i_wd_adr, i_wd;                          // non-root DoFs of warp w by number of non-root ancestors dd: adr[w * (maxdd + 1) + dd .. + 1], list
+  int i_wk_adr, i_wk;                          // non-root DoFs of warp w, descending (descendants before ancestors): adr[w .. w + 1]; list of
+                                               // 4-int descriptors {DoF k, start of its row, number of proper ancestors m, start of its pair list}
+  int i_pair;                                  // elimination of DoF k: m (m + 1) / 2 packed updates (target entry | p << 16 | q << 24)
+  int nHa;                                     // nH rounded up to 4: targets >= nHa address the per-warp root-block accumulators behind H
   int i_total;
   // real table
   int r_body;     // [nb][18]: pos 3, quat 4, ipos 3, inertia about the COM in the body frame (xx yy zz xy xz yz) 6, mass, invweight

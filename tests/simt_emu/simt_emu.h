@@ -198,6 +198,7 @@ inline int __any_sync(unsigned mask, int pred) {
   (void)lane; return acc;
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
+template <typename T> inline T __ldcs(const T* p) { return *p; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline void sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 inline float __fdividef(float a, float b) { return a / b; }
