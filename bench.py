@@ -64,7 +64,7 @@ NCU_LIMITER = {
     "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
                "source": "profiles/ncu_vision_r01s2_summary.txt"},
 }
-TREE_TRAFFIC_PER_FLY_STEP = (274.0, "profiles/ncu_tree_r02_summary.txt (nmf_tree_step_kernel, ALL_BIOLOGICAL, 1480 flies x 20 steps: 8.1 MB read + 0.03 MB written = "
+TREE_TRAFFIC_PER_FLY_STEP = (8.4e6 / (1480 * 20), "profiles/ncu_tree_r02_summary.txt (nmf_tree_step_kernel, ALL_BIOLOGICAL, 1480 flies x 20 steps: 8.4 MB read + 2 KB written = "
                                     "the records and the model tables once; nothing spills)")
 ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
 ODOR_PEAKS = [[1.0, 0.0], [0.0, 1.0]]

@@ -514,7 +514,8 @@ __device__ __forceinline__ void point_and_rot(const real* sw, const real* S, rea
 #pragma unroll
   for (int i = 0; i < 3; i++) out[3 + i] = G[3 * i] * S[0] + G[3 * i + 1] * S[1] + G[3 * i + 2] * S[2];
 }
-__device__ __forceinline__ void weld_setup(const SP& p, real* sw, const real* qh, const real* xh, const real* com,
+template <class PT>      // StepParamsT or TreeParamsT: both carry the weld_* fields
+__device__ __forceinline__ void weld_setup(const PT& p, real* sw, const real* qh, const real* xh, const real* com,
                                            const real* cvel, const real* Sa) {
   real a[3], q[4], pos[6];
   qrot(qh, p.weld_a, a); qmul(qh, p.weld_q, q);

@@ -193,49 +193,50 @@ __device__ __forceinline__ void tree_root_solve(real* S, real* xb) {
     for (int j = 0; j < kk; j++) xb[kk] -= S[kk * (kk + 1) / 2 + j] * xb[j];
 }
 
-// Solves H x = x0 in place (x holds the right-hand side on entry), H in ancestor-sparse rows (destroyed: L and 1/D remain).
+// Solves H x = x0 in place (x holds the right-hand side on entry), H in ancestor-sparse rows (destroyed: the eliminated rows and 1/D
+// remain; L[k][a] = H[k][a] / H[k][k] is applied on the fly, never stored).
 // Every warp eliminates the DoFs of its subtrees from the leaves towards the root; what they contribute to the root block /
 // the root right-hand side is summed per warp, then thread 0 finishes the 6 x 6 root block and the warps substitute back.
+// The tables live in global memory and the 5 resident flies of an SM leave ~28 KB of L1, so every table access on the serial path
+// of these loops costs an L2 round trip: one 8-int descriptor per DoF {k, row start, m, pair-list start, descendant-list start,
+// number of descendants}, fetched one DoF ahead; the pair and descendant lists are streamed past L1 (__ldcs).
 __device__ __forceinline__ void tree_factor_solve(const TP& p, real* sm, int tid) {
   const TreeDims& d = p.d; const int* it = p.it;
   const int lane = tid & 31, w = tid >> 5;
   real* H = sm + d.m_H; real* x = sm + d.m_x; real* dinv = sm + d.m_dinv;
   real* accS = sm + d.m_accS + w * 24; real* rb = sm + d.m_rb + w * 8;
   const int* rowadr = it + d.i_rowadr; const int* col = it + d.i_col;
-  const int* pairs = it + d.i_pair;
+  const int* pairs = it + d.i_pair; const int* desc = it + d.i_desc;
   const int nHa = d.nHa, wofs = w * 24;
   if (lane < 24) accS[lane] = real(0.);
   if (lane < 8) rb[lane] = real(0.);
   __syncwarp(NMF_FULL);
-  // The tables live in global memory and the 5 resident flies of an SM leave ~28 KB of L1: every table access on the serial path
-  // of this loop costs an L2 round trip.  Hence one 4-int descriptor per DoF {k, row start, m, pair-list start}, fetched one DoF
-  // ahead, and the pair list streamed past L1 (__ldcs) four loads at a time.
   const int k0 = it[d.i_wk_adr + w], k1 = it[d.i_wk_adr + w + 1];
   const int* kd = it + d.i_wk;
-  int nk = 0, nr0 = 0, nm = 0, ne0 = 0;
-  if (k0 < k1) { nk = kd[4 * k0]; nr0 = kd[4 * k0 + 1]; nm = kd[4 * k0 + 2]; ne0 = kd[4 * k0 + 3]; }
+  int nk = 0, nr0 = 0, nm = 0, ne0 = 0, na = 0;
+  if (k0 < k1) { nk = kd[8 * k0]; nr0 = kd[8 * k0 + 1]; nm = kd[8 * k0 + 2]; ne0 = kd[8 * k0 + 3]; na = lane < nm ? col[nr0 + lane + 1] : 0; }
   for (int idx = k0; idx < k1; idx++) {
-    const int k = nk, r0 = nr0, m = nm, e0 = ne0, e1 = e0 + m * (m + 1) / 2;     // m proper ancestors
-    if (idx + 1 < k1) { nk = kd[4 * idx + 4]; nr0 = kd[4 * idx + 5]; nm = kd[4 * idx + 6]; ne0 = kd[4 * idx + 7]; }
+    const int k = nk, r0 = nr0, m = nm, e0 = ne0, e1 = e0 + m * (m + 1) / 2, a0 = na;     // m proper ancestors a_1 .. a_m
+    if (idx + 1 < k1) { nk = kd[8 * idx + 8]; nr0 = kd[8 * idx + 9]; nm = kd[8 * idx + 10]; ne0 = kd[8 * idx + 11]; na = lane < nm ? col[nr0 + lane + 1] : 0; }
     const real ik = real(1.) / H[r0], xk = x[k];
-    // H[a_p][a_q] -= (H[k][a_p] / H[k][k]) H[k][a_q] over all pairs p <= q, one pair per lane (distinct targets; the root block's
-    // pairs land in this warp's accumulator behind H)
+    // right-hand side (L^-T rides along): x[a_p] -= L[k][a_p] x[k]
+    if (lane < m) { const real lx = (H[r0 + lane + 1] * ik) * xk; if (a0 >= TREE_NROOT) x[a0] -= lx; else rb[a0] += lx; }
+    for (int pp = lane + 33; pp <= m; pp += 32) { const int a = col[r0 + pp]; const real lx = (H[r0 + pp] * ik) * xk; if (a >= TREE_NROOT) x[a] -= lx; else rb[a] += lx; }
+    // H[a_p][a_q] -= (H[k][a_p] / H[k][k]) H[k][a_q] over all pairs p <= q, one pair per lane (distinct targets, none in row k; the
+    // root block's pairs land in this warp's accumulator behind H); operands of four pairs are in flight before the first store
     for (int e = e0 + lane; e < e1; e += 128) {
-      int pk[4];
+      int pk[4], ti[4];
+      real hp[4], hq[4], ht[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) pk[j] = e + 32 * j < e1 ? __ldcs(pairs + e + 32 * j) : -1;
+      for (int j = 0; j < 4; j++) pk[j] = e + 32 * j < e1 ? __ldcs(pairs + e + 32 * j) : 0;      // 0 = (target 0, p 0, q 0): a harmless dummy
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (pk[j] >= 0) {
-          const int tgt = pk[j] & 0xffff;
-          H[tgt + (tgt >= nHa ? wofs : 0)] -= (H[r0 + ((pk[j] >> 16) & 0xff)] * ik) * H[r0 + (pk[j] >> 24)];
-        }
-    }
-    __syncwarp(NMF_FULL);
-    for (int pp = lane + 1; pp <= m; pp += 32) {
-      const int a = col[r0 + pp]; const real l = H[r0 + pp] * ik;
-      H[r0 + pp] = l;
-      if (a >= TREE_NROOT) x[a] -= l * xk; else rb[a] += l * xk;
+      for (int j = 0; j < 4; j++) {
+        const int tgt = pk[j] & 0xffff;
+        ti[j] = tgt + (tgt >= nHa ? wofs : 0);
+        hp[j] = H[r0 + ((pk[j] >> 16) & 0xff)]; hq[j] = H[r0 + (pk[j] >> 24)]; ht[j] = H[ti[j]];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (pk[j]) H[ti[j]] = ht[j] - (hp[j] * ik) * hq[j];
     }
     if (lane == 0) dinv[k] = ik;
     __syncwarp(NMF_FULL);
@@ -260,22 +261,33 @@ __device__ __forceinline__ void tree_factor_solve(const TP& p, real* sm, int tid
     for (int i = 0; i < 6; i++) x[i] = xb[i];
   }
   tree_sync();
-  for (int idx = k0 + lane; idx < k1; idx += 32) { const int k = kd[4 * idx]; x[k] *= dinv[k]; }
-  __syncwarp(NMF_FULL);
-  // x[k] -= sum_p L[k][a_p] x[a_p], the warp's DoFs in ascending order (ancestors first): the products spread over the lanes; the
-  // descriptor and the column indices of the next DoF are fetched while this one is reduced
-  int na = 0;
-  if (k0 < k1) { nk = kd[4 * k1 - 4]; nr0 = kd[4 * k1 - 3]; nm = kd[4 * k1 - 2]; na = lane < nm ? col[nr0 + lane + 1] : 0; }
-  for (int idx = k1 - 1; idx >= k0; idx--) {
-    const int k = nk, r0 = nr0, m = nm, a0 = na;
-    if (idx > k0) { nk = kd[4 * idx - 4]; nr0 = kd[4 * idx - 3]; nm = kd[4 * idx - 2]; na = lane < nm ? col[nr0 + lane + 1] : 0; }
-    real s = lane < m ? H[r0 + lane + 1] * x[a0] : real(0.);
-    for (int pp = lane + 33; pp <= m; pp += 32) s += H[r0 + pp] * x[col[r0 + pp]];
+  // back-substitution  x[k] = (y[k] - sum_a H[k][a] x[a]) / H[k][k]: the root solution first (the last six entries of every row),
+  // then the warp's DoFs in ascending order, each pushing its final value to its descendants (one descendant per lane)
+  {
+    real xb[6];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(NMF_FULL, s, off);
-    if (lane == 0) x[k] -= s;
+    for (int r = 0; r < 6; r++) xb[r] = x[r];
+    for (int idx = k0 + lane; idx < k1; idx += 32) {
+      const int k = kd[8 * idx], r0 = kd[8 * idx + 1], m = kd[8 * idx + 2];
+      real t = x[k];
+#pragma unroll
+      for (int r = 0; r < 6; r++) t -= H[r0 + m - r] * xb[r];
+      x[k] = t;
+    }
+  }
+  __syncwarp(NMF_FULL);
+  int nf0 = 0, nnf = 0;
+  if (k0 < k1) { nk = kd[8 * k1 - 8]; nf0 = kd[8 * k1 - 4]; nnf = kd[8 * k1 - 3]; na = lane < nnf ? __ldcs(desc + nf0 + lane) : 0; }
+  for (int idx = k1 - 1; idx >= k0; idx--) {
+    const int k = nk, f0 = nf0, nf = nnf, pk0 = na;
+    if (idx > k0) { nk = kd[8 * idx - 8]; nf0 = kd[8 * idx - 4]; nnf = kd[8 * idx - 3]; na = lane < nnf ? __ldcs(desc + nf0 + lane) : 0; }
+    const real xk = x[k] * dinv[k];
+    if (lane < nf) x[pk0 >> 16] -= H[pk0 & 0xffff] * xk;
+    for (int e = lane + 32; e < nf; e += 32) { const int pk = __ldcs(desc + f0 + e); x[pk >> 16] -= H[pk & 0xffff] * xk; }
     __syncwarp(NMF_FULL);
   }
+  for (int idx = k0 + lane; idx < k1; idx += 32) { const int k = kd[8 * idx]; x[k] *= dinv[k]; }
+  __syncwarp(NMF_FULL);
 }
 
 // body accelerations generated by the DoF vector v:  out_b = out_parent + sum_j cdof_j v_j   (6 reals per body)
@@ -351,6 +363,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
   real* actf = misc + 16;                        // [nu] actuator forces of this step
   TCon* con = reinterpret_cast<TCon*>(sm + d.m_con);
   int* hullv = reinterpret_cast<int*>(sm + d.m_hullv);
+  real* sw = sm + d.m_weld;                      // weld rows of the tethered world (thread 0 owns them; they only touch the root body)
   int parity = 0;
   real* qpos = st + d.s_qpos; real* qvel = st + d.s_qvel; real* qacc = st + d.s_warm; real* ctrl = st + d.s_ctrl;
 
@@ -563,6 +576,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
         c.c.w[0] += ap[0]; c.c.w[1] += ap[1]; c.c.w[2] += ap[2];
       }
     }
+    if (p.weld && tid == 0) weld_setup(p, sw, xquat, xpos, com, cvel, acc);     // six always-active rows on the root body
     tree_sync();
 
     // ================================================================= D. soft-contact solve (primal Newton, exact line search)
@@ -580,6 +594,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
           const TCon& c = con[it[d.i_bg + gi] * nslot + s];
           if (c.c.D > real(0.)) { if (euler) contact_forces<false>(c.c, p.mu, Wc, nullptr, nullptr); else contact_forces<true>(c.c, p.mu, Wc, A, nullptr); }
         }
+        if (p.weld && b == 0) weld_forces(sw, Wc, A);
         real t6[6]; mul_inert(cinert + 10 * b, acc + 6 * b, t6);
 #pragma unroll
         for (int i = 0; i < 6; i++) { yb[12 * b + i] = t6[i] - Wc[i]; yb[12 * b + 6 + i] = Wc[i]; }
@@ -631,6 +646,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
           if (c.c.D > real(0.)) ls_eval(c.c, c.sv, real(0.), red[2], red[3], dummy);
         }
       }
+      if (p.weld && tid == 0) { point_and_rot(sw, Ss, sw + WL_SV); weld_ls(sw, real(0.), red[2], red[3]); }
       tree_reduce<5>(red, s_red, parity, tid);
       real alpha = real(0.);
       nchanged_last = 0;
@@ -648,6 +664,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
           real e[3] = {real(0.), real(0.), real(0.)};
           for (int g = tid; g < ng; g += TREE_CTA)
             for (int s = 0; s < nslot; s++) { const TCon& c = con[g * nslot + s]; if (c.c.D > real(0.)) ls_eval(c.c, c.sv, alpha, e[0], e[1], e[2]); }
+          if (p.weld && tid == 0) weld_ls(sw, alpha, e[0], e[1]);
           tree_reduce<3>(e, s_red, parity, tid);
           d0 = q1 + alpha * q2 + e[0]; d1 = q2 + e[1];
           nchanged_last = (int)e[2];
@@ -659,6 +676,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
       for (int i = tid; i < 6 * nb; i += TREE_CTA) acc[i] += alpha * Ss[i];
       for (int g = tid; g < ng; g += TREE_CTA)
         for (int s = 0; s < nslot; s++) { TCon& c = con[g * nslot + s]; c.c.w[0] += alpha * c.sv[0]; c.c.w[1] += alpha * c.sv[1]; c.c.w[2] += alpha * c.sv[2]; }
+      if (p.weld && tid == 0) for (int i = 0; i < 6; i++) sw[WL_W + i] += alpha * sw[WL_SV + i];
       tree_sync();
     }
     // x now holds the implicit-damping (Euler) acceleration

@@ -38,7 +38,7 @@ struct TreeModel {
     d.m_dinv = take(d.nv);
     d.m_con = take(d.ng * d.nslot * TCON_STRIDE);
     d.m_rb = take(TREE_NW * 8); d.m_red = take(2 * TREE_NW * 8);
-    d.m_hullv = take(d.ng); d.m_misc = take(16 + d.nu_pos + d.nu_adh);
+    d.m_hullv = take(d.ng); d.m_misc = take(16 + d.nu_pos + d.nu_adh); d.m_weld = take(d.ng == 0 ? 48 : 0);   // (weld rows: only the tethered world, which has no contact geoms)
     d.m_total = o;
   }
 
@@ -93,7 +93,6 @@ struct TreeModel {
       hulls = hulls || geom_type[g] == 1;
     }
     for (int sg = 0; sg < nseg; sg++) if (seg_body[sg] < 0 || seg_body[sg] >= nb) { err = "seg_body out of range"; return false; }
-    { int nw = 0; const double* wd = b.get<double>("weld", &nw); if (wd && nw >= 1 && wd[0] != 0.0) { err = "the tree kernels do not handle the tethered (welded) world yet"; return false; } }
     if ((int)opt[8] > 0) { err = "the tree kernels do not run the noslip post-solver (use noslip_iterations = 0)"; return false; }
 
     TreeDims d{};
@@ -169,13 +168,24 @@ struct TreeModel {
           pl.push_back(tgt | (pp << 16) | (q << 24));
         }
       }
+      // descendants of every non-root DoF k (the DoFs whose rows hold an entry in column k), for the push-style back-substitution
+      std::vector<int> dadr(nv + 1, 0), dl;
+      for (int k = 0; k < nv; k++) {
+        dadr[k] = (int)dl.size();
+        if (k < TREE_NROOT) continue;
+        for (int j = k + 1; j < nv; j++) for (int e = rowadr[j] + 1; e < rowadr[j + 1]; e++) if (col[e] == k) dl.push_back(e | (j << 16));
+      }
+      dadr[nv] = (int)dl.size();
       std::vector<int> kadr, kl;
       for (int w = 0; w < TREE_NW; w++) {
-        kadr.push_back((int)kl.size() / 4);
-        for (int k = nv - 1; k >= TREE_NROOT; k--) if (warp_of[dof_body[k]] == w) { kl.push_back(k); kl.push_back(rowadr[k]); kl.push_back(rowadr[k + 1] - rowadr[k] - 1); kl.push_back(padr[k]); }
+        kadr.push_back((int)kl.size() / 8);
+        for (int k = nv - 1; k >= TREE_NROOT; k--) if (warp_of[dof_body[k]] == w) {
+          const int row[8] = {k, rowadr[k], rowadr[k + 1] - rowadr[k] - 1, padr[k], dadr[k], dadr[k + 1] - dadr[k], 0, 0};
+          kl.insert(kl.end(), row, row + 8);
+        }
       }
-      kadr.push_back((int)kl.size() / 4); d.i_wk_adr = put(kadr); d.i_wk = put(kl);
-      d.i_pair = put(pl);
+      kadr.push_back((int)kl.size() / 8); d.i_wk_adr = put(kadr); d.i_wk = put(kl);
+      d.i_pair = put(pl); d.i_desc = put(dl);
     }
     d.i_total = (int)itab.size();
 
@@ -264,6 +274,20 @@ struct TreeModel {
         for (int i = 0; i < 7; i++) P.terr[i] = terr[1 + i];
       }
     }
+    {  // optional weld section (TetheredWorld): see flygym_b200/model.py WELD_FIELDS
+      int nw = 0; const double* wd = b.get<double>("weld", &nw);
+      if (wd && nw >= 18 && wd[0] != 0.0) {
+        if (ng != 0) { err = "a tethered (welded) world cannot have ground-contact geoms"; return false; }
+        P.weld = 1;
+        for (int i = 0; i < 3; i++) P.weld_a[i] = wd[1 + i];
+        for (int i = 0; i < 4; i++) P.weld_q[i] = wd[4 + i];
+        const double wtc = std::fmax(wd[8], 2 * opt[0]), wdmax = clampimp(wd[11]);
+        P.weld_K = 1.0 / (wdmax * wdmax * wtc * wtc * wd[9] * wd[9]); P.weld_B = 2.0 / (wdmax * wtc);
+        P.weld_imp[0] = clampimp(wd[10]); P.weld_imp[1] = wdmax; P.weld_imp[2] = std::fmax(0.0, wd[12]);
+        P.weld_imp[3] = clampimp(wd[13]); P.weld_imp[4] = std::fmax(1.0, wd[14]);
+        P.weld_ts = wd[15]; P.weld_invw[0] = wd[16]; P.weld_invw[1] = wd[17];
+      }
+    }
     P.d = d; plan_smem<double>(P.d);
     TreeParamsT<float>& F = par;
     F = TreeParamsT<float>{};
@@ -273,6 +297,11 @@ struct TreeModel {
     for (int i = 0; i < 5; i++) F.solimp[i] = (float)P.solimp[i];
     for (int i = 0; i < 8; i++) F.terr[i] = (float)P.terr[i];
     F.max_newton = P.max_newton; F.max_ls = P.max_ls; F.multiccd = P.multiccd; F.terrain = P.terrain;
+    F.weld = P.weld; F.weld_K = (float)P.weld_K; F.weld_B = (float)P.weld_B; F.weld_ts = (float)P.weld_ts;
+    for (int i = 0; i < 3; i++) F.weld_a[i] = (float)P.weld_a[i];
+    for (int i = 0; i < 4; i++) F.weld_q[i] = (float)P.weld_q[i];
+    for (int i = 0; i < 5; i++) F.weld_imp[i] = (float)P.weld_imp[i];
+    F.weld_invw[0] = (float)P.weld_invw[0]; F.weld_invw[1] = (float)P.weld_invw[1];
     return true;
   }
 };

@@ -29,8 +29,10 @@ struct TreeDims {
   int i_adh_body;                              // [nu_adh]
   int i_wb_adr, i_wb;                          // bodies of warp w at tree depth d (d >= 1): adr[w * (maxd + 1) + d .. + 1], list
   int i_wk_adr, i_wk;                          // non-root DoFs of warp w, descending (descendants before ancestors): adr[w .. w + 1]; list of
-                                               // 4-int descriptors {DoF k, start of its row, number of proper ancestors m, start of its pair list}
+                                               // 8-int descriptors {DoF k, start of its row, number of proper ancestors m, start of its pair list,
+                                               // start of its descendant list, number of descendants, 0, 0}
   int i_pair;                                  // elimination of DoF k: m (m + 1) / 2 packed updates (target entry | p << 16 | q << 24)
+  int i_desc;                                  // descendants j of DoF k: packed (entry of H[j][k] | j << 16)
   int nHa;                                     // nH rounded up to 4: targets >= nHa address the per-warp root-block accumulators behind H
   int i_total;
   // real table
@@ -41,7 +43,7 @@ struct TreeDims {
   int r_total;
   // shared-memory plan (reals)
   int m_state, m_stage, m_xpos, m_xquat, m_cinert, m_crb, m_cdof, m_cvel, m_acc, m_y, m_P, m_fs, m_grad, m_x, m_u, m_H, m_dinv,
-      m_con, m_accS, m_rb, m_red, m_hullv, m_misc, m_total;
+      m_con, m_accS, m_rb, m_red, m_hullv, m_misc, m_weld, m_total;
 };
 constexpr int TR_BODY = 18, TR_DOF = 11, TR_GEOM = 8, TR_ADH = 3;
 
@@ -65,6 +67,9 @@ struct TreeParamsT {
   real solimp[5];
   int max_newton, max_ls, multiccd, terrain;
   real terr[8];
+  // TetheredWorld weld on the root body (reference world.py:350-366), same fields and meaning as in StepParamsT
+  int weld;
+  real weld_a[3], weld_q[4], weld_K, weld_B, weld_imp[5], weld_ts, weld_invw[2];
 };
 
 constexpr int TDBG_NITER = 0, TDBG_NCON = 1, TDBG_NLS = 2, TDBG_STRIDE = 4;

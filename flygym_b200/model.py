@@ -180,14 +180,14 @@ class NMFModel:
         return m if terrain in (None, "flat") else m.with_terrain(terrain)
 
     @classmethod
-    def tethered(cls, spawn_position=(0.0, 0.0, 1.5), spawn_quat=(1.0, 0.0, 0.0, 0.0)) -> "NMFModel":
+    def tethered(cls, spawn_position=(0.0, 0.0, 1.5), spawn_quat=(1.0, 0.0, 0.0, 0.0), joint_preset: str = "legs_only") -> "NMFModel":
         """The same fly in the reference's ``TetheredWorld`` (``world.py:334-366``, the world behind the reference's own
         ``tests/core/test_simulation.py`` fixtures): no ground, no contact pairs, and a soft weld
         ``weld(body1=c_thorax, body2=world, relpose=(*spawn_position, *spawn_rotation), solref=(2e-4, 1),
         solimp=(0.98, 0.99, 1e-5, 0.5, 3))``.  MuJoCo reads ``relpose`` as the pose of body 2 in the frame of body 1, so the
         constraint pulls the thorax-frame point ``spawn_position`` onto the world origin and ``q_thorax * spawn_quat`` onto
         the identity ([PRIOR] mjEQ_WELD semantics); that effective behaviour is what is reproduced."""
-        m = cls.load(ASSETS_DIR / "nmf_bench_capsule.npz")
+        m = cls.bench(True, joint_preset=joint_preset)      # (any skeleton: the full ones run on the general-topology kernels)
         a = dict(m.arrays)
         dims = a["dims"].copy(); dims[DIM_FIELDS.index("ngeom")] = 0; dims[DIM_FIELDS.index("nhullvert")] = 0
         a["dims"] = dims

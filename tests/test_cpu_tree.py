@@ -126,3 +126,24 @@ def test_from_mjmodel_ingests_general_skeletons():
         assert np.abs(np.asarray(m.arrays[k], float).ravel() - np.asarray(m2.arrays[k], float).ravel()).max() < 1e-9, k
     o1, o2 = Oracle(m), Oracle(m2); o1.step(200); o2.step(200)
     assert np.abs(o1.qpos - o2.qpos).max() < 1e-12
+
+
+def test_tethered_world_with_the_full_skeleton():
+    """TetheredWorld (reference world.py:334-366) with the ALL_BIOLOGICAL skeleton: the six weld rows sit on the root body, so they
+    enter the tree kernels like a contact on the root (wrench + augmentation of the root's spatial inertia).  f64 source vs oracle."""
+    m = NMFModel.tethered(joint_preset="all_biological")
+    info = emu.tree_info(m)
+    assert info["nv"] == 132
+    st = emu.tree_key_state(m)[None].copy()
+    o = Oracle(m); o.reset()
+    emu.tree_step(m, st, 10, precision=64)
+    o.step(10)
+    q = st[0, :info["nq"]].astype(np.float64)
+    print(np.abs(q - o.qpos).max(), np.abs(o.qpos - m.arrays["key_qpos"]).max())
+    assert np.abs(o.qpos - m.arrays["key_qpos"]).max() > 1e-3            # the weld really pulls
+    assert np.abs(q - o.qpos).max() < 5e-6 * max(1.0, np.abs(o.qpos).max())
+    # the benchmark skeleton through both kernel families
+    mb = NMFModel.tethered()
+    a = emu.key_state(mb)[None].copy(); emu.step(mb, a, 10)
+    ib = emu.tree_info(mb); b = emu.tree_key_state(mb)[None].copy(); emu.tree_step(mb, b, 10)
+    assert np.abs(a[0, :73] - b[0, :73]).max() < 2e-4 * np.abs(a[0, :73]).max()

@@ -30,6 +30,7 @@ def _worlds():
         "allbio_blocks": (lambda: NMFModel.bench(True, terrain="blocks", joint_preset="all_biological"), -0.15, True),
         "allpossible_allcontacts": (lambda: NMFModel.bench(True, joint_preset="all_possible", contact_preset="all"), -0.17, False),
         "legsonly_allcontacts": (lambda: NMFModel.bench(True, contact_preset="all"), -0.17, False),
+        "allbio_tethered": (lambda: NMFModel.tethered(joint_preset="all_biological"), None, False),
     }
 
 

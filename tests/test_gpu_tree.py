@@ -32,6 +32,16 @@ def test_every_output_of_the_tree_kernels_matches_the_oracle(wname):
         assert e100[k][0] < 1e-3, k
 
 
+def test_tethered_world_with_the_full_skeleton():
+    """TetheredWorld (world.py:334-366) + ALL_BIOLOGICAL: the weld rows on the root body of the general-topology kernels."""
+    errs = run_world("allbio_tethered")
+    e1, e100 = errs[1], errs[100]
+    print({cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    assert max(e1["qpos_rel"]) < 1e-4 and max(e1["qvel_rel"]) < 5e-4 and max(e1["actf_abs"]) < 1e-4      # the weld snaps the thorax by ~1 mm in the first step
+    assert max(e1["xpos_abs"]) < 2e-6 and max(e1["xquat_abs"]) < 2e-6 and max(e1["found_mismatch"]) == 0
+    assert max(e100["qpos_rel"]) < 1e-4 and max(e100["qvel_rel"]) < 1e-3 and max(e100["xpos_abs"]) < 5e-4     # measured 3.8e-5 / 5e-5 / 1.5e-4 (float32 against the stiff weld)
+
+
 @pytest.mark.parametrize("wname", ["allbio_capsule", "allpossible_allcontacts"])
 def test_tree_kernels_in_double_precision(wname):
     errs = run_world(wname, precision=64)

@@ -18,5 +18,7 @@ for r in csv.reader(io.StringIO(out)):
 T, S = sum(files.values()), sum(smp.values())
 print("instructions by file:", {k: f"{100*v/T:.1f}%" for k, v in files.most_common(6)}, "total", T)
 src = (Path(__file__).resolve().parent.parent / "flygym_b200/csrc" / fname).read_text().split("\n")
-for ln, v in inst.most_common(top):
+order = smp.most_common(top) if len(sys.argv) > 4 and sys.argv[4] == "samples" else inst.most_common(top)
+for ln, _ in order:
+    v = inst[ln]
     print(f"{ln:5d} inst {100*v/T:5.1f}% smp {100*smp[ln]/max(1,S):5.1f}%  {src[ln-1].strip()[:110]}")
