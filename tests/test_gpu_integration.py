@@ -65,7 +65,8 @@ class _World:
         return self._mj, None
 
 
-def test_integration_md_subclass_runs_and_matches_the_package_class(monkeypatch):
+@pytest.mark.parametrize("skeleton", ["legs_only", "all_biological"])
+def test_integration_md_subclass_runs_and_matches_the_package_class(monkeypatch, skeleton):
     import torch
     from flygym_b200 import B200Simulation as Packaged, NMFModel, _lib
     from flygym_b200.actions import cpg_table
@@ -75,7 +76,7 @@ def test_integration_md_subclass_runs_and_matches_the_package_class(monkeypatch)
     ns = {}
     exec(compile(code, "INTEGRATION.md", "exec"), ns)
     Stub = ns["B200Simulation"]
-    model = NMFModel.bench(True)
+    model = NMFModel.bench(True, joint_preset=skeleton)         # star kernels / general-topology kernels behind the same stub
     n = 3
     a = Stub(_World(model), n)                                   # reference-side subclass over the C ABI, MuJoCo numbering
     b = Packaged(model, n_worlds=n)                              # the package's own class, record numbering
