@@ -196,6 +196,8 @@ def from_mjmodel(m, *, fly_root: str | None = None, segments: list[str] | None =
         kp = float(gainprm[a, 0])
         if abs(biasprm[a, 0]) > 0 or abs(biasprm[a, 1] + kp) > 1e-12 * max(1.0, kp):
             raise ConversionError(f"actuator {act_names[a]} is not a position actuator (bias must be (0, -kp, -kv))")
+        if k_of_mjdof[jnt_dofadr[j]] < 0:
+            raise ConversionError(f"actuator {act_names[a]} drives a joint that is not part of the fly's articulated tree")
         act_dof.append(int(k_of_mjdof[jnt_dofadr[j]])); act_kp.append(kp); act_kv.append(-float(biasprm[a, 2]))
         fr = np.asarray(m.actuator_forcerange).reshape(nu_mj, 2)[a]
         limited = bool(np.asarray(getattr(m, "actuator_forcelimited", np.ones(nu_mj)))[a]) and fr[0] < fr[1]
