@@ -74,11 +74,18 @@ def test_eye_cameras_bit_exact_and_fused_path():
     from flygym_b200 import B200Simulation
     from flygym_b200.retina import EyeCameras
     from oracle.retina_oracle import eye_render_oracle, retina_oracle
-    n = 3
+    n = 6
     sim = B200Simulation(None, n_worlds=n)
     q = torch.tensor([1.0, 0.05, -0.1, 0.2]); q = q / q.norm()
     sim.qpos[1, 3:7] = q.cuda()                       # tilt one fly so that the horizon is not axis-aligned
     sim.qpos[2, 0:3] = torch.tensor([3.3, -1.7, 2.0]).cuda()
+    # tumbling flies with bent legs: capsules at every angle to the image rows, next to / behind the cameras, vanishing points of
+    # their axes inside the image (the silhouette-strip culling of the body raster takes all of its branches)
+    g = torch.Generator().manual_seed(11)
+    for i, quat in zip((3, 4, 5), ([0.8, 0.3, -0.4, 0.33], [0.1, 0.9, 0.2, -0.3], [0.5, -0.5, 0.6, 0.4])):
+        qq = torch.tensor(quat); sim.qpos[i, 3:7] = (qq / qq.norm()).cuda()
+        sim.qpos[i, 2] = 2.0
+        sim.qpos[i, 7:] += (0.5 * torch.randn(sim.qpos.shape[1] - 7, generator=g)).cuda()
     sim.step(2)
     xp, xq = sim.seg_xpos.cpu().numpy(), sim.seg_xquat.cpu().numpy()
     plain = EyeCameras(sim, body=False)                  # ground and sky only (round-1 behaviour)
