@@ -51,8 +51,8 @@ NCU_TRAFFIC_PER_FLY_STEP = {
     "terrain": ((0.0896e9 + 0.5587e9) / (4096 * 100), "profiles/ncu_step_terrain_r01_summary.txt (4096 flies x 100 steps, 80-register build)"),
     "olfaction": ((0.0774e9 + 0.6436e9) / 32768, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs)"),
 }
-VISION_TRAFFIC = (0.81e6 / 1024, "profiles/ncu_vision_r01s2_summary.txt: the fused kernel reads 0.81 MB per 1024 flies (run table, poses) and never materialises the eye buffers")
-RETINA_BUFFERS_TRAFFIC = (1.009e9 + 8.3e6, "profiles/ncu_vision_r01s2_summary.txt: 1.009 GB read + 8.3 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
+VISION_TRAFFIC = (2.92e6 / 1024, "profiles/ncu_eye_body_r02b_summary.txt: the fused kernel reads 2.9 MB per 1024 flies (run table, poses, body capsules) and never materialises the eye buffers")
+RETINA_BUFFERS_TRAFFIC = (1.0096e9 + 6.9e6, "profiles/ncu_retina_r02_summary.txt: 1.010 GB read + 6.9 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
 # what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
 NCU_LIMITER = {
     "flat": {"issue_slots_busy": 0.542, "top_stall": "barrier 24.5 % (lockstep passes of the 8 flies of a block + the fly's own barriers), short scoreboard 24.5 % "
@@ -61,8 +61,8 @@ NCU_LIMITER = {
              "source": "profiles/ncu_step_r02f_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
     "olfaction": {"issue_slots_busy": 0.509, "top_stall": "no_inst (instruction fetch)", "source": "profiles/ncu_step_olfaction_r01_summary.txt"},
-    "vision": {"issue_slots_busy": 0.834, "top_stall": "issue-bound: ~47 thread-instructions per shaded pixel (fused eye + Retina kernel)",
-               "source": "profiles/ncu_vision_r01s2_summary.txt"},
+    "vision": {"issue_slots_busy": 0.764, "top_stall": "issue-bound: 1.34 G warp instructions per 1024 flies (fused eye + Retina kernel: ~46 % shading, ~45 % body raster, "
+               "the explicitly rounded FADD / FMUL of the capsule hit test being the largest single item)", "source": "profiles/ncu_eye_body_r02b_summary.txt"},
 }
 TREE_TRAFFIC_PER_FLY_STEP = (8.4e6 / (1480 * 20), "profiles/ncu_tree_r02_summary.txt (nmf_tree_step_kernel, ALL_BIOLOGICAL, 1480 flies x 20 steps: 8.4 MB read + 2 KB written = "
                                     "the records and the model tables once; nothing spills)")
@@ -426,7 +426,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
                                         "note": "the HBM-bound form of the operator: eye buffers materialised in HBM (two 1.4 GB sets alternated); a pure "
                                                 "read stream that skips chunks outside the ommatidia hexagon, hence above the copy-measured peak"},
                 "note": f"algorithmic bytes = the Retina operator's {RETINA_ALG_BYTES} B per fly-frame (SURVEY.md 8d); the fused kernel shades "
-                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (83 % busy), not HBM"}
+                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (76 % busy, 3 blocks per SM), not HBM"}
         del imgs
     else:
         per_launch_steps = 1 if per_step else chunk
@@ -450,7 +450,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
                         f"= {per_fly} B per fly-step"}
 
     # ---- end-to-end through the public API with HOST buffers, every step: H2D actions, step (+ sensors), D2H result
-    e2e_steps = min(steps, e2e_cap)
+    e2e_steps = min(max(steps, 100), e2e_cap)     # a steady-state figure: at least 100 calls (the driver's --steps 20 would time 5 ms)
     act_cols = table.shape[2] if wl == "terrain" else nu_pos        # terrain: the six adhesion inputs travel with the position targets
     act_host = table[:, :e2e_steps, :act_cols].permute(1, 0, 2).contiguous().cpu().pin_memory()
     if not per_step:
@@ -466,7 +466,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
             r = eyes.retina(sens_out) if eyes is not None else odor()
             res_host.copy_(r, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-    for s in range(3):
+    for s in range(10):
         e2e_step(s)
     ctx.barrier()
     w0 = time.perf_counter()

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/nmf_b200.h"
 #include "nmf_host.h"
@@ -121,10 +122,21 @@ struct nmf_handle {
   int fpb = 0;                                 // fly slots per block of the f32 flat / terrain kernels: 1, 2, 4, 8 or 0 = chosen per launch (see step_block)
   int resident[9] = {};                        // resident blocks of the model's f32 kernel per fpb (index = fpb)
   int sms = 0;
-  static constexpr int MAX_PARTS = 4;          // nmf_step_host: slices of the batch pipelined over private streams
-  int host_parts = 4;                          // measured on B200, 4096 flies: 13.4 / 14.4 / 14.6 M env-steps/s end to end with 1 / 2 / 4 slices
-  cudaStream_t part_stream[MAX_PARTS] = {};
+  static constexpr int MAX_PARTS = 16;         // nmf_step_host: slices of the batch pipelined over private streams
+  int host_parts = 4;                          // issued call by call; measured on B200, 4096 flies: 13.4 / 14.4 / 14.6 M env-steps/s end to end with 1 / 2 / 4 slices
+  int graph_parts = 4;                         // replayed as a CUDA graph (pinned host buffers).  B200, 4096 flies, us per call (tools/e2e_sweep.py): call by call 278 / 253 with 1 / 4 slices; graph 262 / 248 / 253 / 256 / 256 with 2 / 4 / 6 / 8 / 16
+  bool host_graph = true;                      // env NMF_HOST_GRAPH=0 switches the graph path off
+  cudaStream_t part_stream[MAX_PARTS] = {}, cap_stream = nullptr;
   cudaEvent_t part_done[MAX_PARTS] = {}, fork = nullptr;
+  // the captured pipeline of nmf_step_host (see there); rebuilt when anything that enters the kernels' parameters changes
+  struct HostGraph {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t h2d[MAX_PARTS] = {}, d2h[MAX_PARTS] = {};
+    int parts = 0, cols = 0, nsteps = 0, launches = 0; uint64_t epoch = 0;
+    const float* act = nullptr; float* qpos = nullptr;
+  } hg;
+  uint64_t epoch = 1;                          // bumped by nmf_bind and every setter
+  int graph_failures = 0;
   nmf_buffers buf{};
   bool bound = false;
   int64_t launches = 0;
@@ -207,6 +219,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
     CK(cudaEventCreateWithFlags(&h->part_done[k], cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   if (const char* e = getenv("NMF_FPB64")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->fpb64 = v; }
   if (const char* e = getenv("NMF_FPB")) { int v = atoi(e); if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8) h->fpb = v; }
   if (h->hm.par.weld) h->fpb = 1;
@@ -215,7 +228,8 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
     if (rc2) return rc2;
   }
   if (const char* e = getenv("NMF_QUEUE_SUBSTEPS")) h->sub_steps = atoi(e);
-  if (const char* e = getenv("NMF_HOST_PARTS")) { int v = atoi(e); if (v >= 1 && v <= nmf_handle::MAX_PARTS) h->host_parts = v; }
+  if (const char* e = getenv("NMF_HOST_PARTS")) { int v = atoi(e); if (v >= 1 && v <= nmf_handle::MAX_PARTS) h->host_parts = h->graph_parts = v; }
+  if (const char* e = getenv("NMF_HOST_GRAPH")) h->host_graph = atoi(e) != 0;
   return NMF_OK;
 }
 
@@ -225,6 +239,9 @@ extern "C" int nmf_destroy(nmf_handle* h) {
   cudaFree(h->d_it); cudaFree(h->d_rt); cudaFree(h->d_rt64); cudaFree(h->d_role); cudaFree(h->d_hull); cudaFree(h->d_seg); cudaFree(h->d_key); cudaFree(h->d_nbr_adr); cudaFree(h->d_nbr); cudaFree(h->d_act); cudaFree(h->d_qpos); cudaFree(h->d_queue); cudaFree(h->d_role64); cudaFree(h->d_hull64); cudaFree(h->d_state64); cudaFree(h->d_shadow);
   for (int k = 0; k < nmf_handle::MAX_PARTS; k++) { if (h->part_stream[k]) cudaStreamDestroy(h->part_stream[k]); if (h->part_done[k]) cudaEventDestroy(h->part_done[k]); }
   if (h->fork) cudaEventDestroy(h->fork);
+  if (h->hg.exec) cudaGraphExecDestroy(h->hg.exec);
+  if (h->hg.graph) cudaGraphDestroy(h->hg.graph);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
   return NMF_OK;
 }
@@ -244,13 +261,13 @@ extern "C" int nmf_model_info(const nmf_handle* h, nmf_info* info) {
 
 extern "C" int nmf_bind(nmf_handle* h, const nmf_buffers* b) {
   if (!h || !b || !b->state) { if (h) h->err = "nmf_bind: state buffer is required"; return NMF_EINVAL; }
-  h->buf = *b; h->bound = true;
+  h->buf = *b; h->bound = true; h->epoch++;
   return NMF_OK;
 }
 
 extern "C" int nmf_set_solver(nmf_handle* h, int max_newton, int max_ls) {
   if (!h || max_newton < 1 || max_ls < 1) return NMF_EINVAL;
-  h->hm.par.max_newton = max_newton; h->hm.par.max_ls = max_ls;
+  h->hm.par.max_newton = max_newton; h->hm.par.max_ls = max_ls; h->epoch++;
   h->tm.par.max_newton = max_newton; h->tm.par.max_ls = max_ls;
   return NMF_OK;
 }
@@ -267,12 +284,13 @@ extern "C" int nmf_reset(nmf_handle* h, const uint8_t* mask, void* stream) {
 
 extern "C" int nmf_set_schedule(nmf_handle* h, int sub_steps) {
   if (!h || sub_steps < -1) return NMF_EINVAL;
-  h->sub_steps = sub_steps;
+  h->sub_steps = sub_steps; h->epoch++;
   return NMF_OK;
 }
 
 extern "C" int nmf_set_flies_per_block(nmf_handle* h, int fpb) {
   if (!h || (fpb != 0 && fpb != 1 && fpb != 2 && fpb != 4 && fpb != 8)) return NMF_EINVAL;
+  h->epoch++;
   if (h->tree) return NMF_OK;                       // one fly per block in the tree kernels
   h->fpb = (h->hm.par.weld || h->hm.par.noslip_iterations > 0) ? 1 : fpb;
   return NMF_OK;
@@ -494,7 +512,7 @@ extern "C" int nmf_set_precision(nmf_handle* h, int bits) {
     CK(cudaMemset(h->d_state64, 0, sizeof(double) * nrec));
     CK(cudaMemset(h->d_shadow, 0xff, sizeof(float) * nrec));
   }
-  h->precision = bits;
+  h->precision = bits; h->epoch++;
   return NMF_OK;
 }
 
@@ -520,23 +538,15 @@ extern "C" int nmf_gather_state(nmf_handle* h, int off, const int32_t* cols, int
   return NMF_OK;
 }
 
-// Host-buffer step.  With a few thousand flies the batch is cut into HOST_PARTS slices that run on the handle's own streams,
-// forked from and joined to the caller's stream with events: slice k's H2D copy and D2H read-back overlap the other slices'
-// kernels (the kernels of all slices are co-resident, so the device sees the same 4096 blocks as one launch would give it).
-extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, void* stream_) {
-  if (!h || !actions_host || !qpos_host) return NMF_EINVAL;
-  if (!h->bound) return NMF_ENOTBOUND;
-  DeviceGuard guard(h->device);
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const int nu = h->nu_pos + h->nu_adh, n = h->n_flies, NQ = h->nq;
-  if (action_cols != h->nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
-  if (!h->d_act) { h->err = "nmf_step_host: staging buffers missing"; return NMF_EINVAL; }     // allocated by nmf_create
-  int parts = h->host_parts;
-  while (parts > 1 && n < 1024 * parts) parts--;   // at least 1024 flies per slice
-  if (parts > 1) CK(cudaEventRecord(h->fork, stream));
+// Host-buffer step.  With a few thousand flies the batch is cut into slices that run on the handle's own streams, forked from and
+// joined to one stream with events: slice k's H2D copy and D2H read-back overlap the other slices' kernels (the kernels of all
+// slices are co-resident, so the device sees the same blocks as one launch would give it).
+static int issue_host_slices(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, cudaStream_t root, int parts) {
+  const int n = h->n_flies, NQ = h->nq;
+  if (parts > 1) CK(cudaEventRecord(h->fork, root));
   for (int k = 0; k < parts; k++) {
     const int f0 = (int)((long long)n * k / parts), cnt = (int)((long long)n * (k + 1) / parts) - f0;
-    cudaStream_t s = parts > 1 ? h->part_stream[k] : stream;
+    cudaStream_t s = parts > 1 ? h->part_stream[k] : root;
     if (parts > 1) CK(cudaStreamWaitEvent(s, h->fork, 0));
     float* d_act = h->d_act + (size_t)f0 * action_cols;
     CK(cudaMemcpyAsync(d_act, actions_host + (size_t)f0 * action_cols, sizeof(float) * (size_t)cnt * action_cols, cudaMemcpyHostToDevice, s));
@@ -545,8 +555,108 @@ extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int actio
     int rc = launch_steps(h, nsteps, h->d_act, 1, 0, action_cols, false, s, f0, cnt, h->d_qpos + (size_t)f0 * NQ);
     if (rc) return rc;
     CK(cudaMemcpyAsync(qpos_host + (size_t)f0 * NQ, h->d_qpos + (size_t)f0 * NQ, sizeof(float) * (size_t)cnt * NQ, cudaMemcpyDeviceToHost, s));
-    if (parts > 1) { CK(cudaEventRecord(h->part_done[k], s)); CK(cudaStreamWaitEvent(stream, h->part_done[k], 0)); }
+    if (parts > 1) { CK(cudaEventRecord(h->part_done[k], s)); CK(cudaStreamWaitEvent(root, h->part_done[k], 0)); }
   }
+  return NMF_OK;
+}
+
+static bool pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// The same pipeline as a CUDA graph: issuing 2 copies + 1 launch + 3 event calls per slice costs the host ~15 us per slice; captured
+// once and replayed it costs one launch.  Measured on B200 this buys little end to end (248 us against 253 us per call at 4096
+// flies, finer slices do not help: the call is bounded by the two waves of the 1-step kernels, 180-200 us, plus the exposed ends of
+// the copies), but the host thread is free for ~45 us more per step.  The graph is keyed on everything
+// that enters the kernels' parameters (handle epoch, nsteps, columns); only the host addresses may change from call to call -- they
+// are patched into the memcpy nodes of the instantiated graph.  Needs pinned (or registered) host buffers; anything else, the f64
+// build and a failed capture take the call-by-call path.
+static int build_host_graph(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, int parts) {
+  nmf_handle::HostGraph& g = h->hg;
+  if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  if (g.graph) { cudaGraphDestroy(g.graph); g.graph = nullptr; }
+  if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return NMF_ECUDA; }
+  const int64_t before = h->launches;
+  int rc = issue_host_slices(h, actions_host, action_cols, nsteps, qpos_host, h->cap_stream, parts);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+  const int launches = (int)(h->launches - before);
+  h->launches = before;                                  // (nothing ran yet)
+  if (rc != NMF_OK || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return rc != NMF_OK ? rc : NMF_ECUDA; }
+  g.graph = graph;
+  if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; return NMF_ECUDA; }
+  // find the copy nodes of every slice by their device addresses
+  size_t nn = 0;
+  if (cudaGraphGetNodes(graph, nullptr, &nn) != cudaSuccess) { cudaGetLastError(); return NMF_ECUDA; }
+  std::vector<cudaGraphNode_t> nodes(nn);
+  if (cudaGraphGetNodes(graph, nodes.data(), &nn) != cudaSuccess) { cudaGetLastError(); return NMF_ECUDA; }
+  const int n = h->n_flies, NQ = h->nq;
+  int found = 0;
+  for (int k = 0; k < parts; k++) { g.h2d[k] = nullptr; g.d2h[k] = nullptr; }
+  for (size_t i = 0; i < nn; i++) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeMemcpy) continue;
+    cudaMemcpy3DParms mp;
+    if (cudaGraphMemcpyNodeGetParams(nodes[i], &mp) != cudaSuccess) continue;
+    for (int k = 0; k < parts; k++) {
+      const int f0 = (int)((long long)n * k / parts);
+      if (mp.dstPtr.ptr == (void*)(h->d_act + (size_t)f0 * action_cols) && !g.h2d[k]) { g.h2d[k] = nodes[i]; found++; }
+      if (mp.srcPtr.ptr == (void*)(h->d_qpos + (size_t)f0 * NQ) && !g.d2h[k]) { g.d2h[k] = nodes[i]; found++; }
+    }
+  }
+  if (found != 2 * parts) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; return NMF_ECUDA; }
+  g.parts = parts; g.cols = action_cols; g.nsteps = nsteps; g.launches = launches; g.epoch = h->epoch; g.act = actions_host; g.qpos = qpos_host;
+  return NMF_OK;
+}
+
+extern "C" int nmf_step_host(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, void* stream_) {
+  if (!h || !actions_host || !qpos_host) return NMF_EINVAL;
+  if (!h->bound) return NMF_ENOTBOUND;
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nu = h->nu_pos + h->nu_adh, n = h->n_flies, NQ = h->nq;
+  if (action_cols != h->nu_pos && action_cols != nu) { h->err = "nmf_step_host: actions must have nu_pos or nu_pos + nu_adh columns"; return NMF_EINVAL; }
+  if (!h->d_act) { h->err = "nmf_step_host: staging buffers missing"; return NMF_EINVAL; }     // allocated by nmf_create
+  if (nsteps <= 0) return NMF_OK;
+  // ---- graph path
+  int gparts = h->graph_parts;
+  while (gparts > 1 && n < 512 * gparts) gparts--;       // at least 512 flies per slice
+  if (h->host_graph && h->precision == 32 && gparts > 1 && h->graph_failures < 3) {
+    nmf_handle::HostGraph& g = h->hg;
+    const bool same = g.exec && g.epoch == h->epoch && g.cols == action_cols && g.nsteps == nsteps && g.parts == gparts;
+    bool ok = same;
+    if (!same || actions_host != g.act || qpos_host != g.qpos) ok = pinned_host(actions_host) && pinned_host(qpos_host);
+    if (ok && !same) {
+      ok = build_host_graph(h, actions_host, action_cols, nsteps, qpos_host, gparts) == NMF_OK;
+      if (!ok) h->graph_failures++;
+    }
+    if (ok) {
+      for (int k = 0; k < g.parts && ok; k++) {
+        const int f0 = (int)((long long)n * k / g.parts), cnt = (int)((long long)n * (k + 1) / g.parts) - f0;
+        if (actions_host != g.act)
+          ok = cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.h2d[k], h->d_act + (size_t)f0 * action_cols, actions_host + (size_t)f0 * action_cols,
+                                                  sizeof(float) * (size_t)cnt * action_cols, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok && qpos_host != g.qpos)
+          ok = cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.d2h[k], qpos_host + (size_t)f0 * NQ, h->d_qpos + (size_t)f0 * NQ,
+                                                  sizeof(float) * (size_t)cnt * NQ, cudaMemcpyDeviceToHost) == cudaSuccess;
+      }
+      if (ok) {
+        g.act = actions_host; g.qpos = qpos_host;
+        CK(cudaGraphLaunch(g.exec, stream));
+        h->launches += g.launches;
+        CK(cudaStreamSynchronize(stream));
+        return NMF_OK;
+      }
+      cudaGetLastError(); h->graph_failures++; g.epoch = 0;      // a node update was refused: rebuild next time, this call goes the plain way
+    }
+  }
+  // ---- call by call
+  int parts = h->host_parts;
+  while (parts > 1 && n < 1024 * parts) parts--;   // at least 1024 flies per slice
+  int rc = issue_host_slices(h, actions_host, action_cols, nsteps, qpos_host, stream, parts);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(stream));
   return NMF_OK;
 }

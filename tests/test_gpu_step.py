@@ -368,6 +368,45 @@ def test_step_host_pipelined_slices_match_device_path():
     assert torch.equal(a.state, b.state) and torch.equal(a.seg_xpos, b.seg_xpos) and torch.equal(a.sensordata, b.sensordata)
 
 
+def test_step_host_graph_replay_with_pinned_buffers():
+    """With pinned host buffers nmf_step_host replays its slice pipeline as a CUDA graph (finer slices, host addresses patched into
+    the copy nodes from call to call).  Same bits as the plain device path: action rows at changing addresses, two result buffers,
+    the 42- and 48-column forms (a new graph), a setter in between (new epoch), nsteps > 1, and a pageable call in the middle."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from flygym_b200.actions import cpg_table
+    m = NMFModel.bench(simplify_geom=True)
+    n = 4099
+    T = 10
+    tab = cpg_table(m, n, T)
+    adh = np.where(np.arange(n * 6).reshape(n, 6) % 3 == 0, 50.0, 1.0).astype(np.float32)
+    a, b = B200Simulation(m, n_worlds=n, outputs=True), B200Simulation(m, n_worlds=n, outputs=True)
+    for s in (a, b):
+        s.qpos[:, 2] = -0.15
+    act42 = torch.from_numpy(np.ascontiguousarray(tab.transpose(1, 0, 2))).pin_memory()                  # (T, n, 42): row t at its own address
+    act48 = torch.from_numpy(np.ascontiguousarray(np.concatenate([tab.transpose(1, 0, 2), np.broadcast_to(adh, (T, n, 6))], axis=2))).pin_memory()
+    res = [torch.empty((n, m.nq), dtype=torch.float32).pin_memory() for _ in range(2)]
+    l0 = a.launch_count
+    for t in range(T):
+        k = 1 if t != 7 else 3
+        if t in (3, 4, 8):
+            act = act48[t]; b.ctrl[:, :48] = act.cuda()
+        else:
+            act = act42[t]; b.ctrl[:, :42] = act.cuda()
+        if t == 5:
+            a.set_flies_per_block(4); b.set_flies_per_block(4)                                            # new epoch -> the graph is rebuilt
+        out = res[t % 2]
+        if t == 6:                                                                                          # pageable buffers: call-by-call path
+            qh = np.empty((n, m.nq), np.float32); a.step_host(act.numpy().copy(), k, qh); got = qh
+        else:
+            a.step_host(act.numpy(), k, out.numpy()); got = out.numpy()
+        b.step(k)
+        torch.cuda.synchronize()
+        assert np.array_equal(got, b.qpos.cpu().numpy()), t
+    assert a.launch_count - l0 >= T                      # the replayed launches are counted
+    assert torch.equal(a.state, b.state) and torch.equal(a.seg_xpos, b.seg_xpos) and torch.equal(a.sensordata, b.sensordata)
+
+
 def test_replay_table_built_on_device():
     """nmf_replay_table (cubic resampling of the recorded clip + per-world tiling on the GPU) equals the host construction the
     reference uses (MotionSnippet.get_joint_angles + ReplayTargetData.make_target_angles_all_worlds), incl. the rank offset."""
