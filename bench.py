@@ -58,6 +58,8 @@ NCU_LIMITER = {
     "flat": {"issue_slots_busy": 0.542, "top_stall": "barrier 24.5 % (lockstep passes of the 8 flies of a block + the fly's own barriers), short scoreboard 24.5 % "
              "(shuffles / shared memory), long scoreboard 16.3 % (register spills); no_inst 0.8 % (46 % before the flies of a block shared their fetches)",
              "warp_instructions_per_fly_step": 23330, "issue_ceiling_env_steps_per_s": 148 * 4 * 1.965e9 / 23330,
+             # executed FP32 work of the same capture: (2 FFMA + FADD + FMUL) warp instructions x 27.85 active lanes / 409600 fly-steps
+             "fp32_flop_per_fly_step": 453000, "fp32_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
              "source": "profiles/ncu_step_r02f_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
     "olfaction": {"issue_slots_busy": 0.509, "top_stall": "no_inst (instruction fetch)", "source": "profiles/ncu_step_olfaction_r01_summary.txt"},
@@ -78,7 +80,7 @@ def workload_config(args, n_flies, chunk):
     what = {
         "flat": "flat terrain, CPG tripod gait (12 Hz sinusoids), adhesion on, no vision",
         "terrain": f"{args.terrain} terrain (box columns), CPG tripod gait, adhesion 100 in stance / 1 in swing, no vision",
-        "vision": "flat terrain, CPG tripod gait, adhesion on, two 512x450 eye-camera renders (checker ground, sky" + (", the fly's own body" if args.eye_body == "on" else "") + ") -> 721-ommatidia Retina after EVERY step",
+        "vision": "flat terrain, CPG tripod gait, adhesion on, two 512x450 eye-camera renders (checker ground, sky" + (", the fly's own body" if args.eye_body == "on" else "") + ") -> 721-ommatidia Retina " + ("after EVERY step" if getattr(args, "vision_every", 1) <= 1 else f"after every {args.vision_every}th step (vision refresh at {1e4 / args.vision_every:.0f} Hz, the v1 default)"),
         "olfaction": "flat terrain, CPG tripod gait, adhesion on, 4 odor sensors x 2 sources x 2 odor dims after every step",
     }[args.workload]
     cfg = {
@@ -93,7 +95,10 @@ def workload_config(args, n_flies, chunk):
     if args.workload in ("flat", "terrain"):
         cfg["steps_per_launch"] = chunk
     else:
-        cfg["steps_per_timed_group"] = chunk; cfg["launches_per_step"] = 2
+        ve = getattr(args, "vision_every", 1) if args.workload == "vision" else 1
+        cfg["steps_per_timed_group"] = chunk; cfg["launches_per_step"] = 2 / ve
+        if ve > 1:
+            cfg["physics_steps_per_vision_frame"] = ve
     return cfg
 
 
@@ -347,6 +352,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
         odor = OdorSensor(sim, ODOR_SOURCES, ODOR_PEAKS)
 
     state = {"t0": 0, "launches": 0}
+    vis_every = max(1, getattr(args, "vision_every", 1))
 
     def advance(c):
         """c physics steps (+ the workload's sensors after every step); returns nothing, counts our kernel launches"""
@@ -354,9 +360,13 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
             sim.step(c, table, state["t0"]); state["launches"] += 1
             state["t0"] = (state["t0"] + c) % table_T
             return
-        for _ in range(c):
-            sim.step(1, table, state["t0"]); state["launches"] += 1
-            state["t0"] = (state["t0"] + 1) % table_T
+        k = vis_every if eyes is not None else 1       # physics steps fused into one launch between two sensor evaluations
+        left = c
+        while left > 0:
+            kk = min(k, left)
+            sim.step(kk, table, state["t0"]); state["launches"] += 1
+            state["t0"] = (state["t0"] + kk) % table_T
+            left -= kk
             if eyes is not None:
                 eyes.retina(sens_out)
             else:
@@ -463,6 +473,8 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
         def e2e_step(s):
             sim.set_actuator_inputs("nmf", ActuatorType.POSITION, act_host[s])     # H2D inside
             sim.step()
+            if eyes is not None and (s + 1) % vis_every:
+                return                                                              # no vision frame after this step: nothing to read back
             r = eyes.retina(sens_out) if eyes is not None else odor()
             res_host.copy_(r, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
@@ -487,7 +499,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
            "clocks": clocks, "launches": int(n_launch), "roof": roof, "wall": wall, "finite": finite, "gathered_slabs": gathered_slabs,
            "gather_ms": gather_ms, "kernel_ms": kernel_ms,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * act_cols * 4),
-                   "d2h_bytes_per_step": int(res_host.numel() * 4), "steps": e2e_steps}}
+                   "d2h_bytes_per_step": int(res_host.numel() * 4) // (vis_every if eyes is not None else 1), "steps": e2e_steps}}
     del sim, table
     torch.cuda.empty_cache()
     return out
@@ -543,6 +555,10 @@ def run_ours(args, rank, world, local_rank):
             a6 = copy.copy(args); a6.workload = "vision"; a6.n_flies = DEFAULT_FLIES["vision"]; a6.chunk = DEFAULT_CHUNK["vision"]
             extras["config4_vision"] = sub_record(a6, measure(ctx, a6, steps=100, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
                                                   "BASELINE config 4: 1024 flies, two eye-camera renders (ground, sky, the fly's own body) -> Retina after every step")
+            a8 = copy.copy(a6); a8.vision_every = 20; a8.chunk = 20
+            extras["config4_vision_every20"] = sub_record(a8, measure(ctx, a8, steps=400, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
+                                                          "config 4 with the v1 vision refresh (SURVEY.md 8d): 20 physics steps fused per launch, one vision frame "
+                                                          "(render + Retina) after every 20th; end to end the frame is read back every 20th step")
         else:
             a5 = copy.copy(args); a5.workload = "olfaction"; a5.n_flies = DEFAULT_FLIES["olfaction"]; a5.chunk = DEFAULT_CHUNK["olfaction"]
             extras["config5"] = sub_record(a5, measure(ctx, a5, steps=200, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
@@ -577,7 +593,11 @@ def run_ours(args, rank, world, local_rank):
             line["roofline"]["traffic_source"] = TREE_TRAFFIC_PER_FLY_STEP[1]
             line["roofline"]["note"] = "general-topology kernel: the fly lives in shared memory, bound by instruction issue (DESIGN.md 4.5); algorithmic bytes = 4 (2 nq + 4 nv + nu) per fly-step"
         if wl in NCU_LIMITER and args.actions == "cpg" and not args.mesh and args.precision == 32 and args.skeleton == "legs_only":
-            line["roofline"]["limiter"] = NCU_LIMITER[wl]
+            line["roofline"]["limiter"] = dict(NCU_LIMITER[wl])
+            if "fp32_flop_per_fly_step" in NCU_LIMITER[wl]:       # achieved FP32 rate of the fused step, per GPU
+                lim = line["roofline"]["limiter"]
+                lim["fp32_tflops_achieved"] = m["value"] / world * lim["fp32_flop_per_fly_step"] / 1e12
+                lim["fp32_frac_of_cuda_core_peak"] = lim["fp32_tflops_achieved"] / lim["fp32_peak_tflops"]
         if "retina_over_buffers" in roof:
             rb = dict(roof["retina_over_buffers"]); rb["frac"] = rb["achieved"] / peak
             if n == 1024:
@@ -610,6 +630,7 @@ def main():
     ap.add_argument("--skeleton", default="legs_only", choices=list(SKELETON_DIMS), help="JointPreset of the fly: legs_only = the reference benchmark "
                     "model (star kernels); all_biological / all_possible = the full skeletons (general-topology kernels)")
     ap.add_argument("--actions", default="cpg", choices=["cpg", "replay"], help="cpg = BASELINE config 2; replay = the reference benchmark's kinematic-replay clip")
+    ap.add_argument("--vision-every", type=int, default=1, help="vision workload: physics steps per vision frame (1 = BASELINE's 'per step'; 20 = v1's 500 Hz refresh)")
     ap.add_argument("--eye-body", default="on", choices=["on", "off"], help="vision workload: the eye cameras also see the fly's own body (capsule proxies)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary records (mesh / f64 at N = 1, config 5 at N > 1)")
