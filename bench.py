@@ -68,6 +68,7 @@ NCU_LIMITER = {
 }
 TREE_TRAFFIC_PER_FLY_STEP = (8.4e6 / (1480 * 20), "profiles/ncu_tree_r02_summary.txt (nmf_tree_step_kernel, ALL_BIOLOGICAL, 1480 flies x 20 steps: 8.4 MB read + 2 KB written = "
                                     "the records and the model tables once; nothing spills)")
+CONFIG5_TOTAL_FLIES = 262144   # BASELINE configs[4]: 262144 flies over 8 GPUs
 ODOR_SOURCES = [[12.0, 4.0, 1.5], [12.0, -4.0, 1.5]]     # config 5: 2 sources x 2 odor dimensions, fixed constants
 ODOR_PEAKS = [[1.0, 0.0], [0.0, 1.0]]
 
@@ -318,7 +319,7 @@ class Ctx:
         return float(t.item())
 
 
-def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=True):
+def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=True, table_rows=TABLE_T):
     """One workload (args.workload / mesh / precision / n_flies / chunk ...) measured three ways: device-timed `value` over
     exactly `steps` steps, the dominant kernel alone (roofline), and `e2e` through the host-buffer API.  Returns a dict."""
     torch, dist, rank, world, dev = ctx.torch, ctx.dist, ctx.rank, ctx.world, ctx.dev
@@ -335,7 +336,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
         from flygym_b200.actions import replay_table_device
         table = replay_table_device(model, n, 1000, dev, fly_offset=rank * n)                 # sim_steps = 1000 as run_gpu_benchmark.py
     else:
-        table = device_cpg_table(torch, model, n, TABLE_T, dev, rank * n, world * n, adhesion_stance=(wl == "terrain"))
+        table = device_cpg_table(torch, model, n, table_rows, dev, rank * n, world * n, adhesion_stance=(wl == "terrain"))
     table_T = table.shape[1]
     sim.set_leg_adhesion_states("nmf", np.ones((n, 6), np.float32))     # as the reference benchmark (time_gpu_simulation.py:130)
     sim.warmup()                                                        # 500 steps at the neutral pose
@@ -559,11 +560,16 @@ def run_ours(args, rank, world, local_rank):
             extras["config4_vision_every20"] = sub_record(a8, measure(ctx, a8, steps=400, warmup=3, sample_clocks=False, e2e_cap=100, dominant=False),
                                                           "config 4 with the v1 vision refresh (SURVEY.md 8d): 20 physics steps fused per launch, one vision frame "
                                                           "(render + Retina) after every 20th; end to end the frame is read back every 20th step")
-        else:
-            a5 = copy.copy(args); a5.workload = "olfaction"; a5.n_flies = DEFAULT_FLIES["olfaction"]; a5.chunk = DEFAULT_CHUNK["olfaction"]
-            extras["config5"] = sub_record(a5, measure(ctx, a5, steps=200, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
-                                           "BASELINE config 5: 32768 flies per GPU, odor sensors after every step, all_gather of a (n, 8) metrics slab every "
-                                           "100 steps issued on the stepping stream (its device time is inside ms_per_step)")
+        # BASELINE config 5 at every N: weak (32768 flies per GPU) and strong (262144 flies in total) scaling records
+        a5 = copy.copy(args); a5.workload = "olfaction"; a5.n_flies = DEFAULT_FLIES["olfaction"]; a5.chunk = DEFAULT_CHUNK["olfaction"]
+        extras["config5"] = sub_record(a5, measure(ctx, a5, steps=200, warmup=3, sample_clocks=False, e2e_cap=50, dominant=False),
+                                       "BASELINE config 5 (weak scaling): 32768 flies per GPU, odor sensors after every step, all_gather of a (n, 8) metrics slab "
+                                       "every 100 steps issued on the stepping stream (its device time is inside ms_per_step)")
+        a9 = copy.copy(a5); a9.n_flies = CONFIG5_TOTAL_FLIES // world
+        extras["config5_strong"] = sub_record(a9, measure(ctx, a9, steps=100, warmup=3, sample_clocks=False, e2e_cap=20, dominant=False, table_rows=250),   # (a 2500-row table of 262144 flies would be 110 GB)
+                                              f"BASELINE config 5 with the TOTAL fixed (strong scaling): {CONFIG5_TOTAL_FLIES} flies over {world} GPU(s) = "
+                                              f"{CONFIG5_TOTAL_FLIES // world} per GPU, same sensors and all_gather")
+        extras["config5_strong"]["scaling"] = "strong"
 
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
