@@ -51,9 +51,14 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS) nmf_step_tether
 #define NMF_MINBLOCKS_F64 4
 #endif
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT>(p); }
-// the f64 flat kernel with 2 / 4 flies per block in lockstep passes (same register budget per SM: 255 x 64 x 4 threads)
+// the f64 flat kernel with 2 / 4 flies per block in lockstep passes.  Four flies per block run at 128 registers, two blocks per SM
+// (8 flies per SM, 952 B of stack): 10.4 M env-steps/s against 9.5 M for one block at 255 registers -- with fetches shared inside a
+// block, occupancy wins over spills here as it does in float32 (B200, 4096 flies; one fly per block gains nothing from it: 6.9 M both ways)
+#ifndef NMF_MINBLOCKS_F64_X4
+#define NMF_MINBLOCKS_F64_X4 2
+#endif
 extern "C" __global__ void __launch_bounds__(2 * CTA, NMF_MINBLOCKS_F64 / 2) nmf_step_f64_x2_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 2>(p); }
-extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS_F64 / 4) nmf_step_f64_x4_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 4>(p); }
+extern "C" __global__ void __launch_bounds__(4 * CTA, NMF_MINBLOCKS_F64_X4) nmf_step_f64_x4_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_FLAT, 4>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_mesh_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_MESH>(p); }
