@@ -69,6 +69,9 @@ extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_me
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_terrain_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TERRAIN, 1, true>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, NMF_MINBLOCKS_F64) nmf_step_tether_noslip_f64_kernel(const StepParamsT<double> p) { f64::step_entry<f64::W_TETHER, 1, true>(p); }
 extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_FLAT, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_mesh_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_MESH, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_terrain_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_TERRAIN, 1, true>(p); }
+extern "C" __global__ void __launch_bounds__(CTA, 8) nmf_step_tether_noslip_kernel(const StepParams p) { f32::step_entry<f32::W_TETHER, 1, true>(p); }
 
 // general-topology models (JointPreset.ALL_BIOLOGICAL / ALL_POSSIBLE, ContactBodiesPreset.ALL, ...): nmf_tree.cuh, one block of
 // 128 threads per fly, the whole fly in (dynamic) shared memory
@@ -314,8 +317,8 @@ template <class real> struct KernelSet;
 typedef void (*step_kernel_f32)(const StepParams);
 static step_kernel_f32 kernel_f32(const StepParams& q, int fpb) {
   const bool weld = q.weld, terrain = q.terrain;
-  if (weld) return nmf_step_tether_kernel;
-  if (q.noslip_iterations > 0) return nmf_step_noslip_kernel;       // flat world with capsule geoms only (checked in launch_steps)
+  if (weld) return q.noslip_iterations > 0 ? nmf_step_tether_noslip_kernel : nmf_step_tether_kernel;
+  if (q.noslip_iterations > 0) return q.multiccd ? nmf_step_mesh_noslip_kernel : terrain ? nmf_step_terrain_noslip_kernel : nmf_step_noslip_kernel;
   if (q.multiccd) return fpb == 8 ? nmf_step_mesh_x8_kernel : fpb == 4 ? nmf_step_mesh_x4_kernel : fpb == 2 ? nmf_step_mesh_x2_kernel : nmf_step_mesh_kernel;
   if (terrain) return fpb == 8 ? nmf_step_terrain_x8_kernel : fpb == 4 ? nmf_step_terrain_x4_kernel : fpb == 2 ? nmf_step_terrain_x2_kernel : nmf_step_terrain_kernel;
   return fpb == 8 ? nmf_step_x8_kernel : fpb == 4 ? nmf_step_x4_kernel : fpb == 2 ? nmf_step_x2_kernel : nmf_step_kernel;
@@ -481,9 +484,6 @@ static int launch_steps(nmf_handle* h, int nsteps, const float* table, int table
   if (h->tree)
     return h->precision == 64 ? launch_tree_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos)
                               : launch_tree_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos);
-  if (h->hm.par.noslip_iterations > 0 && h->precision != 64 && (h->hm.par.terrain || h->hm.par.multiccd || h->hm.par.weld)) {
-    h->err = "nmf_step: noslip on terrain / mesh-hull / tethered worlds needs nmf_set_precision(h, 64) (float32 noslip is built for the flat capsule world only)"; return NMF_EINVAL;
-  }
   return h->precision == 64 ? launch_steps_t<double>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos)
                             : launch_steps_t<float>(h, nsteps, table, table_T, table_t0, table_cols, forward_only, stream, fly0, count, out_qpos);
 }
