@@ -581,9 +581,130 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
 
     // ================================================================= D. soft-contact solve (primal Newton, exact line search)
     int niter = 0, nls_total = 0, nchanged_last = 0, fault = 0;
+    bool explicit_f = false;         // after noslip the contact forces are explicit (no longer a function of the rows)
+    real* ns = sm + d.m_ns; int* nsrank = reinterpret_cast<int*>(sm + d.m_nsrank); int* nsidx = reinterpret_cast<int*>(ns + TNS_IDX);
     for (int iter = 0;; iter++) {
       const bool euler = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
       if (euler && nchanged_last != 0) fault |= ST_NEWTON_CAP;
+      if (euler && p.noslip_iterations > 0 && ng > 0) {
+        // =================================================================
+        // noslip post-solver of the reference's CPU path (mujoco_globals.yaml:15; [PRIOR] mj_solNoSlip), as in nmf_step.cuh: projected
+        // Gauss-Seidel on the friction dimensions of the dual problem without the regulariser.  In the basis (n, mu t1, mu t2) of a
+        // contact a pair of opposing pyramid edges is one tangential component g with |g| <= the normal force the pair carries;
+        //     g <- clamp(g - h / B_gg),   h = jar_t(qacc) + B_tt (g - g_newton),   B_tt = E_t M^-1 E_t'  (2C x 2C, C <= 24).
+        // B_tt is built column by column -- a unit wrench at the contact, subtree sums, a solve with the plain inertia matrix in the
+        // ancestor-sparse storage, body accelerations, projection on every contact's tangents -- the sweeps run on it in shared memory
+        // in the oracle's contact order (geom, then slot), and qacc moves by M^-1 E_t' (g - g_newton).
+        // =================================================================
+        real* Ss = cvel;
+        if (tid == 0) {
+          int C = 0;
+          for (int i = 0; i < ng * nslot; i++) {
+            nsrank[i] = -1;
+            if (con[i].c.D > real(0.)) { if (C < TNS_MAXC) { nsidx[C] = i; nsrank[i] = C; } C++; }
+          }
+          reinterpret_cast<int*>(ns + TNS_MISC)[0] = C;
+        }
+        tree_sync();
+        const int C = reinterpret_cast<int*>(ns + TNS_MISC)[0];
+        if (C > TNS_MAXC) fault |= ST_NOSLIP_SKIP;
+        else if (C > 0) {
+          real c0r[1] = {real(0.)};
+          if (tid < C) {
+            const TCon& c = con[nsidx[tid]];
+            real G[3], lim[2]; basis_forces(c.c, G, lim, c0r[0]);
+            for (int q = 0; q < 3; q++) ns[TNS_GX + 3 * tid + q] = G[q];
+            for (int q = 0; q < 2; q++) { const int i = 2 * tid + q; ns[TNS_G + i] = G[1 + q]; ns[TNS_G0 + i] = G[1 + q]; ns[TNS_LIM + i] = lim[q]; ns[TNS_JT + i] = c.c.w[1 + q]; }
+          }
+          tree_reduce<1>(c0r, s_red, parity, tid);
+          // x = M^-1 J'(body wrenches in yb[12 b + 6 ..]); afterwards Ss holds the body accelerations of x
+          auto m_solve = [&]() {
+            tree_backward<12, 0>(p, tid, yb, Pb);
+            for (int k = tid; k < nv; k += TREE_CTA) {
+              const int b = it[d.i_dof_body + k];
+              x[k] = dot6(cdof + 6 * k, yb + 12 * b + 6);
+              real P[21]; expand_inert(crb + 10 * b, P);
+              real uk[6]; sym6_mul(P, cdof + 6 * k, uk);
+#pragma unroll
+              for (int i = 0; i < 6; i++) u[6 * k + i] = uk[i];
+            }
+            tree_sync();
+            for (int e = tid; e < d.nH; e += TREE_CTA) {
+              const int rc = __ldcs(it + d.i_erow + e), row = rc & 0xffff, cl = rc >> 16;
+              real v = dot6(cdof + 6 * cl, u + 6 * row);
+              if (row == cl) v += rt[d.r_dof + TR_DOF * row + 5];
+              H[e] = v;
+            }
+            tree_sync();
+            tree_factor_solve(p, sm, tid);
+            tree_sync();
+            tree_dof_to_body(p, sm, tid, x, Ss);
+          };
+          for (int j = 0; j < 2 * C; j++) {
+            for (int i = tid; i < 12 * nb; i += TREE_CTA) yb[i] = real(0.);
+            tree_sync();
+            if (tid == 0) {
+              const int ci = nsidx[j >> 1], b = it[d.i_gbody + ci / nslot];
+              const TCon& c = con[ci];
+              real dd[3], T[3]; contact_tangent(c.c, j & 1, p.mu, dd); cross3(c.c.r, dd, T);
+              real* W = yb + 12 * b + 6;
+              W[0] = T[0]; W[1] = T[1]; W[2] = T[2]; W[3] = dd[0]; W[4] = dd[1]; W[5] = dd[2];
+            }
+            tree_sync();
+            m_solve();
+            if (tid < C) {
+              const int ci = nsidx[tid], b = it[d.i_gbody + ci / nslot];
+              real o3[3]; project_point(con[ci].c, Ss + 6 * b, p.mu, o3);
+              ns[TNS_B + (2 * tid) * TNS_LD + j] = o3[1]; ns[TNS_B + (2 * tid + 1) * TNS_LD + j] = o3[2];
+            }
+            tree_sync();
+          }
+          // ---- the sweeps (serial Gauss-Seidel, one thread; 2C <= 48 unknowns)
+          if (tid == 0) {
+            const int n2 = 2 * C;
+            for (int sweep = 0; sweep < p.noslip_iterations; sweep++) {
+              real improvement = sweep == 0 ? c0r[0] : real(0.);
+              for (int i = 0; i < n2; i++) {
+                real h = ns[TNS_JT + i];
+                for (int q = 0; q < n2; q++) h += ns[TNS_B + i * TNS_LD + q] * (ns[TNS_G + q] - ns[TNS_G0 + q]);
+                const real Bii = ns[TNS_B + i * TNS_LD + i], gold = ns[TNS_G + i], l = ns[TNS_LIM + i];
+                real gnew = real(0.);                           // K1 = 4 B_ii below MuJoCo's mjMINVAL: both edges get the mean
+                if (real(4.) * Bii >= real(1e-15)) gnew = m_min(l, m_max(-l, gold - h / Bii));
+                const real dy = real(0.5) * (gnew - gold);      // y = (f_j - f_j+1) / 2
+                real change = real(2.) * Bii * dy * dy + real(2.) * h * dy;
+                if (change > real(1e-10)) { gnew = gold; change = real(0.); }
+                ns[TNS_G + i] = gnew; improvement -= change;
+              }
+              if (improvement * p.noslip_scale < p.noslip_tol) break;
+            }
+          }
+          // ---- move: qacc += M^-1 E_t' (g - g_newton); rows and explicit forces follow
+          for (int i = tid; i < 12 * nb; i += TREE_CTA) yb[i] = real(0.);
+          tree_sync();
+          if (tid == 0) {
+            for (int r = 0; r < C; r++) {
+              const int ci = nsidx[r], b = it[d.i_gbody + ci / nslot];
+              real dG[3] = {real(0.), ns[TNS_G + 2 * r] - ns[TNS_GX + 3 * r + 1], ns[TNS_G + 2 * r + 1] - ns[TNS_GX + 3 * r + 2]};
+              basis_wrench(con[ci].c, dG, p.mu, yb + 12 * b + 6, nullptr);
+              ns[TNS_GX + 3 * r + 1] += dG[1]; ns[TNS_GX + 3 * r + 2] += dG[2];
+            }
+          }
+          tree_sync();
+          m_solve();
+          for (int k = tid; k < nv; k += TREE_CTA) qacc[k] += x[k];
+          for (int i = tid; i < 6 * nb; i += TREE_CTA) acc[i] += Ss[i];
+          for (int g = tid; g < ng; g += TREE_CTA) {
+            const int b = it[d.i_gbody + g];
+            for (int s2 = 0; s2 < nslot; s2++) {
+              TCon& c = con[g * nslot + s2];
+              real o3[3]; project_point(c.c, Ss + 6 * b, p.mu, o3);
+              c.c.w[0] += o3[0]; c.c.w[1] += o3[1]; c.c.w[2] += o3[2];
+            }
+          }
+          tree_sync();
+          explicit_f = true;
+        }
+      }
       // ---- forces of the contacts of every body, contact augmentation of its inertia
       for (int b = tid; b < nb; b += TREE_CTA) {
         real Wc[6] = {0, 0, 0, 0, 0, 0}, A[21];
@@ -591,8 +712,13 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
         for (int i = 0; i < 21; i++) A[i] = real(0.);
         const int g0 = it[d.i_bg_adr + b], g1 = it[d.i_bg_adr + b + 1];
         for (int gi = g0; gi < g1; gi++) for (int s = 0; s < nslot; s++) {
-          const TCon& c = con[it[d.i_bg + gi] * nslot + s];
-          if (c.c.D > real(0.)) { if (euler) contact_forces<false>(c.c, p.mu, Wc, nullptr, nullptr); else contact_forces<true>(c.c, p.mu, Wc, A, nullptr); }
+          const int ci = it[d.i_bg + gi] * nslot + s;
+          const TCon& c = con[ci];
+          if (c.c.D > real(0.)) {
+            if (explicit_f) basis_wrench(c.c, ns + TNS_GX + 3 * nsrank[ci], p.mu, Wc, nullptr);
+            else if (euler) contact_forces<false>(c.c, p.mu, Wc, nullptr, nullptr);
+            else contact_forces<true>(c.c, p.mu, Wc, A, nullptr);
+          }
         }
         if (p.weld && b == 0) weld_forces(sw, Wc, A);
         real t6[6]; mul_inert(cinert + 10 * b, acc + 6 * b, t6);
@@ -694,7 +820,9 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
           for (int s = 0; s < nslot; s++) {
             const TCon& c = con[g * nslot + s];
             if (!(c.c.D > real(0.))) continue;
-            real Wt[6] = {0, 0, 0, 0, 0, 0}, fn = real(0.); contact_forces<false>(c.c, p.mu, Wt, nullptr, &fn);
+            real Wt[6] = {0, 0, 0, 0, 0, 0}, fn = real(0.);
+            if (explicit_f) { const real* gx = ns + TNS_GX + 3 * nsrank[g * nslot + s]; basis_wrench(c.c, gx, p.mu, Wt, nullptr); fn = gx[0]; }
+            else contact_forces<false>(c.c, p.mu, Wt, nullptr, &fn);
 #pragma unroll
             for (int i = 0; i < 3; i++) { F[i] += Wt[3 + i]; Pw[i] += fn * (c.c.r[i] + com[i]); Pp[i] += c.c.r[i] + com[i]; }
             wsum += fn; cnt += real(1.);
@@ -707,7 +835,9 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
           for (int s = 0; s < nslot; s++) {
             const TCon& c = con[g * nslot + s];
             if (!(c.c.D > real(0.))) continue;
-            real Wt[6] = {0, 0, 0, 0, 0, 0}, fn = real(0.); contact_forces<false>(c.c, p.mu, Wt, nullptr, &fn);
+            real Wt[6] = {0, 0, 0, 0, 0, 0}, fn = real(0.);
+            if (explicit_f) basis_wrench(c.c, ns + TNS_GX + 3 * nsrank[g * nslot + s], p.mu, Wt, nullptr);
+            else contact_forces<false>(c.c, p.mu, Wt, nullptr, &fn);
             real rr[3] = {c.c.r[0] + com[0] - P3[0], c.c.r[1] + com[1] - P3[1], c.c.r[2] + com[2] - P3[2]}, tt[3];
             cross3(rr, Wt + 3, tt); T[0] += tt[0]; T[1] += tt[1]; T[2] += tt[2];
           }

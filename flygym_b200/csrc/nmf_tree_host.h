@@ -39,6 +39,7 @@ struct TreeModel {
     d.m_con = take(d.ng * d.nslot * TCON_STRIDE);
     d.m_rb = take(TREE_NW * 8); d.m_red = take(2 * TREE_NW * 8);
     d.m_hullv = take(d.ng); d.m_misc = take(16 + d.nu_pos + d.nu_adh); d.m_weld = take(d.ng == 0 ? 48 : 0);   // (weld rows: only the tethered world, which has no contact geoms)
+    d.m_ns = take(d.noslip ? TNS_TOTAL : 0); d.m_nsrank = take(d.noslip ? d.ng * d.nslot : 0);
     d.m_total = o;
   }
 
@@ -93,9 +94,8 @@ struct TreeModel {
       hulls = hulls || geom_type[g] == 1;
     }
     for (int sg = 0; sg < nseg; sg++) if (seg_body[sg] < 0 || seg_body[sg] >= nb) { err = "seg_body out of range"; return false; }
-    if ((int)opt[8] > 0) { err = "the tree kernels do not run the noslip post-solver (use noslip_iterations = 0)"; return false; }
-
     TreeDims d{};
+    d.noslip = (int)opt[8] > 0 ? 1 : 0;
     d.nb = nb; d.nq = nq; d.nv = nv; d.nu_pos = nu_pos; d.nu_adh = nu_adh; d.ng = ng; d.nseg = nseg; d.nleg = nleg; d.maxd = maxd;
     int nopt = 0; b.get<double>("opt", &nopt);
     const int multiccd = (hulls && nopt > 11 && opt[11] != 0.0) ? 1 : 0;
@@ -261,6 +261,9 @@ struct TreeModel {
     P.margin = contact[8] - contact[9];
     P.multiccd = multiccd;
     P.max_newton = (int)opt[4]; P.max_ls = (int)opt[6];
+    P.noslip_iterations = d.noslip ? (int)opt[8] : 0;
+    P.noslip_tol = 1e-6;                                  // MuJoCo default; the reference does not set it
+    P.noslip_scale = 1.0 / ((opt[9] > 0 ? opt[9] : 1.0) * nv);
     if (P.max_newton < 1) P.max_newton = 100;
     if (P.max_ls < 1) P.max_ls = 50;
     {
@@ -278,6 +281,7 @@ struct TreeModel {
       int nw = 0; const double* wd = b.get<double>("weld", &nw);
       if (wd && nw >= 18 && wd[0] != 0.0) {
         if (ng != 0) { err = "a tethered (welded) world cannot have ground-contact geoms"; return false; }
+        if (d.noslip) { err = "the tree kernels run the noslip post-solver on contact rows only, not on the weld of a tethered world (use noslip_iterations = 0, or the LEGS_ONLY skeleton)"; return false; }
         P.weld = 1;
         for (int i = 0; i < 3; i++) P.weld_a[i] = wd[1 + i];
         for (int i = 0; i < 4; i++) P.weld_q[i] = wd[4 + i];
@@ -297,6 +301,7 @@ struct TreeModel {
     for (int i = 0; i < 5; i++) F.solimp[i] = (float)P.solimp[i];
     for (int i = 0; i < 8; i++) F.terr[i] = (float)P.terr[i];
     F.max_newton = P.max_newton; F.max_ls = P.max_ls; F.multiccd = P.multiccd; F.terrain = P.terrain;
+    F.noslip_iterations = P.noslip_iterations; F.noslip_tol = (float)P.noslip_tol; F.noslip_scale = (float)P.noslip_scale;
     F.weld = P.weld; F.weld_K = (float)P.weld_K; F.weld_B = (float)P.weld_B; F.weld_ts = (float)P.weld_ts;
     for (int i = 0; i < 3; i++) F.weld_a[i] = (float)P.weld_a[i];
     for (int i = 0; i < 4; i++) F.weld_q[i] = (float)P.weld_q[i];

@@ -14,6 +14,12 @@ constexpr int TREE_NW = TREE_CTA / 32;         // warps per fly: each owns a set
 constexpr int TREE_NROOT = 6;                  // DoFs of the free root joint
 constexpr int TREE_MAXBODY = 96, TREE_MAXNV = 256, TREE_MAXGEOM = 96, TREE_MAXNU = 256, TREE_MAXDEPTH = 40;
 constexpr int TCON_STRIDE = 18;                // reals per contact slot in shared memory: ContactG (14) + sv (3) + adhesion pull (1)
+// noslip post-solver (models baked with noslip_iterations > 0): at most TNS_MAXC simultaneous contacts, two friction dimensions each.
+// Region of TNS_TOTAL reals: B_tt (TNS_LD x TNS_LD) | g | g at Newton | pair limits | tangential rows | explicit basis forces (n, t1, t2)
+// per ranked contact | slot of every ranked contact (ints) | count
+constexpr int TNS_MAXC = 24, TNS_LD = 2 * TNS_MAXC;
+constexpr int TNS_B = 0, TNS_G = TNS_LD * TNS_LD, TNS_G0 = TNS_G + TNS_LD, TNS_LIM = TNS_G0 + TNS_LD, TNS_JT = TNS_LIM + TNS_LD,
+              TNS_GX = TNS_JT + TNS_LD, TNS_IDX = TNS_GX + 3 * TNS_MAXC, TNS_MISC = TNS_IDX + TNS_MAXC, TNS_TOTAL = TNS_MISC + 4;
 
 struct TreeDims {
   int nb, nq, nv, nu_pos, nu_adh, ng, nseg, nleg, nslot, nH, maxd;
@@ -44,6 +50,8 @@ struct TreeDims {
   // shared-memory plan (reals)
   int m_state, m_stage, m_xpos, m_xquat, m_cinert, m_crb, m_cdof, m_cvel, m_acc, m_y, m_P, m_fs, m_grad, m_x, m_u, m_H, m_dinv,
       m_con, m_accS, m_rb, m_red, m_hullv, m_misc, m_weld, m_total;
+  int noslip;     // the model asks for the noslip post-solver: the two regions below exist
+  int m_ns, m_nsrank;   // noslip region (TNS_TOTAL reals); rank of every contact slot among the active ones, -1 = inactive ([ng * nslot] ints)
 };
 constexpr int TR_BODY = 18, TR_DOF = 11, TR_GEOM = 8, TR_ADH = 3;
 
@@ -66,6 +74,7 @@ struct TreeParamsT {
   real mu, cK, cB, margin, impratio;
   real solimp[5];
   int max_newton, max_ls, multiccd, terrain;
+  int noslip_iterations; real noslip_tol, noslip_scale;      // as in StepParamsT
   real terr[8];
   // TetheredWorld weld on the root body (reference world.py:350-366), same fields and meaning as in StepParamsT
   int weld;

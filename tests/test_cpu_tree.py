@@ -73,6 +73,35 @@ def test_other_general_models_f64(kw):
     assert e["qpos"] < 3e-7 and e["qvel"] < 2e-5 and e["xpos"] < 5e-7 and e["found"] == 0 and e["force"] < 1e-5
 
 
+@pytest.mark.parametrize("kw,precision", [(dict(joint_preset="all_biological"), 64), (dict(joint_preset="all_biological"), 32),
+                                          (dict(joint_preset="all_biological", simplify_geom=False), 64)],
+                         ids=["capsule_f64", "capsule_f32", "mesh_multiccd_f64"])
+def test_noslip_on_the_tree_kernels_matches_the_oracle(kw, precision):
+    """`noslip_iterations: 5` (mujoco_globals.yaml:15, the CPU `Simulation` semantics) on the general-topology kernels: a settled
+    ALL_BIOLOGICAL fly pushed sideways, 10 steps, against the oracle's noslip ([PRIOR] mj_solNoSlip) -- and the post-solver has to
+    matter (the plain solve of the same state ends somewhere else)."""
+    base = NMFModel.bench(**kw)
+    m = base.with_options(noslip_iterations=5)
+    o, st, info = _settled(m, 800)
+    v0 = info["s_qvel"]
+    st[0, v0:v0 + 2] += np.float32([3.0, -2.0]); o.qvel[0:2] = st[0, v0:v0 + 2]
+    plain = Oracle(base); plain.reset()
+    plain.qpos[:] = o.qpos; plain.qvel[:] = o.qvel; plain.get("qacc_warmstart")[:] = o.get("qacc_warmstart"); plain.ctrl[:] = o.ctrl
+    r = emu.tree_step(m, st, 10, precision=precision, outputs=True, dbg=True)
+    o.step(10); plain.step(10)
+    qpos = st[0, :info["nq"]].astype(np.float64); qvel = st[0, v0:v0 + info["nv"]].astype(np.float64)
+    so = o.get("sensordata").reshape(-1, 16); sg = r["sensor"][0].reshape(-1, 16)
+    e = dict(qpos=np.abs(qpos - o.qpos).max(), qvel=np.abs(qvel - o.qvel).max() / max(1.0, np.abs(o.qvel).max()),
+             force=np.abs(sg[:, 1:10] - so[:, 1:10]).max() / max(1.0, np.abs(so[:, 1:4]).max()), found=np.abs(sg[:, 0] - so[:, 0]).max(),
+             gap=np.abs(plain.qvel - o.qvel).max() / max(1.0, np.abs(o.qvel).max()), status=float(st[0, info["s_time"] + 1]))
+    print(kw, precision, e)
+    assert e["status"] == 0 and e["found"] == 0 and e["gap"] > 1e-3
+    if precision == 64:
+        assert e["qpos"] < 3e-7 and e["qvel"] < 2e-5 and e["force"] < 2e-5
+    else:
+        assert e["qpos"] < 3e-6 and e["qvel"] < 1e-3 and e["force"] < 2e-3
+
+
 def test_tree_kernel_equals_star_kernel_on_the_benchmark_model():
     """The benchmark skeleton stepped by both kernel families (float32, 4 CPG walkers, 15 steps): same physics, different
     factorisation order -> agreement at float32 rounding."""

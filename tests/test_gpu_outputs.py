@@ -31,6 +31,9 @@ def _worlds():
         "allpossible_allcontacts": (lambda: NMFModel.bench(True, joint_preset="all_possible", contact_preset="all"), -0.17, False),
         "legsonly_allcontacts": (lambda: NMFModel.bench(True, contact_preset="all"), -0.17, False),
         "allbio_tethered": (lambda: NMFModel.tethered(joint_preset="all_biological"), None, False),
+        # ... with MuJoCo's noslip post-solver (the CPU `Simulation` semantics, mujoco_globals.yaml:15)
+        "allbio_capsule_noslip": (lambda: NMFModel.bench(True, joint_preset="all_biological").with_options(noslip_iterations=5), -0.17, False),
+        "allbio_mesh_noslip": (lambda: NMFModel.bench(False, joint_preset="all_biological").with_options(noslip_iterations=5), -0.17, False),
     }
 
 
@@ -42,8 +45,9 @@ def _stance_adhesion(model, n, T):
     return np.where(np.sin(2 * np.pi * 12.0 * t[None, :, None] + psi[:, None, None] + legph[None, None, :]) < 0, 100.0, 1.0)
 
 
-def run_world(wname, precision=32, check=CHECK):
-    """-> {checkpoint: {quantity: [per-case error]}} for the standing fly + 4 CPG walkers of one world."""
+def run_world(wname, precision=32, check=CHECK, settle=0):
+    """-> {checkpoint: {quantity: [per-case error]}} for the standing fly + 4 CPG walkers of one world.  settle: oracle steps that let
+    the fly come to rest on its tarsi before the comparison starts (otherwise it is dropped from the keyframe height)."""
     import torch
     from flygym_b200 import B200Simulation
     from flygym_b200.actions import cpg_table
@@ -56,6 +60,9 @@ def run_world(wname, precision=32, check=CHECK):
     stand = key.copy()
     if stand_z is not None:
         stand[2] = stand_z
+    if settle:
+        o = Oracle(model); o.reset(); o.qpos[:] = stand; o.ctrl[nu_pos:] = 1.0; o.step(settle)
+        stand = o.qpos.astype(np.float32).astype(np.float64)
     cpg = cpg_table(model, 4, T).astype(np.float64)
     hold = np.tile(model.arrays["key_ctrl"][:nu_pos], (T, 1))
     adh_on = np.ones((T, 6))
@@ -77,7 +84,7 @@ def run_world(wname, precision=32, check=CHECK):
         sim.step(cp - done, tabd, done); done = cp
         f64 = lambda t: t.cpu().numpy().astype(np.float64)
         got[cp] = dict(qpos=f64(sim.qpos), qvel=f64(sim.qvel), actf=f64(sim.act_force), xpos=f64(sim.seg_xpos), xquat=f64(sim.seg_xquat),
-                       sens=f64(sim.sensordata).reshape(n, 6, 16))
+                       sens=f64(sim.sensordata).reshape(n, 6, 16), status=f64(sim.status))
     errs = {cp: {} for cp in check}
     for i, (q0, pos, adh) in enumerate(cases):
         o = Oracle(model); o.reset(); o.qpos[:] = q0
@@ -88,6 +95,7 @@ def run_world(wname, precision=32, check=CHECK):
             e = errs[cp]
             def add(k, v): e.setdefault(k, []).append(float(v))
             qv = o.qvel.copy()
+            add("status", g["status"][i])
             add("qpos_rel", np.abs(g["qpos"][i] - o.qpos).max() / np.abs(o.qpos).max())
             add("qvel_rel", np.abs(g["qvel"][i] - qv).max() / max(1.0, np.abs(qv).max()))
             af = o.get("actuator_force").copy()

@@ -55,6 +55,27 @@ def test_tree_kernels_in_double_precision(wname):
         assert max(e["found_mismatch"]) == 0 and max(e["force_rel"]) < 2e-4 and max(e["torque_rel"]) < 2e-4 and max(e["pos_abs"]) < 2e-6
 
 
+@pytest.mark.parametrize("wname", ["allbio_capsule_noslip", "allbio_mesh_noslip"])
+def test_noslip_on_the_tree_kernels(wname):
+    """`noslip_iterations: 5` on the general-topology kernels (ALL_BIOLOGICAL skeleton; capsule geoms and mesh hulls with multiccd):
+    every output against the oracle's noslip after 1 and 100 steps -- double precision to the float32 resolution of the buffers,
+    float32 within the bands of the plain solve."""
+    errs = run_world(wname, precision=64, settle=800)      # (a fly dropped from the keyframe height lands on more than 24 hull contacts at once)
+    print(wname, "f64", {cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    for cp in CHECK:
+        e = errs[cp]
+        assert max(e["qpos_rel"]) < 5e-7 and max(e["qvel_rel"]) < 3e-5 and max(e["actf_abs"]) < 2e-5 and max(e["xpos_abs"]) < 5e-6
+        assert max(e["found_mismatch"]) == 0 and max(e["force_rel"]) < 2e-4 and max(e["torque_rel"]) < 2e-4 and max(e["pos_abs"]) < 2e-6
+        assert max(e["status"]) == 0                      # in particular: the post-solver was never skipped
+    errs = run_world(wname, precision=32, settle=800)
+    print(wname, "f32", {cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    e1, e100 = errs[1], errs[100]
+    assert max(e1["qpos_rel"]) < 1e-6 and max(e1["qvel_rel"]) < 5e-4 and max(e1["actf_abs"]) < 1e-4 and max(e1["found_mismatch"]) == 0
+    assert max(e1["force_rel"]) < 1e-4 and max(e1["torque_rel"]) < 1e-4
+    assert np.median(e100["qpos_rel"]) < 1e-4 and np.median(e100["qvel_rel"]) < 1e-3 and np.median(e100["force_rel"]) < 1e-3
+    assert e100["qpos_rel"][0] < 1e-4 and e100["force_rel"][0] < 1e-3          # the standing fly
+
+
 def test_tree_and_star_kernels_agree_on_the_benchmark_model():
     """NMF_FORCE_TREE routes the benchmark skeleton through the general kernels: both families must walk the same 64 flies (300
     CPG steps, float32) to float32 rounding, and every reference-facing call works on both layouts."""
