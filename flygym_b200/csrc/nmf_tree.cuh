@@ -586,7 +586,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
     for (int iter = 0;; iter++) {
       const bool euler = iter > 0 && (nchanged_last == 0 || iter >= p.max_newton);
       if (euler && nchanged_last != 0) fault |= ST_NEWTON_CAP;
-      if (euler && p.noslip_iterations > 0 && ng > 0) {
+      if (euler && p.noslip_iterations > 0 && (ng > 0 || p.weld)) {
         // =================================================================
         // noslip post-solver of the reference's CPU path (mujoco_globals.yaml:15; [PRIOR] mj_solNoSlip), as in nmf_step.cuh: projected
         // Gauss-Seidel on the friction dimensions of the dual problem without the regulariser.  In the basis (n, mu t1, mu t2) of a
@@ -594,10 +594,86 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
         //     g <- clamp(g - h / B_gg),   h = jar_t(qacc) + B_tt (g - g_newton),   B_tt = E_t M^-1 E_t'  (2C x 2C, C <= 24).
         // B_tt is built column by column -- a unit wrench at the contact, subtree sums, a solve with the plain inertia matrix in the
         // ancestor-sparse storage, body accelerations, projection on every contact's tangents -- the sweeps run on it in shared memory
-        // in the oracle's contact order (geom, then slot), and qacc moves by M^-1 E_t' (g - g_newton).
+        // in the oracle's contact order (geom, then slot), and qacc moves by M^-1 E_t' (g - g_newton).  (Tethered world: see below.)
         // =================================================================
         real* Ss = cvel;
-        if (tid == 0) {
+        // x = M^-1 J'(body wrenches in yb[12 b + 6 ..]); afterwards Ss holds the body accelerations of x
+        auto m_solve = [&]() {
+          tree_backward<12, 0>(p, tid, yb, Pb);
+          for (int k = tid; k < nv; k += TREE_CTA) {
+            const int b = it[d.i_dof_body + k];
+            x[k] = dot6(cdof + 6 * k, yb + 12 * b + 6);
+            real P[21]; expand_inert(crb + 10 * b, P);
+            real uk[6]; sym6_mul(P, cdof + 6 * k, uk);
+#pragma unroll
+            for (int i = 0; i < 6; i++) u[6 * k + i] = uk[i];
+          }
+          tree_sync();
+          for (int e = tid; e < d.nH; e += TREE_CTA) {
+            const int rc = __ldcs(it + d.i_erow + e), row = rc & 0xffff, cl = rc >> 16;
+            real v = dot6(cdof + 6 * cl, u + 6 * row);
+            if (row == cl) v += rt[d.r_dof + TR_DOF * row + 5];
+            H[e] = v;
+          }
+          tree_sync();
+          tree_factor_solve(p, sm, tid);
+          tree_sync();
+          tree_dof_to_body(p, sm, tid, x, Ss);
+        };
+        if (p.weld) {
+          // TetheredWorld: the six weld rows are equality rows, which noslip sweeps unclamped ( f_i -= residual_i / A_ii ), as in
+          // nmf_step.cuh.  A = J_w M^-1 J_w' (6 x 6) column by column; the rows live on the root body and belong to thread 0.
+          for (int j = 0; j < 6; j++) {
+            for (int i = tid; i < 12 * nb; i += TREE_CTA) yb[i] = real(0.);
+            tree_sync();
+            if (tid == 0) {
+              const real* r = sw + WL_R; const real* Gm = sw + WL_G; real* W = yb + 6;
+              if (j < 3) { real e3[3] = {j == 0 ? real(1.) : real(0.), j == 1 ? real(1.) : real(0.), j == 2 ? real(1.) : real(0.)}, T[3]; cross3(r, e3, T);
+                           W[0] = T[0]; W[1] = T[1]; W[2] = T[2]; W[3] = e3[0]; W[4] = e3[1]; W[5] = e3[2]; }
+              else { W[0] = Gm[3 * (j - 3)]; W[1] = Gm[3 * (j - 3) + 1]; W[2] = Gm[3 * (j - 3) + 2]; }
+            }
+            tree_sync();
+            m_solve();
+            if (tid == 0) { real o6[6]; point_and_rot(sw, Ss, o6); for (int i = 0; i < 6; i++) ns[TNS_B + i * TNS_LD + j] = o6[i]; }
+            tree_sync();
+          }
+          for (int i = tid; i < 12 * nb; i += TREE_CTA) yb[i] = real(0.);
+          tree_sync();
+          if (tid == 0) {
+            real f[6], f0[6], jar[6], improvement0 = real(0.);
+            for (int i = 0; i < 6; i++) {
+              jar[i] = sw[WL_W + i] + sw[WL_C0 + i]; f0[i] = f[i] = -sw[WL_D + i] * jar[i];
+              improvement0 += real(0.5) * f0[i] * f0[i] / sw[WL_D + i];
+            }
+            for (int sweep = 0; sweep < p.noslip_iterations; sweep++) {
+              real improvement = sweep == 0 ? improvement0 : real(0.);
+              for (int i = 0; i < 6; i++) {
+                real res = jar[i];
+                for (int q = 0; q < 6; q++) res += ns[TNS_B + i * TNS_LD + q] * (f[q] - f0[q]);
+                const real Aii = ns[TNS_B + i * TNS_LD + i], old = f[i];
+                f[i] = old - res / m_max(real(1e-15), Aii);
+                const real dd = f[i] - old;
+                real change = real(0.5) * dd * dd * Aii + dd * res;
+                if (change > real(1e-10)) { f[i] = old; change = real(0.); }
+                improvement -= change;
+              }
+              if (improvement * p.noslip_scale < p.noslip_tol) break;
+            }
+            real df[6];
+            for (int i = 0; i < 6; i++) { sw[WL_F + i] = f[i]; df[i] = f[i] - f0[i]; }
+            const real* r = sw + WL_R; const real* Gm = sw + WL_G; real* W = yb + 6;
+            real T[3]; cross3(r, df, T);
+            for (int i = 0; i < 3; i++) { W[i] = T[i] + Gm[i] * df[3] + Gm[3 + i] * df[4] + Gm[6 + i] * df[5]; W[3 + i] = df[i]; }
+          }
+          tree_sync();
+          m_solve();
+          for (int k = tid; k < nv; k += TREE_CTA) qacc[k] += x[k];
+          for (int i = tid; i < 6 * nb; i += TREE_CTA) acc[i] += Ss[i];
+          if (tid == 0) { real o6[6]; point_and_rot(sw, Ss, o6); for (int i = 0; i < 6; i++) sw[WL_W + i] += o6[i]; }
+          tree_sync();
+          explicit_f = true;
+        }
+        if (ng > 0 && tid == 0) {
           int C = 0;
           for (int i = 0; i < ng * nslot; i++) {
             nsrank[i] = -1;
@@ -606,7 +682,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
           reinterpret_cast<int*>(ns + TNS_MISC)[0] = C;
         }
         tree_sync();
-        const int C = reinterpret_cast<int*>(ns + TNS_MISC)[0];
+        const int C = ng > 0 ? reinterpret_cast<int*>(ns + TNS_MISC)[0] : 0;
         if (C > TNS_MAXC) fault |= ST_NOSLIP_SKIP;
         else if (C > 0) {
           real c0r[1] = {real(0.)};
@@ -617,29 +693,6 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
             for (int q = 0; q < 2; q++) { const int i = 2 * tid + q; ns[TNS_G + i] = G[1 + q]; ns[TNS_G0 + i] = G[1 + q]; ns[TNS_LIM + i] = lim[q]; ns[TNS_JT + i] = c.c.w[1 + q]; }
           }
           tree_reduce<1>(c0r, s_red, parity, tid);
-          // x = M^-1 J'(body wrenches in yb[12 b + 6 ..]); afterwards Ss holds the body accelerations of x
-          auto m_solve = [&]() {
-            tree_backward<12, 0>(p, tid, yb, Pb);
-            for (int k = tid; k < nv; k += TREE_CTA) {
-              const int b = it[d.i_dof_body + k];
-              x[k] = dot6(cdof + 6 * k, yb + 12 * b + 6);
-              real P[21]; expand_inert(crb + 10 * b, P);
-              real uk[6]; sym6_mul(P, cdof + 6 * k, uk);
-#pragma unroll
-              for (int i = 0; i < 6; i++) u[6 * k + i] = uk[i];
-            }
-            tree_sync();
-            for (int e = tid; e < d.nH; e += TREE_CTA) {
-              const int rc = __ldcs(it + d.i_erow + e), row = rc & 0xffff, cl = rc >> 16;
-              real v = dot6(cdof + 6 * cl, u + 6 * row);
-              if (row == cl) v += rt[d.r_dof + TR_DOF * row + 5];
-              H[e] = v;
-            }
-            tree_sync();
-            tree_factor_solve(p, sm, tid);
-            tree_sync();
-            tree_dof_to_body(p, sm, tid, x, Ss);
-          };
           for (int j = 0; j < 2 * C; j++) {
             for (int i = tid; i < 12 * nb; i += TREE_CTA) yb[i] = real(0.);
             tree_sync();
@@ -720,7 +773,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
             else contact_forces<true>(c.c, p.mu, Wc, A, nullptr);
           }
         }
-        if (p.weld && b == 0) weld_forces(sw, Wc, A);
+        if (p.weld && b == 0) weld_forces(sw, Wc, A, explicit_f);
         real t6[6]; mul_inert(cinert + 10 * b, acc + 6 * b, t6);
 #pragma unroll
         for (int i = 0; i < 6; i++) { yb[12 * b + i] = t6[i] - Wc[i]; yb[12 * b + 6 + i] = Wc[i]; }

@@ -25,6 +25,7 @@ struct TreeModel {
   std::string err;
 
   static int align4(int v) { return (v + 3) & ~3; }
+  static constexpr int WELD_REALS = 48;      // >= WL_COUNT of nmf_step.cuh (42: r, G, D, c0, w, sv and the explicit row forces after noslip)
 
   template <class real> static void plan_smem(TreeDims& d) {
     int o = 0;
@@ -38,7 +39,7 @@ struct TreeModel {
     d.m_dinv = take(d.nv);
     d.m_con = take(d.ng * d.nslot * TCON_STRIDE);
     d.m_rb = take(TREE_NW * 8); d.m_red = take(2 * TREE_NW * 8);
-    d.m_hullv = take(d.ng); d.m_misc = take(16 + d.nu_pos + d.nu_adh); d.m_weld = take(d.ng == 0 ? 48 : 0);   // (weld rows: only the tethered world, which has no contact geoms)
+    d.m_hullv = take(d.ng); d.m_misc = take(16 + d.nu_pos + d.nu_adh); d.m_weld = take(d.ng == 0 ? WELD_REALS : 0);   // (weld rows: only the tethered world, which has no contact geoms)
     d.m_ns = take(d.noslip ? TNS_TOTAL : 0); d.m_nsrank = take(d.noslip ? d.ng * d.nslot : 0);
     d.m_total = o;
   }
@@ -281,7 +282,6 @@ struct TreeModel {
       int nw = 0; const double* wd = b.get<double>("weld", &nw);
       if (wd && nw >= 18 && wd[0] != 0.0) {
         if (ng != 0) { err = "a tethered (welded) world cannot have ground-contact geoms"; return false; }
-        if (d.noslip) { err = "the tree kernels run the noslip post-solver on contact rows only, not on the weld of a tethered world (use noslip_iterations = 0, or the LEGS_ONLY skeleton)"; return false; }
         P.weld = 1;
         for (int i = 0; i < 3; i++) P.weld_a[i] = wd[1 + i];
         for (int i = 0; i < 4; i++) P.weld_q[i] = wd[4 + i];

@@ -176,3 +176,18 @@ def test_tethered_world_with_the_full_skeleton():
     a = emu.key_state(mb)[None].copy(); emu.step(mb, a, 10)
     ib = emu.tree_info(mb); b = emu.tree_key_state(mb)[None].copy(); emu.tree_step(mb, b, 10)
     assert np.abs(a[0, :73] - b[0, :73]).max() < 2e-4 * np.abs(a[0, :73]).max()
+
+
+def test_tethered_full_skeleton_with_noslip():
+    """The weld rows of the tethered ALL_BIOLOGICAL world under noslip (equality rows, swept unclamped): f64 source vs the oracle, and
+    far from the plain solve (the soft weld becomes nearly hard)."""
+    base = NMFModel.tethered(joint_preset="all_biological"); m = base.with_options(noslip_iterations=5)
+    info = emu.tree_info(m)
+    st = emu.tree_key_state(m)[None].copy()
+    o = Oracle(m); o.reset(); plain = Oracle(base); plain.reset()
+    emu.tree_step(m, st, 10, precision=64)
+    o.step(10); plain.step(10)
+    q = st[0, :info["nq"]].astype(np.float64)
+    print(np.abs(q - o.qpos).max(), np.abs(plain.qpos - o.qpos).max())
+    assert np.abs(plain.qpos - o.qpos).max() > 1e-3
+    assert np.abs(q - o.qpos).max() < 5e-6 * max(1.0, np.abs(o.qpos).max()) and st[0, info["s_time"] + 1] == 0

@@ -33,6 +33,7 @@ def _worlds():
         "allbio_tethered": (lambda: NMFModel.tethered(joint_preset="all_biological"), None, False),
         # ... with MuJoCo's noslip post-solver (the CPU `Simulation` semantics, mujoco_globals.yaml:15)
         "allbio_capsule_noslip": (lambda: NMFModel.bench(True, joint_preset="all_biological").with_options(noslip_iterations=5), -0.17, False),
+        "allbio_tethered_noslip": (lambda: NMFModel.tethered(joint_preset="all_biological").with_options(noslip_iterations=5), None, False),
         "allbio_mesh_noslip": (lambda: NMFModel.bench(False, joint_preset="all_biological").with_options(noslip_iterations=5), -0.17, False),
     }
 

@@ -554,16 +554,15 @@ def test_noslip_kernels_match_the_oracle(variant):
                 assert e < 1e-4
 
 
-def test_noslip_runs_in_float32_in_every_star_world_and_is_refused_for_the_tethered_tree():
-    """float32 noslip instantiations exist for every world of the star kernels (flat, mesh hulls, terrain, tethered); the
-    general-topology kernels run it on contact rows only and refuse the welded (tethered) full skeleton when the model is created."""
+def test_noslip_runs_in_float32_in_every_world():
+    """float32 noslip instantiations exist for every world of the star kernels (flat, mesh hulls, terrain, tethered) and on the
+    general-topology kernels (contact rows and the weld of a tethered full skeleton): nothing is refused any more."""
     from flygym_b200 import B200Simulation, NMFModel
-    for m in (NMFModel.bench(False), NMFModel.tethered(), NMFModel.bench(True, terrain="gapped")):
+    for m in (NMFModel.bench(False), NMFModel.tethered(), NMFModel.bench(True, terrain="gapped"),
+              NMFModel.bench(True, joint_preset="all_biological"), NMFModel.tethered(joint_preset="all_biological")):
         sim = B200Simulation(m.with_options(noslip_iterations=5), n_worlds=3)
         sim.step(5)
         assert bool(np.isfinite(sim.qpos.cpu().numpy()).all()) and int(sim.status.abs().max()) == 0
-    with pytest.raises(RuntimeError, match="noslip"):
-        B200Simulation(NMFModel.tethered(joint_preset="all_biological").with_options(noslip_iterations=5), n_worlds=1)
 
 
 def test_tethered_world_with_noslip_matches_the_oracle():

@@ -76,6 +76,19 @@ def test_noslip_on_the_tree_kernels(wname):
     assert e100["qpos_rel"][0] < 1e-4 and e100["force_rel"][0] < 1e-3          # the standing fly
 
 
+def test_noslip_on_the_tethered_full_skeleton():
+    """The weld rows of the tethered ALL_BIOLOGICAL world are equality rows, which noslip sweeps unclamped (as the star kernels do for the
+    LEGS_ONLY skeleton of the reference's CPU fixtures): double precision vs the oracle's noslip, float32 within the tethered band."""
+    errs = run_world("allbio_tethered_noslip", precision=64)
+    print({cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    for cp in CHECK:
+        e = errs[cp]
+        assert max(e["qpos_rel"]) < 5e-7 and max(e["qvel_rel"]) < 3e-5 and max(e["xpos_abs"]) < 5e-6 and max(e["status"]) == 0
+    errs = run_world("allbio_tethered_noslip", precision=32)
+    print({cp: {k: "%.1e" % max(v) for k, v in e.items()} for cp, e in errs.items()})
+    assert max(errs[1]["qpos_rel"]) < 1e-4 and max(errs[100]["qpos_rel"]) < 1e-4 and max(errs[100]["xpos_abs"]) < 5e-4
+
+
 def test_tree_and_star_kernels_agree_on_the_benchmark_model():
     """NMF_FORCE_TREE routes the benchmark skeleton through the general kernels: both families must walk the same 64 flies (300
     CPG steps, float32) to float32 rounding, and every reference-facing call works on both layouts."""
