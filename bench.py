@@ -133,12 +133,16 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Rows from here on count (the GPU is under load from this point to stop())."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -150,12 +154,13 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.03)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -343,6 +348,11 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
         table = device_cpg_table(torch, model, n, table_rows, dev, rank, world * n, adhesion_stance=(wl == "terrain"), fly_stride=world)
     table_T = table.shape[1]
     sim.set_leg_adhesion_states("nmf", np.ones((n, 6), np.float32))     # as the reference benchmark (time_gpu_simulation.py:130)
+    # nvidia-smi takes ~0.1 s to initialise NVML: it is started here and its rows count from the physics warm-up on, so that the timed
+    # region (3.6 ms with the driver's --steps 20) is neither disturbed by that start-up nor over before the first sample
+    sampler = ClockSampler(dev.index) if (sample_clocks and rank == 0) else None
+    if sampler is not None:
+        sampler.start(); time.sleep(0.25); sampler.mark()
     sim.warmup()                                                        # 500 steps at the neutral pose
     chunk = max(1, min(args.chunk, steps))
 
@@ -387,10 +397,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream around every launch group
     state["launches"] = 0
-    sampler = ClockSampler(dev.index) if sample_clocks else None
     ctx.barrier()
-    if sampler is not None and rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     ev = []
     done = 0
@@ -420,7 +427,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
         ja.record(); torch.cuda.current_stream(dev).wait_stream(gstream); jb.record(); ev.append((ja, jb, 0))
     ctx.barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+    clocks = sampler.stop() if sampler is not None else None
     kernel_ms = sum(a.elapsed_time(b) for a, b, c in ev if c > 0)
     gather_ms = sum(a.elapsed_time(b) for a, b, c in ev if c == 0)            # what the stepping stream waited for the gathers
     gather_dev_ms = sum(ga.elapsed_time(gb) for ga, gb, _, _ in pending)      # their own duration on the side stream (incl. rank skew)

@@ -126,6 +126,7 @@ struct nmf_handle {
   float *d_act = nullptr, *d_qpos = nullptr;   // staging for nmf_step_host
   int* d_queue = nullptr;                      // work queue: counters, per-fly progress words, ring of ready flies
   int sub_steps = -1;                          // steps per work item: -1 = chosen per launch, 0 = never use the queue
+  bool taper = true;                           // heuristic schedule: shrinking items at the end of a launch (env NMF_QUEUE_TAPER=0: uniform)
   int fpb64 = 4;                               // f64 flat kernel: flies per block (1, 2, 4; env NMF_FPB64).  B200, 4096 flies: 6.8 / 8.3 / 9.2 M env-steps/s
   int fpb = 0;                                 // fly slots per block of the f32 flat / terrain kernels: 1, 2, 4, 8 or 0 = chosen per launch (see step_block)
   int resident[9] = {};                        // resident blocks of the model's f32 kernel per fpb (index = fpb)
@@ -151,7 +152,6 @@ struct nmf_handle {
   std::string err;
 };
 
-constexpr int QUEUE_MAX_CHUNKS = 64;   // sub-chunks per fly and launch the queue buffer is sized for
 
 // every entry point that touches the device runs on the handle's device and leaves the caller's current device as it found it
 struct DeviceGuard {
@@ -236,6 +236,7 @@ extern "C" int nmf_create(const void* blob, size_t nbytes, int n_flies, int devi
     if (rc2) return rc2;
   }
   if (const char* e = getenv("NMF_QUEUE_SUBSTEPS")) h->sub_steps = atoi(e);
+  if (const char* e = getenv("NMF_QUEUE_TAPER")) h->taper = atoi(e) != 0;
   if (const char* e = getenv("NMF_HOST_PARTS")) { int v = atoi(e); if (v >= 1 && v <= nmf_handle::MAX_PARTS) h->host_parts = h->graph_parts = v; }
   if (const char* e = getenv("NMF_HOST_GRAPH")) h->host_graph = atoi(e) != 0;
   return NMF_OK;
@@ -413,7 +414,7 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   const int fpb = KernelSet<real>::fpb(h, p.n_flies);
   const int n_units = (p.n_flies + fpb - 1) / fpb;      // a block steps a unit of fpb consecutive flies
   int grid = n_units;
-  p.queue = nullptr; p.sub_steps = nsteps; p.n_items = n_units;
+  p.queue = nullptr; p.sub_steps = nsteps; p.n_items = n_units; p.n_chunks = 0;
   int sub = h->sub_steps;
   if (sub < 0) {
     // ~8 steps per item.  Measured on B200 with 8 flies per block (profiles/queue_sweep_r02.txt, 4096 flies): a 20-step launch
@@ -426,7 +427,25 @@ static int launch_steps_t(nmf_handle* h, int nsteps, const float* table, int tab
   // more units than resident blocks: work queue (one per handle; sized for the f32 kernels' occupancy, so f32 only)
   if (std::is_same<real, float>::value && !ranged && sub > 0 && n_units > h->resident[fpb] && nsteps >= 2 * sub) {
     if (sub * QUEUE_MAX_CHUNKS < nsteps) sub = (nsteps + QUEUE_MAX_CHUNKS - 1) / QUEUE_MAX_CHUNKS;
-    const int nchunk = (nsteps + sub - 1) / sub;
+    int nchunk = (nsteps + sub - 1) / sub;
+    p.n_chunks = 0;
+    if (h->sub_steps < 0 && h->taper && nsteps <= 30000) {      // (boundaries are stored as shorts)
+      // Tapered schedule (the heuristic only; an explicit nmf_set_schedule stays uniform): the launch ends when the last block has
+      // finished its last item, and while that item runs the blocks that found the queue empty idle -- up to one item of ~8 steps,
+      // 0.7 ms of a 3.6 ms launch of 20 steps.  So the last items of every unit shrink (..., 6, 4, 3, 2 steps): the bulk keeps its
+      // low per-item cost and the tail of the launch is a 2-step item.
+      int taper[8], nt = 0, tsum = 0;
+      for (int t = 2; t < sub && nt < 8 && tsum + t <= nsteps - sub; t = t + 1 > t * 3 / 2 ? t + 1 : t * 3 / 2) { taper[nt++] = t; tsum += t; }
+      const int bulk = nsteps - tsum;
+      int kb = (bulk + sub - 1) / sub;
+      if (kb + nt <= QUEUE_MAX_CHUNKS && nt > 0) {
+        int at = 0, c = 0;
+        for (int i = 0; i < kb; i++) { p.chunk_start[c++] = (short)at; at += bulk / kb + (i < bulk % kb ? 1 : 0); }
+        for (int i = nt - 1; i >= 0; i--) { p.chunk_start[c++] = (short)at; at += taper[i]; }
+        p.chunk_start[c] = (short)at;                 // == nsteps
+        p.n_chunks = nchunk = c;
+      }
+    }
     p.queue = h->d_queue; p.sub_steps = sub; p.n_items = nchunk * n_units;
     grid = h->resident[fpb];
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * ((size_t)n_units * nchunk + 2), (cudaStream_t)stream));

@@ -81,7 +81,8 @@ inline StepParams narrow(const StepParamsT<double>& d) {
   for (int i = 0; i < 4; i++) f.weld_q[i] = (float)d.weld_q[i];
   f.weld_K = (float)d.weld_K; f.weld_B = (float)d.weld_B; f.weld_ts = (float)d.weld_ts;
   f.weld_invw[0] = (float)d.weld_invw[0]; f.weld_invw[1] = (float)d.weld_invw[1];
-  f.sub_steps = d.sub_steps; f.n_items = d.n_items;
+  f.sub_steps = d.sub_steps; f.n_items = d.n_items; f.n_chunks = d.n_chunks;
+  for (int i = 0; i <= QUEUE_MAX_CHUNKS; i++) f.chunk_start[i] = d.chunk_start[i];
   return f;
 }
 

@@ -86,6 +86,8 @@ constexpr int DBG_STRIDE = DBG_HROWS + NLEG * 177 + 21 + 3;
 
 // `real` = the arithmetic of the kernel instantiation (float for the product path, double for the validation build); buffers
 // that live in HBM on behalf of the API (state records, observations, action table) are float32 in both.
+constexpr int QUEUE_MAX_CHUNKS = 64;   // sub-chunks per fly and launch the queue buffer is sized for
+
 template <class real>
 struct StepParamsT {
   float* state;              // [n_flies][S_STRIDE]
@@ -126,6 +128,10 @@ struct StepParamsT {
   // queue[1 + fly] = number of sub-chunks of that fly already written back
   int* queue;
   int sub_steps, n_items;
+  // item boundaries of a tapered schedule (n_chunks > 0): sub-chunk c of every unit covers steps chunk_start[c] .. chunk_start[c + 1];
+  // n_chunks == 0: uniform items of sub_steps steps
+  int n_chunks;
+  short chunk_start[QUEUE_MAX_CHUNKS + 1];
 };
 using StepParams = StepParamsT<float>;
 

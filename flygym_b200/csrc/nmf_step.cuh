@@ -1705,16 +1705,18 @@ __device__ __forceinline__ void step_entry(const SP& p) {
       block_sync(0);
       unit = warp_uniform(s_fly);
       if (unit < 0) return;
-      step0 = warp_uniform(s_chunk) * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0);
+      const int c = warp_uniform(s_chunk);
+      if (p.n_chunks > 0) { step0 = p.chunk_start[c]; nsub = p.chunk_start[c + 1] - step0; }
+      else { step0 = c * p.sub_steps; nsub = min(p.sub_steps, p.nsteps - step0); }
     }
     const int fly = unit * FPB + slot;
     step_block<WORLD, FPB, NOSLIP>(p, sm, fly < p.n_flies ? fly : -1, step0, nsub, p.queue != nullptr);
     if (!p.queue) return;
     block_sync(0);     // every slot's record store has completed (store_record waited for it); s_fly / s_chunk are free again
     if (tid == 0) {    // hand the unit on
-      const int done = step0 / p.sub_steps + 1;
+      const int done = s_chunk + 1;            // (s_chunk is rewritten only after the next block_sync)
       p.queue[2 + unit] = done;
-      if (done * p.sub_steps < p.nsteps) {
+      if (step0 + nsub < p.nsteps) {
         NMF_THREADFENCE();
         const int j = NMF_ATOMIC_ADD(p.queue + 1, 1);
         NMF_ST_RELEASE(p.queue + 2 + n_units + j, unit + 1);
