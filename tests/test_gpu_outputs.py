@@ -88,7 +88,7 @@ def run_world(wname, precision=32, check=CHECK, settle=0):
                        sens=f64(sim.sensordata).reshape(n, 6, 16), status=f64(sim.status))
     errs = {cp: {} for cp in check}
     for i, (q0, pos, adh) in enumerate(cases):
-        o = Oracle(model); o.reset(); o.qpos[:] = q0
+        o = Oracle(model); o.reset(); o.qpos[:] = np.asarray(q0, np.float32)      # the same (float32-representable) initial state as the device record
         done = 0
         for cp in check:
             o.step_table_full(tab[i, done:cp].astype(np.float64)); done = cp

@@ -41,13 +41,14 @@ def _perturbed_states(model, n, seed=0):
     return q, v
 
 
-def _run_cases(model, cases, checkpoints):
+def _run_cases(model, cases, checkpoints, precision=32):
     """cases: list of (qpos0, qvel0, table[T, nu_pos] or None, adhesion ctrl). Returns {cp: [rel err per case]}."""
     import torch
     from flygym_b200 import B200Simulation
     from oracle.oracle import Oracle
     n, nu_pos, T = len(cases), model.dim("nu_pos"), max(checkpoints)
     sim = B200Simulation(model, n_worlds=n, outputs=False)
+    sim.set_precision(precision)
     tab = np.zeros((n, T, nu_pos), np.float32)
     for i, (q0, v0, table, adh) in enumerate(cases):
         sim.qpos[i].copy_(torch.as_tensor(q0, dtype=torch.float32))
@@ -64,8 +65,8 @@ def _run_cases(model, cases, checkpoints):
     for i, (q0, v0, table, adh) in enumerate(cases):
         o = Oracle(model)
         o.reset()
-        o.qpos[:] = q0
-        o.qvel[:] = v0
+        o.qpos[:] = np.asarray(q0, np.float32)         # the SAME initial state: what the float32 record of the device holds (a state
+        o.qvel[:] = np.asarray(v0, np.float32)         # that differs by one float32 rounding is 1e-2 away after 1000 steps of a tumbling fly)
         o.ctrl[nu_pos:] = adh
         done = 0
         for cp in checkpoints:
@@ -87,6 +88,18 @@ def test_config1_1000_steps(simplify):
     errs = _run_cases(model, [(key, np.zeros(model.nv), None, 0.0), (stand, np.zeros(model.nv), None, 1.0)], (1, 100, 1000))
     print("config-1 qpos rel Linf:", errs)
     assert max(errs[1]) < 1e-6 and max(errs[100]) < 1e-5 and max(errs[1000]) < 1e-4
+    # config 1b: "zero action" read literally -- set_actuator_inputs(zeros(42)) as tests/warp/test_simulation.py:284-297
+    # does: every position target 0 rad, so the legs fold away from the neutral pose while the fly drops
+    zero = np.zeros((1000, model.dim("nu_pos")))
+    errs_b = _run_cases(model, [(key, np.zeros(model.nv), zero, 0.0), (stand, np.zeros(model.nv), zero, 1.0)], (1, 100, 1000))
+    print("config-1b (literal zero targets) qpos rel Linf:", errs_b)
+    # float32 at 1000 steps: 1e-6 ... 2e-2 -- with all targets at 0 rad the legs snap away from the neutral pose, the fly jumps, tumbles and
+    # lands on 1-4 contacts: a chaotic trajectory on which float32 rounding (like a one-ulp change of the initial state in float64, see
+    # _run_cases) is amplified 1e5-fold; the f64 build below stays at 2e-8
+    assert max(errs_b[1]) < 1e-6 and max(errs_b[100]) < 1e-4 and max(errs_b[1000]) < 5e-2
+    errs_b64 = _run_cases(model, [(key, np.zeros(model.nv), zero, 0.0), (stand, np.zeros(model.nv), zero, 1.0)], (1000,), precision=64)
+    print("config-1b, f64 build:", errs_b64)
+    assert max(errs_b64[1000]) < 1e-6                                                              # (measured 2e-8: far inside the north star's 1e-4)
 
 
 @pytest.mark.parametrize("simplify", [True, False])
