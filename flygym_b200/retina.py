@@ -105,6 +105,8 @@ class Retina:
         if not torch.cuda.is_available():
             raise RuntimeError("Retina needs a CUDA device (there is no CPU fallback).")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:       # plain "cuda": the current device
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.H, self.W = H, W
         self.id_map = ommatidia_id_map(H, W, n_rings)
         self.n_ommatidia = int(self.id_map.max())
@@ -113,7 +115,7 @@ class Retina:
         self._lib = _lib.load()
         h = ctypes.c_void_p()
         rc = self._lib.nmf_retina_create(self.pixcode.ctypes.data_as(ctypes.c_void_p), self.inv_norm.ctypes.data_as(ctypes.c_void_p),
-                                         H, W, self.n_ommatidia, self.device.index or 0, ctypes.byref(h))
+                                         H, W, self.n_ommatidia, int(self.device.index), ctypes.byref(h))
         self._h = h
         if rc != 0:
             raise RuntimeError("nmf_retina_create failed: " + (self._lib.nmf_retina_last_error(h).decode() if h else "alloc"))

@@ -128,3 +128,29 @@ def test_trajectory_recorder_and_state_export(tmp_path):
     st = sim.export_state(3)
     assert st["qpos"].shape == (73,) and st["qvel"].shape == (72,) and abs(st["time"] - 30e-4) < 1e-7
     assert np.array_equal(st["qpos"].astype(np.float32), sim.qpos[3].cpu().numpy())
+
+
+def test_two_handles_on_two_gpus_in_one_process():
+    """Every C-ABI entry point runs under a device guard: simulations (and their eye cameras) on different GPUs coexist in one process,
+    whatever the caller's current device is, and leave it as they found it.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from flygym_b200 import B200Simulation
+    from flygym_b200.retina import EyeCameras, Retina
+    torch.cuda.set_device(0)
+    a = B200Simulation(None, n_worlds=8, device="cuda:0")
+    b = B200Simulation(None, n_worlds=8, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    for s in (a, b):
+        s.qpos[:, 2] = -0.15
+    a.step(20); b.step(20); a.step(5); b.step(5)
+    ea, eb = EyeCameras(a, Retina(device="cuda:0")), EyeCameras(b, Retina(device="cuda:1"))
+    ra, rb = ea.retina(), eb.retina()
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert a.qpos.device.index == 0 and b.qpos.device.index == 1 and rb.device.index == 1
+    assert torch.equal(a.state.cpu(), b.state.cpu()) and torch.equal(ra.cpu(), rb.cpu())       # same model, same steps: same bits on both GPUs
+    qh = np.empty((8, a.info.nq), np.float32)
+    b.step_host(np.tile(a.model.arrays["key_ctrl"][:42].astype(np.float32), (8, 1)), 1, qh)
+    assert np.isfinite(qh).all() and torch.cuda.current_device() == 0
