@@ -325,14 +325,19 @@ static step_kernel_f32 kernel_f32(const StepParams& q, int fpb) {
   return fpb == 8 ? nmf_step_x8_kernel : fpb == 4 ? nmf_step_x4_kernel : fpb == 2 ? nmf_step_x2_kernel : nmf_step_kernel;
 }
 // blocks of 8 fly slots exceed the 48 KB of static shared memory: their per-fly regions live in (opt-in) dynamic shared memory
-static size_t dyn_smem_f32(int fpb) { return fpb >= 8 ? (size_t)fpb * f32::SM_WELD * sizeof(float) : 0; }
+// the noslip instantiations carry B_tt (96 x 96) behind the fly's regular region: beyond 48 KB as well (step_entry takes the same decision)
+template <class NSreal> static size_t noslip_smem(int sm_total, int ns_count) { const size_t b = (size_t)(sm_total + ns_count) * sizeof(NSreal); return b > 48 * 1024 ? b : 0; }
+static size_t dyn_smem_f32(const StepParams& q, int fpb) {
+  if (q.noslip_iterations > 0) return noslip_smem<float>(f32::SM_TOTAL, f32::NS_COUNT);
+  return fpb >= 8 ? (size_t)fpb * f32::SM_WELD * sizeof(float) : 0;
+}
 static int set_resident_blocks(nmf_handle* h) {
   DeviceGuard guard(h->device);
   CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
   for (int fpb = 1; fpb <= 8; fpb *= 2) {
     if ((h->hm.par.weld || h->hm.par.noslip_iterations > 0) && fpb > 1) break;
     int per_sm = 0;
-    const size_t dyn = dyn_smem_f32(fpb);
+    const size_t dyn = dyn_smem_f32(h->hm.par, fpb);
     if (dyn) CK(cudaFuncSetAttribute(kernel_f32(h->hm.par, fpb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_f32(h->hm.par, fpb), CTA * fpb, dyn));
     h->resident[fpb] = per_sm * h->sms;
@@ -354,7 +359,7 @@ template <> struct KernelSet<float> {
   static const float* hull(const nmf_handle* h) { return h->d_hull; }
   static int fpb(const nmf_handle* h, int n) { return pick_fpb(h, n); }
   static void launch(const StepParamsT<float>& p, int fpb, int grid, cudaStream_t s) {
-    kernel_f32(p, fpb)<<<grid, CTA * fpb, dyn_smem_f32(fpb), s>>>(p);
+    kernel_f32(p, fpb)<<<grid, CTA * fpb, dyn_smem_f32(p, fpb), s>>>(p);
   }
 };
 template <> struct KernelSet<double> {
@@ -368,17 +373,20 @@ template <> struct KernelSet<double> {
   }
   static void launch(const StepParamsT<double>& p, int fpb, int grid, cudaStream_t s) {
     if (fpb == 4) {
-      static bool attr = false;
       const size_t dyn = (size_t)4 * f64::SM_WELD * sizeof(double);
-      if (!attr) { cudaFuncSetAttribute(nmf_step_f64_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); attr = true; }
+      cudaFuncSetAttribute(nmf_step_f64_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);      // (a per-device attribute: a process-wide "done" flag would miss the second GPU)
       nmf_step_f64_x4_kernel<<<grid, 4 * CTA, dyn, s>>>(p); return;
     }
     if (fpb == 2) { nmf_step_f64_x2_kernel<<<grid, 2 * CTA, 0, s>>>(p); return; }
-    if (p.weld && p.noslip_iterations > 0) nmf_step_tether_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
+    if (p.noslip_iterations > 0) {
+      typedef void (*k64)(const StepParamsT<double>);
+      const k64 kern = p.weld ? nmf_step_tether_noslip_f64_kernel : p.multiccd ? nmf_step_mesh_noslip_f64_kernel
+                     : p.terrain ? nmf_step_terrain_noslip_f64_kernel : nmf_step_noslip_f64_kernel;
+      const size_t dyn = noslip_smem<double>(f64::SM_TOTAL, f64::NS_COUNT);
+      if (dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);     // (per device: set on every launch of this validation path)
+      kern<<<grid, CTA, dyn, s>>>(p);
+    }
     else if (p.weld) nmf_step_tether_f64_kernel<<<grid, CTA, 0, s>>>(p);
-    else if (p.noslip_iterations > 0 && p.multiccd) nmf_step_mesh_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
-    else if (p.noslip_iterations > 0 && p.terrain) nmf_step_terrain_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
-    else if (p.noslip_iterations > 0) nmf_step_noslip_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.multiccd) nmf_step_mesh_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else if (p.terrain) nmf_step_terrain_f64_kernel<<<grid, CTA, 0, s>>>(p);
     else nmf_step_f64_kernel<<<grid, CTA, 0, s>>>(p);

@@ -498,7 +498,8 @@ __device__ __forceinline__ void basis_wrench(const Con& c, const real* G, real m
   W[0] += T[0]; W[1] += T[1]; W[2] += T[2]; W[3] += F[0]; W[4] += F[1]; W[5] += F[2];
   if (Fout) { Fout[0] = F[0]; Fout[1] = F[1]; Fout[2] = F[2]; }
 }
-constexpr int NS_MAXC = 24;             // contacts the noslip pass handles (more: the pass is skipped and ST_NOSLIP_SKIP is raised)
+constexpr int NS_MAXC = 48;             // contacts the noslip pass handles (more: the pass is skipped and ST_NOSLIP_SKIP is raised); a mesh-hull fly dropped
+                                        // flat on the ground has 48 with multiccd.  The region (B alone is 96 x 96) puts the noslip kernels into dynamic shared memory
 constexpr int NS_LD = 2 * NS_MAXC;      // two friction dimensions per contact
 
 // ------------------------------------------------------------------ weld equality of the TetheredWorld (hub lane only)

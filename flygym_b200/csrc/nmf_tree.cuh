@@ -591,7 +591,7 @@ __device__ __forceinline__ void tree_step_block(const TP& p, real* sm, const int
         // noslip post-solver of the reference's CPU path (mujoco_globals.yaml:15; [PRIOR] mj_solNoSlip), as in nmf_step.cuh: projected
         // Gauss-Seidel on the friction dimensions of the dual problem without the regulariser.  In the basis (n, mu t1, mu t2) of a
         // contact a pair of opposing pyramid edges is one tangential component g with |g| <= the normal force the pair carries;
-        //     g <- clamp(g - h / B_gg),   h = jar_t(qacc) + B_tt (g - g_newton),   B_tt = E_t M^-1 E_t'  (2C x 2C, C <= 24).
+        //     g <- clamp(g - h / B_gg),   h = jar_t(qacc) + B_tt (g - g_newton),   B_tt = E_t M^-1 E_t'  (2C x 2C, C <= 48).
         // B_tt is built column by column -- a unit wrench at the contact, subtree sums, a solve with the plain inertia matrix in the
         // ancestor-sparse storage, body accelerations, projection on every contact's tangents -- the sweeps run on it in shared memory
         // in the oracle's contact order (geom, then slot), and qacc moves by M^-1 E_t' (g - g_newton).  (Tethered world: see below.)

@@ -17,7 +17,7 @@ constexpr int TCON_STRIDE = 18;                // reals per contact slot in shar
 // noslip post-solver (models baked with noslip_iterations > 0): at most TNS_MAXC simultaneous contacts, two friction dimensions each.
 // Region of TNS_TOTAL reals: B_tt (TNS_LD x TNS_LD) | g | g at Newton | pair limits | tangential rows | explicit basis forces (n, t1, t2)
 // per ranked contact | slot of every ranked contact (ints) | count
-constexpr int TNS_MAXC = 24, TNS_LD = 2 * TNS_MAXC;
+constexpr int TNS_MAXC = 48, TNS_LD = 2 * TNS_MAXC;
 constexpr int TNS_B = 0, TNS_G = TNS_LD * TNS_LD, TNS_G0 = TNS_G + TNS_LD, TNS_LIM = TNS_G0 + TNS_LD, TNS_JT = TNS_LIM + TNS_LD,
               TNS_GX = TNS_JT + TNS_LD, TNS_IDX = TNS_GX + 3 * TNS_MAXC, TNS_MISC = TNS_IDX + TNS_MAXC, TNS_TOTAL = TNS_MISC + 4;
 

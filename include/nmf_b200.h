@@ -42,7 +42,7 @@ enum nmf_fly_status {
   NMF_ST_NONFINITE = 1,    /* a generalised velocity became NaN / infinite */
   NMF_ST_NEWTON_CAP = 2,   /* the Newton solver hit `iterations` (mujoco_globals.yaml:14) with the active set still changing */
   NMF_ST_LS_CAP = 4,       /* a line search used up its evaluation cap (MuJoCo's ls_iterations) */
-  NMF_ST_NOSLIP_SKIP = 8   /* more than 24 simultaneous contacts: the step ran without the noslip pass (noslip models only) */
+  NMF_ST_NOSLIP_SKIP = 8   /* more than 48 simultaneous contacts: the step ran without the noslip pass (noslip models only) */
 };
 
 /* Device buffers owned by the caller (PyTorch tensors in the Python host). `state`

@@ -131,10 +131,10 @@ def test_tree_host_tables_and_limits():
         assert info["s_stride"] % 4 == 0 and info["s_qvel"] >= info["nq"] and info["s_time"] >= info["s_ctrl"] + info["nu"]
     m = NMFModel.bench(joint_preset="all_biological")
     assert emu.tree_info(m)["nH"] == sum(len(_anc(m, k)) for k in range(m.nv))
-    # a model that asks for the noslip post-solver gets its B_tt / force region (2.6 k reals + one int per contact slot) on top
+    # a model that asks for the noslip post-solver gets its B_tt / force region (9.8 k reals + one int per contact slot) on top
     for kw in (dict(joint_preset="all_biological"), dict(joint_preset="all_possible", contact_preset="all")):
         plain, ns = emu.tree_info(NMFModel.bench(**kw)), emu.tree_info(NMFModel.bench(**kw).with_options(noslip_iterations=5))
-        assert 2500 * 4 < ns["smem_f32"] - plain["smem_f32"] < 3200 * 4 and ns["smem_f64"] < 227 * 1024, (plain, ns)
+        assert 9500 * 4 < ns["smem_f32"] - plain["smem_f32"] < 10500 * 4 and ns["smem_f64"] < 227 * 1024, (plain, ns)
 
 
 def _anc(m, k):

@@ -578,6 +578,27 @@ def test_noslip_runs_in_float32_in_every_world():
         assert bool(np.isfinite(sim.qpos.cpu().numpy()).all()) and int(sim.status.abs().max()) == 0
 
 
+@pytest.mark.parametrize("skeleton", ["legs_only", "all_biological"])
+def test_noslip_with_many_contacts(skeleton):
+    """A mesh-hull fly dropped flat onto the ground has 48 contacts at once with multiccd (4 per hull): the noslip pass takes up to 48
+    (star and general-topology kernels; B_tt is 96 x 96 in dynamic shared memory) and must follow the oracle there too, without
+    raising NMF_ST_NOSLIP_SKIP.  f64 build, 30 steps from a 0.02 mm penetration."""
+    import torch
+    from flygym_b200 import B200Simulation, NMFModel
+    from oracle.oracle import Oracle
+    m = NMFModel.bench(False, joint_preset=skeleton).with_options(noslip_iterations=5)
+    q0 = m.arrays["key_qpos"].astype(np.float32).astype(np.float64); q0[2] = np.float32(-0.17)
+    o = Oracle(m); o.reset(); o.qpos[:] = q0; o.ctrl[m.dim("nu_pos"):] = 1.0
+    o.step(1); ncon1 = o.dim("ncon"); o.step(29)
+    for prec, tol in ((64, 5e-7), (32, 2e-5)):
+        sim = B200Simulation(m, n_worlds=2); sim.set_precision(prec)
+        sim.qpos.copy_(torch.as_tensor(np.tile(q0, (2, 1)), dtype=torch.float32)); sim.ctrl[:, m.dim("nu_pos"):] = 1.0
+        sim.step(30)
+        err = np.abs(sim.qpos[0].cpu().numpy() - o.qpos).max() / np.abs(o.qpos).max()
+        print(f"{skeleton} f{prec}: {ncon1} contacts in the first step, qpos rel Linf after 30 steps {err:.1e}, status {int(sim.status.abs().max())}")
+        assert ncon1 > 24 and err < tol and int(sim.status.abs().max()) == 0
+
+
 def test_tethered_world_with_noslip_matches_the_oracle():
     """The world of the reference's own `tests/core/test_simulation.py` fixtures (TetheredWorld) under the CPU `Simulation`
     semantics (noslip_iterations = 5): the six weld rows are equality rows, which MuJoCo's noslip sweeps unclamped -- the soft
