@@ -103,7 +103,9 @@ int nmf_gather_state(nmf_handle* h, int section_offset, const int32_t* cols, int
 
 /* Host-buffer convenience used for end-to-end timing: copies `actions` (HOST [n_flies][action_cols], action_cols = nu_pos or
  * nu_pos + nu_adh) to the device, steps `nsteps`, copies qpos (HOST [n_flies][nq]) back.  Synchronises the stream.  Large batches
- * are cut into up to four slices pipelined over streams owned by the handle (copies of one slice overlap kernels of the others). */
+ * are cut into up to four slices pipelined over streams owned by the handle (copies of one slice overlap kernels of the others).
+ * With page-locked (pinned / registered) host buffers the pipeline is captured once as a CUDA graph and replayed, the host addresses
+ * of the call patched into its copy nodes; pageable buffers, the f64 build and a failed capture take the call-by-call path. */
 int nmf_step_host(nmf_handle* h, const float* actions_host, int action_cols, int nsteps, float* qpos_host, void* cuda_stream);
 
 int nmf_set_solver(nmf_handle* h, int max_newton_iterations, int max_linesearch_iterations);
