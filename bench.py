@@ -489,8 +489,9 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
     act_host = table[:, :e2e_steps, :act_cols].permute(1, 0, 2).contiguous().cpu().pin_memory()
     if not per_step:
         res_host = torch.empty((n, model.nq), dtype=torch.float32).pin_memory()
+        act_rows, res_np = [act_host[s].numpy() for s in range(act_host.shape[0])], res_host.numpy()     # views of the pinned buffers
         def e2e_step(s):
-            sim.step_host(act_host[s].numpy(), 1, res_host.numpy())
+            sim.step_host(act_rows[s], 1, res_np)
     else:
         res_dev = sens_out if eyes is not None else state["odor"]
         res_host = torch.empty(res_dev.shape, dtype=torch.float32).pin_memory()

@@ -359,12 +359,19 @@ class B200Simulation:
                 "time": float(rec[i.off_time])}
 
     def step_host(self, actions_host: np.ndarray, nsteps: int, qpos_host: np.ndarray) -> None:
-        """End-to-end call with HOST buffers (H2D actions, ``nsteps`` steps, D2H qpos); synchronous."""
-        assert actions_host.dtype == np.float32 and actions_host.ndim == 2 and actions_host.shape[0] == self.n_worlds
-        assert actions_host.shape[1] in (self.info.nu_pos, self.info.nu_pos + self.info.nu_adh) and actions_host.flags.c_contiguous
-        assert qpos_host.dtype == np.float32 and qpos_host.shape == (self.n_worlds, self.info.nq)
-        self._check(self._lib.nmf_step_host(self._h, actions_host.ctypes.data_as(ctypes.c_void_p), int(actions_host.shape[1]), int(nsteps),
-                                            qpos_host.ctypes.data_as(ctypes.c_void_p), self._stream()))
+        """End-to-end call with HOST buffers (H2D actions, ``nsteps`` steps, D2H qpos); synchronous.  With page-locked buffers
+        (``torch.Tensor.pin_memory().numpy()``) the library replays the whole pipeline as one CUDA graph."""
+        a, q, info = actions_host, qpos_host, self.info
+        if (a.dtype != np.float32 or a.ndim != 2 or a.shape[0] != self.n_worlds or not a.flags.c_contiguous
+                or a.shape[1] not in (info.nu_pos, info.nu_pos + info.nu_adh)):
+            raise ValueError(f"actions_host must be a C-contiguous float32 array of shape ({self.n_worlds}, {info.nu_pos}) or "
+                             f"({self.n_worlds}, {info.nu_pos + info.nu_adh})")
+        if q.dtype != np.float32 or q.shape != (self.n_worlds, info.nq) or not q.flags.c_contiguous:
+            raise ValueError(f"qpos_host must be a C-contiguous float32 array of shape ({self.n_worlds}, {info.nq})")
+        # (plain integers for the pointer arguments: this call is made once per step, every microsecond of wrapper shows end to end)
+        rc = self._lib.nmf_step_host(self._h, a.ctypes.data, a.shape[1], nsteps, q.ctypes.data, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            self._check(rc)
 
     def set_solver(self, max_newton: int = 8, max_linesearch: int = 8) -> None:
         self._check(self._lib.nmf_set_solver(self._h, int(max_newton), int(max_linesearch)))
