@@ -51,7 +51,7 @@ NCU_TRAFFIC_PER_FLY_STEP = {
     "terrain": ((0.0896e9 + 0.5587e9) / (4096 * 100), "profiles/ncu_step_terrain_r01_summary.txt (4096 flies x 100 steps, 80-register build)"),
     "olfaction": ((0.0774e9 + 0.6436e9) / 32768, "profiles/ncu_step_olfaction_r01_summary.txt (one 1-step launch of 32768 flies with outputs)"),
 }
-VISION_TRAFFIC = (2.92e6 / 1024, "profiles/ncu_eye_body_r02b_summary.txt: the fused kernel reads 2.9 MB per 1024 flies (run table, poses, body capsules) and never materialises the eye buffers")
+VISION_TRAFFIC = (2.92e6 / 1024, "profiles/ncu_eye_body_r02c_summary.txt: the fused kernel reads 2.9 MB per 1024 flies (run table, poses, body capsules) and never materialises the eye buffers")
 RETINA_BUFFERS_TRAFFIC = (1.0096e9 + 6.9e6, "profiles/ncu_retina_r02_summary.txt: 1.010 GB read + 6.9 MB written = 0.71 x algorithmic (chunks outside the hexagon skipped)")
 # what actually bounds the step kernel (same captures): issue-slot utilisation and the dominant stall reason
 NCU_LIMITER = {
@@ -63,8 +63,9 @@ NCU_LIMITER = {
              "source": "profiles/ncu_step_r02f_summary.txt"},
     "terrain": {"issue_slots_busy": 0.314, "top_stall": "no_inst (instruction fetch) 56 % of samples", "source": "profiles/ncu_step_terrain_r01_summary.txt"},
     "olfaction": {"issue_slots_busy": 0.509, "top_stall": "no_inst (instruction fetch)", "source": "profiles/ncu_step_olfaction_r01_summary.txt"},
-    "vision": {"issue_slots_busy": 0.764, "top_stall": "issue-bound: 1.34 G warp instructions per 1024 flies (fused eye + Retina kernel: ~46 % shading, ~45 % body raster, "
-               "the explicitly rounded FADD / FMUL of the capsule hit test being the largest single item)", "source": "profiles/ncu_eye_body_r02b_summary.txt"},
+    "vision": {"issue_slots_busy": 0.698, "top_stall": "issue-bound: 1.11 G warp instructions per 1024 flies (fused eye + Retina kernel: shading and body raster in about "
+               "equal parts, the explicitly rounded FADD / FMUL of the capsule hit test being the largest single item), 3 blocks per SM",
+               "source": "profiles/ncu_eye_body_r02c_summary.txt"},
 }
 TREE_TRAFFIC_PER_FLY_STEP = (8.4e6 / (1480 * 20), "profiles/ncu_tree_r02_summary.txt (nmf_tree_step_kernel, ALL_BIOLOGICAL, 1480 flies x 20 steps: 8.4 MB read + 2 KB written = "
                                     "the records and the model tables once; nothing spills)")
@@ -460,7 +461,7 @@ def measure(ctx, args, *, steps, warmup, sample_clocks, e2e_cap=200, dominant=Tr
                                         "note": "the HBM-bound form of the operator: eye buffers materialised in HBM (two 1.4 GB sets alternated); a pure "
                                                 "read stream that skips chunks outside the ommatidia hexagon, hence above the copy-measured peak"},
                 "note": f"algorithmic bytes = the Retina operator's {RETINA_ALG_BYTES} B per fly-frame (SURVEY.md 8d); the fused kernel shades "
-                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (76 % busy, 3 blocks per SM), not HBM"}
+                        "the pixels in registers and never materialises the eye buffers, so it is bound by instruction issue (70 % busy, 3 blocks per SM), not HBM"}
         del imgs
     else:
         per_launch_steps = 1 if per_step else chunk
