@@ -245,7 +245,7 @@ def test_step_is_cuda_graph_capturable():
 
 def test_work_queue_schedule_is_bit_identical():
     """Multi-step launches of more flies than the GPU holds resident blocks are served from a device-side work queue
-    (sub-chunks of `sub_steps` steps); the schedule must not change a single bit of any fly's trajectory."""
+    (sub-chunks of `sub_steps` steps, or the heuristic's tapered items); the schedule must not change a single bit of any fly's trajectory."""
     import torch
     from flygym_b200 import B200Simulation, NMFModel
     from flygym_b200.actions import cpg_table
@@ -253,7 +253,7 @@ def test_work_queue_schedule_is_bit_identical():
     n = 3001                                         # > 148 SMs x 16 resident blocks, and not a multiple of anything
     table = torch.from_numpy(cpg_table(m, n, 64)).cuda()
     finals = []
-    for sub in (0, 10, 7):
+    for sub in (0, 10, 7, -1):                       # no queue, uniform items of 10 / 7 steps, the heuristic (tapered: 8 8 7 7 6 4 3 2)
         sim = B200Simulation(m, n_worlds=n, outputs=True)
         sim.set_schedule(sub)
         sim.qpos[:, 2] = -0.15                       # feet on the ground
